@@ -1,0 +1,512 @@
+// fd_api.cu -- the C ABI of libfacedeform_gpu.so (include/facedeform_gpu.h): handles, memory, phase timing,
+// host-pointer wrappers around the device-pointer entry points.  No CPU fallback anywhere: every numeric
+// result comes out of the CUDA kernels in this directory.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "fd_internal.h"
+
+namespace {
+
+#define FD_SET_ERR(ctx, ...) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int stage(fd_ctx* ctx, int slot, size_t bytes, void** out)
+{
+    if (bytes < 256) bytes = 256;
+    if (ctx->stage_bytes[slot] < bytes) {
+        if (ctx->stage_dev[slot]) {
+            FD_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            FD_CUDA_OK(ctx, cudaFree(ctx->stage_dev[slot]));
+            ctx->stage_dev[slot] = nullptr;
+            ctx->stage_bytes[slot] = 0;
+        }
+        cudaError_t e = cudaMalloc(&ctx->stage_dev[slot], bytes);
+        if (e != cudaSuccess) {
+            FD_SET_ERR(ctx, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? FD_E_NOMEM : FD_E_CUDA;
+        }
+        ctx->stage_bytes[slot] = bytes;
+    }
+    *out = ctx->stage_dev[slot];
+    return FD_OK;
+}
+
+void phase_begin(fd_ctx* ctx, int ph) { cudaEventRecord(ctx->ev_begin[ph], ctx->stream); }
+void phase_end(fd_ctx* ctx, int ph)
+{
+    cudaEventRecord(ctx->ev_end[ph], ctx->stream);
+    ctx->phase_valid[ph] = true;
+}
+
+template <typename T> int dev_alloc(fd_ctx* ctx, T** p, size_t count)
+{
+    cudaError_t e = cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        FD_SET_ERR(ctx, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        *p = nullptr;
+        return e == cudaErrorMemoryAllocation ? FD_E_NOMEM : FD_E_CUDA;
+    }
+    return FD_OK;
+}
+
+int check_params(fd_ctx* ctx, const fd_params* p)
+{
+    if (p->model != FD_MODEL_QNN && p->model != FD_MODEL_ML) { FD_SET_ERR(ctx, "model must be 0 (QNN) or 1 (Multilayer)"); return FD_E_INVALID; }
+    if (p->term < 0 || p->term > 2) { FD_SET_ERR(ctx, "term must be 0 (linear), 1 (const) or 2 (zero)"); return FD_E_INVALID; }
+    if (p->kernel < 0 || p->kernel > 2) { FD_SET_ERR(ctx, "kernel must be 0 (gaussian), 1 (multiquadric) or 2 (thin plate)"); return FD_E_INVALID; }
+    if (!(p->radius > 0.f) || !isfinite(p->radius)) { FD_SET_ERR(ctx, "radius must be positive"); return FD_E_INVALID; }
+    if (!(p->lambda >= 0.f)) { FD_SET_ERR(ctx, "lambda must be >= 0"); return FD_E_INVALID; }
+    if (p->eval_precision < 0 || p->eval_precision > 2 || p->eval_path < 0 || p->eval_path > 2) { FD_SET_ERR(ctx, "bad eval_precision / eval_path"); return FD_E_INVALID; }
+    return FD_OK;
+}
+
+// allocates everything that depends only on N (fit-time state)
+int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, fd_model** out)
+{
+    fd_model* m = new (std::nothrow) fd_model();
+    if (!m) return FD_E_NOMEM;
+    memset(m, 0, sizeof(*m));
+    m->ctx = ctx;
+    m->prm = *params;
+    m->N = N;
+    m->np = fd_poly_terms(params->term);
+    m->n = N + m->np;
+    m->lda = fd_round_up(m->n, 32);
+    m->receiver = !with_factor;
+    m->eval64 = params->eval_precision == FD_EVAL_FP64 ||
+                (params->eval_precision == FD_EVAL_AUTO && params->kernel != FD_KERNEL_GAUSSIAN);
+    int st = FD_OK;
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_rest, (size_t)N * 3);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_radii, (size_t)N);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_flags, FD_NUM_FLAGS);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_pivstat, 2);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_ctab32, (size_t)N);
+    if (st == FD_OK && m->eval64) st = dev_alloc(ctx, &m->d_ctab64, (size_t)N);
+    if (st == FD_OK && with_factor) {
+        st = dev_alloc(ctx, &m->d_A, (size_t)m->lda * m->n);
+        if (st == FD_OK) st = dev_alloc(ctx, &m->d_ipiv, (size_t)m->n);
+        if (st == FD_OK) st = dev_alloc(ctx, &m->d_perm, (size_t)m->n);
+    }
+    if (st != FD_OK) {
+        fd_model_destroy(m);
+        return st;
+    }
+    cudaMemsetAsync(m->d_flags, 0, FD_NUM_FLAGS * sizeof(int), ctx->stream);
+    *out = m;
+    return FD_OK;
+}
+
+int model_reserve_frames(fd_model* m, int F)
+{
+    fd_ctx* ctx = m->ctx;
+    if (F <= m->capF) return FD_OK;
+    if (m->d_W) { cudaStreamSynchronize(ctx->stream); cudaFree(m->d_W); m->d_W = nullptr; }
+    if (m->d_W32) { cudaFree(m->d_W32); m->d_W32 = nullptr; }
+    m->capF = 0;
+    const int ld = fd_round_up(3 * F, 4);
+    int st = dev_alloc(ctx, &m->d_W, (size_t)m->n * ld);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_W32, (size_t)m->n * ld);
+    if (st != FD_OK) return st;
+    m->capF = F;
+    return FD_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int fd_abi_version(void) { return FD_ABI_VERSION; }
+
+const char* fd_status_string(int status)
+{
+    switch (status) {
+    case FD_OK: return "ok";
+    case FD_E_INVALID: return "invalid argument";
+    case FD_E_MISMATCH_POINT: return "Rest and deform geometry should match.";
+    case FD_E_BUILD: return "Can't build RBF model.";
+    case FD_E_SINGULAR: return "Can't solve the problem.";
+    case FD_E_CUDA: return "CUDA error";
+    case FD_E_NOMEM: return "out of device memory";
+    case FD_E_CAPTURE: return "Can't capture geometry with a rig!";
+    case FD_E_UNSUPPORTED: return "unsupported";
+    case FD_E_STATE: return "call order";
+    default: return "unknown status";
+    }
+}
+
+// defaults of the parameter templates, SOP_FaceDeform.cpp:117-137
+void fd_params_default(fd_params* p)
+{
+    memset(p, 0, sizeof(*p));
+    p->model = FD_MODEL_QNN;
+    p->term = FD_TERM_LINEAR;
+    p->kernel = FD_KERNEL_GAUSSIAN;
+    p->qcoef = 1.0f;
+    p->zcoef = 5.0f;
+    p->radius = 1.0f;
+    p->layers = 4;
+    p->lambda = 0.1f;
+    p->maxedges = 4;
+    p->weightrange[0] = 0.0f;
+    p->weightrange[1] = 1.0f;
+    p->falloffradius = 1.0f;
+    p->falloffrate = 1.0f;
+    p->eval_precision = FD_EVAL_AUTO;
+    p->eval_path = FD_PATH_AUTO;
+}
+
+// SYSmax clamps of cookMySop, SOP_FaceDeform.cpp:249-257
+void fd_params_clamp(fd_params* p)
+{
+    if (p->qcoef < 0.1f) p->qcoef = 0.1f;
+    if (p->zcoef < 0.1f) p->zcoef = 0.1f;
+    if (p->radius < 0.01f) p->radius = 0.01f;
+    if (p->layers < 1) p->layers = 1;
+    if (p->lambda < 0.01f) p->lambda = 0.01f;
+    if (p->maxedges < 1) p->maxedges = 1;
+}
+
+int fd_ctx_create(fd_ctx** out, int device, void* stream)
+{
+    if (!out) return FD_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return FD_E_CUDA; // no GPU: fail loudly, no fallback
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return FD_E_CUDA;
+    if (device >= count) return FD_E_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return FD_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FD_E_CUDA;
+    if (prop.major != 10) return FD_E_UNSUPPORTED; // built for sm_100a only
+    fd_ctx* ctx = new (std::nothrow) fd_ctx();
+    if (!ctx) return FD_E_NOMEM;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FD_E_CUDA; }
+        ctx->own_stream = true;
+    }
+    for (int i = 0; i < FD_PH_COUNT; ++i) {
+        cudaEventCreate(&ctx->ev_begin[i]);
+        cudaEventCreate(&ctx->ev_end[i]);
+    }
+    *out = ctx;
+    return FD_OK;
+}
+
+void fd_ctx_destroy(fd_ctx* ctx)
+{
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < FD_NUM_STAGE; ++i)
+        if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
+    for (int i = 0; i < FD_PH_COUNT; ++i) {
+        cudaEventDestroy(ctx->ev_begin[i]);
+        cudaEventDestroy(ctx->ev_end[i]);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int fd_ctx_synchronize(fd_ctx* ctx)
+{
+    if (!ctx) return FD_E_INVALID;
+    FD_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+const char* fd_last_error(const fd_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+float fd_ctx_phase_ms(fd_ctx* ctx, int phase)
+{
+    if (!ctx || phase < 0 || phase >= FD_PH_COUNT || !ctx->phase_valid[phase]) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(ctx->ev_end[phase]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_begin[phase], ctx->ev_end[phase]) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+int64_t fd_ctx_launch_count(const fd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void fd_model_destroy(fd_model* m)
+{
+    if (!m) return;
+    DeviceGuard g(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(m->d_rest);
+    cudaFree(m->d_radii);
+    cudaFree(m->d_A);
+    cudaFree(m->d_ipiv);
+    cudaFree(m->d_perm);
+    cudaFree(m->d_W);
+    cudaFree(m->d_flags);
+    cudaFree(m->d_pivstat);
+    cudaFree(m->d_ctab32);
+    cudaFree(m->d_W32);
+    cudaFree(m->d_ctab64);
+    delete m;
+}
+
+// rbfcreate + rbfsetpoints + rbfsetalgo* + rbfset*term + the factorisation half of rbfbuildmodel
+int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_dev, int32_t n_ctrl, fd_model** out)
+{
+    if (!ctx || !params || !out) return FD_E_INVALID;
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    int st = check_params(ctx, params);
+    if (st != FD_OK) return st;
+    if (n_ctrl < 1 || !rest_ctrl_dev) { FD_SET_ERR(ctx, "Can't build RBF model: no control points"); return FD_E_BUILD; }
+    if ((size_t)(n_ctrl + 4) * sizeof(int) > 64 * 1024) { FD_SET_ERR(ctx, "more than 16380 control points are not supported"); return FD_E_UNSUPPORTED; }
+    fd_model* m = nullptr;
+    st = model_alloc(ctx, params, n_ctrl, true, &m);
+    if (st != FD_OK) return st;
+    void* scratch;
+    st = stage(ctx, FD_STAGE_MISC, 256, &scratch);
+    if (st != FD_OK) { fd_model_destroy(m); return st; }
+    cudaError_t e = cudaMemcpyAsync(m->d_rest, rest_ctrl_dev, (size_t)n_ctrl * 3 * sizeof(float), cudaMemcpyDefault, ctx->stream);
+    phase_begin(ctx, FD_PH_ASSEMBLE);
+    if (e == cudaSuccess) e = fd_launch_radii(ctx, m->prm, m->d_rest, m->N, m->d_radii, m->d_flags);
+    if (e == cudaSuccess) e = fd_launch_assemble(ctx, m->prm, m->d_rest, m->d_radii, m->N, m->np, m->d_A, m->lda);
+    phase_end(ctx, FD_PH_ASSEMBLE);
+    phase_begin(ctx, FD_PH_FACTOR);
+    if (e == cudaSuccess) e = fd_launch_lu(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat);
+    phase_end(ctx, FD_PH_FACTOR);
+    if (e != cudaSuccess) {
+        FD_SET_ERR(ctx, "fit: %s", cudaGetErrorString(e));
+        fd_model_destroy(m);
+        return FD_E_CUDA;
+    }
+    m->fitted = true;
+    *out = m;
+    return FD_OK;
+}
+
+int fd_rbf_fit(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl, int32_t n_ctrl, fd_model** out,
+               fd_report* report)
+{
+    // rest_ctrl is a host pointer: cudaMemcpyDefault inside fit_dev copies it (pageable memory is staged by the driver)
+    int st = fd_rbf_fit_dev(ctx, params, rest_ctrl, n_ctrl, out);
+    if (st != FD_OK) return st;
+    st = fd_model_report(*out, report);
+    if (st != FD_OK) {
+        fd_model_destroy(*out);
+        *out = nullptr;
+    }
+    return st;
+}
+
+int fd_rbf_solve_dev(fd_model* m, const float* deform_ctrl_dev, int32_t n_ctrl, int32_t frames)
+{
+    if (!m || !deform_ctrl_dev) return FD_E_INVALID;
+    fd_ctx* ctx = m->ctx;
+    DeviceGuard g(ctx->device);
+    if (m->receiver || !m->fitted) { FD_SET_ERR(ctx, "solve: the model holds no factorisation"); return FD_E_STATE; }
+    if (n_ctrl != m->N) { FD_SET_ERR(ctx, "%s", fd_status_string(FD_E_MISMATCH_POINT)); return FD_E_MISMATCH_POINT; } // :231-234
+    if (frames < 1) { FD_SET_ERR(ctx, "frames must be >= 1"); return FD_E_INVALID; }
+    int st = model_reserve_frames(m, frames);
+    if (st != FD_OK) return st;
+    m->F = frames;
+    m->ldw = fd_round_up(3 * frames, 4);
+    m->ldw32 = m->ldw;
+    phase_begin(ctx, FD_PH_SOLVE);
+    cudaError_t e = fd_launch_solve(ctx, m, deform_ctrl_dev, frames);
+    if (e == cudaSuccess) e = fd_launch_pack(ctx, m);
+    phase_end(ctx, FD_PH_SOLVE);
+    if (e != cudaSuccess) { FD_SET_ERR(ctx, "solve: %s", cudaGetErrorString(e)); return FD_E_CUDA; }
+    m->solved = true;
+    return FD_OK;
+}
+
+int fd_rbf_solve(fd_model* m, const float* deform_ctrl, int32_t n_ctrl, int32_t frames, fd_report* report)
+{
+    if (!m || !deform_ctrl) return FD_E_INVALID;
+    fd_ctx* ctx = m->ctx;
+    DeviceGuard g(ctx->device);
+    if (n_ctrl != m->N) { FD_SET_ERR(ctx, "%s", fd_status_string(FD_E_MISMATCH_POINT)); return FD_E_MISMATCH_POINT; }
+    if (frames < 1) { FD_SET_ERR(ctx, "frames must be >= 1"); return FD_E_INVALID; }
+    const size_t bytes = (size_t)frames * n_ctrl * 3 * sizeof(float);
+    void* d_def;
+    int st = stage(ctx, FD_STAGE_P, bytes, &d_def);
+    if (st != FD_OK) return st;
+    FD_CUDA_OK(ctx, cudaMemcpyAsync(d_def, deform_ctrl, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    st = fd_rbf_solve_dev(m, (const float*)d_def, n_ctrl, frames);
+    if (st != FD_OK) return st;
+    return fd_model_report(m, report);
+}
+
+int fd_model_report(fd_model* m, fd_report* report)
+{
+    if (!m) return FD_E_INVALID;
+    fd_ctx* ctx = m->ctx;
+    DeviceGuard g(ctx->device);
+    int flags[FD_NUM_FLAGS];
+    double piv[2] = {0, 0};
+    FD_CUDA_OK(ctx, cudaMemcpyAsync(flags, m->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA_OK(ctx, cudaMemcpyAsync(piv, m->d_pivstat, sizeof(piv), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    int term = 1;
+    if (flags[FD_FLAG_ZERO_RADIUS]) term = -5;
+    else if (flags[FD_FLAG_SINGULAR] || flags[FD_FLAG_NONFINITE]) term = -3;
+    if (report) {
+        report->terminationtype = term;
+        report->iterationscount = 0;
+        report->n = m->N;
+        report->npoly = m->np;
+        report->frames = m->F;
+        report->reserved = flags[FD_FLAG_SINGULAR];
+        report->min_pivot = piv[0];
+        report->max_pivot = piv[1];
+    }
+    if (term != 1) { // SOP_FaceDeform.cpp:365-368
+        FD_SET_ERR(ctx, "%s (terminationtype %d)", fd_status_string(FD_E_SINGULAR), term);
+        return FD_E_SINGULAR;
+    }
+    return FD_OK;
+}
+
+int fd_rbf_eval_dev(fd_model* m, const float* P, int64_t n_vtx, const float* dist2, const float* tangentu,
+                    const float* tangentv, const float* normal, float* P_out, float* falloff_out)
+{
+    if (!m || (n_vtx > 0 && (!P || !P_out)) || n_vtx < 0) return FD_E_INVALID;
+    fd_ctx* ctx = m->ctx;
+    DeviceGuard g(ctx->device);
+    if (!m->solved) { FD_SET_ERR(ctx, "eval: no weights (call fd_rbf_solve or fd_model_commit_weights first)"); return FD_E_STATE; }
+    phase_begin(ctx, FD_PH_EVAL);
+    cudaError_t e = fd_launch_eval(ctx, m, P, n_vtx, dist2, tangentu, tangentv, normal, P_out, falloff_out);
+    phase_end(ctx, FD_PH_EVAL);
+    if (e != cudaSuccess) { FD_SET_ERR(ctx, "eval: %s", cudaGetErrorString(e)); return FD_E_CUDA; }
+    return FD_OK;
+}
+
+int fd_rbf_eval(fd_model* m, const float* P, int64_t n_vtx, const float* dist2, const float* tangentu,
+                const float* tangentv, const float* normal, float* P_out, float* falloff_out)
+{
+    if (!m || (n_vtx > 0 && (!P || !P_out)) || n_vtx < 0) return FD_E_INVALID;
+    fd_ctx* ctx = m->ctx;
+    DeviceGuard g(ctx->device);
+    if (!m->solved) { FD_SET_ERR(ctx, "eval: no weights (call fd_rbf_solve or fd_model_commit_weights first)"); return FD_E_STATE; }
+    if (n_vtx == 0) return FD_OK;
+    const size_t v3 = (size_t)n_vtx * 3 * sizeof(float), v1 = (size_t)n_vtx * sizeof(float);
+    void *dP = nullptr, *dD = nullptr, *dU = nullptr, *dV = nullptr, *dN = nullptr, *dO = nullptr, *dF = nullptr;
+    int st = stage(ctx, FD_STAGE_P, v3, &dP);
+    if (st == FD_OK && dist2) st = stage(ctx, FD_STAGE_DIST, v1, &dD);
+    const bool tang = m->prm.tangent && tangentu && tangentv && normal;
+    if (st == FD_OK && tang) st = stage(ctx, FD_STAGE_TU, v3, &dU);
+    if (st == FD_OK && tang) st = stage(ctx, FD_STAGE_TV, v3, &dV);
+    if (st == FD_OK && tang) st = stage(ctx, FD_STAGE_N, v3, &dN);
+    if (st == FD_OK) st = stage(ctx, FD_STAGE_OUT, v3 * (size_t)m->F, &dO);
+    if (st == FD_OK && falloff_out) st = stage(ctx, FD_STAGE_FALLOFF, v1, &dF);
+    if (st != FD_OK) return st;
+    cudaStream_t s = ctx->stream;
+    FD_CUDA_OK(ctx, cudaMemcpyAsync(dP, P, v3, cudaMemcpyHostToDevice, s));
+    if (dD) FD_CUDA_OK(ctx, cudaMemcpyAsync(dD, dist2, v1, cudaMemcpyHostToDevice, s));
+    if (tang) {
+        FD_CUDA_OK(ctx, cudaMemcpyAsync(dU, tangentu, v3, cudaMemcpyHostToDevice, s));
+        FD_CUDA_OK(ctx, cudaMemcpyAsync(dV, tangentv, v3, cudaMemcpyHostToDevice, s));
+        FD_CUDA_OK(ctx, cudaMemcpyAsync(dN, normal, v3, cudaMemcpyHostToDevice, s));
+    }
+    st = fd_rbf_eval_dev(m, (const float*)dP, n_vtx, (const float*)dD, (const float*)dU, (const float*)dV,
+                         (const float*)dN, (float*)dO, (float*)dF);
+    if (st != FD_OK) return st;
+    FD_CUDA_OK(ctx, cudaMemcpyAsync(P_out, dO, v3 * (size_t)m->F, cudaMemcpyDeviceToHost, s));
+    if (dF) FD_CUDA_OK(ctx, cudaMemcpyAsync(falloff_out, dF, v1, cudaMemcpyDeviceToHost, s));
+    FD_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    return FD_OK;
+}
+
+// ---- multi-GPU plumbing ------------------------------------------------------------------------------------
+
+int fd_model_create_receiver(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl, int32_t n_ctrl,
+                             int32_t frames, fd_model** out)
+{
+    if (!ctx || !params || !out || !rest_ctrl || n_ctrl < 1 || frames < 1) return FD_E_INVALID;
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    int st = check_params(ctx, params);
+    if (st != FD_OK) return st;
+    fd_model* m = nullptr;
+    st = model_alloc(ctx, params, n_ctrl, false, &m);
+    if (st != FD_OK) return st;
+    st = model_reserve_frames(m, frames);
+    if (st != FD_OK) { fd_model_destroy(m); return st; }
+    m->F = frames;
+    m->ldw = fd_round_up(3 * frames, 4);
+    m->ldw32 = m->ldw;
+    cudaError_t e = cudaMemcpyAsync(m->d_rest, rest_ctrl, (size_t)n_ctrl * 3 * sizeof(float), cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { FD_SET_ERR(ctx, "receiver: %s", cudaGetErrorString(e)); fd_model_destroy(m); return FD_E_CUDA; }
+    *out = m;
+    return FD_OK;
+}
+
+int fd_model_weights_dev(fd_model* m, void** ptr, size_t* bytes)
+{
+    if (!m || !ptr || !bytes) return FD_E_INVALID;
+    if (!m->d_W || m->F < 1) { FD_SET_ERR(m->ctx, "weights: nothing solved or reserved yet"); return FD_E_STATE; }
+    *ptr = m->d_W;
+    *bytes = (size_t)m->n * m->ldw * sizeof(double);
+    return FD_OK;
+}
+
+int fd_model_radii_dev(fd_model* m, void** ptr, size_t* bytes)
+{
+    if (!m || !ptr || !bytes) return FD_E_INVALID;
+    *ptr = m->d_radii;
+    *bytes = (size_t)m->N * sizeof(double);
+    return FD_OK;
+}
+
+int fd_model_commit_weights(fd_model* m)
+{
+    if (!m) return FD_E_INVALID;
+    fd_ctx* ctx = m->ctx;
+    DeviceGuard g(ctx->device);
+    if (!m->d_W || m->F < 1) { FD_SET_ERR(ctx, "commit: no weight block reserved"); return FD_E_STATE; }
+    cudaError_t e = fd_launch_pack(ctx, m);
+    if (e != cudaSuccess) { FD_SET_ERR(ctx, "commit: %s", cudaGetErrorString(e)); return FD_E_CUDA; }
+    m->solved = true;
+    return FD_OK;
+}
+
+int fd_model_info(const fd_model* m, int32_t* n_ctrl, int32_t* npoly, int32_t* frames, int32_t* weights_ld)
+{
+    if (!m) return FD_E_INVALID;
+    if (n_ctrl) *n_ctrl = m->N;
+    if (npoly) *npoly = m->np;
+    if (frames) *frames = m->F;
+    if (weights_ld) *weights_ld = m->ldw;
+    return FD_OK;
+}
+
+int fd_model_get_weights(fd_model* m, double* weights, double* radii)
+{
+    if (!m) return FD_E_INVALID;
+    fd_ctx* ctx = m->ctx;
+    DeviceGuard g(ctx->device);
+    if (weights) {
+        if (!m->solved) { FD_SET_ERR(ctx, "get_weights: nothing solved yet"); return FD_E_STATE; }
+        FD_CUDA_OK(ctx, cudaMemcpy2DAsync(weights, (size_t)3 * m->F * sizeof(double), m->d_W, (size_t)m->ldw * sizeof(double),
+                                          (size_t)3 * m->F * sizeof(double), m->n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (radii) FD_CUDA_OK(ctx, cudaMemcpyAsync(radii, m->d_radii, (size_t)m->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+} // extern "C"
+
+// exposed to fd_capture_host.cu
+int fd_stage(fd_ctx* ctx, int slot, size_t bytes, void** out) { return stage(ctx, slot, bytes, out); }

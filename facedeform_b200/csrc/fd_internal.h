@@ -1,0 +1,101 @@
+// fd_internal.h -- shared declarations of libfacedeform_gpu.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "facedeform_gpu.h"
+
+#define FD_NUM_FLAGS 8
+// device-side status words (ints): written by kernels, read by fd_model_report
+#define FD_FLAG_ZERO_RADIUS 0 // != 0: a QNN radius was zero (duplicate centres)      -> terminationtype -5
+#define FD_FLAG_SINGULAR 1    // k+1 of the first zero pivot                           -> terminationtype -3
+#define FD_FLAG_NONFINITE 2   // weights contain NaN/Inf                               -> terminationtype -3
+
+// device staging slots owned by the ctx (host-pointer entry points copy through them)
+enum fd_stage_slot {
+    FD_STAGE_P = 0, FD_STAGE_DIST = 1, FD_STAGE_TU = 2, FD_STAGE_TV = 3, FD_STAGE_N = 4, FD_STAGE_MISC = 5,
+    FD_STAGE_OUT = 6, FD_STAGE_FALLOFF = 7, FD_NUM_STAGE = 8
+};
+int fd_stage(struct fd_ctx* ctx, int slot, size_t bytes, void** out); // grows the slot on demand (fd_api.cu)
+
+enum fd_phase { FD_PH_ASSEMBLE = 0, FD_PH_FACTOR = 1, FD_PH_SOLVE = 2, FD_PH_EVAL = 3, FD_PH_COUNT = 4 };
+
+struct fd_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    bool own_stream;
+    char err[512];
+    cudaEvent_t ev_begin[FD_PH_COUNT];
+    cudaEvent_t ev_end[FD_PH_COUNT];
+    bool phase_valid[FD_PH_COUNT];
+    int64_t launches;
+    // host<->device staging owned by the ctx (grown on demand)
+    void* stage_dev[FD_NUM_STAGE];
+    size_t stage_bytes[FD_NUM_STAGE];
+};
+
+struct fd_model {
+    fd_ctx* ctx;
+    fd_params prm;
+    int N;    // control points
+    int np;   // polynomial terms (4 / 1 / 0)
+    int n;    // N + np
+    int lda;  // column stride of the FP64 system (column-major)
+    int F;    // frames of the last solve (0: none)
+    int capF; // allocated frames
+    int ldw;  // row stride (doubles) of the FP64 weight block, row-major n x ldw
+    bool receiver;
+    bool fitted;
+    bool solved;
+    bool eval64;     // resolved evaluation precision
+    float* d_rest;   // N x 3
+    double* d_radii; // N
+    double* d_A;     // lda x n, LU in place
+    int* d_ipiv;     // n (global row index swapped with row k)
+    int* d_perm;     // n: row i of P*A is row perm[i] of A
+    double* d_W;     // n x ldw weights (solve in place over the right-hand sides)
+    int* d_flags;    // FD_NUM_FLAGS
+    double* d_pivstat; // [min |u_kk|, max |u_kk|]
+    // evaluation tables (built by pack)
+    float4* d_ctab32;  // N: (cx, cy, cz, kernel parameter)
+    float* d_W32;      // n x ldw32 floats
+    int ldw32;
+    double4* d_ctab64; // N (only when eval64)
+};
+
+#define FD_CUDA_OK(ctx, call)                                                                      \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call,    \
+                     cudaGetErrorString(e__));                                                     \
+            return FD_E_CUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+static inline int fd_poly_terms(int term) { return term == FD_TERM_LINEAR ? 4 : (term == FD_TERM_CONST ? 1 : 0); }
+static inline int fd_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- kernel launchers (each returns a cudaError_t from the launch; all asynchronous on ctx->stream) -------
+// fd_assemble.cu
+cudaError_t fd_launch_radii(fd_ctx* ctx, const fd_params& prm, const float* d_rest, int N, double* d_radii, int* d_flags);
+cudaError_t fd_launch_assemble(fd_ctx* ctx, const fd_params& prm, const float* d_rest, const double* d_radii, int N,
+                               int np, double* d_A, int lda);
+// fd_factor.cu
+cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
+                         double* d_pivstat);
+// fd_solve.cu
+cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_deform, int F);
+cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);
+// fd_eval.cu
+cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
+                           const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out);
+// fd_capture.cu
+cudaError_t fd_launch_nearest(fd_ctx* ctx, const float* d_P, int64_t V, const float* d_rig, int N,
+                              unsigned long long* d_keys /* N scratch */, int32_t* d_nearest);
+cudaError_t fd_launch_capture_dist(fd_ctx* ctx, const float* d_P, int64_t V, const uint8_t* d_member,
+                                   const float* d_rig, const int32_t* d_tri /* ntri x 3, -1 in [2] = segment */,
+                                   int ntri, float radius, int dofalloff, float* d_dist2);

@@ -1,0 +1,186 @@
+// fd_solve.cu -- K2c: multi-RHS triangular solves for all 3F per-frame control displacements at once, and the
+// packing of the solved weights into the evaluation tables.
+//
+// Replaces the delta half of the pack loop (reference SOP_FaceDeform.cpp:268-287: FP32 subtract, FP64 store)
+// and the solve inside alglib::rbfbuildmodel (:363).  Right-hand sides / weights live row-major as
+// (N + npoly) x ldw doubles, column 3f + k = frame f, axis k, so one row is one control point's weights for
+// every frame -- the layout the evaluation kernels stage.
+#include "fd_internal.h"
+
+namespace {
+
+constexpr int SB = 32; // block size of the triangular sweeps
+
+// B[i][3f+k] = (double)(deform[f][perm[i]][k] - rest[perm[i]][k])   (FP32 subtract), 0 for polynomial rows
+__global__ void __launch_bounds__(256) k_build_rhs(const float* __restrict__ rest, const float* __restrict__ deform,
+                                                   const int* __restrict__ perm, int N, int n, int F,
+                                                   double* __restrict__ B, int ldw)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (c >= ldw) return;
+    double v = 0.0;
+    const int src = perm[i];
+    if (c < 3 * F && src < N) {
+        const int f = c / 3, k = c - 3 * f;
+        const float d = deform[((size_t)f * N + src) * 3 + k] - rest[3 * src + k];
+        v = (double)d;
+    }
+    B[(size_t)i * ldw + c] = v;
+}
+
+// X_k = T_kk^-1 B_k for one diagonal block; one thread per right-hand-side column.
+template <bool LOWER>
+__global__ void __launch_bounds__(128) k_trsm_diag(const double* __restrict__ A, int lda, int k0, int nb,
+                                                   double* __restrict__ B, int ldw, int nrhs)
+{
+    __shared__ double s_T[SB][SB + 1];
+    for (int t = threadIdx.x; t < SB * SB; t += blockDim.x) {
+        const int r = t % SB, c = t / SB;
+        s_T[r][c] = (r < nb && c < nb) ? A[(size_t)(k0 + c) * lda + k0 + r] : (r == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nrhs) return;
+    double x[SB];
+#pragma unroll
+    for (int j = 0; j < SB; ++j) x[j] = j < nb ? B[(size_t)(k0 + j) * ldw + c] : 0.0;
+    if (LOWER) {
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+            const double xj = x[j];
+#pragma unroll
+            for (int r = j + 1; r < SB; ++r) x[r] -= s_T[r][j] * xj;
+        }
+    } else {
+#pragma unroll
+        for (int j = SB - 1; j >= 0; --j) {
+            const double xj = x[j] / s_T[j][j];
+            x[j] = xj;
+#pragma unroll
+            for (int r = 0; r < j; ++r) x[r] -= s_T[r][j] * xj;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SB; ++j)
+        if (j < nb) B[(size_t)(k0 + j) * ldw + c] = x[j];
+}
+
+// B[rows][c] -= T[rows, k0:k0+nb] * X[k0:k0+nb][c]; rows below the block (LOWER) or above it (UPPER).
+// CTA tile: 64 rows x 32 columns, 256 threads, 8 rows per thread.
+template <bool LOWER>
+__global__ void __launch_bounds__(256) k_trsm_update(const double* __restrict__ A, int lda, int n, int k0, int nb,
+                                                     double* __restrict__ B, int ldw, int nrhs)
+{
+    __shared__ double s_t[SB][64 + 1]; // [k][row]
+    __shared__ double s_x[SB][32 + 1]; // [k][col]
+    const int row_begin = LOWER ? k0 + nb : 0;
+    const int row_end = LOWER ? n : k0;
+    const int r0 = row_begin + blockIdx.y * 64;
+    const int c0 = blockIdx.x * 32;
+    for (int t = threadIdx.x; t < SB * 64; t += 256) {
+        const int rr = t % 64, k = t / 64;
+        s_t[k][rr] = (k < nb && r0 + rr < row_end) ? A[(size_t)(k0 + k) * lda + r0 + rr] : 0.0;
+    }
+    for (int t = threadIdx.x; t < SB * 32; t += 256) {
+        const int cc = t % 32, k = t / 32;
+        s_x[k][cc] = (k < nb && c0 + cc < nrhs) ? B[(size_t)(k0 + k) * ldw + c0 + cc] : 0.0;
+    }
+    __syncthreads();
+    const int cc = threadIdx.x % 32, rg = threadIdx.x / 32;
+    double acc[8] = {};
+#pragma unroll 8
+    for (int k = 0; k < SB; ++k) {
+        const double xv = s_x[k][cc];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += s_t[k][rg * 8 + i] * xv;
+    }
+    if (c0 + cc < nrhs) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + rg * 8 + i;
+            if (r < row_end) B[(size_t)r * ldw + c0 + cc] -= acc[i];
+        }
+    }
+}
+
+// weights -> evaluation tables.  FP32: centre table (cx, cy, cz, kernel parameter) and weights n x ldw32;
+// FP64 centre table when the evaluation runs in double.  Flags non-finite weights.
+__global__ void __launch_bounds__(256) k_pack_tables(const float* __restrict__ rest, const double* __restrict__ radii,
+                                                     int N, int kernel, float4* __restrict__ ctab32,
+                                                     double4* __restrict__ ctab64)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const double R = radii[j];
+    double prm;
+    if (kernel == FD_KERNEL_GAUSSIAN) prm = -1.0 / (R * R);
+    else if (kernel == FD_KERNEL_MULTIQUADRIC) prm = R * R;
+    else prm = 0.0;
+    const float x = rest[3 * j], y = rest[3 * j + 1], z = rest[3 * j + 2];
+    // FP32 Gaussian evaluates ex2(r2 * (-log2(e) / R^2))
+    const double prm32 = kernel == FD_KERNEL_GAUSSIAN ? prm * 1.4426950408889634074 : prm;
+    ctab32[j] = make_float4(x, y, z, (float)prm32);
+    if (ctab64) ctab64[j] = make_double4((double)x, (double)y, (double)z, prm);
+}
+
+__global__ void __launch_bounds__(256) k_pack_weights(const double* __restrict__ W, int n, int ldw, int nrhs,
+                                                      float* __restrict__ W32, int ldw32, int* __restrict__ flags)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (c >= ldw32) return;
+    double v = 0.0;
+    if (c < nrhs) {
+        v = W[(size_t)i * ldw + c];
+        if (!isfinite(v)) atomicExch(&flags[FD_FLAG_NONFINITE], 1);
+    }
+    W32[(size_t)i * ldw32 + c] = (float)v;
+}
+
+} // namespace
+
+cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_deform, int F)
+{
+    cudaStream_t s = ctx->stream;
+    const int n = m->n, nrhs = 3 * F, ldw = m->ldw;
+    {
+        dim3 grid((ldw + 255) / 256, n);
+        k_build_rhs<<<grid, 256, 0, s>>>(m->d_rest, d_deform, m->d_perm, m->N, n, F, m->d_W, ldw);
+        ctx->launches += 1;
+    }
+    const int cblocks = (nrhs + 127) / 128;
+    for (int k0 = 0; k0 < n; k0 += SB) { // L y = P b
+        const int nb = min(SB, n - k0);
+        k_trsm_diag<true><<<cblocks, 128, 0, s>>>(m->d_A, m->lda, k0, nb, m->d_W, ldw, nrhs);
+        ctx->launches += 1;
+        const int rows = n - k0 - nb;
+        if (rows > 0) {
+            dim3 grid((nrhs + 31) / 32, (rows + 63) / 64);
+            k_trsm_update<true><<<grid, 256, 0, s>>>(m->d_A, m->lda, n, k0, nb, m->d_W, ldw, nrhs);
+            ctx->launches += 1;
+        }
+    }
+    for (int k0 = (n - 1) / SB * SB; k0 >= 0; k0 -= SB) { // U x = y
+        const int nb = min(SB, n - k0);
+        k_trsm_diag<false><<<cblocks, 128, 0, s>>>(m->d_A, m->lda, k0, nb, m->d_W, ldw, nrhs);
+        ctx->launches += 1;
+        if (k0 > 0) {
+            dim3 grid((nrhs + 31) / 32, (k0 + 63) / 64);
+            k_trsm_update<false><<<grid, 256, 0, s>>>(m->d_A, m->lda, n, k0, nb, m->d_W, ldw, nrhs);
+            ctx->launches += 1;
+        }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
+{
+    cudaStream_t s = ctx->stream;
+    k_pack_tables<<<(m->N + 255) / 256, 256, 0, s>>>(m->d_rest, m->d_radii, m->N, m->prm.kernel, m->d_ctab32,
+                                                    m->eval64 ? m->d_ctab64 : nullptr);
+    dim3 grid((m->ldw32 + 255) / 256, m->n);
+    k_pack_weights<<<grid, 256, 0, s>>>(m->d_W, m->n, m->ldw, 3 * m->F, m->d_W32, m->ldw32, m->d_flags);
+    ctx->launches += 2;
+    return cudaGetLastError();
+}

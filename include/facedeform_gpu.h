@@ -1,0 +1,175 @@
+/*
+ * facedeform_gpu.h -- C ABI of libfacedeform_gpu.so, the B200 (sm_100a) replacement for the RBF deformation
+ * path of symek/facedeform.
+ *
+ * Every entry point replaces a region of the reference's SOP cook (paths are under the reference's src/):
+ *
+ *   fd_params / fd_params_default / fd_params_clamp
+ *        the cook parameters and their clamps          SOP_FaceDeform.cpp:99-137 (templates), :244-263 (clamps)
+ *   fd_rbf_fit        rbfcreate + rbfsetpoints + rbfsetalgo* + rbfset*term + rbfbuildmodel
+ *                                                      SOP_FaceDeform.cpp:331-363 (the centres half of :268-287)
+ *   fd_rbf_solve      the delta half of the pack loop + the solve inside rbfbuildmodel, for F frames at once
+ *                                                      SOP_FaceDeform.cpp:268-287, :363-368
+ *   fd_rbf_eval       the evaluation loop: gate, rbfcalc, project_to_tangents, falloff, P += disp
+ *                                                      SOP_FaceDeform.cpp:384-439, SOP_FaceDeform.hpp:28-41
+ *   fd_capture        ProximityCapture::init / capture / findIslands
+ *                                                      capture.cpp:10-44, :46-105, :107-141 (capture.hpp:21-27)
+ *   fd_model_report   alglib::rbfreport checked at     SOP_FaceDeform.cpp:365-373
+ *   fd_last_error     addError / addWarning strings    SOP_FaceDeform.cpp:231-234, :337-340, :365-368
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host pointer, the
+ * library owns device memory; every function returns an fd_status and never throws or aborts; handles carry all
+ * state (no globals), so different handles may be used from different host threads.  One fd_ctx drives one GPU:
+ * multi-GPU runs use one process (or thread) and one ctx per GPU, vertex ranges sharded by the caller, weights
+ * moved with fd_model_weights_dev + fd_model_commit_weights around the caller's broadcast.
+ *
+ * The `*_dev` variants take device pointers, enqueue on the ctx stream and return without synchronising.
+ */
+#ifndef FACEDEFORM_GPU_H
+#define FACEDEFORM_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FD_ABI_VERSION 1
+
+typedef struct fd_ctx fd_ctx;     /* one GPU + stream + scratch; replaces the node-member state, SOP_FaceDeform.hpp:108-113 */
+typedef struct fd_model fd_model; /* replaces alglib::rbfmodel (SOP_FaceDeform.cpp:332): centres, radii, LU factors, weights */
+
+typedef enum fd_status {
+    FD_OK = 0,
+    FD_E_INVALID = 1,        /* bad argument */
+    FD_E_MISMATCH_POINT = 2, /* SOP_ERR_MISMATCH_POINT, SOP_FaceDeform.cpp:231-234 */
+    FD_E_BUILD = 3,          /* "Can't build RBF model." (alglib::ap_error), SOP_FaceDeform.cpp:337-340 */
+    FD_E_SINGULAR = 4,       /* "Can't solve the problem." (terminationtype != 1), SOP_FaceDeform.cpp:365-368 */
+    FD_E_CUDA = 5,
+    FD_E_NOMEM = 6,
+    FD_E_CAPTURE = 7,        /* "Can't capture geometry with a rig!", SOP_FaceDeform.cpp:318-321 */
+    FD_E_UNSUPPORTED = 8,
+    FD_E_STATE = 9           /* call order (eval before solve, ...) */
+} fd_status;
+
+/* menu values, SOP_FaceDeform.hpp:13-18 */
+#define FD_MODEL_QNN 0        /* per-centre radii from the nearest-neighbour rule (qcoef, zcoef) */
+#define FD_MODEL_ML 1         /* uniform `radius` */
+#define FD_TERM_LINEAR 0
+#define FD_TERM_CONST 1
+#define FD_TERM_ZERO 2
+/* north_star "kernel type" (the reference itself is Gaussian only) */
+#define FD_KERNEL_GAUSSIAN 0     /* exp(-r^2 / R^2) */
+#define FD_KERNEL_MULTIQUADRIC 1 /* sqrt(r^2 + R^2) */
+#define FD_KERNEL_THINPLATE 2    /* r^2 log r */
+/* arithmetic of the vertex evaluation */
+#define FD_EVAL_AUTO 0   /* FP32 for the Gaussian, FP64 for multiquadric / thin plate (cancellation) */
+#define FD_EVAL_FP32 1
+#define FD_EVAL_FP64 2
+/* evaluation kernel */
+#define FD_PATH_AUTO 0   /* tensor cores when 3F is wide enough, else FMA/SFU */
+#define FD_PATH_SIMT 1
+#define FD_PATH_TENSOR 2
+
+/* The SOP's parameter surface, names = the reference parm tokens (SOP_FaceDeform.cpp:99-115). */
+typedef struct fd_params {
+    int32_t model;         /* "model"  default 0 (QNN)        :48-53, :121 */
+    int32_t term;          /* "term"   default 0 (linear)     :55-61, :122 */
+    int32_t kernel;        /* extension, default gaussian */
+    float qcoef;           /* default 1, clamp >= 0.1         :123, :249 */
+    float zcoef;           /* default 5, clamp >= 0.1         :124, :250 */
+    float radius;          /* default 1, clamp >= 0.01        :125, :251  (RBF radius AND capture/falloff radius :318, :402) */
+    int32_t layers;        /* default 4, clamp >= 1           :126, :252  (only 1 layer is solved) */
+    float lambda;          /* default 0.1, clamp >= 0.01      :128, :253  (K + lambda I) */
+    int32_t tangent;       /* default 0                       :129 */
+    int32_t maxedges;      /* default 4, clamp >= 1           :127, :257 */
+    int32_t morphspace;    /* default 0                       :130  (dbse post-pass: carried, not executed) */
+    int32_t doclampweight; /* default 0                       :131 */
+    float weightrange[2];  /* default (0, 1)                  :132 */
+    int32_t dofalloff;     /* default 0                       :133 */
+    float falloffradius;   /* default 1                       :134 */
+    float falloffrate;     /* default 1                       :135 */
+    int32_t eval_precision;/* FD_EVAL_* */
+    int32_t eval_path;     /* FD_PATH_* */
+} fd_params;
+
+/* analogue of alglib::rbfreport (SOP_FaceDeform.cpp:333, :365-373) */
+typedef struct fd_report {
+    int32_t terminationtype; /* 1 = ok; -3 = singular / non-finite weights; -5 = zero radius (duplicate centres) */
+    int32_t iterationscount; /* refinement iterations (0: direct FP64 solve) */
+    int32_t n;               /* control points */
+    int32_t npoly;           /* polynomial terms 4 / 1 / 0 */
+    int32_t frames;          /* F of the last solve */
+    int32_t reserved;
+    double min_pivot;        /* min |u_kk| of the LU */
+    double max_pivot;
+} fd_report;
+
+int fd_abi_version(void);
+const char* fd_status_string(int status);
+
+void fd_params_default(fd_params* p);
+void fd_params_clamp(fd_params* p); /* SOP_FaceDeform.cpp:249-257 */
+
+/* device < 0: current CUDA device.  stream: a cudaStream_t (NULL = the ctx creates its own). */
+int fd_ctx_create(fd_ctx** out, int device, void* stream);
+void fd_ctx_destroy(fd_ctx* ctx);
+int fd_ctx_synchronize(fd_ctx* ctx);
+const char* fd_last_error(const fd_ctx* ctx);
+
+/* ---- fit: assemble + factor, once per rest pose ---------------------------------------------------------- */
+int fd_rbf_fit(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl /* N x 3 host */, int32_t n_ctrl,
+               fd_model** out, fd_report* report /* may be NULL */);
+int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_dev, int32_t n_ctrl, fd_model** out);
+void fd_model_destroy(fd_model* m);
+
+/* ---- solve: weights for F frames at once (multi-RHS) ------------------------------------------------------ */
+int fd_rbf_solve(fd_model* m, const float* deform_ctrl /* F x N x 3 host */, int32_t n_ctrl, int32_t frames,
+                 fd_report* report /* may be NULL */);
+int fd_rbf_solve_dev(fd_model* m, const float* deform_ctrl_dev, int32_t n_ctrl, int32_t frames);
+
+/* synchronises the ctx stream and reads the status flags of the last fit/solve; returns FD_OK or FD_E_SINGULAR */
+int fd_model_report(fd_model* m, fd_report* report);
+
+/* ---- eval: P_out[f][v] = P[v] + falloff(v) * tangent_project(rbf_f(P[v])) ------------------------------- */
+int fd_rbf_eval(fd_model* m, const float* P /* V x 3 */, int64_t n_vtx,
+                const float* dist2 /* V or NULL */, const float* tangentu, const float* tangentv,
+                const float* normal /* V x 3 each or NULL */,
+                float* P_out /* F x V x 3 */, float* falloff_out /* V or NULL */);
+int fd_rbf_eval_dev(fd_model* m, const float* P, int64_t n_vtx, const float* dist2, const float* tangentu,
+                    const float* tangentv, const float* normal, float* P_out, float* falloff_out);
+
+/* ---- multi-GPU plumbing: a model that receives weights instead of solving for them ------------------------ */
+int fd_model_create_receiver(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl /* host */, int32_t n_ctrl,
+                             int32_t frames, fd_model** out);
+/* device pointer + size of the FP64 weight block ((N + npoly) x ld doubles, ld = fd_model_weights_ld) */
+int fd_model_weights_dev(fd_model* m, void** ptr, size_t* bytes);
+int fd_model_radii_dev(fd_model* m, void** ptr, size_t* bytes); /* N doubles */
+/* after the caller has written (e.g. NCCL-broadcast) the weight and radii blocks: build the evaluation tables */
+int fd_model_commit_weights(fd_model* m);
+int fd_model_info(const fd_model* m, int32_t* n_ctrl, int32_t* npoly, int32_t* frames, int32_t* weights_ld);
+/* copies weights to the host as (N + npoly) x 3F row-major doubles, radii as N doubles (either may be NULL) */
+int fd_model_get_weights(fd_model* m, double* weights, double* radii);
+
+/* ---- capture ------------------------------------------------------------------------------------------------
+ * mesh P + polygons (CSR) and rig points + primitives (CSR; 2 vertices = segment, >= 3 = fan-triangulated
+ * polygon) + optional class attribute.  Outputs (host): nearest_idx[N]; member[V]; dist2[V]; groups as CSR
+ * (grp_class[G] ascending, grp_off[G+1], grp_idx[] ascending; grp_idx may be NULL to query sizes).
+ * *n_groups receives G; G == 0 returns FD_E_CAPTURE like the reference (capture.cpp:54-56). */
+int fd_capture(fd_ctx* ctx, const float* P, int64_t n_vtx, const int32_t* poly_off, const int32_t* poly_vtx,
+               int32_t n_poly, const float* rig_P, int32_t n_rig, const int32_t* rig_off, const int32_t* rig_vtx,
+               int32_t n_rig_prim, const int32_t* rig_class /* or NULL */, int32_t max_edges, float radius,
+               int32_t dofalloff, int32_t* nearest_idx, uint8_t* member, float* dist2, int32_t* n_groups,
+               int32_t* grp_class, int64_t* grp_off, int32_t* grp_idx, int32_t grp_cap, int64_t idx_cap);
+
+/* timing of the last call on this ctx, measured with CUDA events on the ctx stream (ms); phase: 0 assemble,
+ * 1 factor, 2 solve, 3 eval.  Returns < 0 when the phase has not run. */
+float fd_ctx_phase_ms(fd_ctx* ctx, int phase);
+/* number of kernels this library launched on the ctx since creation */
+int64_t fd_ctx_launch_count(const fd_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACEDEFORM_GPU_H */

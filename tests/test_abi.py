@@ -1,0 +1,68 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "facedeform_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from facedeform_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build libfacedeform_gpu.so first (__graft_entry__.build())"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in facedeform_gpu.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert L.fd_abi_version() == 1
+
+
+def test_params_defaults_and_clamps_match_the_sop():
+    """defaults = SOP_FaceDeform.cpp:117-137, clamps = :249-257 (no GPU needed)."""
+    from facedeform_b200 import make_params
+    p = make_params()
+    assert (p.model, p.term, p.kernel, p.layers, p.maxedges) == (0, 0, 0, 4, 4)
+    assert (p.qcoef, p.zcoef, p.radius, p.falloffradius, p.falloffrate) == (1.0, 5.0, 1.0, 1.0, 1.0)
+    assert p.lambda_ == pytest.approx(0.1) and tuple(p.weightrange) == (0.0, 1.0)
+    assert (p.tangent, p.morphspace, p.doclampweight, p.dofalloff) == (0, 0, 0, 0)
+    q = make_params(clamp=True, qcoef=0.0, zcoef=0.01, radius=0.0, layers=-3, maxedges=0, **{"lambda": 0.0})
+    assert (q.qcoef, q.zcoef, q.radius, q.lambda_) == pytest.approx((0.1, 0.1, 0.01, 0.01))
+    assert (q.layers, q.maxedges) == (1, 1)
+
+
+def test_params_struct_layout_matches_oracle_semantics(oracle):
+    """the oracle's and the product's parameter structs are separate definitions of the same SOP surface."""
+    from facedeform_b200 import make_params
+    p, o = make_params(), oracle.make_params()
+    for f in ("model", "term", "kernel", "qcoef", "zcoef", "radius", "layers", "lambda_", "tangent", "maxedges",
+              "dofalloff", "falloffradius", "falloffrate"):
+        assert getattr(p, f) == getattr(o, f), f
+
+
+def test_status_strings_quote_the_reference_messages():
+    from facedeform_b200 import _lib
+    L = _lib.load()
+    assert L.fd_status_string(2) == b"Rest and deform geometry should match."   # SOP_FaceDeform.cpp:232
+    assert L.fd_status_string(3) == b"Can't build RBF model."                   # :338
+    assert L.fd_status_string(4) == b"Can't solve the problem."                 # :366
+    assert L.fd_status_string(7) == b"Can't capture geometry with a rig!"       # :319
+
+
+def test_no_gpu_fails_loudly():
+    """without a GPU fd_ctx_create must fail (FD_E_CUDA), never fall back to a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from facedeform_b200 import Context, FdError
+    with pytest.raises(FdError) as e:
+        Context()
+    assert e.value.status == 5

@@ -1,0 +1,183 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+
+Stated tolerance (north_star): max |P_gpu - P_oracle| <= 1e-5 x bounding-box diagonal of the mesh.  Weights of
+the FP64 factor/solve are compared with a conditioning-aware bound.  Indices are bit-exact (test_gpu_capture).
+"""
+import numpy as np
+import pytest
+
+from facedeform_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # of the bounding-box diagonal
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from facedeform_b200 import Context
+    c = Context()
+    yield c
+    c.close()
+
+
+def _oracle_params(oracle, p):
+    return oracle.make_params(model=p.model, term=p.term, kernel=p.kernel, qcoef=p.qcoef, zcoef=p.zcoef,
+                              radius=p.radius, layers=p.layers, tangent=p.tangent, maxedges=p.maxedges,
+                              dofalloff=p.dofalloff, falloffradius=p.falloffradius, falloffrate=p.falloffrate,
+                              **{"lambda": p.lambda_})
+
+
+def _run(ctx, oracle, N, V, F, kernel, term, model=1, lam=0.0, radius=None, tangent=0, falloff=False,
+         eval_precision=0, seed_shift=0, tol=REL_TOL):
+    from facedeform_b200 import make_params
+    rig = synth.control_rig(N, seed=synth.SEED_CTRL + seed_shift)
+    deform = synth.deformed_rig(rig, F)
+    mesh = synth.face_mesh(V, topology=False)
+    R = radius if radius is not None else synth.default_radius(["gaussian", "multiquadric", "thin_plate"][kernel], rig.spacing)
+    p = make_params(model=model, term=term, kernel=kernel, radius=R, tangent=tangent, dofalloff=int(falloff),
+                    falloffrate=1.7, eval_precision=eval_precision, **{"lambda": lam})
+    dist2 = None
+    if falloff:
+        rng = np.random.default_rng(9)
+        dist2 = rng.uniform(0, 1.2 * R * R, V).astype(np.float32)
+        dist2[::13] = -1.0
+    tu, tv, nn = (mesh.tangentu, mesh.tangentv, mesh.N) if tangent else (None, None, None)
+    model_h = ctx.fit(p, rig.rest)
+    model_h.solve(deform)
+    out, fall = model_h.eval(mesh.P, dist2, tu, tv, nn)
+    Wg, Rg = model_h.weights()
+    op = _oracle_params(oracle, p)
+    st, rad, W = oracle.fit(op, rig.rest, deform)
+    assert st == 1
+    ref, rfall = oracle.evaluate(op, rig.rest, rad, W, mesh.P, dist2, tu, tv, nn, nthreads=8)
+    np.testing.assert_allclose(Rg, rad, rtol=1e-12)
+    err = np.abs(out.astype(np.float64) - ref.astype(np.float64)).max()
+    assert err <= tol * mesh.bbox_diag, f"max err {err:.3e} > {tol * mesh.bbox_diag:.3e}"
+    np.testing.assert_allclose(fall, rfall, rtol=2e-6, atol=1e-7)
+    model_h.close()
+    return err / mesh.bbox_diag, Wg, W
+
+
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("term", [0, 1, 2])
+def test_small_all_kernels_terms(ctx, oracle, kernel, term):
+    if kernel == 2 and term == 2:
+        pytest.skip("thin plate needs a polynomial block")
+    rel, Wg, W = _run(ctx, oracle, N=50, V=3000, F=3, kernel=kernel, term=term)
+    scale = np.abs(W).max()
+    np.testing.assert_allclose(Wg, W, rtol=0, atol=1e-7 * scale)
+
+
+def test_config_c1(ctx, oracle):
+    """BASELINE.json configs[0]: 64 control points, 10k vertices, Gaussian, single frame."""
+    rel, Wg, W = _run(ctx, oracle, N=64, V=10_000, F=1, kernel=0, term=0)
+    assert rel < 1e-5
+
+
+@pytest.mark.parametrize("F", [1, 2, 3, 4, 5, 9])
+def test_frame_chunk_edges(ctx, oracle, F):
+    _run(ctx, oracle, N=70, V=1000, F=F, kernel=0, term=0)
+
+
+@pytest.mark.parametrize("V", [1, 31, 255, 256, 257, 511, 512, 513, 1025])
+def test_ragged_vertex_counts(ctx, oracle, V):
+    _run(ctx, oracle, N=33, V=V, F=2, kernel=0, term=0)
+
+
+@pytest.mark.parametrize("N", [1, 2, 5, 31, 32, 33, 255, 256, 257, 300])
+def test_ragged_control_counts(ctx, oracle, N):
+    # N below the polynomial degree of freedom makes the linear block singular: use the constant term there
+    term = 0 if N >= 5 else 1
+    kernel = 0
+    _run(ctx, oracle, N=N, V=700, F=2, kernel=kernel, term=term, radius=0.5 if N < 5 else None)
+
+
+def test_epilogue_tangent_falloff(ctx, oracle):
+    _run(ctx, oracle, N=64, V=5000, F=2, kernel=0, term=0, tangent=1, falloff=True)
+    _run(ctx, oracle, N=64, V=5000, F=1, kernel=1, term=0, tangent=1, falloff=True)
+
+
+def test_qnn_model_and_lambda(ctx, oracle):
+    _run(ctx, oracle, N=120, V=4000, F=2, kernel=0, term=0, model=0)
+    _run(ctx, oracle, N=120, V=4000, F=2, kernel=0, term=0, model=1, lam=0.05)
+
+
+def test_mid_size_c2_shape_subsample(ctx, oracle):
+    """C2 control rig (N=256) and frame batching at a vertex count the oracle finishes in seconds."""
+    _run(ctx, oracle, N=256, V=4096, F=24, kernel=0, term=0)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_mid_size_c3_kernels_fp64_eval(ctx, oracle, kernel):
+    """C3 kernels (multiquadric / thin plate + affine block), N=1024: FP64 evaluation keeps 1e-5 of the diagonal."""
+    _run(ctx, oracle, N=1024, V=3000, F=1, kernel=kernel, term=0)
+
+
+def test_fp32_eval_of_multiquadric_states_its_looser_tolerance(ctx, oracle):
+    """FD_EVAL_FP32 on a globally supported kernel suffers cancellation: stated tolerance 5e-4 of the diagonal."""
+    _run(ctx, oracle, N=1024, V=3000, F=1, kernel=1, term=0, eval_precision=1, tol=5e-4)
+
+
+def test_errors_mirror_the_sop(ctx):
+    from facedeform_b200 import FdError, make_params
+    rig = synth.control_rig(20)
+    deform = synth.deformed_rig(rig, 1)
+    p = make_params(model=1, radius=0.3, **{"lambda": 0.0})
+    m = ctx.fit(p, rig.rest)
+    with pytest.raises(FdError) as e:           # point-count mismatch, SOP_FaceDeform.cpp:231-234
+        m.solve(deform[:, :19])
+    assert e.value.status == 2
+    with pytest.raises(FdError) as e:           # eval before solve
+        m.eval(rig.rest)
+    assert e.value.status == 9
+    rest = rig.rest.copy()
+    rest[7] = rest[3]
+    with pytest.raises(FdError) as e:           # duplicate centres: singular system, :365-368
+        ctx.fit(p, rest)
+    assert e.value.status == 4
+    with pytest.raises(FdError) as e:           # QNN zero radius
+        ctx.fit(make_params(model=0), rest)
+    assert e.value.status == 4
+    with pytest.raises(FdError) as e:
+        ctx.fit(make_params(kernel=7), rig.rest)
+    assert e.value.status == 1
+
+
+def test_zero_delta_is_identity_and_interpolation(ctx):
+    from facedeform_b200 import make_params
+    rig = synth.control_rig(90)
+    deform = synth.deformed_rig(rig, 2)
+    p = make_params(model=1, radius=2 * rig.spacing, **{"lambda": 0.0})
+    m = ctx.fit(p, rig.rest)
+    m.solve(rig.rest[None].copy())
+    mesh = synth.face_mesh(2000, topology=False)
+    out, fall = m.eval(mesh.P)
+    assert np.array_equal(out[0], mesh.P) and np.all(fall == 1.0)
+    m.solve(deform)                               # same factorisation, new frames: f(c_i) = c_i + delta_i
+    out, _ = m.eval(rig.rest)
+    np.testing.assert_allclose(out, deform, atol=2e-6)
+    m.close()
+
+
+def test_device_pointer_entry_points(ctx, oracle):
+    """fd_rbf_*_dev on torch CUDA tensors gives the same bits as the host-pointer entry points."""
+    import torch
+    from facedeform_b200 import Context, make_params
+    rig = synth.control_rig(100)
+    deform = synth.deformed_rig(rig, 3)
+    mesh = synth.face_mesh(5000, topology=False)
+    p = make_params(model=1, radius=2 * rig.spacing, **{"lambda": 0.0})
+    m = ctx.fit(p, rig.rest)
+    m.solve(deform)
+    host_out, host_fall = m.eval(mesh.P)
+    c2 = Context(stream=torch.cuda.current_stream().cuda_stream)
+    dm = c2.fit(p, torch.from_numpy(rig.rest).cuda())
+    dm.solve(torch.from_numpy(deform).cuda())
+    dm.report()
+    dout, dfall = dm.eval(torch.from_numpy(mesh.P).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(dout.cpu().numpy(), host_out) and np.array_equal(dfall.cpu().numpy(), host_fall)
+    dm.close()
+    m.close()
+    c2.close()
