@@ -49,9 +49,10 @@ void phase_end(fd_ctx* ctx, int ph)
 
 template <typename T> int dev_alloc(fd_ctx* ctx, T** p, size_t count)
 {
-    cudaError_t e = cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+    // stream-ordered pool allocation: no device-wide synchronisation when models are created and destroyed per cook
+    cudaError_t e = cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), ctx->stream);
     if (e != cudaSuccess) {
-        FD_SET_ERR(ctx, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        FD_SET_ERR(ctx, "cudaMallocAsync(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
         *p = nullptr;
         return e == cudaErrorMemoryAllocation ? FD_E_NOMEM : FD_E_CUDA;
     }
@@ -109,8 +110,8 @@ int model_reserve_frames(fd_model* m, int F)
 {
     fd_ctx* ctx = m->ctx;
     if (F <= m->capF) return FD_OK;
-    if (m->d_W) { cudaStreamSynchronize(ctx->stream); cudaFree(m->d_W); m->d_W = nullptr; }
-    if (m->d_W32) { cudaFree(m->d_W32); m->d_W32 = nullptr; }
+    if (m->d_W) { cudaFreeAsync(m->d_W, ctx->stream); m->d_W = nullptr; }
+    if (m->d_W32) { cudaFreeAsync(m->d_W32, ctx->stream); m->d_W32 = nullptr; }
     m->capF = 0;
     const int ld = fd_round_up(3 * F, 4);
     int st = dev_alloc(ctx, &m->d_W, (size_t)m->n * ld);
@@ -202,6 +203,13 @@ int fd_ctx_create(fd_ctx** out, int device, void* stream)
         cudaEventCreate(&ctx->ev_begin[i]);
         cudaEventCreate(&ctx->ev_end[i]);
     }
+    { // keep freed blocks cached in the device's default pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     *out = ctx;
     return FD_OK;
 }
@@ -245,18 +253,11 @@ void fd_model_destroy(fd_model* m)
 {
     if (!m) return;
     DeviceGuard g(m->ctx->device);
-    cudaStreamSynchronize(m->ctx->stream);
-    cudaFree(m->d_rest);
-    cudaFree(m->d_radii);
-    cudaFree(m->d_A);
-    cudaFree(m->d_ipiv);
-    cudaFree(m->d_perm);
-    cudaFree(m->d_W);
-    cudaFree(m->d_flags);
-    cudaFree(m->d_pivstat);
-    cudaFree(m->d_ctab32);
-    cudaFree(m->d_W32);
-    cudaFree(m->d_ctab64);
+    cudaStream_t s = m->ctx->stream; // stream-ordered frees: later work on the stream may reuse the blocks safely
+    void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
+                      m->d_ctab32, m->d_W32, m->d_ctab64};
+    for (void* b : blocks)
+        if (b) cudaFreeAsync(b, s);
     delete m;
 }
 

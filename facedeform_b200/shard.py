@@ -1,0 +1,55 @@
+"""Vertex-range sharding across GPUs.
+
+Every vertex is independent given the weights (the reference loop SOP_FaceDeform.cpp:404-439 has no cross-vertex
+dependence), so the only exchange step is the broadcast of the solved weights from the rank that factored the
+system; results stay sharded (C5's 192 GB output cannot land on one GPU) or are gathered by the caller.
+One process per GPU; torch.distributed (NCCL over NVLink on the GPUs, gloo in the CPU tests) is the plumbing.
+"""
+from __future__ import annotations
+
+
+def vertex_range(n_vtx: int, rank: int, world: int) -> tuple[int, int]:
+    """contiguous range [begin, end) of rank `rank`: concatenating the ranges in rank order preserves vertex order."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(int(n_vtx), world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class _CudaBlock:
+    """zero-copy view of a device allocation owned by libfacedeform_gpu.so (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3, "strides": None,
+        }
+
+
+def device_view(ptr: int, nbytes: int):
+    import torch
+    return torch.as_tensor(_CudaBlock(ptr, nbytes), device="cuda")
+
+
+def broadcast_block(t, src: int = 0, group=None):
+    """broadcast a tensor in place from `src` (NCCL on CUDA tensors, gloo on CPU tensors)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(t, src=src, group=group)
+    return t
+
+
+def broadcast_model(model, src: int = 0, group=None):
+    """Root: `model` is fitted + solved.  Others: `model` is a receiver (Context.receiver).  After this call every
+    rank can evaluate: the FP64 weight block and the radii travel, the evaluation tables are rebuilt locally."""
+    wp, wb = model.weights_dev()
+    rp, rb = model.radii_dev()
+    model.ctx.synchronize()  # the library's stream and the collective's stream are different streams
+    broadcast_block(device_view(wp, wb), src, group)
+    broadcast_block(device_view(rp, rb), src, group)
+    import torch
+    torch.cuda.current_stream().synchronize()
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_rank(group) != src:
+        model.commit_weights()
+    return model
