@@ -201,7 +201,10 @@ def main():
     params = make_params(model=1, term=synth.TERMS[cfg["term"]], kernel=synth.KERNELS[cfg["kernel"]], radius=radius,
                          eval_path=args.eval_path, **{"lambda": 0.0})
 
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream shared by torch and the library, so torch's CUDA events bracket the kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = Context(local, stream=stream.cuda_stream)
     d_rest = torch.from_numpy(rig.rest).to(dev)
     d_deform = torch.from_numpy(deform).to(dev)
