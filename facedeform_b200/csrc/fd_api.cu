@@ -92,6 +92,7 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_pivstat, 2);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_ctab32, (size_t)N);
     if (st == FD_OK && m->eval64) st = dev_alloc(ctx, &m->d_ctab64, (size_t)N);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_tc_norm, 4);
     if (st == FD_OK && with_factor) {
         st = dev_alloc(ctx, &m->d_A, (size_t)m->lda * m->n);
         if (st == FD_OK) st = dev_alloc(ctx, &m->d_ipiv, (size_t)m->n);
@@ -106,16 +107,36 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
     return FD_OK;
 }
 
+// evaluation kernel choice for F frames (fd_params.eval_path): FP32 only; FD_PATH_AUTO needs a wide 3F
+bool model_wants_tc(const fd_model* m, int F)
+{
+    if (m->eval64 || m->prm.eval_path == FD_PATH_SIMT || !m->d_tc_wt_hi) return false;
+    return m->prm.eval_path == FD_PATH_TENSOR || 3 * F >= FD_TC_MIN_COLUMNS;
+}
+
 int model_reserve_frames(fd_model* m, int F)
 {
     fd_ctx* ctx = m->ctx;
     if (F <= m->capF) return FD_OK;
-    if (m->d_W) { cudaFreeAsync(m->d_W, ctx->stream); m->d_W = nullptr; }
-    if (m->d_W32) { cudaFreeAsync(m->d_W32, ctx->stream); m->d_W32 = nullptr; }
+    void* old[] = {m->d_W, m->d_W32, m->d_tc_scale, m->d_tc_unscale, m->d_tc_wt_hi, m->d_tc_wt_lo};
+    for (void* b : old)
+        if (b) cudaFreeAsync(b, ctx->stream);
+    m->d_W = nullptr; m->d_W32 = nullptr; m->d_tc_scale = nullptr; m->d_tc_unscale = nullptr;
+    m->d_tc_wt_hi = nullptr; m->d_tc_wt_lo = nullptr;
     m->capF = 0;
     const int ld = fd_round_up(3 * F, 4);
     int st = dev_alloc(ctx, &m->d_W, (size_t)m->n * ld);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_W32, (size_t)m->n * ld);
+    if (st == FD_OK && !m->eval64 && m->prm.eval_path != FD_PATH_SIMT) { // tensor-path tables (used when 3F is wide enough)
+        const size_t cols = (size_t)fd_tc_col_pad(F), kpad = (size_t)fd_tc_kpad(m->N);
+        unsigned short *hi = nullptr, *lo = nullptr;
+        st = dev_alloc(ctx, &m->d_tc_scale, cols);
+        if (st == FD_OK) st = dev_alloc(ctx, &m->d_tc_unscale, cols);
+        if (st == FD_OK) st = dev_alloc(ctx, &hi, cols * kpad);
+        if (st == FD_OK) st = dev_alloc(ctx, &lo, cols * kpad);
+        m->d_tc_wt_hi = hi;
+        m->d_tc_wt_lo = lo;
+    }
     if (st != FD_OK) return st;
     m->capF = F;
     return FD_OK;
@@ -255,7 +276,8 @@ void fd_model_destroy(fd_model* m)
     DeviceGuard g(m->ctx->device);
     cudaStream_t s = m->ctx->stream; // stream-ordered frees: later work on the stream may reuse the blocks safely
     void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
-                      m->d_ctab32, m->d_W32, m->d_ctab64};
+                      m->d_ctab32, m->d_W32, m->d_ctab64, m->d_tc_norm, m->d_tc_scale, m->d_tc_unscale,
+                      m->d_tc_wt_hi, m->d_tc_wt_lo};
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;
@@ -322,6 +344,7 @@ int fd_rbf_solve_dev(fd_model* m, const float* deform_ctrl_dev, int32_t n_ctrl, 
     m->F = frames;
     m->ldw = fd_round_up(3 * frames, 4);
     m->ldw32 = m->ldw;
+    m->use_tc = model_wants_tc(m, frames);
     phase_begin(ctx, FD_PH_SOLVE);
     cudaError_t e = fd_launch_solve(ctx, m, deform_ctrl_dev, frames);
     if (e == cudaSuccess) e = fd_launch_pack(ctx, m);
@@ -446,6 +469,7 @@ int fd_model_create_receiver(fd_ctx* ctx, const fd_params* params, const float* 
     m->F = frames;
     m->ldw = fd_round_up(3 * frames, 4);
     m->ldw32 = m->ldw;
+    m->use_tc = model_wants_tc(m, frames);
     cudaError_t e = cudaMemcpyAsync(m->d_rest, rest_ctrl, (size_t)n_ctrl * 3 * sizeof(float), cudaMemcpyDefault, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { FD_SET_ERR(ctx, "receiver: %s", cudaGetErrorString(e)); fd_model_destroy(m); return FD_E_CUDA; }

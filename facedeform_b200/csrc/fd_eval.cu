@@ -263,6 +263,7 @@ cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64
                            const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out)
 {
     if (V <= 0) return cudaSuccess;
+    if (m->use_tc) return fd_launch_eval_tc(ctx, m, P, V, dist2, tu, tv, nrm, P_out, falloff_out);
     EvalArgs a;
     a.N = m->N;
     a.np = m->np;

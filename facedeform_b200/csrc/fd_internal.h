@@ -8,6 +8,8 @@
 #include "facedeform_gpu.h"
 
 #define FD_NUM_FLAGS 8
+#define FD_TMAP_BYTES 128
+#define FD_TC_MIN_COLUMNS 48 // FD_PATH_AUTO takes the tensor-core evaluation from 3F >= 48 columns
 // device-side status words (ints): written by kernels, read by fd_model_report
 #define FD_FLAG_ZERO_RADIUS 0 // != 0: a QNN radius was zero (duplicate centres)      -> terminationtype -5
 #define FD_FLAG_SINGULAR 1    // k+1 of the first zero pivot                           -> terminationtype -3
@@ -64,6 +66,15 @@ struct fd_model {
     float* d_W32;      // n x ldw32 floats
     int ldw32;
     double4* d_ctab64; // N (only when eval64)
+    // tensor-core evaluation tables (fd_eval_tc.cu), present when use_tc
+    bool use_tc;
+    float* d_tc_norm;    // (ox, oy, oz, s)
+    float* d_tc_scale;   // per padded column: 2^e
+    float* d_tc_unscale; // per padded column: 2^-e
+    void* d_tc_wt_hi;    // __half [col_pad][Kpad]
+    void* d_tc_wt_lo;
+    alignas(64) unsigned char tc_map_hi[FD_TMAP_BYTES]; // CUtensorMap
+    alignas(64) unsigned char tc_map_lo[FD_TMAP_BYTES];
 };
 
 #define FD_CUDA_OK(ctx, call)                                                                      \
@@ -93,6 +104,13 @@ cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);
 // fd_eval.cu
 cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
                            const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out);
+// fd_eval_tc.cu
+int fd_tc_kpad(int N);
+int fd_tc_ncb(int F);
+int fd_tc_col_pad(int F);
+cudaError_t fd_launch_pack_tc(fd_ctx* ctx, fd_model* m);
+cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
+                              const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out);
 // fd_capture.cu
 cudaError_t fd_launch_nearest(fd_ctx* ctx, const float* d_P, int64_t V, const float* d_rig, int N,
                               unsigned long long* d_keys /* N scratch */, int32_t* d_nearest);

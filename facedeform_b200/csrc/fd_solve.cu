@@ -182,5 +182,7 @@ cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
     dim3 grid((m->ldw32 + 255) / 256, m->n);
     k_pack_weights<<<grid, 256, 0, s>>>(m->d_W, m->n, m->ldw, 3 * m->F, m->d_W32, m->ldw32, m->d_flags);
     ctx->launches += 2;
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && m->use_tc) e = fd_launch_pack_tc(ctx, m);
+    return e;
 }

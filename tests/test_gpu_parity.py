@@ -29,14 +29,14 @@ def _oracle_params(oracle, p):
 
 
 def _run(ctx, oracle, N, V, F, kernel, term, model=1, lam=0.0, radius=None, tangent=0, falloff=False,
-         eval_precision=0, seed_shift=0, tol=REL_TOL):
+         eval_precision=0, seed_shift=0, tol=REL_TOL, eval_path=0):
     from facedeform_b200 import make_params
     rig = synth.control_rig(N, seed=synth.SEED_CTRL + seed_shift)
     deform = synth.deformed_rig(rig, F)
     mesh = synth.face_mesh(V, topology=False)
     R = radius if radius is not None else synth.default_radius(["gaussian", "multiquadric", "thin_plate"][kernel], rig.spacing)
     p = make_params(model=model, term=term, kernel=kernel, radius=R, tangent=tangent, dofalloff=int(falloff),
-                    falloffrate=1.7, eval_precision=eval_precision, **{"lambda": lam})
+                    falloffrate=1.7, eval_precision=eval_precision, eval_path=eval_path, **{"lambda": lam})
     dist2 = None
     if falloff:
         rng = np.random.default_rng(9)
@@ -185,3 +185,55 @@ def test_device_pointer_entry_points(ctx, oracle):
     dm.close()
     m.close()
     c2.close()
+
+
+# ---- tensor-core evaluation path (tcgen05, fd_eval_tc.cu): same oracle, same tolerance --------------------------
+
+@pytest.mark.parametrize("F", [1, 5, 16, 79, 80, 81, 160, 161])
+def test_tensor_path_frame_blocks(ctx, oracle, F):
+    """column blocks of 240 = 80 frames: partial, exact and multi-block cases; forced FD_PATH_TENSOR."""
+    _run(ctx, oracle, N=70, V=1024, F=F, kernel=0, term=0, eval_path=2)
+
+
+@pytest.mark.parametrize("V", [1, 255, 256, 257, 1023, 4098])
+def test_tensor_path_ragged_vertices(ctx, oracle, V):
+    """V % 4 != 0 takes the scalar store path, partial 256-vertex tiles are masked."""
+    _run(ctx, oracle, N=40, V=V, F=20, kernel=0, term=0, eval_path=2)
+
+
+@pytest.mark.parametrize("N", [1, 5, 27, 28, 29, 60, 61, 255, 256, 257])
+def test_tensor_path_ragged_centres(ctx, oracle, N):
+    """K padding: centres + 4 affine rows rounded up to 32 per stage."""
+    term = 0 if N >= 5 else 1
+    _run(ctx, oracle, N=N, V=1024, F=18, kernel=0, term=term, radius=0.5 if N < 5 else None, eval_path=2)
+
+
+@pytest.mark.parametrize("term", [0, 1, 2])
+def test_tensor_path_terms_and_epilogue(ctx, oracle, term):
+    _run(ctx, oracle, N=64, V=4096, F=30, kernel=0, term=term, tangent=1, falloff=True, eval_path=2)
+
+
+def test_tensor_path_c2_shape(ctx, oracle):
+    """C2: 256 control points x 240 frames (FD_PATH_AUTO selects the tensor path), vertices subsampled for the oracle."""
+    rel, _, _ = _run(ctx, oracle, N=256, V=4096, F=240, kernel=0, term=0)
+    assert rel < 1e-5
+
+
+def test_tensor_path_matches_simt_closely(ctx):
+    from facedeform_b200 import make_params
+    rig = synth.control_rig(256)
+    deform = synth.deformed_rig(rig, 48)
+    mesh = synth.face_mesh(20_000, topology=False)
+    outs = []
+    for path in (1, 2):
+        p = make_params(model=1, radius=2 * rig.spacing, eval_path=path, **{"lambda": 0.0})
+        m = ctx.fit(p, rig.rest).solve(deform)
+        outs.append(m.eval(mesh.P)[0])
+        m.close()
+    assert np.abs(outs[0] - outs[1]).max() <= 1e-5 * mesh.bbox_diag
+
+
+def test_tensor_path_other_kernels_fp32(ctx, oracle):
+    """multiquadric / thin plate through the tensor path in FP32 mode: the stated looser FP32 tolerance applies."""
+    _run(ctx, oracle, N=256, V=2048, F=20, kernel=1, term=0, eval_precision=1, eval_path=2, tol=5e-4)
+    _run(ctx, oracle, N=256, V=2048, F=20, kernel=2, term=0, eval_precision=1, eval_path=2, tol=5e-4)
