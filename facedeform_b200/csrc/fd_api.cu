@@ -90,7 +90,7 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_radii, (size_t)N);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_flags, FD_NUM_FLAGS);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_pivstat, 2);
-    if (st == FD_OK) st = dev_alloc(ctx, &m->d_ctab32, (size_t)N);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_ctab32, (size_t)fd_tc_kpad(N)); // padded: the tensor path bulk-copies 32-centre tiles
     if (st == FD_OK && m->eval64) st = dev_alloc(ctx, &m->d_ctab64, (size_t)N);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_tc_norm, 4);
     if (st == FD_OK && with_factor) {

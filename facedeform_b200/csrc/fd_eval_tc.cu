@@ -19,6 +19,8 @@
 // control rig's bounding box), which holds the 1e-5 x bbox-diagonal tolerance of the FP32 path.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "fd_internal.h"
 
@@ -30,14 +32,19 @@ constexpr int BK = 32;                        // k per pipeline stage (64-byte r
 constexpr int STAGES = 3;
 constexpr int A_SPLIT_BYTES = TM * BK * 2;    // 16384
 constexpr int B_SPLIT_BYTES = CB * BK * 2;    // 15360
-constexpr int STAGE_BYTES = 2 * A_SPLIT_BYTES + 2 * B_SPLIT_BYTES; // 63488
+constexpr int C_TILE_BYTES = BK * 16;         // the stage's 32 centres (float4 each), bulk-copied next to the weights
+constexpr int C_TILE_OFF = 2 * A_SPLIT_BYTES + 2 * B_SPLIT_BYTES; // 63488
+constexpr int STAGE_BYTES = C_TILE_OFF + C_TILE_BYTES;             // 64000
 constexpr int PRODUCER_WARPS = 8;
-constexpr int THREADS = 32 * (2 + PRODUCER_WARPS);
+constexpr int EPILOGUE_WARPS = 8;              // one per (M tile, TMEM lane quarter)
+constexpr int THREADS = 32 * (2 + PRODUCER_WARPS + EPILOGUE_WARPS);
 constexpr int TMEM_COLS = 512;
 constexpr int ACC1_COL = 256;                 // TMEM column of the second M tile's accumulator
-constexpr int EPI_FRAMES = 16;                // frames per epilogue chunk (48 accumulator columns)
-constexpr int EPI_WARP_FLOATS = EPI_FRAMES * 96; // staging floats per warp (16 frames x 32 vertices x 3)
-constexpr int SMEM_BARRIERS = STAGES * STAGE_BYTES;
+constexpr int EPI_FRAMES = 8;                 // frames per epilogue chunk (24 accumulator columns)
+constexpr int EPI_WARP_FLOATS = EPI_FRAMES * 96; // staging floats per warp (8 frames x 32 vertices x 3)
+constexpr int EPI_COLS = EPI_FRAMES * 3;
+constexpr int SMEM_EPI_STAGING = STAGES * STAGE_BYTES;                          // 4 warps x 6 KB transpose buffers
+constexpr int SMEM_BARRIERS = SMEM_EPI_STAGING + EPILOGUE_WARPS * EPI_WARP_FLOATS * 4;
 constexpr int SMEM_COLSCALE = SMEM_BARRIERS + 128;
 constexpr int SMEM_TOTAL = SMEM_COLSCALE + CB * 4;
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024; // slack for the 1024-byte alignment of the dynamic window
@@ -90,6 +97,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
         : "memory");
 }
 
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem], M=128, K=16, FP16 inputs, FP32 accumulate
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
 {
@@ -124,6 +139,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
         : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v)
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -200,6 +224,8 @@ struct Args {
     float radius2, falloffrate;
     int do_tangent;
     int vec_store_ok;       // V % 4 == 0 and P_out 16-byte aligned
+    long long* dbg;         // optional per-unit phase timestamps of CTA 0 (FD_TC_DEBUG=1), else NULL
+    int dbg_nostore;        // FD_TC_DEBUG=2: skip the global stores (bandwidth experiment)
 };
 
 // 8 basis values -> FP16 hi (RN) and lo (RN of the remainder), packed as two 16-byte chunks
@@ -218,19 +244,23 @@ __device__ __forceinline__ void split8(const float* ph, uint4& hi, uint4& lo)
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <int KERNEL>
+template <int KERNEL, bool TANGENT>
 __global__ void __launch_bounds__(THREADS, 1)
-k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo)
+k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+          const __grid_constant__ CUtensorMap map_out)
 {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // align inside the shared window with pointer arithmetic only: a uintptr_t round trip would demote every
+    // access below to generic LD/ST (long-scoreboard) instead of LDS/STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t smem_base = smem_u32(smem);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BARRIERS);
     const uint32_t bar_full_a = smem_u32(bars + 0);          // [STAGES], count PRODUCER_WARPS
     const uint32_t bar_full_b = smem_u32(bars + STAGES);     // [STAGES], count 1 + tx bytes
     const uint32_t bar_empty = smem_u32(bars + 2 * STAGES);  // [STAGES], count 1 (tcgen05.commit)
-    const uint32_t bar_tmem_full = smem_u32(bars + 3 * STAGES);
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    const uint32_t bar_tmem_full = smem_u32(bars + 3 * STAGES);        // count 1: all MMAs of the unit retired
+    const uint32_t bar_tmem_empty = smem_u32(bars + 3 * STAGES + 1);   // [2], count 4 warps: accumulator mt drained
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 3);
     float* s_colscale = reinterpret_cast<float*>(smem + SMEM_COLSCALE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,6 +271,8 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_tmem_full, 1);
+        mbar_init(bar_tmem_empty, EPILOGUE_WARPS / 2);
+        mbar_init(bar_tmem_empty + 8, EPILOGUE_WARPS / 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -267,7 +299,8 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     const uint32_t sb = smem_base + s * STAGE_BYTES + 2 * A_SPLIT_BYTES;
-                    mbar_expect_tx(bar_full_b + 8 * s, 2 * B_SPLIT_BYTES);
+                    mbar_expect_tx(bar_full_b + 8 * s, 2 * B_SPLIT_BYTES + C_TILE_BYTES);
+                    bulk_load_1d(smem_base + s * STAGE_BYTES + C_TILE_OFF, a.ctab + kb * BK, C_TILE_BYTES, bar_full_b + 8 * s);
                     tma_load_2d(sb, &map_hi, bar_full_b + 8 * s, kb * BK, cb * CB);
                     tma_load_2d(sb + B_SPLIT_BYTES, &map_lo, bar_full_b + 8 * s, kb * BK, cb * CB);
                 }
@@ -276,8 +309,8 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+            uint32_t it = 0, unit_iter = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
                 const int cb = (int)(u % a.ncb);
                 const int ncols = min(CB, (3 * a.F - cb * CB + 15) & ~15);
                 const uint32_t idesc = make_idesc(ncols);
@@ -299,6 +332,10 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                             const uint64_t b_hi = make_desc_sw64(sb + kk * 32);
                             const uint64_t b_lo = make_desc_sw64(sb + B_SPLIT_BYTES + kk * 32);
                             const uint32_t d = tmem_base + mt * ACC1_COL;
+                            if ((kb | kk) == 0) { // first write of this unit: the epilogue must have drained the accumulator
+                                mbar_wait(bar_tmem_empty + 8 * mt, (unit_iter & 1) ^ 1);
+                                tc_fence_after();
+                            }
                             umma_f16(d, a_hi, b_hi, idesc, (kb | kk) != 0);
                             umma_f16(d, a_hi, b_lo, idesc, 1);
                             umma_f16(d, a_lo, b_hi, idesc, 1);
@@ -309,151 +346,219 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                 }
             }
         }
-    } else {
-        // ================= Phi producers, then epilogue =================
-        const int pw = warp - 2;              // 0..7
-        const int mt = pw >> 2;               // M tile
-        const int q = warp & 3;               // TMEM lane quarter this warp may access
-        const int row = mt * 128 + q * 32 + lane;
+    } else if (warp < 2 + PRODUCER_WARPS) {
+        // ================= Phi producers =================
+        const int row = (warp - 2) * 32 + lane; // vertex row of the 256-row tile this thread generates
         const float4 nrm4 = *reinterpret_cast<const float4*>(a.norm);
-        float* stg = reinterpret_cast<float*>(smem + (pw < 5 ? 0 : STAGE_BYTES)) + (pw < 5 ? pw : pw - 5) * EPI_WARP_FLOATS;
         uint32_t it = 0, unit_iter = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
-            const int cb = (int)(u % a.ncb);
             const int64_t vt = u / a.ncb;
             const int64_t v = vt * TM + row;
-            const bool valid = v < a.V;
             float px = 0.f, py = 0.f, pz = 0.f;
-            if (valid) {
+            if (v < a.V) {
                 px = a.P[3 * v];
                 py = a.P[3 * v + 1];
                 pz = a.P[3 * v + 2];
             }
-            for (int t = threadIdx.x - 64; t < CB; t += 32 * PRODUCER_WARPS) s_colscale[t] = a.colscale[cb * CB + t];
-
-            // ---- produce the Phi tile, 32 columns of K per stage ----
+            const bool dbg = a.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && unit_iter < 15;
+            if (dbg) a.dbg[unit_iter * 8 + 0] = clock64();
             for (int kb = 0; kb < nk; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                mbar_wait(bar_full_b + 8 * s, ph); // the stage's centre tile has landed (same barrier as the weights)
                 uint8_t* a_hi = smem + s * STAGE_BYTES + row * (BK * 2);
                 uint8_t* a_lo = a_hi + A_SPLIT_BYTES;
+                const float4* s_ctr = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES + C_TILE_OFF);
                 const int k0 = kb * BK;
                 const int swz = (row >> 1) & 3;
+                if (k0 + BK <= a.N) {
 #pragma unroll
-                for (int c16 = 0; c16 < 4; ++c16) {
-                    float f[8];
-                    if (k0 + c16 * 8 + 8 <= a.N) {
+                    for (int c32 = 0; c32 < 2; ++c32) { // 16 independent basis evaluations in flight per thread
+                        float f[16];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 c = __ldg(&a.ctab[k0 + c16 * 8 + j]);
+                        for (int j = 0; j < 16; ++j) {
+                            const float4 c = s_ctr[c32 * 16 + j]; // warp-wide broadcast LDS.128
                             const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
                             f[j] = phi<KERNEL>(dx * dx + dy * dy + dz * dz, c.w);
                         }
-                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 hi, lo;
+                            split8(f + 8 * h, hi, lo);
+                            const int off = ((c32 * 2 + h) ^ swz) * 16;
+                            *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                            *reinterpret_cast<uint4*>(a_lo + off) = lo;
+                        }
+                    }
+                } else { // the last stage(s): remaining centres, then the affine rows [1, x', y', z'], then zero padding
+#pragma unroll 1
+                    for (int c16 = 0; c16 < 4; ++c16) {
+                        float f[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int k = k0 + c16 * 8 + j;
-                            float val = 0.f;
-                            if (k < a.N) {
-                                const float4 c = __ldg(&a.ctab[k]);
-                                const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
-                                val = phi<KERNEL>(dx * dx + dy * dy + dz * dz, c.w);
-                            } else if (k == a.N) {
-                                val = 1.0f;
-                            } else if (k == a.N + 1) {
-                                val = (px - nrm4.x) * nrm4.w;
-                            } else if (k == a.N + 2) {
-                                val = (py - nrm4.y) * nrm4.w;
-                            } else if (k == a.N + 3) {
-                                val = (pz - nrm4.z) * nrm4.w;
+                            const float4 c = s_ctr[c16 * 8 + j];
+                            const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
+                            float val = phi<KERNEL>(dx * dx + dy * dy + dz * dz, c.w);
+                            if (k >= a.N) {
+                                const int r = k - a.N;
+                                val = r == 0 ? 1.0f
+                                    : r == 1 ? (px - nrm4.x) * nrm4.w
+                                    : r == 2 ? (py - nrm4.y) * nrm4.w
+                                    : r == 3 ? (pz - nrm4.z) * nrm4.w : 0.0f;
                             }
                             f[j] = val;
                         }
+                        uint4 hi, lo;
+                        split8(f, hi, lo);
+                        const int off = (c16 ^ swz) * 16;
+                        *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                        *reinterpret_cast<uint4*>(a_lo + off) = lo;
                     }
-                    uint4 hi, lo;
-                    split8(f, hi, lo);
-                    const int off = (c16 ^ swz) * 16;
-                    *reinterpret_cast<uint4*>(a_hi + off) = hi;
-                    *reinterpret_cast<uint4*>(a_lo + off) = lo;
                 }
                 fence_proxy_async(); // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_full_a + 8 * s);
             }
-
-            // ---- epilogue: TMEM -> registers -> (transpose in shared memory) -> global ----
-            float fo = 0.f;
-            bool skip = true;
-            if (valid) {
-                const float d2 = a.dist2 ? a.dist2[v] : 0.f;
-                skip = d2 > a.radius2;                                  // SOP_FaceDeform.cpp:408-410
-                fo = powf(1.0f - fminf(d2 / a.radius2, 1.0f), a.falloffrate); // :423-424
-                if (skip) fo = 0.f;
-                if (a.falloff_out && cb == 0) a.falloff_out[v] = fo;
-            }
-            float tu[3] = {0, 0, 0}, tv[3] = {0, 0, 0}, tn[3] = {0, 0, 0};
-            if (a.do_tangent && valid) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    tu[k] = a.tu[3 * v + k];
-                    tv[k] = a.tv[3 * v + k];
-                    tn[k] = a.nrm[3 * v + k];
-                }
-                normalize3(tu);
-                normalize3(tv);
-                normalize3(tn);
-            }
-            const int64_t v_warp0 = vt * TM + mt * 128 + q * 32;
-            const bool vec = a.vec_store_ok && (v_warp0 + 32 <= a.V);
+            if (dbg) a.dbg[unit_iter * 8 + 1] = clock64();
+        }
+    } else {
+        // ================= epilogue warps: TMEM -> registers -> (transpose in shared memory) -> global =================
+        // They run one unit behind the producers: while they drain and store unit u, Phi generation and the MMAs of
+        // unit u+1 proceed (the MMA issuer re-acquires each accumulator through bar_tmem_empty[mt]).
+        const int ew = warp - (2 + PRODUCER_WARPS);
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        float* stg = reinterpret_cast<float*>(smem + SMEM_EPI_STAGING) + ew * EPI_WARP_FLOATS;
+        const int et = threadIdx.x - 32 * (2 + PRODUCER_WARPS);
+        uint32_t unit_iter = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
+            const int cb = (int)(u % a.ncb);
+            const int64_t vt = u / a.ncb;
             const int f_base = cb * (CB / 3);
             const int nframes = min(CB / 3, a.F - f_base);
-            asm volatile("bar.sync 1, 256;" ::: "memory"); // s_colscale visible to all producer warps
+            asm volatile("bar.sync 2, 256;" ::: "memory"); // previous unit's readers of s_colscale are done
+            for (int t = et; t < CB; t += 32 * EPILOGUE_WARPS) s_colscale[t] = a.colscale[cb * CB + t];
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            const bool dbg = a.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && unit_iter < 15;
+            if (dbg) a.dbg[unit_iter * 8 + 2] = clock64();
             mbar_wait(bar_tmem_full, unit_iter & 1);
             tc_fence_after();
-            for (int ch = 0; ch * EPI_FRAMES < nframes; ++ch) {
-                float acc[48];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + mt * ACC1_COL + ch * 48;
-                tmem_ld16(taddr, acc);
-                tmem_ld16(taddr + 16, acc + 16);
-                tmem_ld16(taddr + 32, acc + 32);
-                tmem_ld_wait();
-                const int fcnt = min(EPI_FRAMES, nframes - ch * EPI_FRAMES);
-#pragma unroll
-                for (int i = 0; i < EPI_FRAMES; ++i) {
-                    float d[3];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) d[k] = acc[3 * i + k] * s_colscale[ch * 48 + 3 * i + k];
-                    if (a.do_tangent) project_to_tangents(tu, tv, tn, d);
-                    float o[3] = {skip ? px : px + d[0] * fo, skip ? py : py + d[1] * fo, skip ? pz : pz + d[2] * fo};
-                    if (vec) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) stg[(i * 32 + lane) * 3 + k] = o[k];
-                    } else if (valid && i < fcnt) {
-                        float* dst = a.P_out + ((size_t)(f_base + ch * EPI_FRAMES + i) * (size_t)a.V + (size_t)v) * 3;
-                        dst[0] = o[0];
-                        dst[1] = o[1];
-                        dst[2] = o[2];
-                    }
+            if (dbg) a.dbg[unit_iter * 8 + 3] = clock64();
+            {
+                const int mt = ew >> 2; // this warp's accumulator
+                const int64_t v_warp0 = vt * TM + mt * 128 + q * 32;
+                const int64_t v = v_warp0 + lane;
+                const bool valid = v < a.V;
+                float px = 0.f, py = 0.f, pz = 0.f, fo = 0.f;
+                bool skip = true;
+                if (valid) {
+                    px = a.P[3 * v];
+                    py = a.P[3 * v + 1];
+                    pz = a.P[3 * v + 2];
+                    const float d2 = a.dist2 ? a.dist2[v] : 0.f;
+                    skip = d2 > a.radius2;                                        // SOP_FaceDeform.cpp:408-410
+                    fo = powf(1.0f - fminf(d2 / a.radius2, 1.0f), a.falloffrate); // :423-424
+                    if (skip) fo = 0.f;
+                    if (a.falloff_out && cb == 0) a.falloff_out[v] = fo;
                 }
+                float tu[3] = {0, 0, 0}, tv[3] = {0, 0, 0}, tn[3] = {0, 0, 0};
+                if (TANGENT && valid) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        tu[k] = a.tu[3 * v + k];
+                        tv[k] = a.tv[3 * v + k];
+                        tn[k] = a.nrm[3 * v + k];
+                    }
+                    normalize3(tu);
+                    normalize3(tv);
+                    normalize3(tn);
+                }
+                const bool vec = a.vec_store_ok != 0;
                 if (vec) {
-                    __syncwarp();
-                    const float4* stg4 = reinterpret_cast<const float4*>(stg);
+                    // fast path: out = P + acc * (colscale * falloff) (colscale is a power of two, so the product order
+                    // does not change the rounding; a skipped vertex has falloff 0 and keeps P exactly), transposed
+                    // through shared memory into [frame][vertex][xyz] rows that one lane hands to the bulk-copy engine
+#pragma unroll 1
+                    for (int ch = 0; ch * EPI_FRAMES < nframes; ++ch) {
+                        float acc[EPI_COLS];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + mt * ACC1_COL + ch * EPI_COLS;
+                        const bool dbg2 = dbg && unit_iter == 1 && mt == 0 && ch == 1;
+                        if (dbg2) a.dbg[120] = clock64();
+                        tmem_ld16(taddr, acc);
+                        tmem_ld8(taddr + 16, acc + 16);
+                        float* buf = stg; // single buffer, guarded by wait_group.read below
+                        // the bulk stores of the previous chunk must have finished reading the staging buffer
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        if (dbg2) a.dbg[121] = clock64();
+                        __syncwarp();
+                        tmem_ld_wait();
+                        if (dbg2) a.dbg[122] = clock64();
+                        const int fcnt = min(EPI_FRAMES, nframes - ch * EPI_FRAMES);
+                        const float4* cs4 = reinterpret_cast<const float4*>(s_colscale + ch * EPI_COLS);
 #pragma unroll
-                    for (int r = 0; r < 12; ++r) {
-                        const int q4 = r * 32 + lane;
-                        const int fr = q4 / 24, w = q4 - fr * 24;
-                        if (fr < fcnt) {
-                            float4* dst = reinterpret_cast<float4*>(
-                                a.P_out + ((size_t)(f_base + ch * EPI_FRAMES + fr) * (size_t)a.V + (size_t)v_warp0) * 3);
-                            dst[w] = stg4[fr * 24 + w];
+                        for (int g = 0; g < EPI_COLS / 4; ++g) { // 4 columns at a time
+                            const float4 cs = cs4[g];
+                            const float c4[4] = {cs.x, cs.y, cs.z, cs.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int col = 4 * g + e, i = col / 3, k = col - 3 * i;
+                                const float p = k == 0 ? px : (k == 1 ? py : pz);
+                                buf[(i * 32 + lane) * 3 + k] = fmaf(acc[col], c4[e] * fo, p);
+                            }
                         }
+                        if (dbg2) a.dbg[123] = clock64();
+                        fence_proxy_async(); // staging writes -> visible to the bulk-copy engine (async proxy)
+                        __syncwarp();
+                        if (dbg2) a.dbg[124] = clock64();
+                        if (lane == 0) {
+                            // one TMA store of the [16 frames][32 vertices x 3] tile; frames >= F and vertices >= V are clipped
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(reinterpret_cast<uint64_t>(&map_out)), "r"(smem_u32(buf)),
+                                           "r"((int)(v_warp0 * 3)), "r"(f_base + ch * EPI_FRAMES)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        (void)fcnt;
+                        if (dbg2) a.dbg[125] = clock64();
                     }
-                    __syncwarp();
+                } else {
+                    // general path (partial tile, V not a multiple of 4, tangent projection): per-lane scalar stores
+#pragma unroll 1
+                    for (int ch = 0; ch * EPI_FRAMES < nframes; ++ch) {
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + mt * ACC1_COL + ch * EPI_COLS;
+                        const int fcnt = min(EPI_FRAMES, nframes - ch * EPI_FRAMES);
+#pragma unroll 1
+                        for (int part = 0; part < EPI_COLS / 8; ++part) {
+                            float acc[8];
+                            tmem_ld8(taddr + 8 * part, acc);
+                            tmem_ld_wait();
+                            // frames straddle the 8-column parts: gather through the staging buffer as [col][lane]
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) stg[(part * 8 + c) * 32 + lane] = acc[c] * s_colscale[ch * EPI_COLS + part * 8 + c];
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int i = 0; i < fcnt; ++i) {
+                            float d[3] = {stg[(3 * i) * 32 + lane], stg[(3 * i + 1) * 32 + lane], stg[(3 * i + 2) * 32 + lane]};
+                            if (TANGENT) project_to_tangents(tu, tv, tn, d);
+                            if (valid) {
+                                float* dst = a.P_out + ((size_t)(f_base + ch * EPI_FRAMES + i) * (size_t)a.V + (size_t)v) * 3;
+                                dst[0] = skip ? px : px + d[0] * fo;
+                                dst[1] = skip ? py : py + d[1] * fo;
+                                dst[2] = skip ? pz : pz + d[2] * fo;
+                            }
+                        }
+                        __syncwarp();
+                    }
                 }
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                // accumulator mt is drained (for this warp's 32 lanes): hand it back to the MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tmem_empty + 8 * mt);
             }
-            tc_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory"); // TMEM and the staging area are free for the next unit
+            if (dbg) a.dbg[unit_iter * 8 + 4] = clock64();
         }
     }
 
@@ -582,6 +687,19 @@ static EncodeTiledFn get_encode()
     return fn;
 }
 
+// P_out viewed as a [F][V*3] float tensor; one box = 16 frames x (32 vertices x 3 floats)
+static bool make_out_map(CUtensorMap* map, float* P_out, int64_t V, int F)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)V * 3, (cuuint64_t)F};
+    cuuint64_t strides[1] = {(cuuint64_t)V * 12};
+    cuuint32_t box[2] = {96, EPI_FRAMES};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, P_out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static bool make_map(CUtensorMap* map, void* ptr, int Kpad, int rows)
 {
     EncodeTiledFn enc = get_encode();
@@ -624,13 +742,6 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
                               const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out)
 {
     if (V <= 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(tc::k_eval_tc<FD_KERNEL_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC);
-        cudaFuncSetAttribute(tc::k_eval_tc<FD_KERNEL_MULTIQUADRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC);
-        cudaFuncSetAttribute(tc::k_eval_tc<FD_KERNEL_THINPLATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC);
-        attr_set = true;
-    }
     tc::Args a;
     a.ctab = m->d_ctab32;
     a.norm = m->d_tc_norm;
@@ -650,21 +761,47 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
     a.radius2 = m->prm.radius * m->prm.radius;
     a.falloffrate = m->prm.falloffrate;
     a.do_tangent = (m->prm.tangent && tu && tv && nrm) ? 1 : 0;
-    a.vec_store_ok = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(P_out) & 15) == 0);
+    a.vec_store_ok = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(P_out) & 15) == 0) && !a.do_tangent;
+    alignas(64) CUtensorMap mo;
+    memset(&mo, 0, sizeof(mo));
+    if (a.vec_store_ok && !tc::make_out_map(&mo, P_out, V, m->F)) a.vec_store_ok = 0;
+    static long long* d_dbg = nullptr;
+    static const bool want_dbg = getenv("FD_TC_DEBUG") != nullptr;
+    if (want_dbg && !d_dbg) { cudaMalloc(&d_dbg, 16 * 8 * sizeof(long long)); cudaMemset(d_dbg, 0, 16 * 8 * sizeof(long long)); }
+    a.dbg = want_dbg ? d_dbg : nullptr;
+    a.dbg_nostore = want_dbg && atoi(getenv("FD_TC_DEBUG")) == 2;
     const int64_t n_units = ((V + tc::TM - 1) / tc::TM) * a.ncb;
     const int grid = (int)(n_units < ctx->sm_count ? n_units : ctx->sm_count);
     const CUtensorMap& mh = *(const CUtensorMap*)m->tc_map_hi;
     const CUtensorMap& ml = *(const CUtensorMap*)m->tc_map_lo;
+    const bool tang = a.do_tangent != 0;
+#define FD_TC_LAUNCH(KERNEL, TANG)                                                                                  \
+    do {                                                                                                            \
+        auto kfn = tc::k_eval_tc<KERNEL, TANG>;                                                                     \
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC);                     \
+        kfn<<<grid, tc::THREADS, tc::SMEM_ALLOC, ctx->stream>>>(a, mh, ml, mo);                                        \
+    } while (0)
     switch (m->prm.kernel) {
     case FD_KERNEL_GAUSSIAN:
-        tc::k_eval_tc<FD_KERNEL_GAUSSIAN><<<grid, tc::THREADS, tc::SMEM_ALLOC, ctx->stream>>>(a, mh, ml);
+        if (tang) FD_TC_LAUNCH(FD_KERNEL_GAUSSIAN, true); else FD_TC_LAUNCH(FD_KERNEL_GAUSSIAN, false);
         break;
     case FD_KERNEL_MULTIQUADRIC:
-        tc::k_eval_tc<FD_KERNEL_MULTIQUADRIC><<<grid, tc::THREADS, tc::SMEM_ALLOC, ctx->stream>>>(a, mh, ml);
+        if (tang) FD_TC_LAUNCH(FD_KERNEL_MULTIQUADRIC, true); else FD_TC_LAUNCH(FD_KERNEL_MULTIQUADRIC, false);
         break;
     default:
-        tc::k_eval_tc<FD_KERNEL_THINPLATE><<<grid, tc::THREADS, tc::SMEM_ALLOC, ctx->stream>>>(a, mh, ml);
+        if (tang) FD_TC_LAUNCH(FD_KERNEL_THINPLATE, true); else FD_TC_LAUNCH(FD_KERNEL_THINPLATE, false);
         break;
+    }
+#undef FD_TC_LAUNCH
+    if (want_dbg) { // development aid: per-unit phase timestamps of CTA 0 (cycles)
+        long long h[128];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[fd_tc] chunk: issue-ldtm+bulkwait %lld  ldtm-wait %lld  math+sts %lld  fence %lld  bulk-issue %lld\n",
+                h[121] - h[120], h[122] - h[121], h[123] - h[122], h[124] - h[123], h[125] - h[124]);
+        for (int u = 0; u < 15 && h[u * 8]; ++u)
+            fprintf(stderr, "[fd_tc] unit %d: produce %lld | epilogue: wait-tmem %lld  drain+store %lld | producer start->epilogue end %lld\n", u,
+                    h[u * 8 + 1] - h[u * 8], h[u * 8 + 3] - h[u * 8 + 2], h[u * 8 + 4] - h[u * 8 + 3], h[u * 8 + 4] - h[u * 8]);
     }
     ctx->launches += 1;
     return cudaGetLastError();

@@ -107,11 +107,15 @@ __global__ void __launch_bounds__(256) k_trsm_update(const double* __restrict__ 
 // weights -> evaluation tables.  FP32: centre table (cx, cy, cz, kernel parameter) and weights n x ldw32;
 // FP64 centre table when the evaluation runs in double.  Flags non-finite weights.
 __global__ void __launch_bounds__(256) k_pack_tables(const float* __restrict__ rest, const double* __restrict__ radii,
-                                                     int N, int kernel, float4* __restrict__ ctab32,
+                                                     int N, int Npad, int kernel, float4* __restrict__ ctab32,
                                                      double4* __restrict__ ctab64)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
+    if (j >= Npad) return;
+    if (j >= N) { // padding of the centre table (multiquadric parameter 1 keeps the padded basis finite)
+        ctab32[j] = make_float4(0.f, 0.f, 0.f, kernel == FD_KERNEL_MULTIQUADRIC ? 1.f : 0.f);
+        return;
+    }
     const double R = radii[j];
     double prm;
     if (kernel == FD_KERNEL_GAUSSIAN) prm = -1.0 / (R * R);
@@ -177,7 +181,8 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_defor
 cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
 {
     cudaStream_t s = ctx->stream;
-    k_pack_tables<<<(m->N + 255) / 256, 256, 0, s>>>(m->d_rest, m->d_radii, m->N, m->prm.kernel, m->d_ctab32,
+    const int npad = fd_tc_kpad(m->N);
+    k_pack_tables<<<(npad + 255) / 256, 256, 0, s>>>(m->d_rest, m->d_radii, m->N, npad, m->prm.kernel, m->d_ctab32,
                                                     m->eval64 ? m->d_ctab64 : nullptr);
     dim3 grid((m->ldw32 + 255) / 256, m->n);
     k_pack_weights<<<grid, 256, 0, s>>>(m->d_W, m->n, m->ldw, 3 * m->F, m->d_W32, m->ldw32, m->d_flags);
