@@ -622,16 +622,22 @@ __device__ __forceinline__ double tc_weight(const double* __restrict__ W, int ld
     return 0.0;
 }
 
-// per column: power-of-two scale that brings max |w| to <= 16384 (FP16 range with head-room for hi + lo)
+// per column: power-of-two scale that brings max |w| to <= 16384 (FP16 range with head-room for hi + lo);
+// CTA = 32 columns x 8 row groups, row-major reads stay coalesced
 __global__ void __launch_bounds__(256) k_tc_colscale(const double* __restrict__ W, int ldw, int N, int np, int ncol,
                                                      int ncol_pad, const float* __restrict__ norm,
                                                      float* __restrict__ unscale, float* __restrict__ scale)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncol_pad) return;
+    __shared__ double s_mx[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     double mx = 0.0;
     if (c < ncol)
-        for (int k = 0; k < N + 4; ++k) mx = fmax(mx, fabs(tc_weight(W, ldw, N, np, k, c, norm)));
+        for (int k = ty; k < N + 4; k += 8) mx = fmax(mx, fabs(tc_weight(W, ldw, N, np, k, c, norm)));
+    s_mx[ty][tx] = mx;
+    __syncthreads();
+    if (ty != 0 || c >= ncol_pad) return;
+    for (int g = 1; g < 8; ++g) mx = fmax(mx, s_mx[g][tx]);
     int e = 0;
     if (mx > 0.0 && isfinite(mx)) {
         frexp(mx, &e);      // mx = m * 2^e, m in [0.5, 1)
@@ -726,7 +732,7 @@ cudaError_t fd_launch_pack_tc(fd_ctx* ctx, fd_model* m)
     cudaStream_t s = ctx->stream;
     const int ncol = 3 * m->F, ncol_pad = fd_tc_col_pad(m->F), Kpad = fd_tc_kpad(m->N);
     tc::k_tc_norm<<<1, 256, 0, s>>>(m->d_rest, m->N, m->d_tc_norm);
-    tc::k_tc_colscale<<<(ncol_pad + 255) / 256, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad, m->d_tc_norm,
+    tc::k_tc_colscale<<<(ncol_pad + 31) / 32, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad, m->d_tc_norm,
                                                             m->d_tc_unscale, m->d_tc_scale);
     dim3 grid((ncol_pad + 31) / 32, (Kpad + 31) / 32);
     tc::k_tc_pack<<<grid, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad, Kpad, m->d_tc_norm, m->d_tc_scale,

@@ -58,6 +58,7 @@ struct fd_model {
     double* d_A;     // lda x n, LU in place
     int* d_ipiv;     // n (global row index swapped with row k)
     int* d_perm;     // n: row i of P*A is row perm[i] of A
+    double* d_Tinv;  // [ceil(n/32)][2][32x32]: inverses of the diagonal blocks of L and U
     double* d_W;     // n x ldw weights (solve in place over the right-hand sides)
     int* d_flags;    // FD_NUM_FLAGS
     double* d_pivstat; // [min |u_kk|, max |u_kk|]
@@ -101,6 +102,7 @@ cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, 
 // fd_solve.cu
 cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_deform, int F);
 cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);
+cudaError_t fd_launch_invdiag(fd_ctx* ctx, fd_model* m);
 // fd_eval.cu
 cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
                            const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out);

@@ -104,6 +104,129 @@ __global__ void __launch_bounds__(256) k_trsm_update(const double* __restrict__ 
     }
 }
 
+// ---- slab solve: one CTA owns RC right-hand-side columns for the whole forward/backward substitution --------------
+// The slab (n x RC doubles) lives in shared memory, L and U stream once from L2; no inter-CTA dependency, one launch.
+// Warp w owns slab columns {2w, 2w+1}; inside a 32-row diagonal block lane r holds row r, so the triangular solve
+// of the block needs only warp shuffles.  The rows outside the block are updated by all 256 threads.
+constexpr int RC = 16;
+constexpr int SLAB_THREADS = 256;
+
+template <bool LOWER>
+__device__ __forceinline__ void slab_sweep_block(const double* __restrict__ A, int lda, int n, int k0, int nb,
+                                                 const double* __restrict__ Tinv, double* __restrict__ s_B,
+                                                 double (*s_T)[SB + 1], double (*s_X)[RC])
+{
+    const int tid = threadIdx.x;
+    // stage the inverted diagonal block (k_lu_invdiag): the block solve becomes a 32x32 by 32xRC product
+    for (int t = tid; t < SB * SB; t += SLAB_THREADS) s_T[t / SB][t % SB] = Tinv[t];
+    __syncthreads();
+    {
+        const int r = tid & 31, cpair = (tid >> 5) * 2;
+        double x0 = 0.0, x1 = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < SB; ++k) {
+            const double t = s_T[r][k];
+            const double* bk = s_B + (size_t)(k0 + k) * RC + cpair;
+            if (k < nb) {
+                x0 += t * bk[0];
+                x1 += t * bk[1];
+            }
+        }
+        s_X[r][cpair] = r < nb ? x0 : 0.0;
+        s_X[r][cpair + 1] = r < nb ? x1 : 0.0;
+    }
+    __syncthreads();
+    for (int t = tid; t < nb * RC; t += SLAB_THREADS) s_B[(size_t)k0 * RC + t] = s_X[t / RC][t % RC];
+    // rows outside the block: B[i][:] -= T[i][k0:k0+nb] * X  (all loads of a row are issued before the FMAs)
+    const int row_begin = LOWER ? k0 + nb : 0;
+    const int row_end = LOWER ? n : k0;
+    const int half = tid & 1; // 8 of the 16 columns
+    for (int i = row_begin + (tid >> 1); i < row_end; i += SLAB_THREADS / 2) {
+        const double* Ti = A + (size_t)k0 * lda + i;
+        double l[SB];
+#pragma unroll
+        for (int k = 0; k < SB; ++k) l[k] = k < nb ? Ti[(size_t)k * lda] : 0.0;
+        double acc[8] = {};
+#pragma unroll
+        for (int k = 0; k < SB; ++k) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] += l[k] * s_X[k][half * 8 + c];
+        }
+        double* bi = s_B + (size_t)i * RC + half * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bi[c] -= acc[c];
+    }
+    __syncthreads();
+}
+
+// inverse of every 32x32 diagonal block of L (unit lower) and U, once per factorisation; thread c computes column c
+__global__ void __launch_bounds__(64) k_lu_invdiag(const double* __restrict__ A, int lda, int n, double* __restrict__ Tinv)
+{
+    __shared__ double s_T[SB][SB + 1];
+    const int blk = blockIdx.x, k0 = blk * SB, nb = min(SB, n - k0);
+    for (int t = threadIdx.x; t < SB * SB; t += 64) {
+        const int r = t % SB, c = t / SB;
+        s_T[r][c] = (r < nb && c < nb) ? A[(size_t)(k0 + c) * lda + k0 + r] : (r == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int c = threadIdx.x & 31;
+    const bool upper = threadIdx.x >= 32;
+    double x[SB];
+#pragma unroll
+    for (int r = 0; r < SB; ++r) x[r] = r == c ? 1.0 : 0.0;
+    if (!upper) {
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+            const double xj = x[j];
+#pragma unroll
+            for (int r = j + 1; r < SB; ++r) x[r] -= s_T[r][j] * xj;
+        }
+    } else {
+#pragma unroll
+        for (int j = SB - 1; j >= 0; --j) {
+            const double xj = x[j] / s_T[j][j];
+            x[j] = xj;
+#pragma unroll
+            for (int r = 0; r < j; ++r) x[r] -= s_T[r][j] * xj;
+        }
+    }
+    double* out = Tinv + ((size_t)blk * 2 + (upper ? 1 : 0)) * SB * SB; // row-major [r][c]
+#pragma unroll
+    for (int r = 0; r < SB; ++r) out[r * SB + c] = x[r];
+}
+
+__global__ void __launch_bounds__(SLAB_THREADS) k_solve_slab(const double* __restrict__ A, int lda, int n, int N,
+                                                             const int* __restrict__ perm, const float* __restrict__ rest,
+                                                             const float* __restrict__ deform, int F,
+                                                             const double* __restrict__ Tinv, double* __restrict__ W, int ldw)
+{
+    extern __shared__ double s_B[]; // n x RC
+    __shared__ double s_T[SB][SB + 1];
+    __shared__ double s_X[SB][RC];
+    const int c0 = blockIdx.x * RC;
+    const int nrhs = 3 * F;
+    // right-hand sides, permuted: delta subtracted in FP32 then widened (SOP_FaceDeform.cpp:276-284)
+    for (int t = threadIdx.x; t < n * RC; t += SLAB_THREADS) {
+        const int i = t / RC, c = c0 + (t % RC);
+        double v = 0.0;
+        const int src = perm[i];
+        if (c < nrhs && src < N) {
+            const int f = c / 3, k = c - 3 * f;
+            v = (double)(deform[((size_t)f * N + src) * 3 + k] - rest[3 * src + k]);
+        }
+        s_B[t] = v;
+    }
+    __syncthreads();
+    for (int k0 = 0; k0 < n; k0 += SB)
+        slab_sweep_block<true>(A, lda, n, k0, min(SB, n - k0), Tinv + (size_t)(k0 / SB) * 2 * SB * SB, s_B, s_T, s_X);
+    for (int k0 = (n - 1) / SB * SB; k0 >= 0; k0 -= SB)
+        slab_sweep_block<false>(A, lda, n, k0, min(SB, n - k0), Tinv + ((size_t)(k0 / SB) * 2 + 1) * SB * SB, s_B, s_T, s_X);
+    for (int t = threadIdx.x; t < n * RC; t += SLAB_THREADS) {
+        const int i = t / RC, c = c0 + (t % RC);
+        if (c < ldw) W[(size_t)i * ldw + c] = s_B[t];
+    }
+}
+
 // weights -> evaluation tables.  FP32: centre table (cx, cy, cz, kernel parameter) and weights n x ldw32;
 // FP64 centre table when the evaluation runs in double.  Flags non-finite weights.
 __global__ void __launch_bounds__(256) k_pack_tables(const float* __restrict__ rest, const double* __restrict__ radii,
@@ -148,6 +271,19 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_defor
 {
     cudaStream_t s = ctx->stream;
     const int n = m->n, nrhs = 3 * F, ldw = m->ldw;
+    const size_t slab_bytes = (size_t)n * RC * sizeof(double);
+    if (slab_bytes <= 200 * 1024 && (nrhs >= 2 * RC || n <= 1024)) {
+        // one launch: every CTA solves its 16 right-hand sides start to finish out of shared memory
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_solve_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        k_solve_slab<<<(ldw + RC - 1) / RC, SLAB_THREADS, slab_bytes, s>>>(m->d_A, m->lda, n, m->N, m->d_perm, m->d_rest,
+                                                                          d_deform, F, m->d_Tinv, m->d_W, ldw);
+        ctx->launches += 1;
+        return cudaGetLastError();
+    }
     {
         dim3 grid((ldw + 255) / 256, n);
         k_build_rhs<<<grid, 256, 0, s>>>(m->d_rest, d_deform, m->d_perm, m->N, n, F, m->d_W, ldw);
@@ -190,4 +326,13 @@ cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && m->use_tc) e = fd_launch_pack_tc(ctx, m);
     return e;
+}
+
+// after the LU: inverted diagonal blocks for the slab solve
+cudaError_t fd_launch_invdiag(fd_ctx* ctx, fd_model* m)
+{
+    const int nblk = (m->n + SB - 1) / SB;
+    k_lu_invdiag<<<nblk, 64, 0, ctx->stream>>>(m->d_A, m->lda, m->n, m->d_Tinv);
+    ctx->launches += 1;
+    return cudaGetLastError();
 }
