@@ -21,6 +21,7 @@ EXPORTS = [
     "fd_model_create_receiver", "fd_model_weights_dev", "fd_model_radii_dev", "fd_model_commit_weights",
     "fd_model_info", "fd_model_get_weights",
     "fd_capture", "fd_ctx_phase_ms", "fd_ctx_launch_count",
+    "fd_sop_create", "fd_sop_destroy", "fd_sop_params", "fd_sop_cook", "fd_sop_messages", "fd_sop_fit_count",
 ]
 
 
@@ -93,5 +94,16 @@ def load() -> C.CDLL:
     L.fd_ctx_phase_ms.restype = C.c_float
     L.fd_ctx_launch_count.argtypes = [vp]
     L.fd_ctx_launch_count.restype = C.c_int64
+    L.fd_sop_create.argtypes = [C.c_int]
+    L.fd_sop_create.restype = vp
+    L.fd_sop_destroy.argtypes = [vp]
+    L.fd_sop_destroy.restype = None
+    L.fd_sop_params.argtypes = [vp]
+    L.fd_sop_params.restype = pp
+    L.fd_sop_cook.argtypes = [vp, fp, C.c_int64, ip, ip, C.c_int32, fp, fp, fp, C.c_int64, C.c_int64, fp, C.c_int32,
+                              ip, ip, C.c_int32, ip, C.c_int64, C.c_int64, fp, C.c_int32, C.c_int32, fp, fp]
+    L.fd_sop_messages.argtypes = [vp, C.c_int]
+    L.fd_sop_messages.restype = C.c_char_p
+    L.fd_sop_fit_count.argtypes = [vp]
     _lib = L
     return L

@@ -1,0 +1,190 @@
+// facedeform_sop.cpp -- host-side mirror of SOP_FaceDeform::cookMySop and ProximityCapture over the C ABI
+// (see include/facedeform_sop.hpp).  Pure host code: every number comes from libfacedeform_gpu's kernels.
+#include "facedeform_sop.hpp"
+
+#include <cstdio>
+#include <cstring>
+
+namespace fd {
+
+bool ProximityCapture::init(const Geo& mesh, const Geo& rig)
+{
+    // capture.cpp:10-44: the point trees, ray cache and edge structure are built inside fd_capture; here only
+    // the inputs are latched and the detached attributes (re)allocated.
+    m_mesh = mesh;
+    m_rig = rig;
+    m_dist.assign((size_t)mesh.npoints, 0.0f); // dist_a, default 0 (capture.cpp:31)
+    m_member.assign((size_t)mesh.npoints, 0);
+    m_nearest.assign((size_t)rig.npoints, -1);
+    if (!m_ctx || (mesh.npoints > 0 && !mesh.P)) {
+        m_init = false;
+        m_capture = false;
+        init_counter = 0;
+        capture_counter = 0;
+    } else {
+        init_counter++;
+        m_init = true;
+        m_capture = false;
+    }
+    return m_init;
+}
+
+bool ProximityCapture::capture(const int& max_edges, const float& radius, const int& dofalloff, const float& /*falloffrate*/)
+{
+    if (!m_init) return false; // capture.cpp:50-52
+    std::vector<int32_t> grp_class((size_t)m_rig.npoints + 1);
+    std::vector<int64_t> grp_off((size_t)m_rig.npoints + 2);
+    int32_t ngroups = 0;
+    const int st = fd_capture(m_ctx, m_mesh.P, m_mesh.npoints, m_mesh.prim_off, m_mesh.prim_vtx, m_mesh.nprims, m_rig.P,
+                              (int32_t)m_rig.npoints, m_rig.prim_off, m_rig.prim_vtx, m_rig.nprims, m_rig.cls, max_edges,
+                              radius, dofalloff, m_nearest.data(), m_member.data(), m_dist.data(), &ngroups,
+                              grp_class.data(), grp_off.data(), nullptr, (int32_t)grp_class.size(), 0);
+    m_groups = ngroups;
+    if (st != FD_OK) return false; // at least one island should be found (capture.cpp:54-56)
+    capture_counter++;
+    m_capture = true;
+    return m_capture;
+}
+
+FaceDeformOp::FaceDeformOp(int device) : m_mesh_capture(nullptr)
+{
+    fd_params_default(&parms);
+    if (fd_ctx_create(&m_ctx, device, nullptr) != FD_OK) m_ctx = nullptr;
+    m_mesh_capture = ProximityCapture(m_ctx);
+}
+
+FaceDeformOp::~FaceDeformOp()
+{
+    if (m_model) fd_model_destroy(m_model);
+    if (m_ctx) fd_ctx_destroy(m_ctx);
+}
+
+CookStatus FaceDeformOp::cook(const Geo& mesh, const Geo& rest_rig, const float* deform_rig_P, int64_t deform_npoints,
+                              int frames, float* P_out, float* falloff_out)
+{
+    m_errors.clear();
+    m_warnings.clear();
+    m_messages.clear();
+    if (!m_ctx) {
+        addError("No CUDA device: the GPU deformation path has no CPU fallback.");
+        return COOK_ERROR;
+    }
+    // Points count in control rig should match (SOP_FaceDeform.cpp:231-234)
+    if (rest_rig.npoints != deform_npoints) {
+        addError("Rest and deform geometry should match.");
+        return COOK_ERROR;
+    }
+    // parameter clamps (SOP_FaceDeform.cpp:249-257)
+    fd_params p = parms;
+    fd_params_clamp(&p);
+    // Do we do tangent projection? (:289-298)
+    const bool do_tangent_disp = p.tangent && mesh.tangentu && mesh.tangentv && mesh.N;
+    if (p.tangent && !do_tangent_disp)
+        addWarning("Append PolyFrameSOP and enable tangent[u/v] and N attribute to allow tangent displacement.");
+    // change tracking (:222-223, :236-241, :301-305)
+    const bool rest_pose_changed = m_mesh_ids[0] != mesh.p_data_id || m_mesh_ids[1] != mesh.topo_data_id ||
+                                   mesh.p_data_id < 0;
+    const bool rest_rig_changed = m_rig_ids[0] != rest_rig.p_data_id || m_rig_ids[1] != rest_rig.topo_data_id ||
+                                  rest_rig.p_data_id < 0;
+    m_mesh_ids[0] = mesh.p_data_id;
+    m_mesh_ids[1] = mesh.topo_data_id;
+    m_rig_ids[0] = rest_rig.p_data_id;
+    m_rig_ids[1] = rest_rig.topo_data_id;
+    // Proximity capture (:310-322); the FIXME of :310 (re-capture on radius / max_edges change) is not reproduced
+    if (rest_pose_changed || rest_rig_changed || !m_mesh_capture.isInitialized() || !m_mesh_capture.isCaptured()) {
+        if (!m_mesh_capture.init(mesh, rest_rig)) {
+            addError("Can't initialize geometry to capture with a rig!");
+            return COOK_ERROR;
+        }
+        if (!m_mesh_capture.capture(p.maxedges, p.radius, p.dofalloff, p.falloffrate)) {
+            addError("Can't capture geometry with a rig!");
+            return COOK_ERROR;
+        }
+    }
+    // Create / build the model (:331-368).  The reference rebuilds it every cook; here the factorisation is kept
+    // while the rest rig and the fit parameters are unchanged ("once per rest pose").
+    const bool refit = !m_model || rest_rig_changed || std::memcmp(&m_fit_parms, &p, sizeof(p)) != 0;
+    if (refit) {
+        if (m_model) {
+            fd_model_destroy(m_model);
+            m_model = nullptr;
+        }
+        fd_report rep;
+        const int st = fd_rbf_fit(m_ctx, &p, rest_rig.P, (int32_t)rest_rig.npoints, &m_model, &rep);
+        if (st == FD_E_SINGULAR) {
+            addError("Can't solve the problem."); // :365-368
+            return COOK_ERROR;
+        }
+        if (st != FD_OK) {
+            addError("Can't build RBF model."); // :337-340
+            return COOK_ERROR;
+        }
+        m_fit_parms = p;
+        ++m_fit_counter;
+    }
+    fd_report rep;
+    int st = fd_rbf_solve(m_model, deform_rig_P, (int32_t)deform_npoints, frames, &rep);
+    if (st != FD_OK) {
+        addError(st == FD_E_SINGULAR ? "Can't solve the problem." : fd_last_error(m_ctx));
+        return COOK_ERROR;
+    }
+    char info_buffer[200];
+    std::snprintf(info_buffer, sizeof(info_buffer), "Termination type: %d, Iterations: %d", rep.terminationtype,
+                  rep.iterationscount); // :370-373
+    addMessage(info_buffer);
+    const float* dist = m_mesh_capture.getDistanceAttribute();
+    if (!dist) addWarning("Can't find distance capture attribute. Won't apply radius nor falloff."); // :396-398
+    st = fd_rbf_eval(m_model, mesh.P, mesh.npoints, dist, do_tangent_disp ? mesh.tangentu : nullptr,
+                     do_tangent_disp ? mesh.tangentv : nullptr, do_tangent_disp ? mesh.N : nullptr, P_out, falloff_out);
+    if (st != FD_OK) {
+        addError(fd_last_error(m_ctx));
+        return COOK_ERROR;
+    }
+    return m_warnings.empty() ? COOK_OK : COOK_WARNING;
+}
+
+} // namespace fd
+
+// ---- C shim so the operator mirror can be driven (and tested) through the same C ABI -----------------------------
+extern "C" {
+
+struct fd_sop {
+    fd::FaceDeformOp op;
+    std::string joined;
+    explicit fd_sop(int device) : op(device) {}
+};
+
+fd_sop* fd_sop_create(int device) { return new fd_sop(device); }
+void fd_sop_destroy(fd_sop* s) { delete s; }
+fd_params* fd_sop_params(fd_sop* s) { return s ? &s->op.parms : nullptr; }
+
+int fd_sop_cook(fd_sop* s, const float* mesh_P, int64_t n_vtx, const int32_t* poly_off, const int32_t* poly_vtx,
+                int32_t n_poly, const float* tangentu, const float* tangentv, const float* normal, int64_t mesh_p_id,
+                int64_t mesh_topo_id, const float* rest_rig_P, int32_t n_rig, const int32_t* rig_off,
+                const int32_t* rig_vtx, int32_t n_rig_prim, const int32_t* rig_class, int64_t rig_p_id,
+                int64_t rig_topo_id, const float* deform_rig_P, int32_t n_deform, int32_t frames, float* P_out,
+                float* falloff_out)
+{
+    if (!s) return fd::COOK_ERROR;
+    fd::Geo mesh, rig;
+    mesh.P = mesh_P; mesh.npoints = n_vtx; mesh.prim_off = poly_off; mesh.prim_vtx = poly_vtx; mesh.nprims = n_poly;
+    mesh.tangentu = tangentu; mesh.tangentv = tangentv; mesh.N = normal;
+    mesh.p_data_id = mesh_p_id; mesh.topo_data_id = mesh_topo_id;
+    rig.P = rest_rig_P; rig.npoints = n_rig; rig.prim_off = rig_off; rig.prim_vtx = rig_vtx; rig.nprims = n_rig_prim;
+    rig.cls = rig_class; rig.p_data_id = rig_p_id; rig.topo_data_id = rig_topo_id;
+    return s->op.cook(mesh, rig, deform_rig_P, n_deform, frames, P_out, falloff_out);
+}
+
+// kind: 0 errors, 1 warnings, 2 messages; entries joined by '\n'
+const char* fd_sop_messages(fd_sop* s, int kind)
+{
+    if (!s) return "";
+    const std::vector<std::string>& v = kind == 0 ? s->op.errors() : (kind == 1 ? s->op.warnings() : s->op.messages());
+    s->joined.clear();
+    for (size_t i = 0; i < v.size(); ++i) s->joined += (i ? "\n" : "") + v[i];
+    return s->joined.c_str();
+}
+
+int fd_sop_fit_count(const fd_sop* s) { return s ? s->op.fits() : 0; }
+
+} // extern "C"

@@ -39,17 +39,22 @@ def broadcast_block(t, src: int = 0, group=None):
     return t
 
 
-def broadcast_model(model, src: int = 0, group=None):
+def broadcast_model(model, src: int = 0, group=None, shared_stream: bool = False):
     """Root: `model` is fitted + solved.  Others: `model` is a receiver (Context.receiver).  After this call every
-    rank can evaluate: the FP64 weight block and the radii travel, the evaluation tables are rebuilt locally."""
+    rank can evaluate: the FP64 weight block and the radii travel, the evaluation tables are rebuilt locally.
+
+    shared_stream=True: the library's ctx stream IS torch's current stream, so the collective is ordered after the
+    solve and before the evaluation by stream order alone and no host synchronisation is needed."""
+    import torch
+    import torch.distributed as dist
     wp, wb = model.weights_dev()
     rp, rb = model.radii_dev()
-    model.ctx.synchronize()  # the library's stream and the collective's stream are different streams
+    if not shared_stream:
+        model.ctx.synchronize()  # the library's stream and the collective's stream are different streams
     broadcast_block(device_view(wp, wb), src, group)
     broadcast_block(device_view(rp, rb), src, group)
-    import torch
-    torch.cuda.current_stream().synchronize()
-    import torch.distributed as dist
+    if not shared_stream:
+        torch.cuda.current_stream().synchronize()
     if dist.is_initialized() and dist.get_rank(group) != src:
         model.commit_weights()
     return model

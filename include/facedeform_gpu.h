@@ -169,6 +169,22 @@ float fd_ctx_phase_ms(fd_ctx* ctx, int phase);
 /* number of kernels this library launched on the ctx since creation */
 int64_t fd_ctx_launch_count(const fd_ctx* ctx);
 
+/* ---- C shim over the C++ operator mirror (include/facedeform_sop.hpp: fd::FaceDeformOp = cookMySop,
+ * SOP_FaceDeform.cpp:215-489, with ProximityCapture and the data-ID change tracking of SOP_FaceDeform.hpp:47-63).
+ * fd_sop_cook returns 0 ok / 1 warnings / 2 errors; the texts are the reference's addError/addWarning strings. */
+typedef struct fd_sop fd_sop;
+fd_sop* fd_sop_create(int device);
+void fd_sop_destroy(fd_sop* s);
+fd_params* fd_sop_params(fd_sop* s);
+int fd_sop_cook(fd_sop* s, const float* mesh_P, int64_t n_vtx, const int32_t* poly_off, const int32_t* poly_vtx,
+                int32_t n_poly, const float* tangentu, const float* tangentv, const float* normal, int64_t mesh_p_id,
+                int64_t mesh_topo_id, const float* rest_rig_P, int32_t n_rig, const int32_t* rig_off,
+                const int32_t* rig_vtx, int32_t n_rig_prim, const int32_t* rig_class, int64_t rig_p_id,
+                int64_t rig_topo_id, const float* deform_rig_P, int32_t n_deform, int32_t frames, float* P_out,
+                float* falloff_out);
+const char* fd_sop_messages(fd_sop* s, int kind); /* 0 errors, 1 warnings, 2 messages */
+int fd_sop_fit_count(const fd_sop* s);
+
 #ifdef __cplusplus
 }
 #endif
