@@ -81,9 +81,13 @@ def test_cook_errors_and_warnings_quote_the_reference():
     rest = rig.rest.copy()
     rest[3] = rest[2]
     dup = synth.Rig(rest, rig.normals, rig.prim_off, rig.prim_vtx, rig.spacing)
+    # duplicate centres: with the Multilayer model the clamped lambda >= 0.01 (:253) regularises the system, so the
+    # failure shows with the QNN model, whose nearest-neighbour radius becomes zero (terminationtype -5)
+    sop.parms.tangent, sop.parms.model = 0, 0
     st, _, _ = sop.cook(mesh, dup, deform, rig_ids=(5, 5))
     assert st == 2 and sop.msgs(0) == "Can't solve the problem."                       # :365-368
     empty = synth.Rig(np.zeros((0, 3), np.float32), rig.normals[:0], rig.prim_off[:1], rig.prim_vtx[:0], 1.0)
+    sop.parms.model = 1
     st, _, _ = sop.cook(mesh, empty, np.zeros((1, 0, 3), np.float32), rig_ids=(6, 6), cls=np.zeros(0, np.int32))
     assert st == 2 and sop.msgs(0) == "Can't capture geometry with a rig!"             # :318-321
     sop.close()
