@@ -3,11 +3,11 @@
 // Replaces the solver inside alglib::rbfbuildmodel (reference SOP_FaceDeform.cpp:363) by the dense direct
 // factorisation north_star names.  The saddle-point system is symmetric indefinite (and non-symmetric with
 // per-centre QNN radii), so the general path is pivoted LU:
-//   for each block column k0 (width NB):
-//     k_lu_panel   : unblocked LU of the m x NB panel by one CTA (panel staged in shared memory when it fits)
-//     k_lu_swap_trsm: row interchanges on every other column, and U12 = L11^-1 A12 on the columns to the right
-//     k_lu_gemm    : A22 -= L21 * U12  (register-tiled FP64 FMA, 64x64 tile per CTA)
-//   k_lu_perm     : folds the interchanges into one permutation vector for the right-hand-side gather
+//   for each block column k0 (width NB = 32), two launches:
+//     k_lu_panel_cluster : unblocked LU of the m x 32 panel held in the registers of a thread-block cluster
+//     k_lu_update        : interchanges on every column, U12 = L11^-1 A12 and A22 -= L21 * U12, fused per 16 columns
+//   k_lu_perm            : folds the interchanges into one permutation vector for the right-hand-side gather
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "fd_internal.h"
@@ -113,130 +113,194 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_lu_panel(double* __restrict__
     }
 }
 
-// Register-resident panel for short panels (m <= RPT * 256 rows): thread t keeps the not-yet-eliminated part of rows
-// t, t+256, ... in registers.  The row registers are shifted left by one column per step (fused into the rank-1
-// update: a'[c-1] = a[c] - l * u[c]), so the loop body has static register indices and is NOT unrolled over the
-// columns -- a fully unrolled panel is ~200 KB of straight-line code executed once and ran at instruction-fetch
-// speed.  Finished L and U entries are collected in a shared-memory copy of the panel and written out at the end.
-// Two block barriers per column.
-template <int RPT>
-__global__ void __launch_bounds__(256) k_lu_panel_reg(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                      int* __restrict__ ipiv, int* __restrict__ flags,
-                                                      double* __restrict__ pivstat)
+// ---------------------------------------------------------------------------------------------------------------
+// Register-resident, cluster-wide panel factorisation.
+//
+// The m x 32 panel lives in the register files of a thread-block cluster: CTA `cr` of the cluster owns panel rows
+// [cr * 256 * RPT, (cr + 1) * 256 * RPT), thread t of it rows t, t + 256, ... (64 registers per row).  Per column:
+//   local arg-max (registers -> warp REDUX -> CTA) -> candidates exchanged through distributed shared memory
+//   -> cluster barrier -> every CTA picks the same pivot -> the owners of rows j and p publish them in their own
+//   shared memory -> cluster barrier -> every CTA pulls both rows over DSMEM -> rank-1 update of its own rows.
+// The row registers are shifted left by one column per step, fused into the update (a'[c-1] = a[c] - l * u[c]), so
+// the loop over columns has static register indices and is not unrolled (an unrolled panel is ~200 KB of code that
+// runs once, at instruction-fetch speed).  L and U entries go straight to global memory at the row's current
+// position; the interchange inside the already finished columns is a fire-and-forget global swap by CTA 0.
+// A cluster of 1 covers 256 * RPT rows (N = 256: one CTA); 16 CTAs x RPT = 3 cover 12288 rows.
+// ---------------------------------------------------------------------------------------------------------------
+struct Cand {
+    double v; // signed pivot candidate
+    int i;    // panel row
+    int pad;
+};
+
+__device__ __forceinline__ Cand cand_better(Cand a, Cand b)
 {
-    extern __shared__ double s_out[]; // [NB][ldo] finished panel, column-major
-    __shared__ ArgMax s_red[2][8];
-    __shared__ double s_rowj[2][NB]; // the row that sat at position j before the swap
-    __shared__ double s_rowp[2][NB]; // the pivot row
+    const double fa = fabs(a.v), fb = fabs(b.v);
+    if (fb > fa || (fb == fa && b.i < a.i)) return b;
+    return a;
+}
+
+__device__ __forceinline__ Cand cand_warp_reduce(Cand c)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Cand other;
+        other.v = __shfl_xor_sync(0xffffffffu, c.v, o);
+        other.i = __shfl_xor_sync(0xffffffffu, c.i, o);
+        c = cand_better(c, other);
+    }
+    return c;
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(256, 1) k_lu_panel_cluster(double* __restrict__ A, int lda, int n, int k0, int nb,
+                                                             int* __restrict__ ipiv, int* __restrict__ flags,
+                                                             double* __restrict__ pivstat)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cr = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+    __shared__ Cand s_wred[2][8];      // per-warp candidates of this CTA
+    __shared__ Cand s_cand[2][16];     // per-CTA candidates of the whole cluster (filled remotely)
+    __shared__ double s_pub[2][2][NB]; // [parity][0: row j, 1: row p] published by the owner thread of this CTA
+    __shared__ double s_row[2][2][NB]; // local copies pulled from the owners
     const int m = n - k0;
-    const int ldo = m | 1;
+    const int rows_per_cta = 256 * RPT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* G = A + (size_t)k0 * lda + k0;
     double a[RPT][NB];
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
-        const int r = tid + q * 256;
+        const int r = cr * rows_per_cta + tid + q * 256;
 #pragma unroll
         for (int c = 0; c < NB; ++c) a[q][c] = (r < m && c < nb) ? G[(size_t)c * lda + r] : 0.0;
     }
-    double pmin = pivstat[0], pmax = pivstat[1];
+    double pmin = INFINITY, pmax = 0.0;
 #pragma unroll 1
     for (int j = 0; j < nb; ++j) {
-        ArgMax best = {-1.0, 0x7fffffff};
+        const int par = j & 1;
+        // (1) local candidate
+        Cand best = {0.0, 0x7fffffff, 0};
+        bool have = false;
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
-            const int r = tid + q * 256;
-            const double v = fabs(a[q][0]);
-            if (r >= j && r < m && v > best.v) best = {v, r};
+            const int r = cr * rows_per_cta + tid + q * 256;
+            if (r >= j && r < m) {
+                Cand c = {a[q][0], r, 0};
+                best = have ? cand_better(best, c) : c;
+                have = true;
+            }
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            ArgMax other = {__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
-            best = argmax_combine(best, other);
-        }
-        if (lane == 0) s_red[j & 1][warp] = best;
+        if (!have) best = Cand{0.0, 0x7fffffff, 0};
+        best = cand_warp_reduce(best);
+        if (lane == 0) s_wred[par][warp] = best;
         __syncthreads();
-        best = lane < 8 ? s_red[j & 1][lane] : ArgMax{-1.0, 0x7fffffff};
-        for (int o = 4; o > 0; o >>= 1) {
-            ArgMax other = {__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
-            best = argmax_combine(best, other);
+        if (warp == 0) {
+            Cand c = lane < 8 ? s_wred[par][lane] : Cand{0.0, 0x7fffffff, 0};
+            c = cand_warp_reduce(c);
+            // (2) hand the CTA candidate to every CTA of the cluster
+            if (lane < CS) *cluster.map_shared_rank(&s_cand[par][cr], lane) = c;
         }
-        best.v = __shfl_sync(0xffffffffu, best.v, 0);
-        best.i = __shfl_sync(0xffffffffu, best.i, 0);
-        if (best.i >= m) best.i = j;
-        const int p = best.i;
-        if (tid == 0) {
+        cluster.sync();
+        Cand win = lane < CS ? s_cand[par][lane] : Cand{0.0, 0x7fffffff, 0};
+        win = cand_warp_reduce(win);
+        int p = win.i;
+        const double pivabs = fabs(win.v);
+        if (p >= m) p = j; // nothing but NaNs: keep the diagonal, flagged singular below
+        const double inv = win.v != 0.0 ? 1.0 / win.v : 0.0; // overlaps the row exchange below
+        if (cr == 0 && tid == 0) {
             ipiv[k0 + j] = k0 + p;
-            if (!(best.v > 0.0) && flags[FD_FLAG_SINGULAR] == 0) flags[FD_FLAG_SINGULAR] = k0 + j + 1;
-            pmin = fmin(pmin, best.v);
-            pmax = fmax(pmax, best.v);
+            if (!(pivabs > 0.0) && flags[FD_FLAG_SINGULAR] == 0) flags[FD_FLAG_SINGULAR] = k0 + j + 1;
+            pmin = fmin(pmin, pivabs);
+            pmax = fmax(pmax, pivabs);
         }
-        // publish rows j and p (by their owners)
+        // (3) the owners publish rows j and p in their own shared memory
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
-            const int r = tid + q * 256;
+            const int r = cr * rows_per_cta + tid + q * 256;
             if (r == j) {
 #pragma unroll
-                for (int c = 0; c < NB; ++c) s_rowj[j & 1][c] = a[q][c];
+                for (int c = 0; c < NB; ++c) s_pub[par][0][c] = a[q][c];
             }
             if (r == p) {
 #pragma unroll
-                for (int c = 0; c < NB; ++c) s_rowp[j & 1][c] = a[q][c];
+                for (int c = 0; c < NB; ++c) s_pub[par][1][c] = a[q][c];
             }
         }
+        cluster.sync();
+        // (4) pull both rows from their owners
+        if (tid < 2 * NB) {
+            const int which = tid >> 5, c = tid & 31;
+            const int owner = (which == 0 ? j : p) / rows_per_cta;
+            s_row[par][which][c] = *cluster.map_shared_rank(&s_pub[par][which][c], owner);
+        }
         __syncthreads();
-        const double* u = s_rowp[j & 1]; // u[c] = U(j, j + c)
-        const double piv = u[0];
-        const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
-        if (tid < nb - j) s_out[(size_t)(j + tid) * ldo + j] = u[tid];          // row j of U is final
-        if (tid < j && p != j) {                                                 // interchange in the finished L columns
-            const double x = s_out[(size_t)tid * ldo + j];
-            s_out[(size_t)tid * ldo + j] = s_out[(size_t)tid * ldo + p];
-            s_out[(size_t)tid * ldo + p] = x;
+        const double* u = s_row[par][1]; // u[c] = U(j, j + c)
+        if (cr == 0 && tid < nb - j) G[(size_t)(j + tid) * lda + j] = u[tid]; // row j of U is final
+        if (cr == 0 && tid < j && p != j) {
+            // interchange inside the finished L columns (written by their row owners at least one cluster barrier
+            // ago); nobody waits for it: only this thread touches column `tid` of rows j and p again
+            double* col = G + (size_t)tid * lda;
+            const double x = col[j];
+            col[j] = col[p];
+            col[p] = x;
         }
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
-            const int r = tid + q * 256;
-            if (r == p && p != j) { // the row that was at position j moves to position p
+            const int r = cr * rows_per_cta + tid + q * 256;
+            if (r == p && p != j) { // the row that sat at position j moves to position p
 #pragma unroll
-                for (int c = 0; c < NB; ++c) a[q][c] = s_rowj[j & 1][c];
+                for (int c = 0; c < NB; ++c) a[q][c] = s_row[par][0][c];
             }
             if (r > j && r < m) {
                 const double l = a[q][0] * inv;
-                s_out[(size_t)j * ldo + r] = l;
+                G[(size_t)j * lda + r] = l;
 #pragma unroll
                 for (int c = 1; c < NB; ++c) a[q][c - 1] = a[q][c] - l * u[c]; // rank-1 update fused with the shift
                 a[q][NB - 1] = 0.0;
             }
         }
     }
-    __syncthreads();
-    for (int c = 0; c < nb; ++c)
-        for (int r = tid; r < m; r += 256) G[(size_t)c * lda + r] = s_out[(size_t)c * ldo + r];
-    if (tid == 0) {
-        pivstat[0] = pmin;
-        pivstat[1] = pmax;
+    if (cr == 0 && tid == 0) {
+        pivstat[0] = fmin(pivstat[0], pmin);
+        pivstat[1] = fmax(pivstat[1], pmax);
     }
+    cluster.sync(); // no CTA may exit while a peer can still read its shared memory
 }
 
-// One thread per column outside the panel: apply the nb interchanges; columns right of the panel also get the
-// unit-lower triangular solve with L11.  The interchanges touch at most 2 nb distinct rows (the nb top rows and the
-// pivot rows); warp 0 lists them once, every thread then gathers its column's values of those rows with independent
-// loads, replays the swaps in shared memory and scatters the rows back -- no chain of dependent global accesses.
-constexpr int SW_THREADS = 128;
-__global__ void __launch_bounds__(SW_THREADS) k_lu_swap_trsm(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                             const int* __restrict__ ipiv)
+// ---------------------------------------------------------------------------------------------------------------
+// k_lu_update: everything that follows a panel, fused, one CTA per tile of 16 columns over ALL columns:
+//   interchanges  (left of the panel: all nb swaps; the panel's own columns: the swaps that came after the column
+//                  was finished; right of the panel: all nb swaps)
+//   U12 = L11^-1 A12 and A22 -= L21 * U12 for the tiles right of the panel.
+// The interchanges touch at most 2 nb distinct rows (the nb top rows and the pivot rows): warp 0 lists them once,
+// the CTA gathers its 16 columns of those rows with independent loads, replays the swaps in shared memory, solves
+// the unit-lower block with warp shuffles (lane = row) and scatters the rows back -- no chain of dependent global
+// accesses.  The trailing update then streams L21 (coalesced, from L2) against the 32 x 16 U tile in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int UT = 16;            // columns per CTA
+constexpr int UPD_THREADS = 256;
+
+__global__ void __launch_bounds__(UPD_THREADS) k_lu_update(double* __restrict__ A, int lda, int n, int k0, int nb,
+                                                           const int* __restrict__ ipiv, int panel_swaps_pending)
 {
-    extern __shared__ double s_vals[]; // [2 * NB][SW_THREADS]
-    __shared__ double s_L[NB][NB + 1];
+    __shared__ double s_vals[2 * NB][UT + 1]; // window rows x tile columns
+    __shared__ double s_L[NB][NB + 1];        // L11 (strictly lower part)
     __shared__ int s_rows[2 * NB];
     __shared__ int s_ib[NB];
     __shared__ int s_cnt;
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int t = tid; t < NB * NB; t += SW_THREADS) {
-        const int r = t % NB, c = t / NB;
-        s_L[r][c] = (r < nb && c < nb && r > c) ? A[(size_t)(k0 + c) * lda + k0 + r] : 0.0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = blockIdx.x * UT;
+    const bool is_left = c0 + UT <= k0;
+    const bool is_right = c0 >= k0 + nb;
+    if (!is_left && !is_right && !panel_swaps_pending) return; // the fallback panel swapped its own columns already
+    if (is_right) {
+        for (int t = tid; t < NB * NB; t += UPD_THREADS) {
+            const int r = t % NB, c = t / NB;
+            s_L[r][c] = (r < nb && c < nb && r > c) ? A[(size_t)(k0 + c) * lda + k0 + r] : 0.0;
+        }
     }
-    if (tid < 32) {
+    if (warp == 0) { // list of the rows the interchanges touch; swap j exchanges list entries j and s_ib[j]
         if (lane < nb) s_rows[lane] = k0 + lane;
         int cnt = nb;
         __syncwarp();
@@ -247,9 +311,9 @@ __global__ void __launch_bounds__(SW_THREADS) k_lu_swap_trsm(double* __restrict_
                 ib = p - k0;
             } else {
                 const bool hit = (nb + lane < cnt) && s_rows[nb + lane] == p;
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (m) {
-                    ib = nb + __ffs(m) - 1;
+                const unsigned mask = __ballot_sync(0xffffffffu, hit);
+                if (mask) {
+                    ib = nb + __ffs(mask) - 1;
                 } else {
                     if (lane == 0) s_rows[cnt] = p;
                     ib = cnt++;
@@ -261,79 +325,64 @@ __global__ void __launch_bounds__(SW_THREADS) k_lu_swap_trsm(double* __restrict_
         if (lane == 0) s_cnt = cnt;
     }
     __syncthreads();
-    int c = blockIdx.x * SW_THREADS + tid; // index over the n - nb columns outside the panel
-    if (c >= n - nb) return;
-    if (c >= k0) c += nb;
-    double* col = A + (size_t)c * lda;
     const int cnt = s_cnt;
-    for (int e = 0; e < cnt; ++e) s_vals[e * SW_THREADS + tid] = col[s_rows[e]];
-    for (int j = 0; j < nb; ++j) {
-        const int ib = s_ib[j];
-        if (ib != j) {
-            const double t = s_vals[j * SW_THREADS + tid];
-            s_vals[j * SW_THREADS + tid] = s_vals[ib * SW_THREADS + tid];
-            s_vals[ib * SW_THREADS + tid] = t;
-        }
-    }
-    if (c > k0) { // right of the panel: forward substitution with the unit-lower L11
-        double x[NB];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) x[j] = j < nb ? s_vals[j * SW_THREADS + tid] : 0.0;
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const double xj = x[j];
-#pragma unroll
-            for (int r = j + 1; r < NB; ++r) x[r] -= s_L[r][j] * xj;
-        }
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-            if (j < nb) s_vals[j * SW_THREADS + tid] = x[j];
-    }
-    for (int e = 0; e < cnt; ++e) col[s_rows[e]] = s_vals[e * SW_THREADS + tid];
-}
-
-// C[m2 x m2] -= L21[m2 x nb] * U12[nb x m2]; 64x64 tile per CTA, 256 threads, 4x4 outputs per thread.
-constexpr int GT = 64;
-__global__ void __launch_bounds__(256) k_lu_gemm(double* __restrict__ A, int lda, int n, int k0, int nb)
-{
-    __shared__ double s_a[NB][GT + 2]; // L21 tile, [k][row]
-    __shared__ double s_b[NB][GT + 2]; // U12 tile, [k][col]
-    const int r0 = k0 + nb + blockIdx.x * GT;
-    const int c0 = k0 + nb + blockIdx.y * GT;
-    const int tid = threadIdx.x;
-    for (int t = tid; t < NB * GT; t += 256) {
-        const int rr = t % GT, k = t / GT;
-        s_a[k][rr] = (k < nb && r0 + rr < n) ? A[(size_t)(k0 + k) * lda + r0 + rr] : 0.0;
-    }
-    for (int t = tid; t < NB * GT; t += 256) {
-        const int k = t % NB, cc = t / NB;
-        s_b[k][cc] = (k < nb && c0 + cc < n) ? A[(size_t)(c0 + cc) * lda + k0 + k] : 0.0;
+    // gather the window
+    for (int t = tid; t < cnt * UT; t += UPD_THREADS) {
+        const int e = t / UT, c = c0 + (t % UT);
+        s_vals[e][t % UT] = c < n ? A[(size_t)c * lda + s_rows[e]] : 0.0;
     }
     __syncthreads();
-    const int tr = (tid % 16) * 4, tc = (tid / 16) * 4;
-    double acc[4][4] = {};
-#pragma unroll 8
-    for (int k = 0; k < NB; ++k) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            a[i] = s_a[k][tr + i];
-            b[i] = s_b[k][tc + i];
+    // replay the interchanges, one thread per column
+    if (tid < UT) {
+        const int c = c0 + tid;
+        const int j_first = (is_left || is_right) ? 0 : (c - k0 + 1); // a panel column only sees the later swaps
+        for (int j = j_first; j < nb; ++j) {
+            const int ib = s_ib[j];
+            if (ib != j) {
+                const double t = s_vals[j][tid];
+                s_vals[j][tid] = s_vals[ib][tid];
+                s_vals[ib][tid] = t;
+            }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
     }
+    __syncthreads();
+    if (is_right) { // U12 tile = L11^-1 * top rows: lane = row, two columns per warp
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c0 + tc + j;
-        if (c >= n) continue;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = r0 + tr + i;
-            if (r < n) A[(size_t)c * lda + r] -= acc[i][j];
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = 2 * warp + cc;
+            double x = lane < nb ? s_vals[lane][c] : 0.0;
+            for (int j = 0; j < nb; ++j) {
+                const double xj = __shfl_sync(0xffffffffu, x, j);
+                if (lane > j) x -= s_L[lane][j] * xj;
+            }
+            if (lane < nb) s_vals[lane][c] = x;
         }
+        __syncthreads();
+    }
+    // scatter the window back
+    for (int t = tid; t < cnt * UT; t += UPD_THREADS) {
+        const int e = t / UT, c = c0 + (t % UT);
+        if (c < n) A[(size_t)c * lda + s_rows[e]] = s_vals[e][t % UT];
+    }
+    if (!is_right) return;
+    __syncthreads(); // the pivot rows just written belong to the trailing matrix updated below
+    // trailing update of this tile's columns: C[r][c] -= sum_k L21[r][k] * U12[k][c]
+    const int r_begin = k0 + nb;
+    for (int r = r_begin + tid; r < n; r += UPD_THREADS) {
+        double l[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) l[k] = k < nb ? A[(size_t)(k0 + k) * lda + r] : 0.0;
+        double acc[UT];
+#pragma unroll
+        for (int c = 0; c < UT; ++c) acc[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+#pragma unroll
+            for (int c = 0; c < UT; ++c) acc[c] += l[k] * s_vals[k][c];
+        }
+#pragma unroll
+        for (int c = 0; c < UT; ++c)
+            if (c0 + c < n) A[(size_t)(c0 + c) * lda + r] -= acc[c];
     }
 }
 
@@ -369,6 +418,25 @@ __global__ void k_lu_init(int* flags, double* pivstat)
 
 } // namespace
 
+template <int RPT>
+static cudaError_t launch_panel_cluster(cudaStream_t s, int cs, double* d_A, int lda, int n, int k0, int nb, int* d_ipiv,
+                                        int* d_flags, double* d_pivstat)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_lu_panel_cluster<RPT>, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
+}
+
 cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                          double* d_pivstat)
 {
@@ -376,59 +444,38 @@ cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, 
     if (!attr_set) {
         cudaFuncSetAttribute(k_lu_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_MAX);
         cudaFuncSetAttribute(k_lu_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(k_lu_panel_reg<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_MAX);
-        cudaFuncSetAttribute(k_lu_panel_reg<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_MAX);
-        cudaFuncSetAttribute(k_lu_swap_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * NB * SW_THREADS * (int)sizeof(double));
+        cudaFuncSetAttribute(k_lu_panel_cluster<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(k_lu_panel_cluster<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(k_lu_panel_cluster<3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         attr_set = true;
     }
     cudaStream_t s = ctx->stream;
     k_lu_init<<<1, 32, 0, s>>>(d_flags, d_pivstat);
     ctx->launches += 1;
-    static const bool dbg = getenv("FD_LU_DEBUG") != nullptr; // development aid: in-stream time per kernel kind
-    static cudaEvent_t ev[4];
-    static bool ev_init = false;
-    if (dbg && !ev_init) { for (auto& e : ev) cudaEventCreate(&e); ev_init = true; }
-    float t_panel = 0, t_swap = 0, t_gemm = 0;
-    for (int k0 = 0; k0 < n; k0 += NB) {
-        if (dbg) cudaEventRecord(ev[0], s);
+    cudaError_t e = cudaSuccess;
+    for (int k0 = 0; k0 < n && e == cudaSuccess; k0 += NB) {
         const int nb = min(NB, n - k0);
         const int m = n - k0;
-        const size_t smem = (size_t)(m | 1) * nb * sizeof(double);
-        // few rows: fewer warps make the two barriers per column cheaper
-        const int threads = m <= 1024 ? 256 : (m <= 4096 ? 512 : PANEL_THREADS);
-        if (m <= 256)
-            k_lu_panel_reg<1><<<1, 256, smem, s>>>(d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
-        else if (m <= 512)
-            k_lu_panel_reg<2><<<1, 256, smem, s>>>(d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
-        else if (smem <= (size_t)PANEL_SMEM_MAX)
-            k_lu_panel<true><<<1, threads, smem, s>>>(d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
-        else
-            k_lu_panel<false><<<1, threads, 0, s>>>(d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
+        // smallest cluster (1, 2, 4, 8, 16 CTAs) x rows per thread (1..3) that holds the m panel rows in registers
+        int cs = 0, rpt = 0;
+        for (int c = 1; c <= 16 && !cs; c *= 2)
+            for (int r = 1; r <= 3; ++r)
+                if (m <= c * 256 * r) { cs = c; rpt = r; break; }
+        if (cs) {
+            e = rpt == 1 ? launch_panel_cluster<1>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat)
+              : rpt == 2 ? launch_panel_cluster<2>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat)
+                         : launch_panel_cluster<3>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
+        } else { // taller than 12288 rows: panel through global memory, then its own interchanges are already applied
+            k_lu_panel<false><<<1, PANEL_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
+            e = cudaGetLastError();
+        }
         ctx->launches += 1;
-        if (dbg) cudaEventRecord(ev[1], s);
-        if (n - nb > 0) {
-            k_lu_swap_trsm<<<(n - nb + SW_THREADS - 1) / SW_THREADS, SW_THREADS, 2 * NB * SW_THREADS * sizeof(double), s>>>(
-                d_A, lda, n, k0, nb, d_ipiv);
-            ctx->launches += 1;
-        }
-        if (dbg) cudaEventRecord(ev[2], s);
-        const int m2 = n - k0 - nb;
-        if (m2 > 0) {
-            dim3 grid((m2 + GT - 1) / GT, (m2 + GT - 1) / GT);
-            k_lu_gemm<<<grid, 256, 0, s>>>(d_A, lda, n, k0, nb);
-            ctx->launches += 1;
-        }
-        if (dbg) {
-            cudaEventRecord(ev[3], s);
-            cudaEventSynchronize(ev[3]);
-            float a, b, c;
-            cudaEventElapsedTime(&a, ev[0], ev[1]);
-            cudaEventElapsedTime(&b, ev[1], ev[2]);
-            cudaEventElapsedTime(&c, ev[2], ev[3]);
-            t_panel += a; t_swap += b; t_gemm += c;
-        }
+        if (e != cudaSuccess) break;
+        k_lu_update<<<(n + UT - 1) / UT, UPD_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_ipiv, 0);
+        ctx->launches += 1;
+        e = cudaGetLastError();
     }
-    if (dbg) fprintf(stderr, "[fd_lu] n=%d: panel %.3f ms, swap+trsm %.3f ms, gemm %.3f ms\n", n, t_panel, t_swap, t_gemm);
+    if (e != cudaSuccess) return e;
     if ((size_t)n * sizeof(int) > 64 * 1024) return cudaErrorInvalidValue;
     k_lu_perm<<<1, 256, (size_t)n * sizeof(int), s>>>(d_ipiv, n, d_perm);
     ctx->launches += 1;
