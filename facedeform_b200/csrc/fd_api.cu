@@ -97,6 +97,7 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
         st = dev_alloc(ctx, &m->d_A, (size_t)m->lda * m->n);
         if (st == FD_OK) st = dev_alloc(ctx, &m->d_ipiv, (size_t)m->n);
         if (st == FD_OK) st = dev_alloc(ctx, &m->d_perm, (size_t)m->n);
+        if (st == FD_OK) st = dev_alloc(ctx, &m->d_win, (size_t)132);
         if (st == FD_OK) st = dev_alloc(ctx, &m->d_Tinv, (size_t)((m->n + 31) / 32) * 2 * 32 * 32);
     }
     if (st != FD_OK) {
@@ -278,7 +279,7 @@ void fd_model_destroy(fd_model* m)
     cudaStream_t s = m->ctx->stream; // stream-ordered frees: later work on the stream may reuse the blocks safely
     void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
                       m->d_ctab32, m->d_W32, m->d_ctab64, m->d_tc_norm, m->d_tc_scale, m->d_tc_unscale,
-                      m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv};
+                      m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win};
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;
@@ -306,7 +307,7 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
     if (e == cudaSuccess) e = fd_launch_assemble(ctx, m->prm, m->d_rest, m->d_radii, m->N, m->np, m->d_A, m->lda);
     phase_end(ctx, FD_PH_ASSEMBLE);
     phase_begin(ctx, FD_PH_FACTOR);
-    if (e == cudaSuccess) e = fd_launch_lu(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat);
+    if (e == cudaSuccess) e = fd_launch_lu(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_win);
     if (e == cudaSuccess) e = fd_launch_invdiag(ctx, m);
     phase_end(ctx, FD_PH_FACTOR);
     if (e != cudaSuccess) {

@@ -128,42 +128,58 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_lu_panel(double* __restrict__
 // A cluster of 1 covers 256 * RPT rows (N = 256: one CTA); 16 CTAs x RPT = 3 cover 12288 rows.
 // ---------------------------------------------------------------------------------------------------------------
 struct Cand {
-    double v; // signed pivot candidate
-    int i;    // panel row
-    int pad;
+    double v;     // signed pivot candidate
+    int i;        // panel row
+    unsigned key; // high word of |v| (exponent + 20 mantissa bits): the magnitude the pivot search compares
 };
 
-__device__ __forceinline__ Cand cand_better(Cand a, Cand b)
+// Pivot search on the 32-bit key with one REDUX per level instead of a 5-round shuffle tree on doubles: any entry
+// within 2^-20 of the largest is as good a pivot for LU stability; ties go to the lowest lane, i.e. a fixed row order.
+__device__ __forceinline__ unsigned mag_key(double v) { return (unsigned)__double2hiint(v) & 0x7fffffffu; }
+
+__device__ __forceinline__ Cand cand_warp_pick(Cand c, bool valid)
 {
-    const double fa = fabs(a.v), fb = fabs(b.v);
-    if (fb > fa || (fb == fa && b.i < a.i)) return b;
-    return a;
+    const unsigned key = valid ? c.key + 1u : 0u; // 0 = no candidate
+    const unsigned best = __reduce_max_sync(0xffffffffu, key);
+    const unsigned who = __ballot_sync(0xffffffffu, key == best);
+    const int src = __ffs(who) - 1;
+    Cand w;
+    w.v = __shfl_sync(0xffffffffu, c.v, src);
+    w.i = __shfl_sync(0xffffffffu, c.i, src);
+    w.key = best ? best - 1u : 0u;
+    if (best == 0u) w.i = 0x7fffffff;
+    return w;
 }
 
-__device__ __forceinline__ Cand cand_warp_reduce(Cand c)
+__device__ __forceinline__ double fast_rcp(double d)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        Cand other;
-        other.v = __shfl_xor_sync(0xffffffffu, c.v, o);
-        other.i = __shfl_xor_sync(0xffffffffu, c.i, o);
-        c = cand_better(c, other);
-    }
-    return c;
+    // MUFU.RCP64H seed + two Newton steps (full double accuracy up to the last ulps; LU does not need a correctly
+    // rounded quotient), 5 dependent instructions instead of the ~20 of an IEEE division
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
 }
 
-template <int RPT>
+template <int RPT, bool CLUSTER>
 __global__ void __launch_bounds__(256, 1) k_lu_panel_cluster(double* __restrict__ A, int lda, int n, int k0, int nb,
                                                              int* __restrict__ ipiv, int* __restrict__ flags,
-                                                             double* __restrict__ pivstat)
+                                                             double* __restrict__ pivstat, int* __restrict__ win)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    const int cr = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+    const int cr = CLUSTER ? (int)cluster.block_rank() : 0, CS = CLUSTER ? (int)cluster.num_blocks() : 1;
+    __shared__ double s_fix[2 * NB][NB + 1]; // epilogue: window of the rows the interchanges touch
+    __shared__ int s_rows[2 * NB];
+    __shared__ int s_ib[NB];
+    __shared__ int s_cnt;
+    __shared__ int s_piv[NB];
     __shared__ Cand s_wred[2][8];      // per-warp candidates of this CTA
     __shared__ Cand s_cand[2][16];     // per-CTA candidates of the whole cluster (filled remotely)
-    __shared__ double s_pub[2][2][NB]; // [parity][0: row j, 1: row p] published by the owner thread of this CTA
-    __shared__ double s_row[2][2][NB]; // local copies pulled from the owners
+    __shared__ __align__(16) double s_pub[2][2][NB]; // [parity][0: row j, 1: row p] published by the owner thread of this CTA
+    __shared__ __align__(16) double s_row[2][2][NB]; // local copies pulled from the owners
     const int m = n - k0;
     const int rows_per_cta = 256 * RPT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -180,36 +196,42 @@ __global__ void __launch_bounds__(256, 1) k_lu_panel_cluster(double* __restrict_
     for (int j = 0; j < nb; ++j) {
         const int par = j & 1;
         // (1) local candidate
-        Cand best = {0.0, 0x7fffffff, 0};
+        Cand best = {0.0, 0x7fffffff, 0u};
         bool have = false;
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
             const int r = cr * rows_per_cta + tid + q * 256;
-            if (r >= j && r < m) {
-                Cand c = {a[q][0], r, 0};
-                best = have ? cand_better(best, c) : c;
+            const unsigned key = mag_key(a[q][0]);
+            if (r >= j && r < m && (!have || key > best.key)) {
+                best = Cand{a[q][0], r, key};
                 have = true;
             }
         }
-        if (!have) best = Cand{0.0, 0x7fffffff, 0};
-        best = cand_warp_reduce(best);
+        best = cand_warp_pick(best, have);
         if (lane == 0) s_wred[par][warp] = best;
         __syncthreads();
-        if (warp == 0) {
-            Cand c = lane < 8 ? s_wred[par][lane] : Cand{0.0, 0x7fffffff, 0};
-            c = cand_warp_reduce(c);
-            // (2) hand the CTA candidate to every CTA of the cluster
-            if (lane < CS) *cluster.map_shared_rank(&s_cand[par][cr], lane) = c;
+        Cand win;
+        if (CLUSTER) {
+            if (warp == 0) {
+                Cand c = lane < 8 ? s_wred[par][lane] : Cand{0.0, 0x7fffffff, 0u};
+                c = cand_warp_pick(c, lane < 8 && c.i != 0x7fffffff);
+                // (2) hand the CTA candidate to every CTA of the cluster
+                if (lane < CS) *cluster.map_shared_rank(&s_cand[par][cr], lane) = c;
+            }
+            cluster.sync();
+            win = lane < CS ? s_cand[par][lane] : Cand{0.0, 0x7fffffff, 0u};
+            win = cand_warp_pick(win, lane < CS && win.i != 0x7fffffff);
+        } else {
+            win = lane < 8 ? s_wred[par][lane] : Cand{0.0, 0x7fffffff, 0u}; // every warp picks among the 8 partials itself
+            win = cand_warp_pick(win, lane < 8 && win.i != 0x7fffffff);
         }
-        cluster.sync();
-        Cand win = lane < CS ? s_cand[par][lane] : Cand{0.0, 0x7fffffff, 0};
-        win = cand_warp_reduce(win);
         int p = win.i;
         const double pivabs = fabs(win.v);
         if (p >= m) p = j; // nothing but NaNs: keep the diagonal, flagged singular below
-        const double inv = win.v != 0.0 ? 1.0 / win.v : 0.0; // overlaps the row exchange below
+        const double inv = (pivabs > 0.0 && pivabs < INFINITY) ? fast_rcp(win.v) : 0.0;
         if (cr == 0 && tid == 0) {
             ipiv[k0 + j] = k0 + p;
+            s_piv[j] = p;
             if (!(pivabs > 0.0) && flags[FD_FLAG_SINGULAR] == 0) flags[FD_FLAG_SINGULAR] = k0 + j + 1;
             pmin = fmin(pmin, pivabs);
             pmax = fmax(pmax, pivabs);
@@ -220,43 +242,55 @@ __global__ void __launch_bounds__(256, 1) k_lu_panel_cluster(double* __restrict_
             const int r = cr * rows_per_cta + tid + q * 256;
             if (r == j) {
 #pragma unroll
-                for (int c = 0; c < NB; ++c) s_pub[par][0][c] = a[q][c];
+                for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(&s_pub[par][0][c]) = make_double2(a[q][c], a[q][c + 1]);
             }
             if (r == p) {
 #pragma unroll
-                for (int c = 0; c < NB; ++c) s_pub[par][1][c] = a[q][c];
+                for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(&s_pub[par][1][c]) = make_double2(a[q][c], a[q][c + 1]);
             }
         }
-        cluster.sync();
-        // (4) pull both rows from their owners
-        if (tid < 2 * NB) {
-            const int which = tid >> 5, c = tid & 31;
-            const int owner = (which == 0 ? j : p) / rows_per_cta;
-            s_row[par][which][c] = *cluster.map_shared_rank(&s_pub[par][which][c], owner);
+        const double* u;
+        const double* oldj;
+        if (CLUSTER) {
+            cluster.sync();
+            // (4) pull both rows from their owners
+            if (tid < 2 * NB) {
+                const int which = tid >> 5, c = tid & 31;
+                const int owner = (which == 0 ? j : p) / rows_per_cta;
+                s_row[par][which][c] = *cluster.map_shared_rank(&s_pub[par][which][c], owner);
+            }
+            __syncthreads();
+            u = s_row[par][1]; // u[c] = U(j, j + c)
+            oldj = s_row[par][0];
+        } else {
+            __syncthreads();
+            u = s_pub[par][1];
+            oldj = s_pub[par][0];
         }
-        __syncthreads();
-        const double* u = s_row[par][1]; // u[c] = U(j, j + c)
         if (cr == 0 && tid < nb - j) G[(size_t)(j + tid) * lda + j] = u[tid]; // row j of U is final
-        if (cr == 0 && tid < j && p != j) {
-            // interchange inside the finished L columns (written by their row owners at least one cluster barrier
-            // ago); nobody waits for it: only this thread touches column `tid` of rows j and p again
-            double* col = G + (size_t)tid * lda;
-            const double x = col[j];
-            col[j] = col[p];
-            col[p] = x;
-        }
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
             const int r = cr * rows_per_cta + tid + q * 256;
             if (r == p && p != j) { // the row that sat at position j moves to position p
 #pragma unroll
-                for (int c = 0; c < NB; ++c) a[q][c] = s_row[par][0][c];
+                for (int c = 0; c < NB; c += 2) {
+                    const double2 t = *reinterpret_cast<const double2*>(&oldj[c]);
+                    a[q][c] = t.x;
+                    a[q][c + 1] = t.y;
+                }
             }
             if (r > j && r < m) {
                 const double l = a[q][0] * inv;
                 G[(size_t)j * lda + r] = l;
+                double uu[NB];
 #pragma unroll
-                for (int c = 1; c < NB; ++c) a[q][c - 1] = a[q][c] - l * u[c]; // rank-1 update fused with the shift
+                for (int c = 0; c < NB; c += 2) {
+                    const double2 t = *reinterpret_cast<const double2*>(&u[c]);
+                    uu[c] = t.x;
+                    uu[c + 1] = t.y;
+                }
+#pragma unroll
+                for (int c = 1; c < NB; ++c) a[q][c - 1] = a[q][c] - l * uu[c]; // rank-1 update fused with the shift
                 a[q][NB - 1] = 0.0;
             }
         }
@@ -265,50 +299,21 @@ __global__ void __launch_bounds__(256, 1) k_lu_panel_cluster(double* __restrict_
         pivstat[0] = fmin(pivstat[0], pmin);
         pivstat[1] = fmax(pivstat[1], pmax);
     }
-    cluster.sync(); // no CTA may exit while a peer can still read its shared memory
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// k_lu_update: everything that follows a panel, fused, one CTA per tile of 16 columns over ALL columns:
-//   interchanges  (left of the panel: all nb swaps; the panel's own columns: the swaps that came after the column
-//                  was finished; right of the panel: all nb swaps)
-//   U12 = L11^-1 A12 and A22 -= L21 * U12 for the tiles right of the panel.
-// The interchanges touch at most 2 nb distinct rows (the nb top rows and the pivot rows): warp 0 lists them once,
-// the CTA gathers its 16 columns of those rows with independent loads, replays the swaps in shared memory, solves
-// the unit-lower block with warp shuffles (lane = row) and scatters the rows back -- no chain of dependent global
-// accesses.  The trailing update then streams L21 (coalesced, from L2) against the 32 x 16 U tile in shared memory.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int UT = 16;            // columns per CTA
-constexpr int UPD_THREADS = 256;
-
-__global__ void __launch_bounds__(UPD_THREADS) k_lu_update(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                           const int* __restrict__ ipiv, int panel_swaps_pending)
-{
-    __shared__ double s_vals[2 * NB][UT + 1]; // window rows x tile columns
-    __shared__ double s_L[NB][NB + 1];        // L11 (strictly lower part)
-    __shared__ int s_rows[2 * NB];
-    __shared__ int s_ib[NB];
-    __shared__ int s_cnt;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = blockIdx.x * UT;
-    const bool is_left = c0 + UT <= k0;
-    const bool is_right = c0 >= k0 + nb;
-    if (!is_left && !is_right && !panel_swaps_pending) return; // the fallback panel swapped its own columns already
-    if (is_right) {
-        for (int t = tid; t < NB * NB; t += UPD_THREADS) {
-            const int r = t % NB, c = t / NB;
-            s_L[r][c] = (r < nb && c < nb && r > c) ? A[(size_t)(k0 + c) * lda + k0 + r] : 0.0;
-        }
-    }
-    if (warp == 0) { // list of the rows the interchanges touch; swap j exchanges list entries j and s_ib[j]
-        if (lane < nb) s_rows[lane] = k0 + lane;
+    // every L entry is in global memory and visible; no CTA may exit while a peer can still read its shared memory
+    if (CLUSTER) cluster.sync(); else __syncthreads();
+    if (cr != 0) return;
+    // Epilogue (CTA 0): the interchanges inside the panel's own finished columns.  Column c only sees the swaps that
+    // came after it was finished (j > c).  The swaps touch at most 2 nb rows: gather that window with independent
+    // loads, replay per column in shared memory, scatter back.
+    if (warp == 0) {
+        if (lane < nb) s_rows[lane] = lane;
         int cnt = nb;
         __syncwarp();
         for (int j = 0; j < nb; ++j) {
-            const int p = ipiv[k0 + j];
+            const int p = s_piv[j];
             int ib;
-            if (p < k0 + nb) {
-                ib = p - k0;
+            if (p < nb) {
+                ib = p;
             } else {
                 const bool hit = (nb + lane < cnt) && s_rows[nb + lane] == p;
                 const unsigned mask = __ballot_sync(0xffffffffu, hit);
@@ -326,26 +331,101 @@ __global__ void __launch_bounds__(UPD_THREADS) k_lu_update(double* __restrict__ 
     }
     __syncthreads();
     const int cnt = s_cnt;
-    // gather the window
-    for (int t = tid; t < cnt * UT; t += UPD_THREADS) {
-        const int e = t / UT, c = c0 + (t % UT);
-        s_vals[e][t % UT] = c < n ? A[(size_t)c * lda + s_rows[e]] : 0.0;
+    if (warp == 1) {
+        // the composition of all nb interchanges on the window, for k_lu_update: after the swaps, window entry e
+        // holds what entry src[e] held before.  win = { cnt, rows[2 NB] (absolute), src[2 NB] }
+        __shared__ int s_src[2 * NB];
+        s_src[lane] = lane;
+        s_src[lane + 32] = lane + 32;
+        __syncwarp();
+        if (lane == 0) {
+            for (int j = 0; j < nb; ++j) {
+                const int ib = s_ib[j];
+                if (ib != j) {
+                    const int t = s_src[j];
+                    s_src[j] = s_src[ib];
+                    s_src[ib] = t;
+                }
+            }
+            win[0] = cnt;
+        }
+        __syncwarp();
+        for (int e = lane; e < 2 * NB; e += 32) {
+            win[1 + e] = e < cnt ? k0 + s_rows[e] : 0;
+            win[1 + 2 * NB + e] = e < cnt ? s_src[e] : e;
+        }
+    }
+    for (int t = tid; t < cnt * NB; t += 256) {
+        const int e = t / NB, c = t % NB;
+        s_fix[e][c] = c < nb ? G[(size_t)c * lda + s_rows[e]] : 0.0;
     }
     __syncthreads();
-    // replay the interchanges, one thread per column
-    if (tid < UT) {
-        const int c = c0 + tid;
-        const int j_first = (is_left || is_right) ? 0 : (c - k0 + 1); // a panel column only sees the later swaps
-        for (int j = j_first; j < nb; ++j) {
+    if (tid < nb) {
+        for (int j = tid + 1; j < nb; ++j) {
             const int ib = s_ib[j];
             if (ib != j) {
-                const double t = s_vals[j][tid];
-                s_vals[j][tid] = s_vals[ib][tid];
-                s_vals[ib][tid] = t;
+                const double t = s_fix[j][tid];
+                s_fix[j][tid] = s_fix[ib][tid];
+                s_fix[ib][tid] = t;
             }
         }
     }
     __syncthreads();
+    for (int t = tid; t < cnt * NB; t += 256) {
+        const int e = t / NB, c = t % NB;
+        // only the part of column c below the diagonal was stored by the column loop as L; rows <= c hold U
+        if (c < nb && s_rows[e] > c) G[(size_t)c * lda + s_rows[e]] = s_fix[e][c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_lu_update: everything that follows a panel, fused, one CTA per tile of 16 columns over ALL columns:
+//   interchanges  (left of the panel: all nb swaps; the panel's own columns: the swaps that came after the column
+//                  was finished; right of the panel: all nb swaps)
+//   U12 = L11^-1 A12 and A22 -= L21 * U12 for the tiles right of the panel.
+// The interchanges touch at most 2 nb distinct rows (the nb top rows and the pivot rows): warp 0 lists them once,
+// the CTA gathers its 16 columns of those rows with independent loads, replays the swaps in shared memory, solves
+// the unit-lower block with warp shuffles (lane = row) and scatters the rows back -- no chain of dependent global
+// accesses.  The trailing update then streams L21 (coalesced, from L2) against the 32 x 16 U tile in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int UT = 16;            // columns per CTA
+constexpr int UPD_THREADS = 256;
+
+__global__ void __launch_bounds__(UPD_THREADS) k_lu_update(double* __restrict__ A, int lda, int n, int k0, int nb,
+                                                           const int* __restrict__ win, long long* dbg)
+{
+    __shared__ double s_vals[2 * NB][UT + 1]; // window rows x tile columns (after the interchanges)
+    __shared__ __align__(16) double s_U[NB][UT]; // U12 tile, rows >= nb zero
+    __shared__ double s_L[NB][NB + 1];        // L11 (strictly lower part)
+    __shared__ int s_rows[2 * NB];
+    __shared__ int s_src[2 * NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = blockIdx.x * UT;
+    const bool is_left = c0 + UT <= k0;
+    const bool is_right = c0 >= k0 + nb;
+    const bool dbgt = dbg && tid == 0 && blockIdx.x == gridDim.x - 2;
+    if (dbgt) dbg[0] = clock64();
+    if (!is_left && !is_right) return; // the panel kernel finished its own columns
+    const int cnt = win[0];
+    if (tid < 2 * NB) {
+        s_rows[tid] = win[1 + tid];
+        s_src[tid] = win[1 + 2 * NB + tid];
+    }
+    if (is_right) {
+        for (int t = tid; t < NB * NB; t += UPD_THREADS) {
+            const int r = t % NB, c = t / NB;
+            s_L[r][c] = (r < nb && c < nb && r > c) ? A[(size_t)(k0 + c) * lda + k0 + r] : 0.0;
+        }
+    }
+    __syncthreads();
+    if (dbgt) dbg[1] = clock64();
+    // gather the window, already permuted: entry e receives the row that the composed interchanges bring there
+    for (int t = tid; t < cnt * UT; t += UPD_THREADS) {
+        const int e = t / UT, c = c0 + (t % UT);
+        s_vals[e][t % UT] = c < n ? A[(size_t)c * lda + s_rows[s_src[e]]] : 0.0;
+    }
+    __syncthreads();
+    if (dbgt) dbg[3] = dbg[2] = clock64();
     if (is_right) { // U12 tile = L11^-1 * top rows: lane = row, two columns per warp
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -356,9 +436,11 @@ __global__ void __launch_bounds__(UPD_THREADS) k_lu_update(double* __restrict__ 
                 if (lane > j) x -= s_L[lane][j] * xj;
             }
             if (lane < nb) s_vals[lane][c] = x;
+            s_U[lane][c] = lane < nb ? x : 0.0;
         }
         __syncthreads();
     }
+    if (dbgt) dbg[4] = clock64();
     // scatter the window back
     for (int t = tid; t < cnt * UT; t += UPD_THREADS) {
         const int e = t / UT, c = c0 + (t % UT);
@@ -366,24 +448,31 @@ __global__ void __launch_bounds__(UPD_THREADS) k_lu_update(double* __restrict__ 
     }
     if (!is_right) return;
     __syncthreads(); // the pivot rows just written belong to the trailing matrix updated below
-    // trailing update of this tile's columns: C[r][c] -= sum_k L21[r][k] * U12[k][c]
+    if (dbgt) dbg[5] = clock64();
+    // trailing update of this tile's columns: C[r][c] -= sum_k L21[r][k] * U12[k][c].  All 48 loads of a row are
+    // issued before the first FMA (unconditional, clamped addresses; rows k >= nb of s_U are zero).
     const int r_begin = k0 + nb;
     for (int r = r_begin + tid; r < n; r += UPD_THREADS) {
-        double l[NB];
+        double l[NB], cv[UT];
 #pragma unroll
-        for (int k = 0; k < NB; ++k) l[k] = k < nb ? A[(size_t)(k0 + k) * lda + r] : 0.0;
-        double acc[UT];
+        for (int k = 0; k < NB; ++k) l[k] = A[(size_t)(k0 + min(k, nb - 1)) * lda + r];
 #pragma unroll
-        for (int c = 0; c < UT; ++c) acc[c] = 0.0;
+        for (int c = 0; c < UT; ++c) cv[c] = A[(size_t)min(c0 + c, n - 1) * lda + r];
+        asm volatile("" ::: "memory");
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
 #pragma unroll
-            for (int c = 0; c < UT; ++c) acc[c] += l[k] * s_vals[k][c];
+            for (int c = 0; c < UT; c += 2) {
+                const double2 u2 = *reinterpret_cast<const double2*>(&s_U[k][c]);
+                cv[c] -= l[k] * u2.x;
+                cv[c + 1] -= l[k] * u2.y;
+            }
         }
 #pragma unroll
         for (int c = 0; c < UT; ++c)
-            if (c0 + c < n) A[(size_t)(c0 + c) * lda + r] -= acc[c];
+            if (c0 + c < n) A[(size_t)(c0 + c) * lda + r] = cv[c];
     }
+    if (dbgt) dbg[6] = clock64();
 }
 
 // perm[i] = original row that ends up in row i after all interchanges (single CTA, shared-memory resident)
@@ -418,9 +507,9 @@ __global__ void k_lu_init(int* flags, double* pivstat)
 
 } // namespace
 
-template <int RPT>
+template <int RPT, bool CLUSTER>
 static cudaError_t launch_panel_cluster(cudaStream_t s, int cs, double* d_A, int lda, int n, int k0, int nb, int* d_ipiv,
-                                        int* d_flags, double* d_pivstat)
+                                        int* d_flags, double* d_pivstat, int* d_win)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs);
@@ -434,22 +523,73 @@ static cudaError_t launch_panel_cluster(cudaStream_t s, int cs, double* d_A, int
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_lu_panel_cluster<RPT>, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
+    return cudaLaunchKernelEx(&cfg, k_lu_panel_cluster<RPT, CLUSTER>, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win);
+}
+
+// window of a panel whose kernel did not export it (fallback panel): same list + composition, one warp
+__global__ void __launch_bounds__(32) k_lu_window(const int* __restrict__ ipiv, int k0, int nb, int* __restrict__ win)
+{
+    __shared__ int s_rows[2 * NB], s_src[2 * NB], s_ib[NB];
+    const int lane = threadIdx.x;
+    if (lane < nb) s_rows[lane] = k0 + lane;
+    const int my_piv = lane < nb ? ipiv[k0 + lane] : 0;
+    int cnt = nb;
+    __syncwarp();
+    for (int j = 0; j < nb; ++j) {
+        const int p = __shfl_sync(0xffffffffu, my_piv, j);
+        int ib;
+        if (p < k0 + nb) {
+            ib = p - k0;
+        } else {
+            const bool hit = (nb + lane < cnt) && s_rows[nb + lane] == p;
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (mask) {
+                ib = nb + __ffs(mask) - 1;
+            } else {
+                if (lane == 0) s_rows[cnt] = p;
+                ib = cnt++;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) s_ib[j] = ib;
+    }
+    s_src[lane] = lane;
+    s_src[lane + 32] = lane + 32;
+    __syncwarp();
+    if (lane == 0) {
+        for (int j = 0; j < nb; ++j) {
+            const int ib = s_ib[j];
+            if (ib != j) {
+                const int t = s_src[j];
+                s_src[j] = s_src[ib];
+                s_src[ib] = t;
+            }
+        }
+        win[0] = cnt;
+    }
+    __syncwarp();
+    for (int e = lane; e < 2 * NB; e += 32) {
+        win[1 + e] = e < cnt ? s_rows[e] : 0;
+        win[1 + 2 * NB + e] = e < cnt ? s_src[e] : e;
+    }
 }
 
 cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
-                         double* d_pivstat)
+                         double* d_pivstat, int* d_win)
 {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_lu_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_MAX);
         cudaFuncSetAttribute(k_lu_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(k_lu_panel_cluster<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        cudaFuncSetAttribute(k_lu_panel_cluster<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        cudaFuncSetAttribute(k_lu_panel_cluster<3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(k_lu_panel_cluster<1, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(k_lu_panel_cluster<2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(k_lu_panel_cluster<3, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         attr_set = true;
     }
     cudaStream_t s = ctx->stream;
+    static long long* d_dbg = nullptr;
+    static const bool want_dbg = getenv("FD_LU_DEBUG") != nullptr;
+    if (want_dbg && !d_dbg) cudaMalloc(&d_dbg, 64);
     k_lu_init<<<1, 32, 0, s>>>(d_flags, d_pivstat);
     ctx->launches += 1;
     cudaError_t e = cudaSuccess;
@@ -462,20 +602,34 @@ cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, 
             for (int r = 1; r <= 3; ++r)
                 if (m <= c * 256 * r) { cs = c; rpt = r; break; }
         if (cs) {
-            e = rpt == 1 ? launch_panel_cluster<1>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat)
-              : rpt == 2 ? launch_panel_cluster<2>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat)
-                         : launch_panel_cluster<3>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
+            if (cs == 1)
+                e = rpt == 1 ? launch_panel_cluster<1, false>(s, 1, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win)
+                  : rpt == 2 ? launch_panel_cluster<2, false>(s, 1, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win)
+                             : launch_panel_cluster<3, false>(s, 1, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win);
+            else
+                e = rpt == 1 ? launch_panel_cluster<1, true>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win)
+                  : rpt == 2 ? launch_panel_cluster<2, true>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win)
+                             : launch_panel_cluster<3, true>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win);
         } else { // taller than 12288 rows: panel through global memory, then its own interchanges are already applied
             k_lu_panel<false><<<1, PANEL_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
+            k_lu_window<<<1, 32, 0, s>>>(d_ipiv, k0, nb, d_win);
+            ctx->launches += 1;
             e = cudaGetLastError();
         }
         ctx->launches += 1;
         if (e != cudaSuccess) break;
-        k_lu_update<<<(n + UT - 1) / UT, UPD_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_ipiv, 0);
+        k_lu_update<<<(n + UT - 1) / UT, UPD_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_win, k0 == 0 ? d_dbg : nullptr);
         ctx->launches += 1;
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e;
+    if (want_dbg) {
+        long long h[8];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, d_dbg, 56, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[fd_lu] n=%d update(k0=0) cycles: list %lld gather %lld replay %lld trsm %lld scatter %lld gemm %lld\n", n,
+                h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
+    }
     if ((size_t)n * sizeof(int) > 64 * 1024) return cudaErrorInvalidValue;
     k_lu_perm<<<1, 256, (size_t)n * sizeof(int), s>>>(d_ipiv, n, d_perm);
     ctx->launches += 1;

@@ -58,6 +58,7 @@ struct fd_model {
     double* d_A;     // lda x n, LU in place
     int* d_ipiv;     // n (global row index swapped with row k)
     int* d_perm;     // n: row i of P*A is row perm[i] of A
+    int* d_win;      // 1 + 4*32 ints: the rows the current panel's interchanges touch and their composition
     double* d_Tinv;  // [ceil(n/32)][2][32x32]: inverses of the diagonal blocks of L and U
     double* d_W;     // n x ldw weights (solve in place over the right-hand sides)
     int* d_flags;    // FD_NUM_FLAGS
@@ -98,7 +99,7 @@ cudaError_t fd_launch_assemble(fd_ctx* ctx, const fd_params& prm, const float* d
                                int np, double* d_A, int lda);
 // fd_factor.cu
 cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
-                         double* d_pivstat);
+                         double* d_pivstat, int* d_win);
 // fd_solve.cu
 cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_deform, int F);
 cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);

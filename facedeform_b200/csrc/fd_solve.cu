@@ -95,11 +95,17 @@ __global__ void __launch_bounds__(256) k_trsm_update(const double* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += s_t[k][rg * 8 + i] * xv;
     }
-    if (c0 + cc < nrhs) {
+    if (c0 + cc < nrhs) { // loads first, stores after: `B[..] -= acc` would serialise on possible aliasing
+        double bv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = r0 + rg * 8 + i;
-            if (r < row_end) B[(size_t)r * ldw + c0 + cc] -= acc[i];
+            bv[i] = r < row_end ? B[(size_t)r * ldw + c0 + cc] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + rg * 8 + i;
+            if (r < row_end) B[(size_t)r * ldw + c0 + cc] = bv[i] - acc[i];
         }
     }
 }
