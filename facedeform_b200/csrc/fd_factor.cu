@@ -392,7 +392,7 @@ constexpr int UT = 16;            // columns per CTA
 constexpr int UPD_THREADS = 256;
 
 __global__ void __launch_bounds__(UPD_THREADS) k_lu_update(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                           const int* __restrict__ win, long long* dbg)
+                                                           const int* __restrict__ win, int do_gemm, long long* dbg)
 {
     __shared__ double s_vals[2 * NB][UT + 1]; // window rows x tile columns (after the interchanges)
     __shared__ __align__(16) double s_U[NB][UT]; // U12 tile, rows >= nb zero
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(UPD_THREADS) k_lu_update(double* __restrict__ 
         const int e = t / UT, c = c0 + (t % UT);
         if (c < n) A[(size_t)c * lda + s_rows[e]] = s_vals[e][t % UT];
     }
-    if (!is_right) return;
+    if (!is_right || !do_gemm) return;
     __syncthreads(); // the pivot rows just written belong to the trailing matrix updated below
     if (dbgt) dbg[5] = clock64();
     // trailing update of this tile's columns: C[r][c] -= sum_k L21[r][k] * U12[k][c].  All 48 loads of a row are
@@ -473,6 +473,63 @@ __global__ void __launch_bounds__(UPD_THREADS) k_lu_update(double* __restrict__ 
             if (c0 + c < n) A[(size_t)(c0 + c) * lda + r] = cv[c];
     }
     if (dbgt) dbg[6] = clock64();
+}
+
+// Trailing update for tall trailing matrices: C[m2 x m2] -= L21[m2 x 32] * U12[32 x m2] with both operands staged in
+// shared memory (CTA tile 128 x 64, 8 x 4 outputs per thread), so L21 and U12 are read from L2 once per tile instead
+// of once per 16 columns.  The C tile is loaded up front and written once.
+constexpr int GM = 128, GN = 64;
+__global__ void __launch_bounds__(256) k_lu_gemm(double* __restrict__ A, int lda, int n, int k0, int nb)
+{
+    __shared__ __align__(16) double s_a[NB][GM]; // L21 tile [k][row]
+    __shared__ __align__(16) double s_b[NB][GN]; // U12 tile [k][col]
+    const int r0 = k0 + nb + blockIdx.x * GM;
+    const int c0 = k0 + nb + blockIdx.y * GN;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < NB * GM; t += 256) {
+        const int rr = t % GM, k = t / GM;
+        s_a[k][rr] = (k < nb && r0 + rr < n) ? A[(size_t)(k0 + k) * lda + r0 + rr] : 0.0;
+    }
+    for (int t = tid; t < NB * GN; t += 256) {
+        const int k = t % NB, cc = t / NB;
+        s_b[k][cc] = (k < nb && c0 + cc < n) ? A[(size_t)(c0 + cc) * lda + k0 + k] : 0.0;
+    }
+    // thread tile: rows tr + 16 i (i < 8) so that the lanes of a warp touch consecutive rows (coalesced column-major
+    // accesses, conflict-free shared-memory reads), columns tc .. tc + 3
+    const int tr = tid % 16, tc = (tid / 16) * 4;
+    double acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            acc[i][j] = A[(size_t)min(c0 + tc + j, n - 1) * lda + min(r0 + tr + 16 * i, n - 1)]; // C tile, clamped addresses
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < NB; ++k) {
+        double a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = s_a[k][tr + 16 * i];
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(&s_b[k][tc + j]);
+            b[j] = t.x;
+            b[j + 1] = t.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] -= a[i] * b[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + tc + j;
+        if (c >= n) continue;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + tr + 16 * i;
+            if (r < n) A[(size_t)c * lda + r] = acc[i][j];
+        }
+    }
 }
 
 // perm[i] = original row that ends up in row i after all interchanges (single CTA, shared-memory resident)
@@ -618,8 +675,15 @@ cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, 
         }
         ctx->launches += 1;
         if (e != cudaSuccess) break;
-        k_lu_update<<<(n + UT - 1) / UT, UPD_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_win, k0 == 0 ? d_dbg : nullptr);
+        const int m2 = n - k0 - nb;
+        const bool big = m2 >= 512; // tall trailing matrix: interchanges + TRSM fused, GEMM by the shared-memory-tiled kernel
+        k_lu_update<<<(n + UT - 1) / UT, UPD_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_win, big ? 0 : 1, k0 == 0 ? d_dbg : nullptr);
         ctx->launches += 1;
+        if (big) {
+            dim3 grid((m2 + GM - 1) / GM, (m2 + GN - 1) / GN);
+            k_lu_gemm<<<grid, 256, 0, s>>>(d_A, lda, n, k0, nb);
+            ctx->launches += 1;
+        }
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e;
