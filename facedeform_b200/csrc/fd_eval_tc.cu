@@ -26,27 +26,34 @@
 
 namespace tc {
 
-constexpr int TM = 256;                       // vertices per unit (two M=128 accumulators)
+constexpr int TM = 128;                       // vertices per unit (one M=128 accumulator; two accumulators ping-pong)
 constexpr int CB = 240;                       // columns per unit (multiple of 3 and of 16)
 constexpr int BK = 32;                        // k per pipeline stage (64-byte rows -> SWIZZLE_64B)
-constexpr int STAGES = 3;
-constexpr int A_SPLIT_BYTES = TM * BK * 2;    // 16384
+constexpr int STAGES = 4;
+constexpr int A_SPLIT_BYTES = TM * BK * 2;    // 8192
 constexpr int B_SPLIT_BYTES = CB * BK * 2;    // 15360
 constexpr int C_TILE_BYTES = BK * 16;         // the stage's 32 centres (float4 each), bulk-copied next to the weights
-constexpr int C_TILE_OFF = 2 * A_SPLIT_BYTES + 2 * B_SPLIT_BYTES; // 63488
-constexpr int STAGE_BYTES = C_TILE_OFF + C_TILE_BYTES;             // 64000
-constexpr int PRODUCER_WARPS = 8;
-constexpr int EPILOGUE_WARPS = 8;              // one per (M tile, TMEM lane quarter)
+constexpr int C_TILE_OFF = 2 * A_SPLIT_BYTES + 2 * B_SPLIT_BYTES; // 47104
+constexpr int STAGE_BYTES = C_TILE_OFF + C_TILE_BYTES;             // 47616
+constexpr int PRODUCER_WARPS = 16;            // two groups of 8 warps: group g fills the stages with (iteration & 1) == g;
+                                              // inside a group two threads share a vertex row, 16 basis functions each
+constexpr int EPILOGUE_WARPS = 8;              // two per TMEM lane quarter (even / odd column chunks)
 constexpr int THREADS = 32 * (2 + PRODUCER_WARPS + EPILOGUE_WARPS);
+// Warp roles.  The SM's warp arbiter favours the highest warp ids, so the two single-lane roles every other warp
+// waits on (TMA producer, MMA issuer) sit at the top: warps 0..15 Phi producers, 16..23 epilogue, 24 TMA, 25 MMA.
+constexpr int WARP_EPI0 = PRODUCER_WARPS;
+constexpr int WARP_TMA = PRODUCER_WARPS + EPILOGUE_WARPS;
+constexpr int WARP_MMA = WARP_TMA + 1;
 constexpr int TMEM_COLS = 512;
-constexpr int ACC1_COL = 256;                 // TMEM column of the second M tile's accumulator
+constexpr int ACC1_COL = 256;                 // TMEM column of the second (ping-pong) accumulator
 constexpr int EPI_FRAMES = 8;                 // frames per epilogue chunk (24 accumulator columns)
 constexpr int EPI_WARP_FLOATS = EPI_FRAMES * 96; // staging floats per warp (8 frames x 32 vertices x 3)
 constexpr int EPI_COLS = EPI_FRAMES * 3;
 constexpr int SMEM_EPI_STAGING = STAGES * STAGE_BYTES;                          // 4 warps x 6 KB transpose buffers
 constexpr int SMEM_BARRIERS = SMEM_EPI_STAGING + EPILOGUE_WARPS * EPI_WARP_FLOATS * 4;
 constexpr int SMEM_COLSCALE = SMEM_BARRIERS + 128;
-constexpr int SMEM_TOTAL = SMEM_COLSCALE + CB * 4;
+constexpr int COLSCALE_RESIDENT_BLOCKS = 15;  // column scales of up to 15 column blocks (F <= 1200) stay resident
+constexpr int SMEM_TOTAL = SMEM_COLSCALE + COLSCALE_RESIDENT_BLOCKS * CB * 4;
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024; // slack for the 1024-byte alignment of the dynamic window
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -258,24 +265,25 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
     const uint32_t bar_full_a = smem_u32(bars + 0);          // [STAGES], count PRODUCER_WARPS
     const uint32_t bar_full_b = smem_u32(bars + STAGES);     // [STAGES], count 1 + tx bytes
     const uint32_t bar_empty = smem_u32(bars + 2 * STAGES);  // [STAGES], count 1 (tcgen05.commit)
-    const uint32_t bar_tmem_full = smem_u32(bars + 3 * STAGES);        // count 1: all MMAs of the unit retired
-    const uint32_t bar_tmem_empty = smem_u32(bars + 3 * STAGES + 1);   // [2], count 4 warps: accumulator mt drained
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 3);
+    const uint32_t bar_tmem_full = smem_u32(bars + 3 * STAGES);        // [2], count 1: all MMAs of the unit retired
+    const uint32_t bar_tmem_empty = smem_u32(bars + 3 * STAGES + 2);   // [2], count EPILOGUE_WARPS: accumulator drained
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
     float* s_colscale = reinterpret_cast<float*>(smem + SMEM_COLSCALE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full_a + 8 * s, PRODUCER_WARPS);
+            mbar_init(bar_full_a + 8 * s, PRODUCER_WARPS / 2);
             mbar_init(bar_full_b + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_tmem_full, 1);
-        mbar_init(bar_tmem_empty, EPILOGUE_WARPS / 2);
-        mbar_init(bar_tmem_empty + 8, EPILOGUE_WARPS / 2);
+        mbar_init(bar_tmem_full + 8, 1);
+        mbar_init(bar_tmem_empty, EPILOGUE_WARPS);
+        mbar_init(bar_tmem_empty + 8, EPILOGUE_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == WARP_TMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -288,7 +296,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
     const int64_t n_vt = (a.V + TM - 1) / TM;
     const int64_t n_units = n_vt * a.ncb;
 
-    if (warp == 0) {
+    if (warp == WARP_TMA) {
         // ================= TMA producer: weight tiles =================
         if (lane == 0) {
             uint32_t it = 0;
@@ -306,49 +314,49 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == WARP_MMA) {
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t it = 0, unit_iter = 0;
+            const uint64_t desc0 = make_desc_sw64(smem_base); // A hi tile of stage 0 (the whole window is < 256 KB: no carry)
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
                 const int cb = (int)(u % a.ncb);
                 const int ncols = min(CB, (3 * a.F - cb * CB + 15) & ~15);
                 const uint32_t idesc = make_idesc(ncols);
+                const int ab = unit_iter & 1;                 // accumulator buffer of this unit
+                const uint32_t d = tmem_base + ab * ACC1_COL;
+                // the epilogue must have drained this buffer (two units ago)
+                mbar_wait(bar_tmem_empty + 8 * ab, ((unit_iter >> 1) & 1) ^ 1);
+                tc_fence_after();
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(bar_full_a + 8 * s, ph);
                     mbar_wait(bar_full_b + 8 * s, ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + s * STAGE_BYTES;
-                    const uint32_t sb = sa + 2 * A_SPLIT_BYTES;
+                    // descriptors differ from the stage-0 ones only in the start-address field (units of 16 bytes)
+                    const uint64_t so = (uint64_t)(s * (STAGE_BYTES >> 4));
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            const uint32_t a_off = mt * (128 * BK * 2) + kk * 32;
-                            const uint64_t a_hi = make_desc_sw64(sa + a_off);
-                            const uint64_t a_lo = make_desc_sw64(sa + A_SPLIT_BYTES + a_off);
-                            const uint64_t b_hi = make_desc_sw64(sb + kk * 32);
-                            const uint64_t b_lo = make_desc_sw64(sb + B_SPLIT_BYTES + kk * 32);
-                            const uint32_t d = tmem_base + mt * ACC1_COL;
-                            if ((kb | kk) == 0) { // first write of this unit: the epilogue must have drained the accumulator
-                                mbar_wait(bar_tmem_empty + 8 * mt, (unit_iter & 1) ^ 1);
-                                tc_fence_after();
-                            }
-                            umma_f16(d, a_hi, b_hi, idesc, (kb | kk) != 0);
-                            umma_f16(d, a_hi, b_lo, idesc, 1);
-                            umma_f16(d, a_lo, b_hi, idesc, 1);
-                        }
+                        const uint64_t a_hi = desc0 + so + kk * 2;
+                        const uint64_t a_lo = a_hi + (A_SPLIT_BYTES >> 4);
+                        const uint64_t b_hi = a_hi + (2 * A_SPLIT_BYTES >> 4);
+                        const uint64_t b_lo = b_hi + (B_SPLIT_BYTES >> 4);
+                        umma_f16(d, a_hi, b_hi, idesc, (kb | kk) != 0);
+                        umma_f16(d, a_hi, b_lo, idesc, 1);
+                        umma_f16(d, a_lo, b_hi, idesc, 1);
                     }
-                    umma_commit(bar_empty + 8 * s);               // frees the stage when these MMAs have read it
-                    if (kb == nk - 1) umma_commit(bar_tmem_full); // accumulators complete
+                    umma_commit(bar_empty + 8 * s);                        // frees the stage when these MMAs have read it
+                    if (kb == nk - 1) umma_commit(bar_tmem_full + 8 * ab); // accumulator complete
                 }
             }
         }
-    } else if (warp < 2 + PRODUCER_WARPS) {
+    } else if (warp < PRODUCER_WARPS) {
         // ================= Phi producers =================
-        const int row = (warp - 2) * 32 + lane; // vertex row of the 256-row tile this thread generates
+        const int pt = threadIdx.x;             // 0..511
+        const int row = pt & (TM - 1);
+        const int khalf = (pt >> 7) & 1;        // which half of the stage's 32 k this thread generates
+        const int grp = pt >> 8;                // producer group: stages of its parity
         const float4 nrm4 = *reinterpret_cast<const float4*>(a.norm);
         uint32_t it = 0, unit_iter = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
@@ -360,9 +368,10 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                 py = a.P[3 * v + 1];
                 pz = a.P[3 * v + 2];
             }
-            const bool dbg = a.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && unit_iter < 15;
+            const bool dbg = a.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && unit_iter < 15;
             if (dbg) a.dbg[unit_iter * 8 + 0] = clock64();
             for (int kb = 0; kb < nk; ++kb, ++it) {
+                if ((it & 1) != (uint32_t)grp) continue; // the other group's stage
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -372,50 +381,38 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                 const float4* s_ctr = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES + C_TILE_OFF);
                 const int k0 = kb * BK;
                 const int swz = (row >> 1) & 3;
+                float f[16];
                 if (k0 + BK <= a.N) {
 #pragma unroll
-                    for (int c32 = 0; c32 < 2; ++c32) { // 16 independent basis evaluations in flight per thread
-                        float f[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float4 c = s_ctr[c32 * 16 + j]; // warp-wide broadcast LDS.128
-                            const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
-                            f[j] = phi<KERNEL>(dx * dx + dy * dy + dz * dz, c.w);
-                        }
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 hi, lo;
-                            split8(f + 8 * h, hi, lo);
-                            const int off = ((c32 * 2 + h) ^ swz) * 16;
-                            *reinterpret_cast<uint4*>(a_hi + off) = hi;
-                            *reinterpret_cast<uint4*>(a_lo + off) = lo;
-                        }
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 c = s_ctr[khalf * 16 + j]; // warp-wide broadcast LDS.128
+                        const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
+                        f[j] = phi<KERNEL>(dx * dx + dy * dy + dz * dz, c.w);
                     }
                 } else { // the last stage(s): remaining centres, then the affine rows [1, x', y', z'], then zero padding
-#pragma unroll 1
-                    for (int c16 = 0; c16 < 4; ++c16) {
-                        float f[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int k = k0 + c16 * 8 + j;
-                            const float4 c = s_ctr[c16 * 8 + j];
-                            const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
-                            float val = phi<KERNEL>(dx * dx + dy * dy + dz * dz, c.w);
-                            if (k >= a.N) {
-                                const int r = k - a.N;
-                                val = r == 0 ? 1.0f
-                                    : r == 1 ? (px - nrm4.x) * nrm4.w
-                                    : r == 2 ? (py - nrm4.y) * nrm4.w
-                                    : r == 3 ? (pz - nrm4.z) * nrm4.w : 0.0f;
-                            }
-                            f[j] = val;
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = k0 + khalf * 16 + j;
+                        const float4 c = s_ctr[khalf * 16 + j];
+                        const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
+                        float val = phi<KERNEL>(dx * dx + dy * dy + dz * dz, c.w);
+                        if (k >= a.N) {
+                            const int r = k - a.N;
+                            val = r == 0 ? 1.0f
+                                : r == 1 ? (px - nrm4.x) * nrm4.w
+                                : r == 2 ? (py - nrm4.y) * nrm4.w
+                                : r == 3 ? (pz - nrm4.z) * nrm4.w : 0.0f;
                         }
-                        uint4 hi, lo;
-                        split8(f, hi, lo);
-                        const int off = (c16 ^ swz) * 16;
-                        *reinterpret_cast<uint4*>(a_hi + off) = hi;
-                        *reinterpret_cast<uint4*>(a_lo + off) = lo;
+                        f[j] = val;
                     }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint4 hi, lo;
+                    split8(f + 8 * h, hi, lo);
+                    const int off = ((khalf * 2 + h) ^ swz) * 16;
+                    *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                    *reinterpret_cast<uint4*>(a_lo + off) = lo;
                 }
                 fence_proxy_async(); // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -427,27 +424,34 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
         // ================= epilogue warps: TMEM -> registers -> (transpose in shared memory) -> global =================
         // They run one unit behind the producers: while they drain and store unit u, Phi generation and the MMAs of
         // unit u+1 proceed (the MMA issuer re-acquires each accumulator through bar_tmem_empty[mt]).
-        const int ew = warp - (2 + PRODUCER_WARPS);
+        const int ew = warp - WARP_EPI0;
         const int q = warp & 3;               // TMEM lane quarter this warp may access
         float* stg = reinterpret_cast<float*>(smem + SMEM_EPI_STAGING) + ew * EPI_WARP_FLOATS;
-        const int et = threadIdx.x - 32 * (2 + PRODUCER_WARPS);
+        const int et = threadIdx.x - 32 * WARP_EPI0;
         uint32_t unit_iter = 0;
+        const bool resident_cs = a.ncb <= COLSCALE_RESIDENT_BLOCKS;
+        if (resident_cs) { // all column scales once, instead of a barrier + global round trip per unit
+            for (int t = et; t < a.ncb * CB; t += 32 * EPILOGUE_WARPS) s_colscale[t] = a.colscale[t];
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
             const int cb = (int)(u % a.ncb);
             const int64_t vt = u / a.ncb;
             const int f_base = cb * (CB / 3);
             const int nframes = min(CB / 3, a.F - f_base);
-            asm volatile("bar.sync 2, 256;" ::: "memory"); // previous unit's readers of s_colscale are done
-            for (int t = et; t < CB; t += 32 * EPILOGUE_WARPS) s_colscale[t] = a.colscale[cb * CB + t];
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            const float* s_cs = s_colscale + (resident_cs ? cb * CB : 0); // this unit's 240 column scales
+            if (!resident_cs) {
+                asm volatile("bar.sync 2, 256;" ::: "memory"); // previous unit's readers of s_colscale are done
+                for (int t = et; t < CB; t += 32 * EPILOGUE_WARPS) s_colscale[t] = a.colscale[cb * CB + t];
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
             const bool dbg = a.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && unit_iter < 15;
             if (dbg) a.dbg[unit_iter * 8 + 2] = clock64();
-            mbar_wait(bar_tmem_full, unit_iter & 1);
-            tc_fence_after();
-            if (dbg) a.dbg[unit_iter * 8 + 3] = clock64();
+            const int ab = unit_iter & 1;
             {
-                const int mt = ew >> 2; // this warp's accumulator
-                const int64_t v_warp0 = vt * TM + mt * 128 + q * 32;
+                const int mt = ab;       // TMEM column block of this unit's accumulator
+                const int chunk0 = ew >> 2; // this warp drains the even (0) or the odd (1) column chunks
+                const int64_t v_warp0 = vt * TM + q * 32;
                 const int64_t v = v_warp0 + lane;
                 const bool valid = v < a.V;
                 float px = 0.f, py = 0.f, pz = 0.f, fo = 0.f;
@@ -460,7 +464,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                     skip = d2 > a.radius2;                                        // SOP_FaceDeform.cpp:408-410
                     fo = powf(1.0f - fminf(d2 / a.radius2, 1.0f), a.falloffrate); // :423-424
                     if (skip) fo = 0.f;
-                    if (a.falloff_out && cb == 0) a.falloff_out[v] = fo;
+                    if (a.falloff_out && cb == 0 && chunk0 == 0) a.falloff_out[v] = fo;
                 }
                 float tu[3] = {0, 0, 0}, tv[3] = {0, 0, 0}, tn[3] = {0, 0, 0};
                 if (TANGENT && valid) {
@@ -475,27 +479,30 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                     normalize3(tn);
                 }
                 const bool vec = a.vec_store_ok != 0;
+                // everything above is independent of the accumulator: it overlaps the MMAs of this unit
+                mbar_wait(bar_tmem_full + 8 * ab, (unit_iter >> 1) & 1);
+                tc_fence_after();
+                if (dbg) a.dbg[unit_iter * 8 + 3] = clock64();
                 if (vec) {
                     // fast path: out = P + acc * (colscale * falloff) (colscale is a power of two, so the product order
                     // does not change the rounding; a skipped vertex has falloff 0 and keeps P exactly), transposed
                     // through shared memory into [frame][vertex][xyz] rows that one lane hands to the bulk-copy engine
 #pragma unroll 1
-                    for (int ch = 0; ch * EPI_FRAMES < nframes; ++ch) {
+                    for (int ch = chunk0; ch * EPI_FRAMES < nframes; ch += 2) {
                         float acc[EPI_COLS];
                         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + mt * ACC1_COL + ch * EPI_COLS;
-                        const bool dbg2 = dbg && unit_iter == 1 && mt == 0 && ch == 1;
+                        const bool dbg2 = dbg && unit_iter == 2 && ch == 2;
                         if (dbg2) a.dbg[120] = clock64();
                         tmem_ld16(taddr, acc);
                         tmem_ld8(taddr + 16, acc + 16);
-                        float* buf = stg; // single buffer, guarded by wait_group.read below
-                        // the bulk stores of the previous chunk must have finished reading the staging buffer
+                        float* buf = stg; // single buffer: the TMA store of the previous chunk must have read it
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                         if (dbg2) a.dbg[121] = clock64();
                         __syncwarp();
                         tmem_ld_wait();
                         if (dbg2) a.dbg[122] = clock64();
                         const int fcnt = min(EPI_FRAMES, nframes - ch * EPI_FRAMES);
-                        const float4* cs4 = reinterpret_cast<const float4*>(s_colscale + ch * EPI_COLS);
+                        const float4* cs4 = reinterpret_cast<const float4*>(s_cs + ch * EPI_COLS);
 #pragma unroll
                         for (int g = 0; g < EPI_COLS / 4; ++g) { // 4 columns at a time
                             const float4 cs = cs4[g];
@@ -508,11 +515,11 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                             }
                         }
                         if (dbg2) a.dbg[123] = clock64();
-                        fence_proxy_async(); // staging writes -> visible to the bulk-copy engine (async proxy)
+                        fence_proxy_async(); // staging writes -> visible to the TMA (async proxy)
                         __syncwarp();
                         if (dbg2) a.dbg[124] = clock64();
                         if (lane == 0) {
-                            // one TMA store of the [16 frames][32 vertices x 3] tile; frames >= F and vertices >= V are clipped
+                            // one TMA store of the [8 frames][32 vertices x 3] tile; frames >= F and vertices >= V are clipped
                             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                          ::"l"(reinterpret_cast<uint64_t>(&map_out)), "r"(smem_u32(buf)),
                                            "r"((int)(v_warp0 * 3)), "r"(f_base + ch * EPI_FRAMES)
@@ -525,7 +532,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                 } else {
                     // general path (partial tile, V not a multiple of 4, tangent projection): per-lane scalar stores
 #pragma unroll 1
-                    for (int ch = 0; ch * EPI_FRAMES < nframes; ++ch) {
+                    for (int ch = chunk0; ch * EPI_FRAMES < nframes; ch += 2) {
                         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + mt * ACC1_COL + ch * EPI_COLS;
                         const int fcnt = min(EPI_FRAMES, nframes - ch * EPI_FRAMES);
 #pragma unroll 1
@@ -535,7 +542,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                             tmem_ld_wait();
                             // frames straddle the 8-column parts: gather through the staging buffer as [col][lane]
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) stg[(part * 8 + c) * 32 + lane] = acc[c] * s_colscale[ch * EPI_COLS + part * 8 + c];
+                            for (int c = 0; c < 8; ++c) stg[(part * 8 + c) * 32 + lane] = acc[c] * s_cs[ch * EPI_COLS + part * 8 + c];
                         }
                         __syncwarp();
 #pragma unroll 1
@@ -553,7 +560,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                     }
                 }
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                // accumulator mt is drained (for this warp's 32 lanes): hand it back to the MMA issuer
+                // this warp's share of the accumulator is drained: hand it back to the MMA issuer
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tmem_empty + 8 * mt);
@@ -564,7 +571,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == WARP_TMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
@@ -805,6 +812,12 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
         cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[fd_tc] chunk: issue-ldtm+bulkwait %lld  ldtm-wait %lld  math+sts %lld  fence %lld  bulk-issue %lld\n",
                 h[121] - h[120], h[122] - h[121], h[123] - h[122], h[124] - h[123], h[125] - h[124]);
+        {
+            int last = 0;
+            while (last + 1 < 15 && h[(last + 1) * 8]) ++last;
+            fprintf(stderr, "[fd_tc] CTA 0: %d units, producer period %.0f cycles/unit, epilogue period %.0f cycles/unit\n", last + 1,
+                    last ? (double)(h[last * 8] - h[0]) / last : 0.0, last ? (double)(h[last * 8 + 4] - h[4]) / last : 0.0);
+        }
         for (int u = 0; u < 15 && h[u * 8]; ++u)
             fprintf(stderr, "[fd_tc] unit %d: produce %lld | epilogue: wait-tmem %lld  drain+store %lld | producer start->epilogue end %lld\n", u,
                     h[u * 8 + 1] - h[u * 8], h[u * 8 + 3] - h[u * 8 + 2], h[u * 8 + 4] - h[u * 8 + 3], h[u * 8 + 4] - h[u * 8]);
