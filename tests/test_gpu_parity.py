@@ -237,3 +237,34 @@ def test_tensor_path_other_kernels_fp32(ctx, oracle):
     """multiquadric / thin plate through the tensor path in FP32 mode: the stated looser FP32 tolerance applies."""
     _run(ctx, oracle, N=256, V=2048, F=20, kernel=1, term=0, eval_precision=1, eval_path=2, tol=5e-4)
     _run(ctx, oracle, N=256, V=2048, F=20, kernel=2, term=0, eval_precision=1, eval_path=2, tol=5e-4)
+
+
+def test_receiver_model_matches_root_bit_for_bit(ctx):
+    """multi-GPU plumbing on one GPU: a receiver model fed the root's weight and radii blocks (what NCCL broadcasts in
+    shard.broadcast_model) evaluates bit-identically to the root."""
+    import torch
+    from facedeform_b200 import make_params, shard
+    rig = synth.control_rig(96)
+    deform = synth.deformed_rig(rig, 20)
+    mesh = synth.face_mesh(3000, topology=False)
+    for model in (0, 1):
+        p = make_params(model=model, radius=2 * rig.spacing, **{"lambda": 0.0})
+        root = ctx.fit(p, rig.rest).solve(deform)
+        want, wfall = root.eval(mesh.P)
+        recv = ctx.receiver(p, rig.rest, 20)
+        assert recv.info() == root.info()
+        for get in ("weights_dev", "radii_dev"):
+            (sp, sb), (dp, db) = getattr(root, get)(), getattr(recv, get)()
+            assert sb == db
+            ctx.synchronize()
+            shard.device_view(dp, db).copy_(shard.device_view(sp, sb))
+        torch.cuda.synchronize()
+        recv.commit_weights()
+        got, gfall = recv.eval(mesh.P)
+        assert np.array_equal(got, want) and np.array_equal(gfall, wfall)
+        from facedeform_b200 import FdError
+        with pytest.raises(FdError) as e:           # a receiver holds no factorisation
+            recv.solve(deform)
+        assert e.value.status == 9
+        root.close()
+        recv.close()
