@@ -473,8 +473,9 @@ int fd_model_create_receiver(fd_ctx* ctx, const fd_params* params, const float* 
     m->ldw = fd_round_up(3 * frames, 4);
     m->ldw32 = m->ldw;
     m->use_tc = model_wants_tc(m, frames);
+    // no host synchronisation: pageable sources are staged by the driver before the call returns, pinned or device
+    // sources must stay valid until the ctx stream has consumed them (like every *_dev entry point)
     cudaError_t e = cudaMemcpyAsync(m->d_rest, rest_ctrl, (size_t)n_ctrl * 3 * sizeof(float), cudaMemcpyDefault, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { FD_SET_ERR(ctx, "receiver: %s", cudaGetErrorString(e)); fd_model_destroy(m); return FD_E_CUDA; }
     *out = m;
     return FD_OK;

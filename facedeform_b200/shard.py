@@ -39,6 +39,29 @@ def broadcast_block(t, src: int = 0, group=None):
     return t
 
 
+def broadcast_block_tree(t, src: int = 0, group=None):
+    """binomial-tree broadcast with point-to-point sends: log2(world) hops instead of the ring's world - 1."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return t
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return t
+    rel = (rank - src) % world
+    step = 1
+    while step < world:
+        step *= 2
+    step //= 2
+    # top-down: in the round with distance `step`, ranks that already hold the data (rel % (2 step) == 0) send to rel + step
+    while step >= 1:
+        if rel % (2 * step) == 0 and rel + step < world:
+            dist.send(t, dst=(rel + step + src) % world, group=group)
+        elif rel % (2 * step) == step:
+            dist.recv(t, src=(rel - step + src) % world, group=group)
+        step //= 2
+    return t
+
+
 def broadcast_model(model, src: int = 0, group=None, shared_stream: bool = False):
     """Root: `model` is fitted + solved.  Others: `model` is a receiver (Context.receiver).  After this call every
     rank can evaluate: the FP64 weight block and the radii travel, the evaluation tables are rebuilt locally.
