@@ -639,8 +639,17 @@ __global__ void __launch_bounds__(256) k_tc_colscale(const double* __restrict__ 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     double mx = 0.0;
-    if (c < ncol)
-        for (int k = ty; k < N + 4; k += 8) mx = fmax(mx, fabs(tc_weight(W, ldw, N, np, k, c, norm)));
+    if (c < ncol) {
+        // four independent running maxima: the loads of consecutive iterations overlap instead of one L2 round trip each
+        double m4[4] = {0.0, 0.0, 0.0, 0.0};
+        int k = ty;
+        for (; k + 24 < N; k += 32) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m4[u] = fmax(m4[u], fabs(W[(size_t)(k + 8 * u) * ldw + c]));
+        }
+        for (; k < N + 4; k += 8) m4[0] = fmax(m4[0], fabs(tc_weight(W, ldw, N, np, k, c, norm)));
+        mx = fmax(fmax(m4[0], m4[1]), fmax(m4[2], m4[3]));
+    }
     s_mx[ty][tx] = mx;
     __syncthreads();
     if (ty != 0 || c >= ncol_pad) return;

@@ -117,51 +117,83 @@ __global__ void __launch_bounds__(256) k_trsm_update(const double* __restrict__ 
 constexpr int RC = 16;
 constexpr int SLAB_THREADS = 256;
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// stage the (transposed) inverse of a diagonal block: 8 KB = two 16-byte cp.async per thread
+__device__ __forceinline__ void slab_prefetch_tinv(double* s_T, const double* __restrict__ Tinv)
+{
+    for (int t = threadIdx.x; t < SB * SB / 2; t += SLAB_THREADS) cp_async16(s_T + 2 * t, Tinv + 2 * t);
+    cp_async_commit();
+}
+
+// One block step of a sweep.  s_T holds TinvT for this step (s_T[k * SB + r] = Tinv[r][k]); the inverse of the next
+// step's block is prefetched into s_Tnext with cp.async, and the first pass of L/U rows is loaded into registers
+// before the block product, so the L2 round trips overlap the arithmetic instead of adding to it.
 template <bool LOWER>
 __device__ __forceinline__ void slab_sweep_block(const double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                 const double* __restrict__ Tinv, double* __restrict__ s_B,
-                                                 double (*s_T)[SB + 1], double (*s_X)[RC])
+                                                 const double* __restrict__ Tinv_next, double* __restrict__ s_B,
+                                                 const double* __restrict__ s_T, double* __restrict__ s_Tnext,
+                                                 double (*s_X)[RC])
 {
     const int tid = threadIdx.x;
-    // stage the inverted diagonal block (k_lu_invdiag): the block solve becomes a 32x32 by 32xRC product
-    for (int t = tid; t < SB * SB; t += SLAB_THREADS) s_T[t / SB][t % SB] = Tinv[t];
-    __syncthreads();
-    {
-        const int r = tid & 31, cpair = (tid >> 5) * 2;
-        double x0 = 0.0, x1 = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < SB; ++k) {
-            const double t = s_T[r][k];
-            const double* bk = s_B + (size_t)(k0 + k) * RC + cpair;
-            if (k < nb) {
-                x0 += t * bk[0];
-                x1 += t * bk[1];
-            }
-        }
-        s_X[r][cpair] = r < nb ? x0 : 0.0;
-        s_X[r][cpair + 1] = r < nb ? x1 : 0.0;
-    }
-    __syncthreads();
-    for (int t = tid; t < nb * RC; t += SLAB_THREADS) s_B[(size_t)k0 * RC + t] = s_X[t / RC][t % RC];
-    // rows outside the block: B[i][:] -= T[i][k0:k0+nb] * X  (all loads of a row are issued before the FMAs)
+    if (Tinv_next) slab_prefetch_tinv(s_Tnext, Tinv_next);
     const int row_begin = LOWER ? k0 + nb : 0;
     const int row_end = LOWER ? n : k0;
     const int half = tid & 1; // 8 of the 16 columns
-    for (int i = row_begin + (tid >> 1); i < row_end; i += SLAB_THREADS / 2) {
-        const double* Ti = A + (size_t)k0 * lda + i;
-        double l[SB];
+    // first pass of the outside rows: loads issued now (clamped, unconditional), consumed after the block product
+    const int i0 = row_begin + (tid >> 1);
+    double l[SB];
+    {
+        const double* Ti = A + (size_t)k0 * lda + min(i0, n - 1);
 #pragma unroll
-        for (int k = 0; k < SB; ++k) l[k] = k < nb ? Ti[(size_t)k * lda] : 0.0;
+        for (int k = 0; k < SB; ++k) l[k] = Ti[(size_t)min(k, nb - 1) * lda];
+    }
+    {
+        const int r = tid & 31, cpair = (tid >> 5) * 2;
+        double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0; // two partial sums per output: shorter dependent chains
+#pragma unroll 8
+        for (int k = 0; k < SB; k += 2) {
+            const double t0 = s_T[k * SB + r], t1 = s_T[(k + 1) * SB + r];
+            const double* b0 = s_B + (size_t)(k0 + min(k, nb - 1)) * RC + cpair;
+            const double* b1 = s_B + (size_t)(k0 + min(k + 1, nb - 1)) * RC + cpair;
+            const double m0 = k < nb ? 1.0 : 0.0, m1 = k + 1 < nb ? 1.0 : 0.0;
+            x0 += t0 * (m0 * b0[0]);
+            x1 += t0 * (m0 * b0[1]);
+            y0 += t1 * (m1 * b1[0]);
+            y1 += t1 * (m1 * b1[1]);
+        }
+        __syncthreads(); // every thread has read its B_k rows
+        s_X[r][cpair] = r < nb ? x0 + y0 : 0.0;
+        s_X[r][cpair + 1] = r < nb ? x1 + y1 : 0.0;
+        if (r < nb) {
+            s_B[(size_t)(k0 + r) * RC + cpair] = x0 + y0;
+            s_B[(size_t)(k0 + r) * RC + cpair + 1] = x1 + y1;
+        }
+    }
+    __syncthreads();
+    // rows outside the block: B[i][:] -= T[i][k0:k0+nb] * X
+    for (int i = i0; i < row_end; i += SLAB_THREADS / 2) {
+        if (i != i0) {
+            const double* Ti = A + (size_t)k0 * lda + i;
+#pragma unroll
+            for (int k = 0; k < SB; ++k) l[k] = Ti[(size_t)min(k, nb - 1) * lda];
+        }
         double acc[8] = {};
 #pragma unroll
         for (int k = 0; k < SB; ++k) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[c] += l[k] * s_X[k][half * 8 + c];
+            for (int c = 0; c < 8; ++c) acc[c] += l[k] * s_X[k][half * 8 + c]; // rows k >= nb of s_X are zero
         }
         double* bi = s_B + (size_t)i * RC + half * 8;
 #pragma unroll
         for (int c = 0; c < 8; ++c) bi[c] -= acc[c];
     }
+    cp_async_wait_all();
     __syncthreads();
 }
 
@@ -196,9 +228,9 @@ __global__ void __launch_bounds__(64) k_lu_invdiag(const double* __restrict__ A,
             for (int r = 0; r < j; ++r) x[r] -= s_T[r][j] * xj;
         }
     }
-    double* out = Tinv + ((size_t)blk * 2 + (upper ? 1 : 0)) * SB * SB; // row-major [r][c]
+    double* out = Tinv + ((size_t)blk * 2 + (upper ? 1 : 0)) * SB * SB; // transposed: out[c * SB + r] = inverse[r][c]
 #pragma unroll
-    for (int r = 0; r < SB; ++r) out[r * SB + c] = x[r];
+    for (int r = 0; r < SB; ++r) out[c * SB + r] = x[r];
 }
 
 __global__ void __launch_bounds__(SLAB_THREADS) k_solve_slab(const double* __restrict__ A, int lda, int n, int N,
@@ -207,10 +239,12 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_solve_slab(const double* __res
                                                              const double* __restrict__ Tinv, double* __restrict__ W, int ldw)
 {
     extern __shared__ double s_B[]; // n x RC
-    __shared__ double s_T[SB][SB + 1];
+    __shared__ __align__(16) double s_T[2][SB * SB];
     __shared__ double s_X[SB][RC];
     const int c0 = blockIdx.x * RC;
     const int nrhs = 3 * F;
+    const int nblk = (n + SB - 1) / SB;
+    slab_prefetch_tinv(s_T[0], Tinv); // block 0 of L, overlapped with the right-hand-side build
     // right-hand sides, permuted: delta subtracted in FP32 then widened (SOP_FaceDeform.cpp:276-284)
     for (int t = threadIdx.x; t < n * RC; t += SLAB_THREADS) {
         const int i = t / RC, c = c0 + (t % RC);
@@ -222,11 +256,17 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_solve_slab(const double* __res
         }
         s_B[t] = v;
     }
+    cp_async_wait_all();
     __syncthreads();
-    for (int k0 = 0; k0 < n; k0 += SB)
-        slab_sweep_block<true>(A, lda, n, k0, min(SB, n - k0), Tinv + (size_t)(k0 / SB) * 2 * SB * SB, s_B, s_T, s_X);
-    for (int k0 = (n - 1) / SB * SB; k0 >= 0; k0 -= SB)
-        slab_sweep_block<false>(A, lda, n, k0, min(SB, n - k0), Tinv + ((size_t)(k0 / SB) * 2 + 1) * SB * SB, s_B, s_T, s_X);
+    int buf = 0;
+    for (int blk = 0; blk < nblk; ++blk, buf ^= 1) { // L y = P b; the last step prefetches the first block of the U sweep
+        const double* next = blk + 1 < nblk ? Tinv + (size_t)(blk + 1) * 2 * SB * SB : Tinv + ((size_t)(nblk - 1) * 2 + 1) * SB * SB;
+        slab_sweep_block<true>(A, lda, n, blk * SB, min(SB, n - blk * SB), next, s_B, s_T[buf], s_T[buf ^ 1], s_X);
+    }
+    for (int blk = nblk - 1; blk >= 0; --blk, buf ^= 1) { // U x = y
+        const double* next = blk > 0 ? Tinv + ((size_t)(blk - 1) * 2 + 1) * SB * SB : nullptr;
+        slab_sweep_block<false>(A, lda, n, blk * SB, min(SB, n - blk * SB), next, s_B, s_T[buf], s_T[buf ^ 1], s_X);
+    }
     for (int t = threadIdx.x; t < n * RC; t += SLAB_THREADS) {
         const int i = t / RC, c = c0 + (t % RC);
         if (c < ldw) W[(size_t)i * ldw + c] = s_B[t];
