@@ -325,6 +325,16 @@ def main():
                 "peak_source": "derived: 148 SM x 128 FP32 lanes x 2 flop x clocks.max.sm (FP32 FMA issue is not in MEASURED_PEAKS.json)",
                 "traffic": None, "launch_ms": eval_ms_mean,
             }
+        # DRAM traffic of one launch from the committed `ncu --set full` capture of this command (profiles/), C2 only
+        try:
+            if args.config == "C2" and tensor_path:
+                with open(os.path.join(ROOT, "profiles", "r1_final_eval_tc_ncu_summary.json")) as f:
+                    nc = json.load(f)
+                roofline["traffic"] = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6
+                roofline["traffic_source"] = "profiles/r1_final_eval_tc_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+                roofline["algorithmic_bytes"] = alg_bytes
+        except Exception:
+            pass
         roofline["hbm"] = {"achieved": alg_bytes / (eval_ms_mean * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                            "frac": alg_bytes / (eval_ms_mean * 1e-3) / 1e9 / peaks["hbm"], "peak_source": peaks["source"]}
         line = {
