@@ -307,7 +307,11 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
     if (e == cudaSuccess) e = fd_launch_assemble(ctx, m->prm, m->d_rest, m->d_radii, m->N, m->np, m->d_A, m->lda);
     phase_end(ctx, FD_PH_ASSEMBLE);
     phase_begin(ctx, FD_PH_FACTOR);
-    if (e == cudaSuccess) e = fd_launch_lu(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_win);
+    // Gaussian kernel with one radius: K + lambda I is symmetric positive definite -> no pivot search needed
+    const bool spd = m->prm.kernel == FD_KERNEL_GAUSSIAN && (m->prm.model == FD_MODEL_ML || m->N == 1) && !getenv("FD_FORCE_PIVOTED_LU");
+    if (e == cudaSuccess)
+        e = spd ? fd_launch_lu_nopivot(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat)
+                : fd_launch_lu(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_win);
     if (e == cudaSuccess) e = fd_launch_invdiag(ctx, m);
     phase_end(ctx, FD_PH_FACTOR);
     if (e != cudaSuccess) {

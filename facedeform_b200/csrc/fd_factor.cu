@@ -532,6 +532,113 @@ __global__ void __launch_bounds__(256) k_lu_gemm(double* __restrict__ A, int lda
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Symmetric positive definite fast path (Gaussian kernel, uniform radius): LU WITHOUT pivoting.
+// K + lambda I is SPD, so eliminating it in natural order is backward stable, and the Schur complement that the
+// polynomial rows leave behind, -P^T K^-1 P, is negative definite -- no row interchange is ever needed for the
+// saddle-point system [[K, P], [P^T, 0]].  Without a pivot search a block column needs no per-column reduction or
+// barrier across the rows: every CTA factors the 32 x 32 diagonal block redundantly in shared memory, then each
+// thread finishes one row of L21 (x U11^-1) or one column of U12 (L11^-1 x) on its own.  The factors have the same
+// layout as the pivoted path (unit-lower L, U, identity permutation), so the solve kernels are shared.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NP_THREADS = 256;
+
+__global__ void __launch_bounds__(NP_THREADS) k_lu_nopiv_panel(double* __restrict__ A, int lda, int n, int k0, int nb,
+                                                               int* __restrict__ flags, double* __restrict__ pivstat)
+{
+    __shared__ __align__(16) double s_D[NB][NB + 2]; // diagonal block, row-major [r][c]; becomes L11 \ U11
+    __shared__ double s_inv[NB];
+    const int tid = threadIdx.x;
+    for (int t = tid; t < NB * NB; t += NP_THREADS) {
+        const int r = t % NB, c = t / NB;
+        s_D[r][c] = (r < nb && c < nb) ? A[(size_t)(k0 + c) * lda + k0 + r] : (r == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    // LU of the diagonal block: step j updates the (r > j, c > j) entries with the un-scaled column j; the column
+    // is scaled by 1/u_jj once at the end
+    for (int j = 0; j < NB; ++j) {
+        const double ujj = s_D[j][j];
+        const double inv = (ujj != 0.0 && isfinite(ujj)) ? fast_rcp(ujj) : 0.0;
+        if (tid == 0) s_inv[j] = inv;
+        for (int t = tid; t < NB * NB; t += NP_THREADS) {
+            const int r = t / NB, c = t % NB;
+            if (r > j && c > j) s_D[r][c] -= (s_D[r][j] * inv) * s_D[j][c];
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        double pmin = pivstat[0], pmax = pivstat[1];
+        for (int j = 0; j < nb; ++j) {
+            const double v = fabs(s_D[j][j]);
+            if (!(v > 0.0) || !isfinite(v)) {
+                if (flags[FD_FLAG_SINGULAR] == 0) flags[FD_FLAG_SINGULAR] = k0 + j + 1;
+            }
+            pmin = fmin(pmin, v);
+            pmax = fmax(pmax, v);
+        }
+        pivstat[0] = pmin;
+        pivstat[1] = pmax;
+    }
+    for (int t = tid; t < NB * NB; t += NP_THREADS) {
+        const int r = t / NB, c = t % NB;
+        if (r > c) s_D[r][c] *= s_inv[c];
+    }
+    __syncthreads();
+    const int m2 = n - k0 - nb; // rows below / columns right of the block
+    const int row_ctas = (m2 + NP_THREADS - 1) / NP_THREADS;
+    if (blockIdx.x == 0) { // write the factored diagonal block back
+        for (int t = tid; t < NB * NB; t += NP_THREADS) {
+            const int r = t % NB, c = t / NB;
+            if (r < nb && c < nb) A[(size_t)(k0 + c) * lda + k0 + r] = s_D[r][c];
+        }
+    }
+    if (m2 <= 0) return;
+    if ((int)blockIdx.x < row_ctas) {
+        // one row of L21 per thread: l = a U11^-1, i.e. forward substitution against the columns of U11
+        const int r = k0 + nb + blockIdx.x * NP_THREADS + tid;
+        if (r >= n) return;
+        double x[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) x[c] = A[(size_t)(k0 + min(c, nb - 1)) * lda + r];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const double l = x[j] * s_inv[j];
+            x[j] = l;
+#pragma unroll
+            for (int c = j + 1; c < NB; ++c) x[c] -= l * s_D[j][c];
+        }
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+            if (c < nb) A[(size_t)(k0 + c) * lda + r] = x[c];
+    } else {
+        // one column of U12 per thread: u = L11^-1 a (unit lower)
+        const int c = k0 + nb + (blockIdx.x - row_ctas) * NP_THREADS + tid;
+        if (c >= n) return;
+        double* col = A + (size_t)c * lda + k0;
+        double x[NB];
+#pragma unroll
+        for (int r = 0; r < NB; ++r) x[r] = col[min(r, nb - 1)];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const double xj = x[j];
+#pragma unroll
+            for (int r = j + 1; r < NB; ++r) x[r] -= s_D[r][j] * xj;
+        }
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+            if (r < nb) col[r] = x[r];
+    }
+}
+
+__global__ void k_lu_identity_perm(int n, int* __restrict__ ipiv, int* __restrict__ perm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        ipiv[i] = i;
+        perm[i] = i;
+    }
+}
+
 // perm[i] = original row that ends up in row i after all interchanges (single CTA, shared-memory resident)
 __global__ void __launch_bounds__(256) k_lu_perm(const int* __restrict__ ipiv, int n, int* __restrict__ perm)
 {
@@ -697,5 +804,28 @@ cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, 
     if ((size_t)n * sizeof(int) > 64 * 1024) return cudaErrorInvalidValue;
     k_lu_perm<<<1, 256, (size_t)n * sizeof(int), s>>>(d_ipiv, n, d_perm);
     ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+// LU without pivoting for the symmetric positive definite case (see k_lu_nopiv_panel)
+cudaError_t fd_launch_lu_nopivot(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
+                                 double* d_pivstat)
+{
+    cudaStream_t s = ctx->stream;
+    k_lu_init<<<1, 32, 0, s>>>(d_flags, d_pivstat);
+    k_lu_identity_perm<<<(n + 255) / 256, 256, 0, s>>>(n, d_ipiv, d_perm);
+    ctx->launches += 2;
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int nb = min(NB, n - k0);
+        const int m2 = n - k0 - nb;
+        const int ctas = m2 > 0 ? 2 * ((m2 + NP_THREADS - 1) / NP_THREADS) : 1;
+        k_lu_nopiv_panel<<<ctas, NP_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_flags, d_pivstat);
+        ctx->launches += 1;
+        if (m2 > 0) {
+            dim3 grid((m2 + GM - 1) / GM, (m2 + GN - 1) / GN);
+            k_lu_gemm<<<grid, 256, 0, s>>>(d_A, lda, n, k0, nb);
+            ctx->launches += 1;
+        }
+    }
     return cudaGetLastError();
 }

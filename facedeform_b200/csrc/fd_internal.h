@@ -100,6 +100,8 @@ cudaError_t fd_launch_assemble(fd_ctx* ctx, const fd_params& prm, const float* d
 // fd_factor.cu
 cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                          double* d_pivstat, int* d_win);
+cudaError_t fd_launch_lu_nopivot(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
+                                 double* d_pivstat);
 // fd_solve.cu
 cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_deform, int F);
 cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);
