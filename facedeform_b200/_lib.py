@@ -54,6 +54,13 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        # the library is built in-tree by __graft_entry__.build(); on a checkout without it, try once with nvcc
+        import shutil
+        import subprocess
+        if shutil.which("make") and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+            subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8", "all"], check=False,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `make -C facedeform_b200/csrc` (or __graft_entry__.build()). "
             "facedeform_b200 has no CPU fallback.")
