@@ -157,6 +157,41 @@ def run_reference(args):
     return 0
 
 
+def factor_table(ctx, sizes, cpu=True):
+    """factor ms at N control points (assemble + factor, device resident, median of 3 after one warm-up):
+    `gaussian_spd` = Gaussian + uniform radius (symmetric positive definite: LU without pivot search),
+    `multiquadric_pivoted` = the general pivoted LU; `cpu_oracle` = the FP64 oracle's assemble + LU on the host cores
+    (N <= 2048 only: the 8192 case takes minutes on a CPU)."""
+    import torch
+    from facedeform_b200 import make_params, synth
+    out = {}
+    for n in sizes:
+        rig = synth.control_rig(n)
+        d_rest = torch.from_numpy(rig.rest).cuda()
+        row = {}
+        for name, kern in (("gaussian_spd", "gaussian"), ("multiquadric_pivoted", "multiquadric")):
+            p = make_params(model=1, term=0, kernel=synth.KERNELS[kern], radius=synth.default_radius(kern, rig.spacing),
+                            **{"lambda": 0.0})
+            ts = []
+            for i in range(4):
+                m = ctx.fit(p, d_rest)
+                m.report()
+                if i:
+                    ts.append(ctx.phase_ms("assemble") + ctx.phase_ms("factor"))
+                m.close()
+            row[name] = float(np.median(ts))
+        if cpu and n <= 2048:
+            from oracle import fd_oracle as o
+            op = o.make_params(model=1, term=0, kernel=0, radius=synth.default_radius("gaussian", rig.spacing), **{"lambda": 0.0})
+            st, rad = o.radii(op, rig.rest)
+            t0 = time.perf_counter()
+            A = o.assemble(op, rig.rest, rad)
+            o.lu_factor(A)
+            row["cpu_oracle"] = (time.perf_counter() - t0) * 1e3
+        out[str(n)] = row
+    return out
+
+
 def describe(cfg):
     return (f"{cfg['N']} control points, {cfg['V']} vertices/GPU, {cfg['F']} frames, {cfg['kernel']} kernel, "
             f"{cfg['term']} term, step = assemble + LU + {3 * cfg['F']}-RHS solve + fused eval")
@@ -172,6 +207,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-path", type=int, default=0)
+    ap.add_argument("--factor-sizes", default="256,1024,2048,4096,8192",
+                    help="control-point counts for the factor-ms table (second half of the metric); empty to skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -352,6 +389,9 @@ def main():
                     "d2h_bytes_per_step": int(h_out.nbytes + h_fall.nbytes)},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if world == 1 and args.factor_sizes:
+            line["factor_ms_by_n"] = factor_table(ctx, [int(x) for x in args.factor_sizes.split(",") if x],
+                                                  cpu=not args.no_cpu_baseline)
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_sample(cfg, rig, deform, radius, seconds_target=args.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
