@@ -12,146 +12,12 @@
 
 #include "fd_internal.h"
 
-namespace {
+// The kernels live in fd_factor_impl.inl and are instantiated twice: FP64 (the default) and FP32 (factor for the
+// FP32 + iterative-refinement mode, fd_params.factor_precision = FD_FACTOR_FP32_IR).
 
-constexpr int NB = 32;            // block-column width
-constexpr int PANEL_THREADS = 1024;
-constexpr int PANEL_SMEM_MAX = 200 * 1024;
-
-struct ArgMax {
-    double v;
-    int i;
-};
-
-__device__ __forceinline__ ArgMax argmax_combine(ArgMax a, ArgMax b)
-{
-    // larger magnitude wins; ties -> lower row index (deterministic, matches a serial first-max scan)
-    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
-    return a;
-}
-
-// Unblocked LU with partial pivoting of the panel A[k0:n, k0:k0+nb].
-// P points at the panel storage (global memory or the shared-memory copy) with leading dimension ldp.
-template <bool IN_SMEM>
-__global__ void __launch_bounds__(PANEL_THREADS) k_lu_panel(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                            int* __restrict__ ipiv, int* __restrict__ flags,
-                                                            double* __restrict__ pivstat)
-{
-    extern __shared__ double s_panel[];
-    __shared__ ArgMax s_red[2][PANEL_THREADS / 32];
-    __shared__ double s_pivrow[2][NB];
-    const int m = n - k0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    double* G = A + (size_t)k0 * lda + k0; // panel origin in global memory
-    const int ldp = IN_SMEM ? (m | 1) : lda;
-    double* P = IN_SMEM ? s_panel : G;
-    if (IN_SMEM) {
-        for (int c = 0; c < nb; ++c)
-            for (int r = tid; r < m; r += blockDim.x) P[(size_t)c * ldp + r] = G[(size_t)c * lda + r];
-        __syncthreads();
-    }
-    double pmin = pivstat[0], pmax = pivstat[1];
-    // Two block-wide barriers per column: every thread owns a fixed set of rows (r = tid mod blockDim), so the pivot
-    // search of column j+1 only reads elements the same thread updated in column j.
-    for (int j = 0; j < nb; ++j) {
-        // (1) pivot search in column j, rows j..m-1
-        ArgMax best = {-1.0, 0x7fffffff};
-        const double* col = P + (size_t)j * ldp;
-        for (int r = tid; r < m; r += blockDim.x) {
-            if (r < j) continue;
-            const double v = fabs(col[r]);
-            if (v > best.v) best = {v, r}; // rows visited in increasing order per thread
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            ArgMax other = {__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
-            best = argmax_combine(best, other);
-        }
-        if (lane == 0) s_red[j & 1][warp] = best;
-        __syncthreads();
-        best = lane < nwarps ? s_red[j & 1][lane] : ArgMax{-1.0, 0x7fffffff}; // every warp reduces the partials itself
-        for (int o = 16; o > 0; o >>= 1) {
-            ArgMax other = {__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
-            best = argmax_combine(best, other);
-        }
-        if (best.i >= m) best.i = j; // an all-NaN column: keep the diagonal, flagged singular below
-        const int p = best.i;
-        if (tid == 0) {
-            ipiv[k0 + j] = k0 + p;
-            if (!(best.v > 0.0) && flags[FD_FLAG_SINGULAR] == 0) flags[FD_FLAG_SINGULAR] = k0 + j + 1;
-            pmin = fmin(pmin, best.v);
-            pmax = fmax(pmax, best.v);
-        }
-        // (2) swap rows j and p inside the panel; keep the pivot row in shared memory
-        if (tid < nb) {
-            const double x = P[(size_t)tid * ldp + j], y = P[(size_t)tid * ldp + p];
-            P[(size_t)tid * ldp + j] = y;
-            P[(size_t)tid * ldp + p] = x;
-            s_pivrow[j & 1][tid] = y;
-        }
-        __syncthreads();
-        // (3) scale the column and rank-1 update the columns to its right (own rows only)
-        const double piv = s_pivrow[j & 1][j];
-        if (piv != 0.0) {
-            const double inv = 1.0 / piv;
-            for (int r = tid; r < m; r += blockDim.x) {
-                if (r <= j) continue;
-                const double l = P[(size_t)j * ldp + r] * inv;
-                P[(size_t)j * ldp + r] = l;
-#pragma unroll 4
-                for (int c = j + 1; c < nb; ++c) P[(size_t)c * ldp + r] -= l * s_pivrow[j & 1][c];
-            }
-        }
-    }
-    __syncthreads();
-    if (IN_SMEM) {
-        for (int c = 0; c < nb; ++c)
-            for (int r = tid; r < m; r += blockDim.x) G[(size_t)c * lda + r] = P[(size_t)c * ldp + r];
-    }
-    if (tid == 0) {
-        pivstat[0] = pmin;
-        pivstat[1] = pmax;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Register-resident, cluster-wide panel factorisation.
-//
-// The m x 32 panel lives in the register files of a thread-block cluster: CTA `cr` of the cluster owns panel rows
-// [cr * 256 * RPT, (cr + 1) * 256 * RPT), thread t of it rows t, t + 256, ... (64 registers per row).  Per column:
-//   local arg-max (registers -> warp REDUX -> CTA) -> candidates exchanged through distributed shared memory
-//   -> cluster barrier -> every CTA picks the same pivot -> the owners of rows j and p publish them in their own
-//   shared memory -> cluster barrier -> every CTA pulls both rows over DSMEM -> rank-1 update of its own rows.
-// The row registers are shifted left by one column per step, fused into the update (a'[c-1] = a[c] - l * u[c]), so
-// the loop over columns has static register indices and is not unrolled (an unrolled panel is ~200 KB of code that
-// runs once, at instruction-fetch speed).  L and U entries go straight to global memory at the row's current
-// position; the interchange inside the already finished columns is a fire-and-forget global swap by CTA 0.
-// A cluster of 1 covers 256 * RPT rows (N = 256: one CTA); 16 CTAs x RPT = 3 cover 12288 rows.
-// ---------------------------------------------------------------------------------------------------------------
-struct Cand {
-    double v;     // signed pivot candidate
-    int i;        // panel row
-    unsigned key; // high word of |v| (exponent + 20 mantissa bits): the magnitude the pivot search compares
-};
-
-// Pivot search on the 32-bit key with one REDUX per level instead of a 5-round shuffle tree on doubles: any entry
-// within 2^-20 of the largest is as good a pivot for LU stability; ties go to the lowest lane, i.e. a fixed row order.
-__device__ __forceinline__ unsigned mag_key(double v) { return (unsigned)__double2hiint(v) & 0x7fffffffu; }
-
-__device__ __forceinline__ Cand cand_warp_pick(Cand c, bool valid)
-{
-    const unsigned key = valid ? c.key + 1u : 0u; // 0 = no candidate
-    const unsigned best = __reduce_max_sync(0xffffffffu, key);
-    const unsigned who = __ballot_sync(0xffffffffu, key == best);
-    const int src = __ffs(who) - 1;
-    Cand w;
-    w.v = __shfl_sync(0xffffffffu, c.v, src);
-    w.i = __shfl_sync(0xffffffffu, c.i, src);
-    w.key = best ? best - 1u : 0u;
-    if (best == 0u) w.i = 0x7fffffff;
-    return w;
-}
-
-__device__ __forceinline__ double fast_rcp(double d)
+__device__ __forceinline__ unsigned fd_mag_key(double v) { return (unsigned)__double2hiint(v) & 0x7fffffffu; }
+__device__ __forceinline__ unsigned fd_mag_key(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+__device__ __forceinline__ double fd_fast_rcp(double d)
 {
     // MUFU.RCP64H seed + two Newton steps (full double accuracy up to the last ulps; LU does not need a correctly
     // rounded quotient), 5 dependent instructions instead of the ~20 of an IEEE division
@@ -162,670 +28,43 @@ __device__ __forceinline__ double fast_rcp(double d)
     e = fma(-d, r, 1.0);
     return fma(r, e, r);
 }
+__device__ __forceinline__ float fd_fast_rcp(float d) { return __frcp_rn(d); }
+__device__ __forceinline__ double2 fd_make2(double a, double b) { return make_double2(a, b); }
+__device__ __forceinline__ float2 fd_make2(float a, float b) { return make_float2(a, b); }
 
-template <int RPT, bool CLUSTER>
-__global__ void __launch_bounds__(256, 1) k_lu_panel_cluster(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                             int* __restrict__ ipiv, int* __restrict__ flags,
-                                                             double* __restrict__ pivstat, int* __restrict__ win)
-{
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int cr = CLUSTER ? (int)cluster.block_rank() : 0, CS = CLUSTER ? (int)cluster.num_blocks() : 1;
-    __shared__ double s_fix[2 * NB][NB + 1]; // epilogue: window of the rows the interchanges touch
-    __shared__ int s_rows[2 * NB];
-    __shared__ int s_ib[NB];
-    __shared__ int s_cnt;
-    __shared__ int s_piv[NB];
-    __shared__ Cand s_wred[2][8];      // per-warp candidates of this CTA
-    __shared__ Cand s_cand[2][16];     // per-CTA candidates of the whole cluster (filled remotely)
-    __shared__ __align__(16) double s_pub[2][2][NB]; // [parity][0: row j, 1: row p] published by the owner thread of this CTA
-    __shared__ __align__(16) double s_row[2][2][NB]; // local copies pulled from the owners
-    const int m = n - k0;
-    const int rows_per_cta = 256 * RPT;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* G = A + (size_t)k0 * lda + k0;
-    double a[RPT][NB];
-#pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-        const int r = cr * rows_per_cta + tid + q * 256;
-#pragma unroll
-        for (int c = 0; c < NB; ++c) a[q][c] = (r < m && c < nb) ? G[(size_t)c * lda + r] : 0.0;
-    }
-    double pmin = INFINITY, pmax = 0.0;
-#pragma unroll 1
-    for (int j = 0; j < nb; ++j) {
-        const int par = j & 1;
-        // (1) local candidate
-        Cand best = {0.0, 0x7fffffff, 0u};
-        bool have = false;
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-            const int r = cr * rows_per_cta + tid + q * 256;
-            const unsigned key = mag_key(a[q][0]);
-            if (r >= j && r < m && (!have || key > best.key)) {
-                best = Cand{a[q][0], r, key};
-                have = true;
-            }
-        }
-        best = cand_warp_pick(best, have);
-        if (lane == 0) s_wred[par][warp] = best;
-        __syncthreads();
-        Cand win;
-        if (CLUSTER) {
-            if (warp == 0) {
-                Cand c = lane < 8 ? s_wred[par][lane] : Cand{0.0, 0x7fffffff, 0u};
-                c = cand_warp_pick(c, lane < 8 && c.i != 0x7fffffff);
-                // (2) hand the CTA candidate to every CTA of the cluster
-                if (lane < CS) *cluster.map_shared_rank(&s_cand[par][cr], lane) = c;
-            }
-            cluster.sync();
-            win = lane < CS ? s_cand[par][lane] : Cand{0.0, 0x7fffffff, 0u};
-            win = cand_warp_pick(win, lane < CS && win.i != 0x7fffffff);
-        } else {
-            win = lane < 8 ? s_wred[par][lane] : Cand{0.0, 0x7fffffff, 0u}; // every warp picks among the 8 partials itself
-            win = cand_warp_pick(win, lane < 8 && win.i != 0x7fffffff);
-        }
-        int p = win.i;
-        const double pivabs = fabs(win.v);
-        if (p >= m) p = j; // nothing but NaNs: keep the diagonal, flagged singular below
-        const double inv = (pivabs > 0.0 && pivabs < INFINITY) ? fast_rcp(win.v) : 0.0;
-        if (cr == 0 && tid == 0) {
-            ipiv[k0 + j] = k0 + p;
-            s_piv[j] = p;
-            if (!(pivabs > 0.0) && flags[FD_FLAG_SINGULAR] == 0) flags[FD_FLAG_SINGULAR] = k0 + j + 1;
-            pmin = fmin(pmin, pivabs);
-            pmax = fmax(pmax, pivabs);
-        }
-        // (3) the owners publish rows j and p in their own shared memory
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-            const int r = cr * rows_per_cta + tid + q * 256;
-            if (r == j) {
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(&s_pub[par][0][c]) = make_double2(a[q][c], a[q][c + 1]);
-            }
-            if (r == p) {
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(&s_pub[par][1][c]) = make_double2(a[q][c], a[q][c + 1]);
-            }
-        }
-        const double* u;
-        const double* oldj;
-        if (CLUSTER) {
-            cluster.sync();
-            // (4) pull both rows from their owners
-            if (tid < 2 * NB) {
-                const int which = tid >> 5, c = tid & 31;
-                const int owner = (which == 0 ? j : p) / rows_per_cta;
-                s_row[par][which][c] = *cluster.map_shared_rank(&s_pub[par][which][c], owner);
-            }
-            __syncthreads();
-            u = s_row[par][1]; // u[c] = U(j, j + c)
-            oldj = s_row[par][0];
-        } else {
-            __syncthreads();
-            u = s_pub[par][1];
-            oldj = s_pub[par][0];
-        }
-        if (cr == 0 && tid < nb - j) G[(size_t)(j + tid) * lda + j] = u[tid]; // row j of U is final
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-            const int r = cr * rows_per_cta + tid + q * 256;
-            if (r == p && p != j) { // the row that sat at position j moves to position p
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) {
-                    const double2 t = *reinterpret_cast<const double2*>(&oldj[c]);
-                    a[q][c] = t.x;
-                    a[q][c + 1] = t.y;
-                }
-            }
-            if (r > j && r < m) {
-                const double l = a[q][0] * inv;
-                G[(size_t)j * lda + r] = l;
-                double uu[NB];
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) {
-                    const double2 t = *reinterpret_cast<const double2*>(&u[c]);
-                    uu[c] = t.x;
-                    uu[c + 1] = t.y;
-                }
-#pragma unroll
-                for (int c = 1; c < NB; ++c) a[q][c - 1] = a[q][c] - l * uu[c]; // rank-1 update fused with the shift
-                a[q][NB - 1] = 0.0;
-            }
-        }
-    }
-    if (cr == 0 && tid == 0) {
-        pivstat[0] = fmin(pivstat[0], pmin);
-        pivstat[1] = fmax(pivstat[1], pmax);
-    }
-    // every L entry is in global memory and visible; no CTA may exit while a peer can still read its shared memory
-    if (CLUSTER) cluster.sync(); else __syncthreads();
-    if (cr != 0) return;
-    // Epilogue (CTA 0): the interchanges inside the panel's own finished columns.  Column c only sees the swaps that
-    // came after it was finished (j > c).  The swaps touch at most 2 nb rows: gather that window with independent
-    // loads, replay per column in shared memory, scatter back.
-    if (warp == 0) {
-        if (lane < nb) s_rows[lane] = lane;
-        int cnt = nb;
-        __syncwarp();
-        for (int j = 0; j < nb; ++j) {
-            const int p = s_piv[j];
-            int ib;
-            if (p < nb) {
-                ib = p;
-            } else {
-                const bool hit = (nb + lane < cnt) && s_rows[nb + lane] == p;
-                const unsigned mask = __ballot_sync(0xffffffffu, hit);
-                if (mask) {
-                    ib = nb + __ffs(mask) - 1;
-                } else {
-                    if (lane == 0) s_rows[cnt] = p;
-                    ib = cnt++;
-                    __syncwarp();
-                }
-            }
-            if (lane == 0) s_ib[j] = ib;
-        }
-        if (lane == 0) s_cnt = cnt;
-    }
-    __syncthreads();
-    const int cnt = s_cnt;
-    if (warp == 1) {
-        // the composition of all nb interchanges on the window, for k_lu_update: after the swaps, window entry e
-        // holds what entry src[e] held before.  win = { cnt, rows[2 NB] (absolute), src[2 NB] }
-        __shared__ int s_src[2 * NB];
-        s_src[lane] = lane;
-        s_src[lane + 32] = lane + 32;
-        __syncwarp();
-        if (lane == 0) {
-            for (int j = 0; j < nb; ++j) {
-                const int ib = s_ib[j];
-                if (ib != j) {
-                    const int t = s_src[j];
-                    s_src[j] = s_src[ib];
-                    s_src[ib] = t;
-                }
-            }
-            win[0] = cnt;
-        }
-        __syncwarp();
-        for (int e = lane; e < 2 * NB; e += 32) {
-            win[1 + e] = e < cnt ? k0 + s_rows[e] : 0;
-            win[1 + 2 * NB + e] = e < cnt ? s_src[e] : e;
-        }
-    }
-    for (int t = tid; t < cnt * NB; t += 256) {
-        const int e = t / NB, c = t % NB;
-        s_fix[e][c] = c < nb ? G[(size_t)c * lda + s_rows[e]] : 0.0;
-    }
-    __syncthreads();
-    if (tid < nb) {
-        for (int j = tid + 1; j < nb; ++j) {
-            const int ib = s_ib[j];
-            if (ib != j) {
-                const double t = s_fix[j][tid];
-                s_fix[j][tid] = s_fix[ib][tid];
-                s_fix[ib][tid] = t;
-            }
-        }
-    }
-    __syncthreads();
-    for (int t = tid; t < cnt * NB; t += 256) {
-        const int e = t / NB, c = t % NB;
-        // only the part of column c below the diagonal was stored by the column loop as L; rows <= c hold U
-        if (c < nb && s_rows[e] > c) G[(size_t)c * lda + s_rows[e]] = s_fix[e][c];
-    }
-}
+#define REAL double
+#define REAL2 double2
+#define FD_LU_NS lu_f64
+#include "fd_factor_impl.inl"
+#undef REAL
+#undef REAL2
+#undef FD_LU_NS
 
-// ---------------------------------------------------------------------------------------------------------------
-// k_lu_update: everything that follows a panel, fused, one CTA per tile of 16 columns over ALL columns:
-//   interchanges  (left of the panel: all nb swaps; the panel's own columns: the swaps that came after the column
-//                  was finished; right of the panel: all nb swaps)
-//   U12 = L11^-1 A12 and A22 -= L21 * U12 for the tiles right of the panel.
-// The interchanges touch at most 2 nb distinct rows (the nb top rows and the pivot rows): warp 0 lists them once,
-// the CTA gathers its 16 columns of those rows with independent loads, replays the swaps in shared memory, solves
-// the unit-lower block with warp shuffles (lane = row) and scatters the rows back -- no chain of dependent global
-// accesses.  The trailing update then streams L21 (coalesced, from L2) against the 32 x 16 U tile in shared memory.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int UT = 16;            // columns per CTA
-constexpr int UPD_THREADS = 256;
-
-__global__ void __launch_bounds__(UPD_THREADS) k_lu_update(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                           const int* __restrict__ win, int do_gemm, long long* dbg)
-{
-    __shared__ double s_vals[2 * NB][UT + 1]; // window rows x tile columns (after the interchanges)
-    __shared__ __align__(16) double s_U[NB][UT]; // U12 tile, rows >= nb zero
-    __shared__ double s_L[NB][NB + 1];        // L11 (strictly lower part)
-    __shared__ int s_rows[2 * NB];
-    __shared__ int s_src[2 * NB];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = blockIdx.x * UT;
-    const bool is_left = c0 + UT <= k0;
-    const bool is_right = c0 >= k0 + nb;
-    const bool dbgt = dbg && tid == 0 && blockIdx.x == gridDim.x - 2;
-    if (dbgt) dbg[0] = clock64();
-    if (!is_left && !is_right) return; // the panel kernel finished its own columns
-    const int cnt = win[0];
-    if (tid < 2 * NB) {
-        s_rows[tid] = win[1 + tid];
-        s_src[tid] = win[1 + 2 * NB + tid];
-    }
-    if (is_right) {
-        for (int t = tid; t < NB * NB; t += UPD_THREADS) {
-            const int r = t % NB, c = t / NB;
-            s_L[r][c] = (r < nb && c < nb && r > c) ? A[(size_t)(k0 + c) * lda + k0 + r] : 0.0;
-        }
-    }
-    __syncthreads();
-    if (dbgt) dbg[1] = clock64();
-    // gather the window, already permuted: entry e receives the row that the composed interchanges bring there
-    for (int t = tid; t < cnt * UT; t += UPD_THREADS) {
-        const int e = t / UT, c = c0 + (t % UT);
-        s_vals[e][t % UT] = c < n ? A[(size_t)c * lda + s_rows[s_src[e]]] : 0.0;
-    }
-    __syncthreads();
-    if (dbgt) dbg[3] = dbg[2] = clock64();
-    if (is_right) { // U12 tile = L11^-1 * top rows: lane = row, two columns per warp
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c = 2 * warp + cc;
-            double x = lane < nb ? s_vals[lane][c] : 0.0;
-            for (int j = 0; j < nb; ++j) {
-                const double xj = __shfl_sync(0xffffffffu, x, j);
-                if (lane > j) x -= s_L[lane][j] * xj;
-            }
-            if (lane < nb) s_vals[lane][c] = x;
-            s_U[lane][c] = lane < nb ? x : 0.0;
-        }
-        __syncthreads();
-    }
-    if (dbgt) dbg[4] = clock64();
-    // scatter the window back
-    for (int t = tid; t < cnt * UT; t += UPD_THREADS) {
-        const int e = t / UT, c = c0 + (t % UT);
-        if (c < n) A[(size_t)c * lda + s_rows[e]] = s_vals[e][t % UT];
-    }
-    if (!is_right || !do_gemm) return;
-    __syncthreads(); // the pivot rows just written belong to the trailing matrix updated below
-    if (dbgt) dbg[5] = clock64();
-    // trailing update of this tile's columns: C[r][c] -= sum_k L21[r][k] * U12[k][c].  All 48 loads of a row are
-    // issued before the first FMA (unconditional, clamped addresses; rows k >= nb of s_U are zero).
-    const int r_begin = k0 + nb;
-    for (int r = r_begin + tid; r < n; r += UPD_THREADS) {
-        double l[NB], cv[UT];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) l[k] = A[(size_t)(k0 + min(k, nb - 1)) * lda + r];
-#pragma unroll
-        for (int c = 0; c < UT; ++c) cv[c] = A[(size_t)min(c0 + c, n - 1) * lda + r];
-        asm volatile("" ::: "memory");
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-#pragma unroll
-            for (int c = 0; c < UT; c += 2) {
-                const double2 u2 = *reinterpret_cast<const double2*>(&s_U[k][c]);
-                cv[c] -= l[k] * u2.x;
-                cv[c + 1] -= l[k] * u2.y;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < UT; ++c)
-            if (c0 + c < n) A[(size_t)(c0 + c) * lda + r] = cv[c];
-    }
-    if (dbgt) dbg[6] = clock64();
-}
-
-// Trailing update for tall trailing matrices: C[m2 x m2] -= L21[m2 x 32] * U12[32 x m2] with both operands staged in
-// shared memory (CTA tile 128 x 64, 8 x 4 outputs per thread), so L21 and U12 are read from L2 once per tile instead
-// of once per 16 columns.  The C tile is loaded up front and written once.
-constexpr int GM = 128, GN = 64;
-__global__ void __launch_bounds__(256) k_lu_gemm(double* __restrict__ A, int lda, int n, int k0, int nb)
-{
-    __shared__ __align__(16) double s_a[NB][GM]; // L21 tile [k][row]
-    __shared__ __align__(16) double s_b[NB][GN]; // U12 tile [k][col]
-    const int r0 = k0 + nb + blockIdx.x * GM;
-    const int c0 = k0 + nb + blockIdx.y * GN;
-    const int tid = threadIdx.x;
-    for (int t = tid; t < NB * GM; t += 256) {
-        const int rr = t % GM, k = t / GM;
-        s_a[k][rr] = (k < nb && r0 + rr < n) ? A[(size_t)(k0 + k) * lda + r0 + rr] : 0.0;
-    }
-    for (int t = tid; t < NB * GN; t += 256) {
-        const int k = t % NB, cc = t / NB;
-        s_b[k][cc] = (k < nb && c0 + cc < n) ? A[(size_t)(c0 + cc) * lda + k0 + k] : 0.0;
-    }
-    // thread tile: rows tr + 16 i (i < 8) so that the lanes of a warp touch consecutive rows (coalesced column-major
-    // accesses, conflict-free shared-memory reads), columns tc .. tc + 3
-    const int tr = tid % 16, tc = (tid / 16) * 4;
-    double acc[8][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            acc[i][j] = A[(size_t)min(c0 + tc + j, n - 1) * lda + min(r0 + tr + 16 * i, n - 1)]; // C tile, clamped addresses
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < NB; ++k) {
-        double a[8], b[4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = s_a[k][tr + 16 * i];
-#pragma unroll
-        for (int j = 0; j < 4; j += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(&s_b[k][tc + j]);
-            b[j] = t.x;
-            b[j + 1] = t.y;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] -= a[i] * b[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c0 + tc + j;
-        if (c >= n) continue;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = r0 + tr + 16 * i;
-            if (r < n) A[(size_t)c * lda + r] = acc[i][j];
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Symmetric positive definite fast path (Gaussian kernel, uniform radius): LU WITHOUT pivoting.
-// K + lambda I is SPD, so eliminating it in natural order is backward stable, and the Schur complement that the
-// polynomial rows leave behind, -P^T K^-1 P, is negative definite -- no row interchange is ever needed for the
-// saddle-point system [[K, P], [P^T, 0]].  Without a pivot search a block column needs no per-column reduction or
-// barrier across the rows: every CTA factors the 32 x 32 diagonal block redundantly in shared memory, then each
-// thread finishes one row of L21 (x U11^-1) or one column of U12 (L11^-1 x) on its own.  The factors have the same
-// layout as the pivoted path (unit-lower L, U, identity permutation), so the solve kernels are shared.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int NP_THREADS = 256;
-
-__global__ void __launch_bounds__(NP_THREADS) k_lu_nopiv_panel(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                               int* __restrict__ flags, double* __restrict__ pivstat)
-{
-    __shared__ __align__(16) double s_D[NB][NB + 2]; // diagonal block, row-major [r][c]; becomes L11 \ U11
-    __shared__ double s_inv[NB];
-    const int tid = threadIdx.x;
-    for (int t = tid; t < NB * NB; t += NP_THREADS) {
-        const int r = t % NB, c = t / NB;
-        s_D[r][c] = (r < nb && c < nb) ? A[(size_t)(k0 + c) * lda + k0 + r] : (r == c ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    // LU of the diagonal block: step j updates the (r > j, c > j) entries with the un-scaled column j; the column
-    // is scaled by 1/u_jj once at the end
-    for (int j = 0; j < NB; ++j) {
-        const double ujj = s_D[j][j];
-        const double inv = (ujj != 0.0 && isfinite(ujj)) ? fast_rcp(ujj) : 0.0;
-        if (tid == 0) s_inv[j] = inv;
-        for (int t = tid; t < NB * NB; t += NP_THREADS) {
-            const int r = t / NB, c = t % NB;
-            if (r > j && c > j) s_D[r][c] -= (s_D[r][j] * inv) * s_D[j][c];
-        }
-        __syncthreads();
-    }
-    if (blockIdx.x == 0 && tid == 0) {
-        double pmin = pivstat[0], pmax = pivstat[1];
-        for (int j = 0; j < nb; ++j) {
-            const double v = fabs(s_D[j][j]);
-            if (!(v > 0.0) || !isfinite(v)) {
-                if (flags[FD_FLAG_SINGULAR] == 0) flags[FD_FLAG_SINGULAR] = k0 + j + 1;
-            }
-            pmin = fmin(pmin, v);
-            pmax = fmax(pmax, v);
-        }
-        pivstat[0] = pmin;
-        pivstat[1] = pmax;
-    }
-    for (int t = tid; t < NB * NB; t += NP_THREADS) {
-        const int r = t / NB, c = t % NB;
-        if (r > c) s_D[r][c] *= s_inv[c];
-    }
-    __syncthreads();
-    const int m2 = n - k0 - nb; // rows below / columns right of the block
-    const int row_ctas = (m2 + NP_THREADS - 1) / NP_THREADS;
-    if (blockIdx.x == 0) { // write the factored diagonal block back
-        for (int t = tid; t < NB * NB; t += NP_THREADS) {
-            const int r = t % NB, c = t / NB;
-            if (r < nb && c < nb) A[(size_t)(k0 + c) * lda + k0 + r] = s_D[r][c];
-        }
-    }
-    if (m2 <= 0) return;
-    if ((int)blockIdx.x < row_ctas) {
-        // one row of L21 per thread: l = a U11^-1, i.e. forward substitution against the columns of U11
-        const int r = k0 + nb + blockIdx.x * NP_THREADS + tid;
-        if (r >= n) return;
-        double x[NB];
-#pragma unroll
-        for (int c = 0; c < NB; ++c) x[c] = A[(size_t)(k0 + min(c, nb - 1)) * lda + r];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const double l = x[j] * s_inv[j];
-            x[j] = l;
-#pragma unroll
-            for (int c = j + 1; c < NB; ++c) x[c] -= l * s_D[j][c];
-        }
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-            if (c < nb) A[(size_t)(k0 + c) * lda + r] = x[c];
-    } else {
-        // one column of U12 per thread: u = L11^-1 a (unit lower)
-        const int c = k0 + nb + (blockIdx.x - row_ctas) * NP_THREADS + tid;
-        if (c >= n) return;
-        double* col = A + (size_t)c * lda + k0;
-        double x[NB];
-#pragma unroll
-        for (int r = 0; r < NB; ++r) x[r] = col[min(r, nb - 1)];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const double xj = x[j];
-#pragma unroll
-            for (int r = j + 1; r < NB; ++r) x[r] -= s_D[r][j] * xj;
-        }
-#pragma unroll
-        for (int r = 0; r < NB; ++r)
-            if (r < nb) col[r] = x[r];
-    }
-}
-
-__global__ void k_lu_identity_perm(int n, int* __restrict__ ipiv, int* __restrict__ perm)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        ipiv[i] = i;
-        perm[i] = i;
-    }
-}
-
-// perm[i] = original row that ends up in row i after all interchanges (single CTA, shared-memory resident)
-__global__ void __launch_bounds__(256) k_lu_perm(const int* __restrict__ ipiv, int n, int* __restrict__ perm)
-{
-    extern __shared__ int s_perm[];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s_perm[i] = i;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < n; ++k) {
-            const int p = ipiv[k];
-            if (p != k) {
-                const int t = s_perm[k];
-                s_perm[k] = s_perm[p];
-                s_perm[p] = t;
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = s_perm[i];
-}
-
-__global__ void k_lu_init(int* flags, double* pivstat)
-{
-    if (threadIdx.x == 0) {
-        flags[FD_FLAG_SINGULAR] = 0;
-        flags[FD_FLAG_NONFINITE] = 0;
-        pivstat[0] = INFINITY;
-        pivstat[1] = 0.0;
-    }
-}
-
-} // namespace
-
-template <int RPT, bool CLUSTER>
-static cudaError_t launch_panel_cluster(cudaStream_t s, int cs, double* d_A, int lda, int n, int k0, int nb, int* d_ipiv,
-                                        int* d_flags, double* d_pivstat, int* d_win)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cs);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_lu_panel_cluster<RPT, CLUSTER>, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win);
-}
-
-// window of a panel whose kernel did not export it (fallback panel): same list + composition, one warp
-__global__ void __launch_bounds__(32) k_lu_window(const int* __restrict__ ipiv, int k0, int nb, int* __restrict__ win)
-{
-    __shared__ int s_rows[2 * NB], s_src[2 * NB], s_ib[NB];
-    const int lane = threadIdx.x;
-    if (lane < nb) s_rows[lane] = k0 + lane;
-    const int my_piv = lane < nb ? ipiv[k0 + lane] : 0;
-    int cnt = nb;
-    __syncwarp();
-    for (int j = 0; j < nb; ++j) {
-        const int p = __shfl_sync(0xffffffffu, my_piv, j);
-        int ib;
-        if (p < k0 + nb) {
-            ib = p - k0;
-        } else {
-            const bool hit = (nb + lane < cnt) && s_rows[nb + lane] == p;
-            const unsigned mask = __ballot_sync(0xffffffffu, hit);
-            if (mask) {
-                ib = nb + __ffs(mask) - 1;
-            } else {
-                if (lane == 0) s_rows[cnt] = p;
-                ib = cnt++;
-                __syncwarp();
-            }
-        }
-        if (lane == 0) s_ib[j] = ib;
-    }
-    s_src[lane] = lane;
-    s_src[lane + 32] = lane + 32;
-    __syncwarp();
-    if (lane == 0) {
-        for (int j = 0; j < nb; ++j) {
-            const int ib = s_ib[j];
-            if (ib != j) {
-                const int t = s_src[j];
-                s_src[j] = s_src[ib];
-                s_src[ib] = t;
-            }
-        }
-        win[0] = cnt;
-    }
-    __syncwarp();
-    for (int e = lane; e < 2 * NB; e += 32) {
-        win[1 + e] = e < cnt ? s_rows[e] : 0;
-        win[1 + 2 * NB + e] = e < cnt ? s_src[e] : e;
-    }
-}
+#define REAL float
+#define REAL2 float2
+#define FD_LU_NS lu_f32
+#include "fd_factor_impl.inl"
+#undef REAL
+#undef REAL2
+#undef FD_LU_NS
 
 cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                          double* d_pivstat, int* d_win)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_lu_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_MAX);
-        cudaFuncSetAttribute(k_lu_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(k_lu_panel_cluster<1, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        cudaFuncSetAttribute(k_lu_panel_cluster<2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        cudaFuncSetAttribute(k_lu_panel_cluster<3, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        attr_set = true;
-    }
-    cudaStream_t s = ctx->stream;
-    static long long* d_dbg = nullptr;
-    static const bool want_dbg = getenv("FD_LU_DEBUG") != nullptr;
-    if (want_dbg && !d_dbg) cudaMalloc(&d_dbg, 64);
-    k_lu_init<<<1, 32, 0, s>>>(d_flags, d_pivstat);
-    ctx->launches += 1;
-    cudaError_t e = cudaSuccess;
-    for (int k0 = 0; k0 < n && e == cudaSuccess; k0 += NB) {
-        const int nb = min(NB, n - k0);
-        const int m = n - k0;
-        // smallest cluster (1, 2, 4, 8, 16 CTAs) x rows per thread (1..3) that holds the m panel rows in registers
-        int cs = 0, rpt = 0;
-        for (int c = 1; c <= 16 && !cs; c *= 2)
-            for (int r = 1; r <= 3; ++r)
-                if (m <= c * 256 * r) { cs = c; rpt = r; break; }
-        if (cs) {
-            if (cs == 1)
-                e = rpt == 1 ? launch_panel_cluster<1, false>(s, 1, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win)
-                  : rpt == 2 ? launch_panel_cluster<2, false>(s, 1, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win)
-                             : launch_panel_cluster<3, false>(s, 1, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win);
-            else
-                e = rpt == 1 ? launch_panel_cluster<1, true>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win)
-                  : rpt == 2 ? launch_panel_cluster<2, true>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win)
-                             : launch_panel_cluster<3, true>(s, cs, d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat, d_win);
-        } else { // taller than 12288 rows: panel through global memory, then its own interchanges are already applied
-            k_lu_panel<false><<<1, PANEL_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_ipiv, d_flags, d_pivstat);
-            k_lu_window<<<1, 32, 0, s>>>(d_ipiv, k0, nb, d_win);
-            ctx->launches += 1;
-            e = cudaGetLastError();
-        }
-        ctx->launches += 1;
-        if (e != cudaSuccess) break;
-        const int m2 = n - k0 - nb;
-        const bool big = m2 >= 512; // tall trailing matrix: interchanges + TRSM fused, GEMM by the shared-memory-tiled kernel
-        k_lu_update<<<(n + UT - 1) / UT, UPD_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_win, big ? 0 : 1, k0 == 0 ? d_dbg : nullptr);
-        ctx->launches += 1;
-        if (big) {
-            dim3 grid((m2 + GM - 1) / GM, (m2 + GN - 1) / GN);
-            k_lu_gemm<<<grid, 256, 0, s>>>(d_A, lda, n, k0, nb);
-            ctx->launches += 1;
-        }
-        e = cudaGetLastError();
-    }
-    if (e != cudaSuccess) return e;
-    if (want_dbg) {
-        long long h[8];
-        cudaStreamSynchronize(s);
-        cudaMemcpy(h, d_dbg, 56, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[fd_lu] n=%d update(k0=0) cycles: list %lld gather %lld replay %lld trsm %lld scatter %lld gemm %lld\n", n,
-                h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
-    }
-    if ((size_t)n * sizeof(int) > 64 * 1024) return cudaErrorInvalidValue;
-    k_lu_perm<<<1, 256, (size_t)n * sizeof(int), s>>>(d_ipiv, n, d_perm);
-    ctx->launches += 1;
-    return cudaGetLastError();
+    return lu_f64::launch_lu(ctx, d_A, lda, n, d_ipiv, d_perm, d_flags, d_pivstat, d_win);
 }
-
-// LU without pivoting for the symmetric positive definite case (see k_lu_nopiv_panel)
 cudaError_t fd_launch_lu_nopivot(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                                  double* d_pivstat)
 {
-    cudaStream_t s = ctx->stream;
-    k_lu_init<<<1, 32, 0, s>>>(d_flags, d_pivstat);
-    k_lu_identity_perm<<<(n + 255) / 256, 256, 0, s>>>(n, d_ipiv, d_perm);
-    ctx->launches += 2;
-    for (int k0 = 0; k0 < n; k0 += NB) {
-        const int nb = min(NB, n - k0);
-        const int m2 = n - k0 - nb;
-        const int ctas = m2 > 0 ? 2 * ((m2 + NP_THREADS - 1) / NP_THREADS) : 1;
-        k_lu_nopiv_panel<<<ctas, NP_THREADS, 0, s>>>(d_A, lda, n, k0, nb, d_flags, d_pivstat);
-        ctx->launches += 1;
-        if (m2 > 0) {
-            dim3 grid((m2 + GM - 1) / GM, (m2 + GN - 1) / GN);
-            k_lu_gemm<<<grid, 256, 0, s>>>(d_A, lda, n, k0, nb);
-            ctx->launches += 1;
-        }
-    }
-    return cudaGetLastError();
+    return lu_f64::launch_lu_nopivot(ctx, d_A, lda, n, d_ipiv, d_perm, d_flags, d_pivstat);
+}
+cudaError_t fd_launch_lu_f32(fd_ctx* ctx, float* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
+                             double* d_pivstat, int* d_win)
+{
+    return lu_f32::launch_lu(ctx, d_A, lda, n, d_ipiv, d_perm, d_flags, d_pivstat, d_win);
+}
+cudaError_t fd_launch_lu_nopivot_f32(fd_ctx* ctx, float* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
+                                     double* d_pivstat)
+{
+    return lu_f32::launch_lu_nopivot(ctx, d_A, lda, n, d_ipiv, d_perm, d_flags, d_pivstat);
 }
