@@ -226,6 +226,10 @@ int fd_ctx_create(fd_ctx** out, int device, void* stream)
         cudaEventCreate(&ctx->ev_begin[i]);
         cudaEventCreate(&ctx->ev_end[i]);
     }
+    if (cudaMalloc(&ctx->d_sync, 256) != cudaSuccess || cudaMemset(ctx->d_sync, 0, 256) != cudaSuccess) {
+        fd_ctx_destroy(ctx);
+        return FD_E_CUDA;
+    }
     { // keep freed blocks cached in the device's default pool instead of returning them to the driver
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -244,6 +248,7 @@ void fd_ctx_destroy(fd_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < FD_NUM_STAGE; ++i)
         if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
+    if (ctx->d_sync) cudaFree(ctx->d_sync);
     for (int i = 0; i < FD_PH_COUNT; ++i) {
         cudaEventDestroy(ctx->ev_begin[i]);
         cudaEventDestroy(ctx->ev_end[i]);
@@ -309,10 +314,16 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
     phase_begin(ctx, FD_PH_FACTOR);
     // Gaussian kernel with one radius: K + lambda I is symmetric positive definite -> no pivot search needed
     const bool spd = m->prm.kernel == FD_KERNEL_GAUSSIAN && (m->prm.model == FD_MODEL_ML || m->N == 1) && !getenv("FD_FORCE_PIVOTED_LU");
-    if (e == cudaSuccess)
-        e = spd ? fd_launch_lu_nopivot(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat)
-                : fd_launch_lu(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_win);
-    if (e == cudaSuccess) e = fd_launch_invdiag(ctx, m);
+    const bool unfused = getenv("FD_LU_UNFUSED") != nullptr; // per-block-column launches (kept for comparison)
+    if (e == cudaSuccess) {
+        if (spd && !unfused) {
+            e = fd_launch_lu_nopivot_fused(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_Tinv);
+        } else {
+            e = spd ? fd_launch_lu_nopivot(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat)
+                    : fd_launch_lu(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_win);
+            if (e == cudaSuccess) e = fd_launch_invdiag(ctx, m);
+        }
+    }
     phase_end(ctx, FD_PH_FACTOR);
     if (e != cudaSuccess) {
         FD_SET_ERR(ctx, "fit: %s", cudaGetErrorString(e));

@@ -58,6 +58,11 @@ cudaError_t fd_launch_lu_nopivot(fd_ctx* ctx, double* d_A, int lda, int n, int* 
 {
     return lu_f64::launch_lu_nopivot(ctx, d_A, lda, n, d_ipiv, d_perm, d_flags, d_pivstat);
 }
+cudaError_t fd_launch_lu_nopivot_fused(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
+                                       double* d_pivstat, double* d_Tinv)
+{
+    return lu_f64::launch_lu_nopivot_fused(ctx, d_A, lda, n, d_ipiv, d_perm, d_flags, d_pivstat, d_Tinv);
+}
 cudaError_t fd_launch_lu_f32(fd_ctx* ctx, float* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                              double* d_pivstat, int* d_win)
 {

@@ -785,6 +785,488 @@ cudaError_t launch_lu(fd_ctx* ctx, REAL* d_A, int lda, int n, int* d_ipiv, int* 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused persistent no-pivot LU: the whole factorisation in ONE launch.
+//
+// For small systems the per-block-column launches above cost more than the arithmetic (N = 256: 17 launches of ~18 us
+// for 12 Mflop).  Here a fixed set of CTAs walks all block columns and synchronises with a barrier instead of a launch
+// boundary: one thread-block cluster (<= 16 CTAs, hardware barrier.cluster, ~0.3 us) for n <= 512, otherwise a
+// cooperative grid of one CTA per SM with a release/acquire counter barrier in global memory.  The matrix stays in
+// L2 / HBM (column-major, in place); all loads of it bypass L1 (ld.global.cg / cp.async.cg).
+//
+// Two-level blocking (outer block nbo, inner NB = 32) keeps the big trailing update compute bound: a rank-32 update
+// of an m x m FP64 matrix moves 16 bytes per 64 flop (HBM bound above ~3000 rows); inside an outer block only the
+// L-shaped border (column panel m x nbo, row panel nbo x m) is updated with K = 32, and the interior takes one
+// C -= L21 * U12 with K = nbo.  nbo = 32 degenerates to the plain right-looking algorithm (empty L-shape).
+//   per inner step : diagonal 32 x 32 block factored redundantly by warp 0 of every CTA (registers + shuffles,
+//                    ~100 cycles per pivot: the critical path of the whole kernel), then one row of L21 (x U11^-1)
+//                    or one column of U12 (L11^-1 x) per thread, barrier, L-shape update, barrier
+//   per outer step : interior update (128 x 128 or 64 x 64 CTA tiles, 8 x 8 / 4 x 4 per thread, K chunks of 16
+//                    double-buffered with cp.async), barrier
+// The inverted diagonal blocks the slab solve wants (k_lu_invdiag) are produced on the way by two spare warps.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FZ_THREADS = 256;
+constexpr int FZ_KC = 16;          // K chunk of the tile product
+constexpr int FZ_LDB = FZ_KC + 2;  // row stride of the U12 stage ([col][k], k contiguous)
+constexpr int FZ_TMAX = 128;       // largest CTA tile edge
+constexpr int FZ_SMEM_REALS = 2 * FZ_KC * FZ_TMAX + 2 * FZ_TMAX * FZ_LDB + 2 * NB * NB + NB;
+
+__device__ __forceinline__ void fz_cp_async(REAL* smem_dst, const REAL* gsrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(REAL2) == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fz_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void fz_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <bool CLUSTER>
+__device__ __forceinline__ void fz_barrier(unsigned* counter, unsigned& target, unsigned G)
+{
+    if (CLUSTER) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += G;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            } while ((int)(v - target) < 0);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+// C[r0:r0+TM, c0:c0+TN] -= A[r0:, ka:kb] * A[ka:kb, c0:]; stores clipped to rows < r1, columns < c1.  kb - ka is a
+// multiple of 16, r0 / ka of 32.  Loads beyond the matrix are clamped to valid addresses (their results are dropped).
+template <int TM, int TN>
+__device__ __forceinline__ void fz_gemm_tile(REAL* A, int lda, int n, int r0, int r1, int c0, int c1, int ka, int kb,
+                                             REAL* s_a, REAL* s_b)
+{
+    constexpr int TMt = TM / 16, TNt = TN / 16, MP = TMt / 2;
+    const int tid = threadIdx.x, tr = tid & 15, tcg = tid >> 4;
+    REAL acc[TMt][TNt];
+#pragma unroll
+    for (int j = 0; j < TNt; ++j) {
+        const int c = min(c0 + tcg + 16 * j, n - 1);
+#pragma unroll
+        for (int i = 0; i < MP; ++i) {
+            const int r = min(r0 + 2 * tr + 32 * i, lda - 2);
+            const REAL2 v = __ldcg(reinterpret_cast<const REAL2*>(A + (size_t)c * lda + r));
+            acc[2 * i][j] = v.x;
+            acc[2 * i + 1][j] = v.y;
+        }
+    }
+    auto issue = [&](int kc, int st) {
+        REAL* sa = s_a + st * FZ_KC * FZ_TMAX;
+        for (int t = tid; t < FZ_KC * (TM / 2); t += FZ_THREADS) {
+            const int kk = t / (TM / 2), q = t % (TM / 2);
+            const int r = min(r0 + 2 * q, lda - 2);
+            fz_cp_async(sa + kk * FZ_TMAX + 2 * q, A + (size_t)(ka + kc + kk) * lda + r);
+        }
+        REAL* sb = s_b + st * FZ_TMAX * FZ_LDB;
+        for (int t = tid; t < TN * (FZ_KC / 2); t += FZ_THREADS) {
+            const int cc = t / (FZ_KC / 2), q = t % (FZ_KC / 2);
+            const int c = min(c0 + cc, n - 1);
+            fz_cp_async(sb + cc * FZ_LDB + 2 * q, A + (size_t)c * lda + ka + kc + 2 * q);
+        }
+        fz_cp_commit();
+    };
+    const int nch = (kb - ka) / FZ_KC;
+    issue(0, 0);
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) {
+            issue((ch + 1) * FZ_KC, (ch + 1) & 1);
+            fz_cp_wait<1>();
+        } else {
+            fz_cp_wait<0>();
+        }
+        __syncthreads();
+        const REAL* sa = s_a + (ch & 1) * FZ_KC * FZ_TMAX + 2 * tr;
+        const REAL* sb = s_b + (ch & 1) * FZ_TMAX * FZ_LDB + tcg * FZ_LDB;
+#pragma unroll 2
+        for (int kk = 0; kk < FZ_KC; kk += 2) {
+            REAL2 a0[MP], a1[MP], b[TNt];
+#pragma unroll
+            for (int i = 0; i < MP; ++i) {
+                a0[i] = *reinterpret_cast<const REAL2*>(sa + kk * FZ_TMAX + 32 * i);
+                a1[i] = *reinterpret_cast<const REAL2*>(sa + (kk + 1) * FZ_TMAX + 32 * i);
+            }
+#pragma unroll
+            for (int j = 0; j < TNt; ++j) b[j] = *reinterpret_cast<const REAL2*>(sb + 16 * j * FZ_LDB + kk);
+#pragma unroll
+            for (int i = 0; i < MP; ++i)
+#pragma unroll
+                for (int j = 0; j < TNt; ++j) {
+                    acc[2 * i][j] -= a0[i].x * b[j].x;
+                    acc[2 * i + 1][j] -= a0[i].y * b[j].x;
+                }
+#pragma unroll
+            for (int i = 0; i < MP; ++i)
+#pragma unroll
+                for (int j = 0; j < TNt; ++j) {
+                    acc[2 * i][j] -= a1[i].x * b[j].y;
+                    acc[2 * i + 1][j] -= a1[i].y * b[j].y;
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < TNt; ++j) {
+        const int c = c0 + tcg + 16 * j;
+        if (c >= c1) continue;
+#pragma unroll
+        for (int i = 0; i < MP; ++i) {
+            const int r = r0 + 2 * tr + 32 * i;
+            REAL* dst = A + (size_t)c * lda + r;
+            if (r + 1 < r1)
+                __stcg(reinterpret_cast<REAL2*>(dst), fd_make2(acc[2 * i][j], acc[2 * i + 1][j]));
+            else if (r < r1)
+                __stcg(dst, acc[2 * i][j]);
+        }
+    }
+}
+
+// One K range applied to up to two rectangular regions (the L-shaped border: column panel + row panel; or the
+// interior alone), tiles dealt round-robin to the CTAs.  One call site per tile size keeps the kernel's code small:
+// every phase runs once per block step, so code that does not fit the instruction cache runs at fetch speed.
+struct FzRegions {
+    int ra0, ra1, ca0, ca1; // region a: rows [ra0, ra1) x columns [ca0, ca1)
+    int rb0, rb1, cb0, cb1; // region b
+    int ka, kb;
+};
+
+template <int T>
+__device__ __noinline__ void fz_update(REAL* A, int lda, int n, const FzRegions R, REAL* s_a, REAL* s_b)
+{
+    const int ta_r = R.ra1 > R.ra0 && R.ca1 > R.ca0 ? (R.ra1 - R.ra0 + T - 1) / T : 0;
+    const int ta = ta_r * ((R.ca1 - R.ca0 + T - 1) / T);
+    const int tb_r = R.rb1 > R.rb0 && R.cb1 > R.cb0 ? (R.rb1 - R.rb0 + T - 1) / T : 0;
+    const int tb = tb_r * ((R.cb1 - R.cb0 + T - 1) / T);
+    for (int t = blockIdx.x; t < ta + tb; t += gridDim.x) {
+        int r0, r1, c0, c1;
+        if (t < ta) {
+            r0 = R.ra0 + (t % ta_r) * T, r1 = R.ra1, c0 = R.ca0 + (t / ta_r) * T, c1 = R.ca1;
+        } else {
+            r0 = R.rb0 + ((t - ta) % tb_r) * T, r1 = R.rb1, c0 = R.cb0 + ((t - ta) / tb_r) * T, c1 = R.cb1;
+        }
+        fz_gemm_tile<T, T>(A, lda, n, r0, r1, c0, c1, R.ka, R.kb, s_a, s_b);
+    }
+}
+
+__device__ __forceinline__ int fz_tiles(const FzRegions& R, int T)
+{
+    const int ta = R.ra1 > R.ra0 && R.ca1 > R.ca0 ? ((R.ra1 - R.ra0 + T - 1) / T) * ((R.ca1 - R.ca0 + T - 1) / T) : 0;
+    const int tb = R.rb1 > R.rb0 && R.cb1 > R.cb0 ? ((R.rb1 - R.rb0 + T - 1) / T) * ((R.cb1 - R.cb0 + T - 1) / T) : 0;
+    return ta + tb;
+}
+
+// x <- x * U11^-1 for a row vector held by one thread (s_U[j][c] = U11[j][c], s_inv[j] = 1 / u_jj); fully unrolled,
+// static register indices, the row of U11 is a broadcast read.
+__device__ __forceinline__ void fz_row_solve(REAL (&x)[NB], const REAL* s_U, const REAL* s_inv)
+{
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        const REAL l = x[j] * s_inv[j];
+        x[j] = l;
+#pragma unroll
+        for (int c = 0; c < NB; c += 2) {
+            if (c + 1 > j) { // pair (c, c+1): at least c+1 lies right of the pivot column
+                const REAL2 u = *reinterpret_cast<const REAL2*>(s_U + j * NB + c);
+                if (c > j) x[c] -= l * u.x;
+                x[c + 1] -= l * u.y;
+            }
+        }
+    }
+}
+
+// x <- L11^-1 x for a column vector held by one thread (s_Lt[j][r] = L11[r][j], unit diagonal)
+__device__ __forceinline__ void fz_col_solve(REAL (&x)[NB], const REAL* s_Lt)
+{
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        const REAL xj = x[j];
+#pragma unroll
+        for (int r = 0; r < NB; r += 2) {
+            if (r + 1 > j) {
+                const REAL2 l2 = *reinterpret_cast<const REAL2*>(s_Lt + j * NB + r);
+                if (r > j) x[r] -= l2.x * xj;
+                x[r + 1] -= l2.y * xj;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ REAL fz_safe_rcp(REAL p) { return (p != (REAL)0 && isfinite(p)) ? fast_rcp(p) : (REAL)0; }
+
+template <bool CLUSTER>
+__global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int lda, int n, int nbo, int* ipiv, int* perm,
+                                                                  int* flags, double* pivstat, double* Tinv,
+                                                                  unsigned* sync_counter, unsigned sync_base, int dbg)
+{
+    extern __shared__ __align__(16) unsigned char fz_smem_raw[];
+    long long tprobe[12];
+    int tstep = 0;
+#define FZ_PROBE(i) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0 && tstep == dbg) tprobe[i] = clock64(); } while (0)
+    REAL* s_a = reinterpret_cast<REAL*>(fz_smem_raw);
+    REAL* s_b = s_a + 2 * FZ_KC * FZ_TMAX;
+    REAL* s_U = s_b + 2 * FZ_TMAX * FZ_LDB; // [NB][NB]: U11 (row j valid from column j & ~1 on)
+    REAL* s_Lt = s_U + NB * NB;             // [NB][NB]: s_Lt[j][r] = L11[r][j]
+    REAL* s_inv = s_Lt + NB * NB;           // 1 / u_jj
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned G = gridDim.x;
+    unsigned target = sync_base;
+    double pmin = INFINITY, pmax = 0.0;
+    int singular = 0;
+    if (blockIdx.x == 0)
+        for (int i = tid; i < n; i += FZ_THREADS) {
+            ipiv[i] = i;
+            perm[i] = i;
+        }
+    for (int K0 = 0; K0 < n; K0 += nbo) {
+        const int Kend = min(K0 + nbo, n);
+#pragma unroll 1
+        for (int k0 = K0; k0 < Kend; k0 += NB) {
+            const int nb = min(NB, n - k0);
+            const int ks = k0 + nb, m2 = n - ks;
+            const int ngr = (m2 + 31) >> 5; // groups of 32 rows of L21; as many groups of 32 columns of U12
+            ++tstep;
+            FZ_PROBE(0);
+            // Warp 0 factors the diagonal block and takes no L21 / U12 group; the branches are exclusive so that the
+            // preloaded x[] is not live (no registers reserved) inside the latency-critical pivot sequence.
+            if (warp == 0) {
+                FZ_PROBE(1);
+                // ---- diagonal block: lane = row, a[c] = A[lane][c]; fully unrolled (static register indices).  Row j
+                // is final at step j: its lane publishes it in shared memory, the rows below read it back as a
+                // broadcast.  The next pivot's reciprocal is started as soon as its element is updated, so the
+                // MUFU + Newton chain overlaps the rest of the rank-1 update.
+                REAL a[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    a[c] = (lane < nb && c < nb) ? __ldcg(A + (size_t)(k0 + c) * lda + k0 + lane) : (lane == c ? (REAL)1 : (REAL)0);
+                REAL mypiv = 1;
+                REAL p = __shfl_sync(0xffffffffu, a[0], 0);
+                REAL inv = fz_safe_rcp(p);
+                FZ_PROBE(9);
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    if (lane == j) {
+                        mypiv = p;
+                        s_inv[j] = inv;
+#pragma unroll
+                        for (int c = 0; c < NB; c += 2)
+                            if (c + 1 >= j) *reinterpret_cast<REAL2*>(s_U + j * NB + c) = fd_make2(a[c], a[c + 1]);
+                    }
+                    const REAL l = a[j] * inv; // meaningful for lanes > j; finished rows carry don't-care values
+                    s_Lt[j * NB + lane] = lane > j ? l : (lane == j ? (REAL)1 : (REAL)0);
+                    __syncwarp();
+                    if (j + 1 < NB) {
+                        a[j + 1] -= l * s_U[j * NB + j + 1];
+                        p = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+                        inv = fz_safe_rcp(p);
+#pragma unroll
+                        for (int c = 0; c < NB; c += 2) {
+                            if (c + 1 > j + 1) {
+                                const REAL2 u = *reinterpret_cast<const REAL2*>(s_U + j * NB + c);
+                                if (c > j + 1) a[c] -= l * u.x;
+                                a[c + 1] -= l * u.y;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                FZ_PROBE(10);
+                if (blockIdx.x == 0) {
+                    const double v = lane < nb ? fabs((double)mypiv) : 1.0;
+                    const bool bad = lane < nb && (!(v > 0.0) || !isfinite(v));
+                    const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+                    if (badmask && !singular) singular = k0 + __ffs(badmask);
+                    double lo = lane < nb ? v : INFINITY, hi = lane < nb ? v : 0.0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                    }
+                    pmin = fmin(pmin, lo);
+                    pmax = fmax(pmax, hi);
+                }
+                FZ_PROBE(2);
+                asm volatile("bar.sync 0;" ::: "memory");
+                FZ_PROBE(3);
+            } else {
+                // ---- L21 = A21 U11^-1 (one row per thread), U12 = L11^-1 A12 (one column per thread), in groups of
+                // 32 dealt round-robin to the warps 1..7 of all CTAs; the first group's loads are in flight while
+                // warp 0 factors.  Two more "groups" apply the same two solves to the identity: the inverses of U11
+                // and L11 that the slab solve (fd_solve.cu) multiplies with.
+                REAL x[NB];
+                const int ngroups = 2 * ngr + (Tinv != nullptr ? 2 : 0);
+                int g = (int)blockIdx.x + (int)G * (warp - 1);
+                auto load_group = [&](int gg) {
+                    if (gg < ngr) {
+                        const int r = min(ks + 32 * gg + lane, n - 1);
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) x[c] = __ldcg(A + (size_t)(k0 + c) * lda + r);
+                    } else if (gg < 2 * ngr) {
+                        const int c = min(ks + 32 * (gg - ngr) + lane, n - 1);
+                        const REAL2* src = reinterpret_cast<const REAL2*>(A + (size_t)c * lda + k0);
+#pragma unroll
+                        for (int r = 0; r < NB; r += 2) {
+                            const REAL2 v = __ldcg(src + r / 2);
+                            x[r] = v.x;
+                            x[r + 1] = v.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) x[c] = c == lane ? (REAL)1 : (REAL)0;
+                    }
+                };
+                if (g < ngroups) load_group(g);
+                asm volatile("bar.sync 0;" ::: "memory");
+                if (blockIdx.x == 0 && warp == 5 && lane < nb) { // the factored diagonal block goes back to the matrix
+#pragma unroll 1
+                    for (int c = 0; c < nb; ++c)
+                        __stcg(A + (size_t)(k0 + c) * lda + k0 + lane, c >= lane ? s_U[lane * NB + c] : s_Lt[c * NB + lane]);
+                }
+#pragma unroll 1
+                for (bool first = true; g < ngroups; g += (int)G * (FZ_THREADS / 32 - 1), first = false) {
+                    if (!first) load_group(g);
+                    const bool row_kind = g < ngr || g == 2 * ngr;
+                    if (row_kind)
+                        fz_row_solve(x, s_U, s_inv);
+                    else
+                        fz_col_solve(x, s_Lt);
+                    if (g < ngr) {
+                        const int r = ks + 32 * g + lane;
+                        if (r < n) {
+#pragma unroll
+                            for (int c = 0; c < NB; ++c) __stcg(A + (size_t)(k0 + c) * lda + r, x[c]);
+                        }
+                    } else if (g < 2 * ngr) {
+                        const int c = ks + 32 * (g - ngr) + lane;
+                        if (c < n) {
+                            REAL2* dst = reinterpret_cast<REAL2*>(A + (size_t)c * lda + k0);
+#pragma unroll
+                            for (int r = 0; r < NB; r += 2) __stcg(dst + r / 2, fd_make2(x[r], x[r + 1]));
+                        }
+                    } else if (g == 2 * ngr) { // x[c] = U11^-1[lane][c]; stored transposed: out[c * 32 + r] = inverse[r][c]
+                        double* out = Tinv + ((size_t)(k0 / NB) * 2 + 1) * NB * NB;
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) out[c * NB + lane] = (double)x[c];
+                    } else { // x[r] = L11^-1[r][lane]
+                        double* out = Tinv + ((size_t)(k0 / NB) * 2) * NB * NB + lane * NB;
+#pragma unroll
+                        for (int r = 0; r < NB; ++r) out[r] = (double)x[r];
+                    }
+                }
+            }
+            if (m2 <= 0) break;
+            FZ_PROBE(5);
+            fz_barrier<CLUSTER>(sync_counter, target, G);
+            FZ_PROBE(6);
+            // ---- L-shaped border of the outer block, K = 32
+            if (ks < Kend) {
+                const FzRegions R = {ks, n, ks, Kend, ks, Kend, Kend, n, k0, ks};
+                if (fz_tiles(R, 128) >= 2 * (int)G)
+                    fz_update<128>(A, lda, n, R, s_a, s_b);
+                else
+                    fz_update<64>(A, lda, n, R, s_a, s_b);
+                fz_barrier<CLUSTER>(sync_counter, target, G);
+            }
+        }
+        if (Kend < n) {
+            // ---- interior of the trailing matrix, K = nbo
+            const FzRegions R = {Kend, n, Kend, n, 0, 0, 0, 0, K0, Kend};
+            if (fz_tiles(R, 128) >= (int)G)
+                fz_update<128>(A, lda, n, R, s_a, s_b);
+            else
+                fz_update<64>(A, lda, n, R, s_a, s_b);
+            FZ_PROBE(7);
+            fz_barrier<CLUSTER>(sync_counter, target, G);
+            FZ_PROBE(8);
+        }
+    }
+    if (dbg && blockIdx.x == 0 && tid == 0 && tstep >= dbg)
+        printf("[fz] n=%d step %d cycles: diag %lld (loads %lld loop %lld tail %lld) sync %lld bar1 %lld update %lld bar2 %lld\n", n, dbg,
+               tprobe[2] - tprobe[1], tprobe[9] - tprobe[1], tprobe[10] - tprobe[9], tprobe[2] - tprobe[10], tprobe[3] - tprobe[2],
+               tprobe[6] - tprobe[5], tprobe[7] - tprobe[6], tprobe[8] - tprobe[7]);
+#undef FZ_PROBE
+    if (blockIdx.x == 0 && tid == 0) {
+        flags[FD_FLAG_SINGULAR] = singular;
+        flags[FD_FLAG_NONFINITE] = 0;
+        pivstat[0] = pmin;
+        pivstat[1] = pmax;
+    }
+}
+
+// number of barriers k_lu_nopiv_fused executes for (n, nbo): the host advances the counter base by G times this
+static unsigned fz_barrier_count(int n, int nbo)
+{
+    unsigned cnt = 0;
+    for (int K0 = 0; K0 < n; K0 += nbo) {
+        const int Kend = min(K0 + nbo, n);
+        for (int k0 = K0; k0 < Kend; k0 += NB) {
+            const int nb = min(NB, n - k0), ks = k0 + nb;
+            if (n - ks <= 0) break;
+            cnt += 1;
+            if (ks < Kend) cnt += 1;
+        }
+        if (Kend < n) cnt += 1;
+    }
+    return cnt;
+}
+
+cudaError_t launch_lu_nopivot_fused(fd_ctx* ctx, REAL* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
+                                    double* d_pivstat, double* d_Tinv)
+{
+    static bool attr_set = false;
+    const size_t smem = (size_t)FZ_SMEM_REALS * sizeof(REAL);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_lu_nopiv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_lu_nopiv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_lu_nopiv_fused<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        attr_set = true;
+    }
+    const char* env_dbg = getenv("FD_LU_DEBUG");
+    int dbg = env_dbg ? atoi(env_dbg) : 0;
+    const char* env_nbo = getenv("FD_LU_NBO");
+    const char* env_cluster_max = getenv("FD_LU_CLUSTER_MAX_N");
+    const int cluster_max_n = env_cluster_max ? atoi(env_cluster_max) : 512;
+    int nbo = env_nbo ? atoi(env_nbo) : (n <= 1536 ? 32 : (n <= 3072 ? 128 : 256));
+    nbo = max(NB, nbo / NB * NB);
+    cudaStream_t s = ctx->stream;
+    unsigned base = ctx->sync_base;
+    if (n <= cluster_max_n) {
+        // one cluster: 4 CTAs up to n = 64, 8 up to 128, else 16
+        const int cs = n <= 64 ? 4 : (n <= 128 ? 8 : 16);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs);
+        cfg.blockDim = dim3(FZ_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ctx->launches += 1;
+        return cudaLaunchKernelEx(&cfg, k_lu_nopiv_fused<true>, d_A, lda, n, nbo, d_ipiv, d_perm, d_flags, d_pivstat, d_Tinv,
+                                  ctx->d_sync, base, dbg);
+    }
+    const int G = ctx->sm_count;
+    ctx->sync_base = base + (unsigned)G * fz_barrier_count(n, nbo);
+    void* args[] = {&d_A, &lda, &n, &nbo, &d_ipiv, &d_perm, &d_flags, &d_pivstat, &d_Tinv, &ctx->d_sync, &base, &dbg};
+    ctx->launches += 1;
+    return cudaLaunchCooperativeKernel((const void*)k_lu_nopiv_fused<false>, dim3(G), dim3(FZ_THREADS), args, smem, s);
+}
+
 // LU without pivoting for the symmetric positive definite case (see k_lu_nopiv_panel)
 cudaError_t launch_lu_nopivot(fd_ctx* ctx, REAL* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                                  double* d_pivstat)

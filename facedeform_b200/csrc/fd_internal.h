@@ -37,6 +37,9 @@ struct fd_ctx {
     // host<->device staging owned by the ctx (grown on demand)
     void* stage_dev[FD_NUM_STAGE];
     size_t stage_bytes[FD_NUM_STAGE];
+    // grid-barrier counter of the persistent factorisation kernels: monotonic, the host tracks its value (sync_base)
+    unsigned* d_sync;
+    unsigned sync_base;
 };
 
 struct fd_model {
@@ -102,6 +105,9 @@ cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, 
                          double* d_pivstat, int* d_win);
 cudaError_t fd_launch_lu_nopivot(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                                  double* d_pivstat);
+// one persistent launch; also writes the inverted diagonal blocks (d_Tinv) the slab solve uses
+cudaError_t fd_launch_lu_nopivot_fused(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
+                                       double* d_pivstat, double* d_Tinv);
 // fd_solve.cu
 cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_deform, int F);
 cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);
