@@ -5,6 +5,8 @@
 // and the solve inside alglib::rbfbuildmodel (:363).  Right-hand sides / weights live row-major as
 // (N + npoly) x ldw doubles, column 3f + k = frame f, axis k, so one row is one control point's weights for
 // every frame -- the layout the evaluation kernels stage.
+#include <stdlib.h>
+
 #include "fd_internal.h"
 
 namespace {
@@ -273,6 +275,155 @@ __global__ void __launch_bounds__(SLAB_THREADS) k_solve_slab(const double* __res
     }
 }
 
+// ---- slab solve on the FP64 tensor pipe -----------------------------------------------------------------------------
+// One CTA owns 8 right-hand-side columns (one n8 tile of mma.sync.m8n8k4.f64) for the whole forward / backward sweep.
+// The slab [n_pad][8] lives in shared memory.  Per 32-row block step: the diagonal block is applied through its
+// pre-computed inverse (4 warps, one m8 tile each), then every row outside the block takes  B_i -= T_i,k * X_k  with
+// the L (or U) panel streamed from L2 in 128-row chunks, double buffered with cp.async so that the round trips hide
+// behind the previous chunk's DMMAs.  A DMMA needs 2 operand loads per 256 FMA (the X fragments stay in registers for
+// the whole step), which takes the shared-memory pipe off the critical path that bounded the DFMA version.
+constexpr int S8_RC = 8;
+constexpr int S8_THREADS = 256;
+constexpr int S8_CH = 128;           // panel rows per chunk
+constexpr int S8_LDP = S8_CH + 8;    // chunk row stride [k][row]: = 8 mod 16 keeps the A-fragment loads conflict free
+constexpr int S8_LDT = SB + 8;       // same for the inverted diagonal block
+constexpr int S8_CHUNK_DOUBLES = SB * S8_LDP;
+constexpr int S8_TINV_DOUBLES = SB * S8_LDT;
+
+__device__ __forceinline__ void dmma8(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// chunk of the panel of block column k0: rows [r0, r0 + 128) x columns [k0, k0 + 32) -> s_P[k][row]
+__device__ __forceinline__ void s8_prefetch_chunk(double* s_P, const double* __restrict__ A, int lda, int k0, int nb, int r0)
+{
+    for (int t = threadIdx.x; t < SB * (S8_CH / 2); t += S8_THREADS) {
+        const int kk = t / (S8_CH / 2), q = t % (S8_CH / 2);
+        const int r = min(r0 + 2 * q, lda - 2); // rows past the matrix: any valid address, their results are masked
+        cp_async16(s_P + kk * S8_LDP + 2 * q, A + (size_t)(k0 + min(kk, nb - 1)) * lda + r);
+    }
+}
+// transposed inverse of a diagonal block ([k][row], 32 x 32 doubles) -> padded rows
+__device__ __forceinline__ void s8_prefetch_tinv(double* s_T, const double* __restrict__ Tinv)
+{
+    for (int t = threadIdx.x; t < SB * SB / 2; t += S8_THREADS) {
+        const int kk = t / (SB / 2), q = t % (SB / 2);
+        cp_async16(s_T + kk * S8_LDT + 2 * q, Tinv + kk * SB + 2 * q);
+    }
+}
+
+__global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __restrict__ A, int lda, int n, int N,
+                                                            const int* __restrict__ perm, const float* __restrict__ rest,
+                                                            const float* __restrict__ deform, int F,
+                                                            const double* __restrict__ Tinv, double* __restrict__ W, int ldw)
+{
+    extern __shared__ __align__(16) double s8_smem[];
+    const int nblk = (n + SB - 1) / SB, n_pad = nblk * SB;
+    double* s_B = s8_smem;                           // [n_pad][8]
+    double* s_P = s_B + (size_t)n_pad * S8_RC;       // [2][32][S8_LDP]
+    double* s_T = s_P + 2 * S8_CHUNK_DOUBLES;        // [2][32][S8_LDT]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;         // fragment coordinates: row (or column) group, k within the k4 step
+    const int c0 = blockIdx.x * S8_RC;
+    const int nrhs = 3 * F;
+    s8_prefetch_tinv(s_T, Tinv); // block 0 of L
+    cp_async_commit();
+    // right-hand sides, permuted: delta subtracted in FP32 then widened (SOP_FaceDeform.cpp:276-284); pad rows are zero
+    for (int t = tid; t < n_pad * S8_RC; t += S8_THREADS) {
+        const int i = t / S8_RC, c = c0 + (t % S8_RC);
+        double v = 0.0;
+        if (i < n) {
+            const int src = perm[i];
+            if (c < nrhs && src < N) {
+                const int f = c / 3, k = c - 3 * f;
+                v = (double)(deform[((size_t)f * N + src) * 3 + k] - rest[3 * src + k]);
+            }
+        }
+        s_B[t] = v;
+    }
+    int tbuf = 0, pbuf = 0;
+    // 2 * nblk block steps: L sweep down, then U sweep up
+    for (int step = 0; step < 2 * nblk; ++step) {
+        const bool lower = step < nblk;
+        const int blk = lower ? step : 2 * nblk - 1 - step;
+        const int k0 = blk * SB, nb = min(SB, n - k0);
+        const int row_lo = lower ? k0 + SB : 0, row_hi = lower ? n : k0; // rows outside the block that depend on it
+        const int nchunks = row_hi > row_lo ? (row_hi - row_lo + S8_CH - 1) / S8_CH : 0;
+        // prefetch: first panel chunk of this step and the inverse of the next step's block (one cp.async group)
+        if (nchunks > 0) s8_prefetch_chunk(s_P + pbuf * S8_CHUNK_DOUBLES, A, lda, k0, nb, row_lo);
+        if (step + 1 < 2 * nblk) {
+            const int nblk_next = step + 1 < nblk ? step + 1 : 2 * nblk - 2 - step;
+            s8_prefetch_tinv(s_T + (tbuf ^ 1) * S8_TINV_DOUBLES, Tinv + ((size_t)nblk_next * 2 + (step + 1 < nblk ? 0 : 1)) * SB * SB);
+        }
+        cp_async_commit();
+        cp_async_wait<1>(); // everything but the group just issued: this step's inverse has landed
+        __syncthreads();    // ... for every thread; the slab updates of the previous step are visible
+        // ---- X_k = T_kk^-1 B_k: warps 0..3, one m8 tile each
+        double x0 = 0.0, x1 = 0.0;
+        if (warp < 4) {
+            const double* T = s_T + tbuf * S8_TINV_DOUBLES + 8 * warp + fr;
+#pragma unroll
+            for (int s4 = 0; s4 < SB / 4; ++s4) {
+                const double av = T[(4 * s4 + fk) * S8_LDT];
+                const double bv = s_B[(size_t)(k0 + 4 * s4 + fk) * S8_RC + fr];
+                dmma8(x0, x1, av, bv);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory"); // the four warps have read B_k
+            *reinterpret_cast<double2*>(s_B + (size_t)(k0 + 8 * warp + fr) * S8_RC + 2 * fk) = make_double2(x0, x1);
+        }
+        __syncthreads();
+        if (nchunks > 0) {
+            // X fragments of the whole block: 8 doubles per lane, reused by every row tile of the step
+            double xf[SB / 4];
+#pragma unroll
+            for (int s4 = 0; s4 < SB / 4; ++s4) xf[s4] = s_B[(size_t)(k0 + 4 * s4 + fk) * S8_RC + fr];
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int r0 = row_lo + ch * S8_CH;
+                if (ch + 1 < nchunks) {
+                    s8_prefetch_chunk(s_P + (pbuf ^ 1) * S8_CHUNK_DOUBLES, A, lda, k0, nb, r0 + S8_CH);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncthreads();
+                const double* P = s_P + pbuf * S8_CHUNK_DOUBLES;
+#pragma unroll
+                for (int tt = 0; tt < S8_CH / 8 / (S8_THREADS / 32); ++tt) {
+                    const int tile = warp + (S8_THREADS / 32) * tt;
+                    const int i0 = r0 + 8 * tile;
+                    if (i0 < row_hi) {
+                        double a0 = 0.0, a1 = 0.0;
+                        const double* Pt = P + 8 * tile + fr;
+#pragma unroll
+                        for (int s4 = 0; s4 < SB / 4; ++s4) dmma8(a0, a1, Pt[(4 * s4 + fk) * S8_LDP], xf[s4]);
+                        if (i0 + fr < row_hi) {
+                            double2* dst = reinterpret_cast<double2*>(s_B + (size_t)(i0 + fr) * S8_RC + 2 * fk);
+                            double2 v = *dst;
+                            v.x -= a0;
+                            v.y -= a1;
+                            *dst = v;
+                        }
+                    }
+                }
+                __syncthreads(); // chunk buffer free for the prefetch after next
+                pbuf ^= 1;
+            }
+        }
+        tbuf ^= 1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int t = tid; t < n * S8_RC; t += S8_THREADS) {
+        const int i = t / S8_RC, c = c0 + (t % S8_RC);
+        if (c < ldw) W[(size_t)i * ldw + c] = s_B[t];
+    }
+}
+
 // weights -> evaluation tables.  FP32: centre table (cx, cy, cz, kernel parameter) and weights n x ldw32;
 // FP64 centre table when the evaluation runs in double.  Flags non-finite weights.
 __global__ void __launch_bounds__(256) k_pack_tables(const float* __restrict__ rest, const double* __restrict__ radii,
@@ -317,6 +468,22 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_defor
 {
     cudaStream_t s = ctx->stream;
     const int n = m->n, nrhs = 3 * F, ldw = m->ldw;
+    {
+        // FP64 tensor-pipe slab solve: 8 right-hand sides per CTA
+        const int n_pad = fd_round_up(n, SB);
+        const size_t bytes8 = ((size_t)n_pad * S8_RC + 2 * S8_CHUNK_DOUBLES + 2 * S8_TINV_DOUBLES) * sizeof(double);
+        if (bytes8 <= 220 * 1024 && !getenv("FD_SOLVE_DFMA")) {
+            static bool attr8_set = false;
+            if (!attr8_set) {
+                cudaFuncSetAttribute(k_solve_slab8, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                attr8_set = true;
+            }
+            k_solve_slab8<<<(ldw + S8_RC - 1) / S8_RC, S8_THREADS, bytes8, s>>>(m->d_A, m->lda, n, m->N, m->d_perm, m->d_rest,
+                                                                               d_deform, F, m->d_Tinv, m->d_W, ldw);
+            ctx->launches += 1;
+            return cudaGetLastError();
+        }
+    }
     const size_t slab_bytes = (size_t)n * RC * sizeof(double);
     if (slab_bytes <= 200 * 1024 && (nrhs >= 2 * RC || n <= 1024)) {
         // one launch: every CTA solves its 16 right-hand sides start to finish out of shared memory
