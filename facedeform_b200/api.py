@@ -8,6 +8,7 @@ solve = the per-frame deltas, eval = the vertex loop, capture = ProximityCapture
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -82,9 +83,12 @@ class Context:
         if st != FD_OK:
             raise FdError(st, "fd_ctx_create failed (no B200 visible?)")
         self._h = h
+        self._models = weakref.WeakSet()   # live models: destroyed before the ctx they point into
 
     def close(self):
         if getattr(self, "_h", None):
+            for m in list(self._models):
+                m.close()
             self._L.fd_ctx_destroy(self._h)
             self._h = None
 
@@ -176,6 +180,7 @@ class RbfModel:
         self.frames = 0
         self.last_report = None
         self._keep = keep
+        ctx._models.add(self)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -91,6 +91,7 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_flags, FD_NUM_FLAGS);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_pivstat, 2);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_ctab32, (size_t)fd_tc_kpad(N)); // padded: the tensor path bulk-copies 32-centre tiles
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_ctab_pair, (size_t)fd_tc_kpad(N));
     if (st == FD_OK && m->eval64) st = dev_alloc(ctx, &m->d_ctab64, (size_t)N);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_tc_norm, 4);
     if (st == FD_OK && with_factor) {
@@ -284,7 +285,7 @@ void fd_model_destroy(fd_model* m)
     cudaStream_t s = m->ctx->stream; // stream-ordered frees: later work on the stream may reuse the blocks safely
     void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
                       m->d_ctab32, m->d_W32, m->d_ctab64, m->d_tc_norm, m->d_tc_scale, m->d_tc_unscale,
-                      m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win};
+                      m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win, m->d_ctab_pair};
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;

@@ -26,15 +26,21 @@
 
 namespace tc {
 
+// The Gaussian basis lives in (0, 1]: its FP16 "lo" parts would fall into the FP16 subnormal range (absolute floor
+// 2^-25 on Phi, times sum |w| of thousands of centres).  Phi is therefore multiplied by 2^14 before the split (one
+// FMUL2 per pair; adding 14 to the exponent instead would cost the low bits of t near Phi = 1) and the factor is
+// undone by the column un-scaling.
+constexpr int GAUSS_SHIFT = 14;
 constexpr int TM = 128;                       // vertices per unit (one M=128 accumulator; two accumulators ping-pong)
 constexpr int CB = 240;                       // columns per unit (multiple of 3 and of 16)
 constexpr int BK = 32;                        // k per pipeline stage (64-byte rows -> SWIZZLE_64B)
 constexpr int STAGES = 4;
 constexpr int A_SPLIT_BYTES = TM * BK * 2;    // 8192
 constexpr int B_SPLIT_BYTES = CB * BK * 2;    // 15360
-constexpr int C_TILE_BYTES = BK * 16;         // the stage's 32 centres (float4 each), bulk-copied next to the weights
-constexpr int C_TILE_OFF = 2 * A_SPLIT_BYTES + 2 * B_SPLIT_BYTES; // 47104
-constexpr int STAGE_BYTES = C_TILE_OFF + C_TILE_BYTES;             // 47616
+constexpr int C_TILE_BYTES = BK * 16;         // a stage's 32 centres (16 pairs of two float4)
+constexpr int CDEPTH = 16;                    // centre tiles travel in their own, deeper ring: Phi production never waits
+                                              // for the 30 KB weight tile of its stage, only for a free A slot
+constexpr int STAGE_BYTES = 2 * A_SPLIT_BYTES + 2 * B_SPLIT_BYTES; // 47104
 constexpr int PRODUCER_WARPS = 16;            // two groups of 8 warps: group g fills the stages with (iteration & 1) == g;
                                               // inside a group two threads share a vertex row, 16 basis functions each
 constexpr int EPILOGUE_WARPS = 8;              // two per TMEM lane quarter (even / odd column chunks)
@@ -51,9 +57,11 @@ constexpr int EPI_WARP_FLOATS = EPI_FRAMES * 96; // staging floats per warp (8 f
 constexpr int EPI_COLS = EPI_FRAMES * 3;
 constexpr int SMEM_EPI_STAGING = STAGES * STAGE_BYTES;                          // 4 warps x 6 KB transpose buffers
 constexpr int SMEM_BARRIERS = SMEM_EPI_STAGING + EPILOGUE_WARPS * EPI_WARP_FLOATS * 4;
-constexpr int SMEM_COLSCALE = SMEM_BARRIERS + 128;
-constexpr int COLSCALE_RESIDENT_BLOCKS = 15;  // column scales of up to 15 column blocks (F <= 1200) stay resident
+constexpr int SMEM_CENTRES = SMEM_BARRIERS + 512;
+constexpr int SMEM_COLSCALE = SMEM_CENTRES + CDEPTH * C_TILE_BYTES;
+constexpr int COLSCALE_RESIDENT_BLOCKS = 6;   // column scales of up to 6 column blocks (F <= 480) stay resident
 constexpr int SMEM_TOTAL = SMEM_COLSCALE + COLSCALE_RESIDENT_BLOCKS * CB * 4;
+static_assert(SMEM_TOTAL + 1024 <= 227 * 1024, "shared-memory budget");
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024; // slack for the 1024-byte alignment of the dynamic window
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,15 +90,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+
 // bounded wait: a protocol bug traps (an error the host sees) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3fff) == 0 && clock64() - t0 > 20000000000ll) __trap();
+        if (++spins > (1u << 26)) __trap();
     }
+}
+// the same wait with its duration added to a counter (debug instantiation only)
+template <bool DBG> __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc)
+{
+    if (DBG) {
+        const long long t0 = clock64();
+        mbar_wait(bar, parity);
+        acc += clock64() - t0;
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -176,6 +200,42 @@ __device__ __forceinline__ float sqrt_approx(float x)
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// packed FP32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a): two basis functions per issue slot
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 template <int KERNEL> __device__ __forceinline__ float phi(float r2, float prm)
 {
     if (KERNEL == FD_KERNEL_GAUSSIAN) return ex2_approx(r2 * prm);
@@ -216,10 +276,10 @@ __device__ __forceinline__ void project_to_tangents(const float u[3], const floa
 }
 
 struct Args {
-    const float4* ctab;     // N centres: (x, y, z, kernel parameter)
+    const float4* ctab;     // centre pairs, two float4 per pair: (x0, x1, y0, y1), (z0, z1, prm0, prm1); padded to 32 centres
     const float* norm;      // (ox, oy, oz, s): affine-row coordinates x' = (x - o) * s
     const float* colscale;  // per column: multiply the accumulator by this to undo the FP16 pre-scaling
-    int N, Kpad, F, ncb;
+    int N, Kpad, Ktot, F, ncb; // Ktot = N + polynomial rows
     const float* P;
     int64_t V;
     const float* dist2;
@@ -232,18 +292,22 @@ struct Args {
     int do_tangent;
     int vec_store_ok;       // V % 4 == 0 and P_out 16-byte aligned
     long long* dbg;         // optional per-unit phase timestamps of CTA 0 (FD_TC_DEBUG=1), else NULL
-    int dbg_nostore;        // FD_TC_DEBUG=2: skip the global stores (bandwidth experiment)
+    int dbg_mode;           // FD_TC_DEBUG bits (debug instantiation only; results are then garbage): 2 skip the epilogue
+                            // math + stores, 4 skip the Phi computation, 8 issue one MMA of three, 16 skip the TMA stores only
 };
 
 // 8 basis values -> FP16 hi (RN) and lo (RN of the remainder), packed as two 16-byte chunks
-__device__ __forceinline__ void split8(const float* ph, uint4& hi, uint4& lo)
+__device__ __forceinline__ void split8(const uint64_t* pf, uint4& hi, uint4& lo)
 {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __half2 h2 = __floats2half2_rn(ph[2 * i], ph[2 * i + 1]);
+        float f0, f1, r0, r1;
+        unpack2(pf[i], f0, f1);
+        const __half2 h2 = __floats2half2_rn(f0, f1);
         const float2 back = __half22float2(h2);
-        const __half2 l2 = __floats2half2_rn(ph[2 * i] - back.x, ph[2 * i + 1] - back.y);
+        unpack2(sub2(pf[i], pack2(back.x, back.y)), r0, r1); // both remainders in one FADD2
+        const __half2 l2 = __floats2half2_rn(r0, r1);
         h[i] = *reinterpret_cast<const uint32_t*>(&h2);
         l[i] = *reinterpret_cast<const uint32_t*>(&l2);
     }
@@ -251,7 +315,7 @@ __device__ __forceinline__ void split8(const float* ph, uint4& hi, uint4& lo)
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <int KERNEL, bool TANGENT>
+template <int KERNEL, bool TANGENT, bool DBG>
 __global__ void __launch_bounds__(THREADS, 1)
 k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
           const __grid_constant__ CUtensorMap map_out)
@@ -267,7 +331,9 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
     const uint32_t bar_empty = smem_u32(bars + 2 * STAGES);  // [STAGES], count 1 (tcgen05.commit)
     const uint32_t bar_tmem_full = smem_u32(bars + 3 * STAGES);        // [2], count 1: all MMAs of the unit retired
     const uint32_t bar_tmem_empty = smem_u32(bars + 3 * STAGES + 2);   // [2], count EPILOGUE_WARPS: accumulator drained
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+    const uint32_t bar_cfull = smem_u32(bars + 3 * STAGES + 4);            // [CDEPTH], count 1 + tx bytes: centre tile landed
+    const uint32_t bar_cempty = smem_u32(bars + 3 * STAGES + 4 + CDEPTH);  // [CDEPTH], count PRODUCER_WARPS / 2: tile consumed
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4 + 2 * CDEPTH);
     float* s_colscale = reinterpret_cast<float*>(smem + SMEM_COLSCALE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,6 +347,10 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
         mbar_init(bar_tmem_full + 8, 1);
         mbar_init(bar_tmem_empty, EPILOGUE_WARPS);
         mbar_init(bar_tmem_empty + 8, EPILOGUE_WARPS);
+        for (int c = 0; c < CDEPTH; ++c) {
+            mbar_init(bar_cfull + 8 * c, 1);
+            mbar_init(bar_cempty + 8 * c, PRODUCER_WARPS / 2);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_TMA) {
@@ -293,63 +363,110 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     const int nk = a.Kpad / BK;
+    const int tail_ksteps = (a.Ktot - (nk - 1) * BK + 15) >> 4; // K=16 steps of the last stage that hold real rows (1 or 2)
     const int64_t n_vt = (a.V + TM - 1) / TM;
     const int64_t n_units = n_vt * a.ncb;
 
+    // The two issuing roles run their loops with the whole warp (waits included) and elect one lane only around the
+    // issue itself: control flow and addresses stay warp-uniform, so descriptors and barrier addresses live in
+    // uniform registers (a loop nested inside `if (lane == 0)` costs ~100 dependent R2UR / PLOP3 instructions per stage
+    // on a single lane -- measured ~900 cycles per stage, more than the 720 cycles of the stage's MMAs).
     if (warp == WARP_TMA) {
-        // ================= TMA producer: weight tiles =================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const int cb = (int)(u % a.ncb);
-                for (int kb = 0; kb < nk; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        // ================= TMA producer: weight tiles + centre tiles =================
+        long long w_ce = 0, w_e = 0;
+        const long long t_begin = DBG ? clock64() : 0;
+        uint32_t it = 0, ic = 0;  // weight stages / centre tiles issued so far
+        int kc = 0;               // k block of centre tile ic
+        const uint32_t my_units = (uint32_t)((n_units - blockIdx.x + gridDim.x - 1) / gridDim.x);
+        const uint32_t total = my_units * (uint32_t)nk;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int cb = (int)(u % a.ncb);
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+                // centre tiles run up to CDEPTH stages ahead of the weights (waiting here cannot deadlock: the
+                // slot of tile ic frees once the producers finished stage ic - CDEPTH <= it, whose A slot only
+                // needs MMAs on weight tiles this warp has already issued)
+                while (ic < total && ic < it + CDEPTH) {
+                    const int c = ic % CDEPTH;
+                    mbar_wait_t<DBG>(bar_cempty + 8 * c, ((ic / CDEPTH) & 1) ^ 1, w_ce);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_cfull + 8 * c, C_TILE_BYTES);
+                        bulk_load_1d(smem_base + SMEM_CENTRES + c * C_TILE_BYTES, a.ctab + kc * BK, C_TILE_BYTES, bar_cfull + 8 * c);
+                    }
+                    ++ic;
+                    if (++kc == nk) kc = 0;
+                }
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait_t<DBG>(bar_empty + 8 * s, ph ^ 1, w_e);
+                if (elect_one()) {
                     const uint32_t sb = smem_base + s * STAGE_BYTES + 2 * A_SPLIT_BYTES;
-                    mbar_expect_tx(bar_full_b + 8 * s, 2 * B_SPLIT_BYTES + C_TILE_BYTES);
-                    bulk_load_1d(smem_base + s * STAGE_BYTES + C_TILE_OFF, a.ctab + kb * BK, C_TILE_BYTES, bar_full_b + 8 * s);
+                    mbar_expect_tx(bar_full_b + 8 * s, 2 * B_SPLIT_BYTES);
                     tma_load_2d(sb, &map_hi, bar_full_b + 8 * s, kb * BK, cb * CB);
                     tma_load_2d(sb + B_SPLIT_BYTES, &map_lo, bar_full_b + 8 * s, kb * BK, cb * CB);
                 }
+                __syncwarp();
             }
+        }
+        if (DBG && a.dbg && blockIdx.x == 0 && lane == 0) {
+            a.dbg[210] = clock64() - t_begin;
+            a.dbg[211] = w_ce;
+            a.dbg[212] = w_e;
         }
     } else if (warp == WARP_MMA) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t it = 0, unit_iter = 0;
-            const uint64_t desc0 = make_desc_sw64(smem_base); // A hi tile of stage 0 (the whole window is < 256 KB: no carry)
-            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
-                const int cb = (int)(u % a.ncb);
-                const int ncols = min(CB, (3 * a.F - cb * CB + 15) & ~15);
-                const uint32_t idesc = make_idesc(ncols);
-                const int ab = unit_iter & 1;                 // accumulator buffer of this unit
-                const uint32_t d = tmem_base + ab * ACC1_COL;
-                // the epilogue must have drained this buffer (two units ago)
-                mbar_wait(bar_tmem_empty + 8 * ab, ((unit_iter >> 1) & 1) ^ 1);
+        long long w_t = 0, w_a = 0, w_b = 0;
+        const long long t_begin = DBG ? clock64() : 0;
+        uint32_t it = 0, unit_iter = 0;
+        const uint64_t desc0 = make_desc_sw64(smem_base); // A hi tile of stage 0 (the whole window is < 256 KB: no carry)
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0); // warp-uniform copy
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
+            const int cb = (int)(u % a.ncb);
+            const int ncols = min(CB, (3 * a.F - cb * CB + 15) & ~15);
+            const uint32_t idesc = make_idesc(ncols);
+            const int ab = unit_iter & 1;                 // accumulator buffer of this unit
+            const uint32_t d = tmem_u + ab * ACC1_COL;
+            // the epilogue must have drained this buffer (two units ago)
+            mbar_wait_t<DBG>(bar_tmem_empty + 8 * ab, ((unit_iter >> 1) & 1) ^ 1, w_t);
+            tc_fence_after();
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait_t<DBG>(bar_full_a + 8 * s, ph, w_a);
+                mbar_wait_t<DBG>(bar_full_b + 8 * s, ph, w_b);
                 tc_fence_after();
-                for (int kb = 0; kb < nk; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(bar_full_a + 8 * s, ph);
-                    mbar_wait(bar_full_b + 8 * s, ph);
-                    tc_fence_after();
+                if (elect_one()) {
                     // descriptors differ from the stage-0 ones only in the start-address field (units of 16 bytes)
-                    const uint64_t so = (uint64_t)(s * (STAGE_BYTES >> 4));
-#pragma unroll
-                    for (int kk = 0; kk < BK / 16; ++kk) {
-                        const uint64_t a_hi = desc0 + so + kk * 2;
-                        const uint64_t a_lo = a_hi + (A_SPLIT_BYTES >> 4);
-                        const uint64_t b_hi = a_hi + (2 * A_SPLIT_BYTES >> 4);
-                        const uint64_t b_lo = b_hi + (B_SPLIT_BYTES >> 4);
-                        umma_f16(d, a_hi, b_hi, idesc, (kb | kk) != 0);
+                    const uint64_t a_hi = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+                    const uint64_t a_lo = a_hi + (A_SPLIT_BYTES >> 4);
+                    const uint64_t b_hi = a_hi + (2 * A_SPLIT_BYTES >> 4);
+                    const uint64_t b_lo = b_hi + (B_SPLIT_BYTES >> 4);
+                    const bool one = DBG && (a.dbg_mode & 8);
+                    // first K=16 step of the stage
+                    umma_f16(d, a_hi, b_hi, idesc, kb != 0);
+                    if (!one) {
                         umma_f16(d, a_hi, b_lo, idesc, 1);
                         umma_f16(d, a_lo, b_hi, idesc, 1);
+                    }
+                    // second step; the last stage holds the tail of the centres + the affine rows and skips it when
+                    // nothing but zero padding lives there
+                    if (kb != nk - 1 || tail_ksteps > 1) {
+                        umma_f16(d, a_hi + 2, b_hi + 2, idesc, 1);
+                        if (!one) {
+                            umma_f16(d, a_hi + 2, b_lo + 2, idesc, 1);
+                            umma_f16(d, a_lo + 2, b_hi + 2, idesc, 1);
+                        }
                     }
                     umma_commit(bar_empty + 8 * s);                        // frees the stage when these MMAs have read it
                     if (kb == nk - 1) umma_commit(bar_tmem_full + 8 * ab); // accumulator complete
                 }
+                __syncwarp();
             }
+        }
+        if (DBG && a.dbg && blockIdx.x == 0 && lane == 0) {
+            a.dbg[200] = clock64() - t_begin;
+            a.dbg[201] = w_t;
+            a.dbg[202] = w_a;
+            a.dbg[203] = w_b;
         }
     } else if (warp < PRODUCER_WARPS) {
         // ================= Phi producers =================
@@ -358,6 +475,8 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
         const int khalf = (pt >> 7) & 1;        // which half of the stage's 32 k this thread generates
         const int grp = pt >> 8;                // producer group: stages of its parity
         const float4 nrm4 = *reinterpret_cast<const float4*>(a.norm);
+        long long w_c = 0, w_e = 0;
+        const long long t_begin = DBG ? clock64() : 0;
         uint32_t it = 0, unit_iter = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
             const int64_t vt = u / a.ncb;
@@ -368,57 +487,101 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                 py = a.P[3 * v + 1];
                 pz = a.P[3 * v + 2];
             }
-            const bool dbg = a.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && unit_iter < 15;
+            const uint64_t px2 = pack2(px, px), py2 = pack2(py, py), pz2 = pack2(pz, pz);
+            const uint64_t shift2 = pack2((float)(1 << GAUSS_SHIFT), (float)(1 << GAUSS_SHIFT));
+            const bool dbg = DBG && a.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && unit_iter < 15;
             if (dbg) a.dbg[unit_iter * 8 + 0] = clock64();
-            for (int kb = 0; kb < nk; ++kb, ++it) {
-                if ((it & 1) != (uint32_t)grp) continue; // the other group's stage
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                mbar_wait(bar_full_b + 8 * s, ph); // the stage's centre tile has landed (same barrier as the weights)
+            // this group's stages of the unit: global stage counter it0 + kb with the group's parity
+            const uint32_t it0 = it;
+            it += nk;
+            for (int kb = (int)((grp ^ it0) & 1); kb < nk; kb += 2) {
+                const uint32_t itk = it0 + kb;
+                const int s = itk % STAGES;
+                const uint32_t ph = (itk / STAGES) & 1;
+                const int cs = itk % CDEPTH;
+                mbar_wait_t<DBG>(bar_cfull + 8 * cs, (itk / CDEPTH) & 1, w_c); // the stage's centre tile (its own deep ring)
+                mbar_wait_t<DBG>(bar_empty + 8 * s, ph ^ 1, w_e);              // the A slot: the MMAs of stage itk - STAGES retired
                 uint8_t* a_hi = smem + s * STAGE_BYTES + row * (BK * 2);
                 uint8_t* a_lo = a_hi + A_SPLIT_BYTES;
-                const float4* s_ctr = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES + C_TILE_OFF);
+                const ulonglong2* s_ctr2 = reinterpret_cast<const ulonglong2*>(smem + SMEM_CENTRES + cs * C_TILE_BYTES);
                 const int k0 = kb * BK;
                 const int swz = (row >> 1) & 3;
-                float f[16];
-                if (k0 + BK <= a.N) {
+                uint64_t f2[8]; // the thread's 16 basis values as 8 packed pairs
+                if (DBG && (a.dbg_mode & 4)) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float4 c = s_ctr[khalf * 16 + j]; // warp-wide broadcast LDS.128
-                        const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
-                        f[j] = phi<KERNEL>(dx * dx + dy * dy + dz * dz, c.w);
+                    for (int j = 0; j < 8; ++j) f2[j] = pack2(px, py);
+                } else if (kb == nk - 1 && khalf >= tail_ksteps) {
+                    // nothing but zero padding in this half of the last stage: the MMA issuer skips its K step
+                } else if (k0 + BK <= a.N) {
+                    // centre pairs (x0 x1 y0 y1 | z0 z1 w0 w1): the distance of two basis functions per FADD2 / FFMA2
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const ulonglong2 cxy = s_ctr2[(khalf * 8 + j) * 2];     // warp-wide broadcast LDS.128
+                        const ulonglong2 czw = s_ctr2[(khalf * 8 + j) * 2 + 1];
+                        const uint64_t dx = sub2(px2, cxy.x), dy = sub2(py2, cxy.y), dz = sub2(pz2, czw.x);
+                        const uint64_t r2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+                        if (KERNEL == FD_KERNEL_GAUSSIAN) {
+                            float t0, t1;
+                            unpack2(mul2(r2, czw.y), t0, t1);
+                            f2[j] = mul2(pack2(ex2_approx(t0), ex2_approx(t1)), shift2);
+                        } else if (KERNEL == FD_KERNEL_MULTIQUADRIC) {
+                            float t0, t1;
+                            unpack2(add2(r2, czw.y), t0, t1);
+                            f2[j] = pack2(sqrt_approx(t0), sqrt_approx(t1));
+                        } else {
+                            float t0, t1;
+                            unpack2(r2, t0, t1);
+                            f2[j] = pack2(phi<KERNEL>(t0, 0.f), phi<KERNEL>(t1, 0.f));
+                        }
                     }
                 } else { // the last stage(s): remaining centres, then the affine rows [1, x', y', z'], then zero padding
+                    const float* s_ctrf = reinterpret_cast<const float*>(s_ctr2);
+                    float f[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int k = k0 + khalf * 16 + j;
-                        const float4 c = s_ctr[khalf * 16 + j];
-                        const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
-                        float val = phi<KERNEL>(dx * dx + dy * dy + dz * dz, c.w);
+                        const float* cp = s_ctrf + ((khalf * 16 + j) >> 1) * 8 + (j & 1);
+                        const float dx = px - cp[0], dy = py - cp[2], dz = pz - cp[4];
+                        const float r2 = dx * dx + dy * dy + dz * dz;
+                        float val = KERNEL == FD_KERNEL_GAUSSIAN ? ex2_approx(r2 * cp[6]) * (float)(1 << GAUSS_SHIFT)
+                                                                 : phi<KERNEL>(r2, cp[6]);
                         if (k >= a.N) {
                             const int r = k - a.N;
-                            val = r == 0 ? 1.0f
-                                : r == 1 ? (px - nrm4.x) * nrm4.w
-                                : r == 2 ? (py - nrm4.y) * nrm4.w
-                                : r == 3 ? (pz - nrm4.z) * nrm4.w : 0.0f;
+                            const float S = KERNEL == FD_KERNEL_GAUSSIAN ? (float)(1 << GAUSS_SHIFT) : 1.0f;
+                            val = r == 0 ? S
+                                : r == 1 ? (px - nrm4.x) * (nrm4.w * S)
+                                : r == 2 ? (py - nrm4.y) * (nrm4.w * S)
+                                : r == 3 ? (pz - nrm4.z) * (nrm4.w * S) : 0.0f;
                         }
                         f[j] = val;
                     }
-                }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint4 hi, lo;
-                    split8(f + 8 * h, hi, lo);
-                    const int off = ((khalf * 2 + h) ^ swz) * 16;
-                    *reinterpret_cast<uint4*>(a_hi + off) = hi;
-                    *reinterpret_cast<uint4*>(a_lo + off) = lo;
+                    for (int j = 0; j < 8; ++j) f2[j] = pack2(f[2 * j], f[2 * j + 1]);
+                }
+                if (!(kb == nk - 1 && khalf >= tail_ksteps)) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 hi, lo;
+                        split8(f2 + 4 * h, hi, lo);
+                        const int off = ((khalf * 2 + h) ^ swz) * 16;
+                        *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                        *reinterpret_cast<uint4*>(a_lo + off) = lo;
+                    }
                 }
                 fence_proxy_async(); // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full_a + 8 * s);
+                if (lane == 0) {
+                    mbar_arrive(bar_full_a + 8 * s);
+                    mbar_arrive(bar_cempty + 8 * cs); // this warp has read the centre tile
+                }
             }
             if (dbg) a.dbg[unit_iter * 8 + 1] = clock64();
+        }
+        if (DBG && a.dbg && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8)) {
+            const int o = warp == 0 ? 204 : 214;
+            a.dbg[o] = clock64() - t_begin;
+            a.dbg[o + 1] = w_c;
+            a.dbg[o + 2] = w_e;
         }
     } else {
         // ================= epilogue warps: TMEM -> registers -> (transpose in shared memory) -> global =================
@@ -429,6 +592,8 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
         float* stg = reinterpret_cast<float*>(smem + SMEM_EPI_STAGING) + ew * EPI_WARP_FLOATS;
         const int et = threadIdx.x - 32 * WARP_EPI0;
         uint32_t unit_iter = 0;
+        long long w_f = 0;
+        const long long t_begin = DBG ? clock64() : 0;
         const bool resident_cs = a.ncb <= COLSCALE_RESIDENT_BLOCKS;
         if (resident_cs) { // all column scales once, instead of a barrier + global round trip per unit
             for (int t = et; t < a.ncb * CB; t += 32 * EPILOGUE_WARPS) s_colscale[t] = a.colscale[t];
@@ -445,7 +610,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                 for (int t = et; t < CB; t += 32 * EPILOGUE_WARPS) s_colscale[t] = a.colscale[cb * CB + t];
                 asm volatile("bar.sync 2, 256;" ::: "memory");
             }
-            const bool dbg = a.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && unit_iter < 15;
+            const bool dbg = DBG && a.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && unit_iter < 15;
             if (dbg) a.dbg[unit_iter * 8 + 2] = clock64();
             const int ab = unit_iter & 1;
             {
@@ -479,8 +644,9 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                     normalize3(tn);
                 }
                 const bool vec = a.vec_store_ok != 0;
+                const bool fo_one = __all_sync(0xffffffffu, fo == 1.0f || !valid);
                 // everything above is independent of the accumulator: it overlaps the MMAs of this unit
-                mbar_wait(bar_tmem_full + 8 * ab, (unit_iter >> 1) & 1);
+                mbar_wait_t<DBG>(bar_tmem_full + 8 * ab, (unit_iter >> 1) & 1, w_f);
                 tc_fence_after();
                 if (dbg) a.dbg[unit_iter * 8 + 3] = clock64();
                 if (vec) {
@@ -489,9 +655,10 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                     // through shared memory into [frame][vertex][xyz] rows that one lane hands to the bulk-copy engine
 #pragma unroll 1
                     for (int ch = chunk0; ch * EPI_FRAMES < nframes; ch += 2) {
+                        if (DBG && (a.dbg_mode & 2)) continue;
                         float acc[EPI_COLS];
                         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + mt * ACC1_COL + ch * EPI_COLS;
-                        const bool dbg2 = dbg && unit_iter == 2 && ch == 2;
+                        const bool dbg2 = DBG && dbg && unit_iter == 2 && ch == 2;
                         if (dbg2) a.dbg[120] = clock64();
                         tmem_ld16(taddr, acc);
                         tmem_ld8(taddr + 16, acc + 16);
@@ -501,24 +668,38 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                         __syncwarp();
                         tmem_ld_wait();
                         if (dbg2) a.dbg[122] = clock64();
-                        const int fcnt = min(EPI_FRAMES, nframes - ch * EPI_FRAMES);
                         const float4* cs4 = reinterpret_cast<const float4*>(s_cs + ch * EPI_COLS);
+                        float* dst = buf + lane * 3;
+                        if (fo_one) { // no falloff anywhere in this warp's 32 vertices (the common cook): one FMA per value
 #pragma unroll
-                        for (int g = 0; g < EPI_COLS / 4; ++g) { // 4 columns at a time
-                            const float4 cs = cs4[g];
-                            const float c4[4] = {cs.x, cs.y, cs.z, cs.w};
+                            for (int g = 0; g < EPI_COLS / 4; ++g) { // 4 columns at a time
+                                const float4 cs = cs4[g];
+                                const float c4[4] = {cs.x, cs.y, cs.z, cs.w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int col = 4 * g + e, i = col / 3, k = col - 3 * i;
-                                const float p = k == 0 ? px : (k == 1 ? py : pz);
-                                buf[(i * 32 + lane) * 3 + k] = fmaf(acc[col], c4[e] * fo, p);
+                                for (int e = 0; e < 4; ++e) {
+                                    const int col = 4 * g + e, i = col / 3, k = col - 3 * i;
+                                    const float p = k == 0 ? px : (k == 1 ? py : pz);
+                                    dst[i * 96 + k] = fmaf(acc[col], c4[e], p);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < EPI_COLS / 4; ++g) {
+                                const float4 cs = cs4[g];
+                                const float c4[4] = {cs.x, cs.y, cs.z, cs.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int col = 4 * g + e, i = col / 3, k = col - 3 * i;
+                                    const float p = k == 0 ? px : (k == 1 ? py : pz);
+                                    dst[i * 96 + k] = fmaf(acc[col], c4[e] * fo, p);
+                                }
                             }
                         }
                         if (dbg2) a.dbg[123] = clock64();
                         fence_proxy_async(); // staging writes -> visible to the TMA (async proxy)
                         __syncwarp();
                         if (dbg2) a.dbg[124] = clock64();
-                        if (lane == 0) {
+                        if (lane == 0 && !(DBG && (a.dbg_mode & 16))) {
                             // one TMA store of the [8 frames][32 vertices x 3] tile; frames >= F and vertices >= V are clipped
                             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                          ::"l"(reinterpret_cast<uint64_t>(&map_out)), "r"(smem_u32(buf)),
@@ -526,7 +707,6 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                                          : "memory");
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
-                        (void)fcnt;
                         if (dbg2) a.dbg[125] = clock64();
                     }
                 } else {
@@ -566,6 +746,10 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                 if (lane == 0) mbar_arrive(bar_tmem_empty + 8 * mt);
             }
             if (dbg) a.dbg[unit_iter * 8 + 4] = clock64();
+        }
+        if (DBG && a.dbg && blockIdx.x == 0 && lane == 0 && ew == 0) {
+            a.dbg[208] = clock64() - t_begin;
+            a.dbg[209] = w_f;
         }
     }
 
@@ -632,7 +816,7 @@ __device__ __forceinline__ double tc_weight(const double* __restrict__ W, int ld
 // per column: power-of-two scale that brings max |w| to <= 16384 (FP16 range with head-room for hi + lo);
 // CTA = 32 columns x 8 row groups, row-major reads stay coalesced
 __global__ void __launch_bounds__(256) k_tc_colscale(const double* __restrict__ W, int ldw, int N, int np, int ncol,
-                                                     int ncol_pad, const float* __restrict__ norm,
+                                                     int ncol_pad, int phi_shift, const float* __restrict__ norm,
                                                      float* __restrict__ unscale, float* __restrict__ scale)
 {
     __shared__ double s_mx[8][33];
@@ -661,7 +845,7 @@ __global__ void __launch_bounds__(256) k_tc_colscale(const double* __restrict__ 
         e = max(-60, min(60, e));
     }
     scale[c] = (float)ldexp(1.0, e);
-    unscale[c] = (float)ldexp(1.0, -e);
+    unscale[c] = (float)ldexp(1.0, -e - phi_shift); // also undoes the 2^phi_shift the kernel folds into Phi
 }
 
 // W^T hi/lo [ncol_pad][Kpad] FP16, k contiguous; 32x32 tile transpose through shared memory
@@ -748,8 +932,9 @@ cudaError_t fd_launch_pack_tc(fd_ctx* ctx, fd_model* m)
     cudaStream_t s = ctx->stream;
     const int ncol = 3 * m->F, ncol_pad = fd_tc_col_pad(m->F), Kpad = fd_tc_kpad(m->N);
     tc::k_tc_norm<<<1, 256, 0, s>>>(m->d_rest, m->N, m->d_tc_norm);
-    tc::k_tc_colscale<<<(ncol_pad + 31) / 32, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad, m->d_tc_norm,
-                                                            m->d_tc_unscale, m->d_tc_scale);
+    tc::k_tc_colscale<<<(ncol_pad + 31) / 32, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad,
+                                                            m->prm.kernel == FD_KERNEL_GAUSSIAN ? tc::GAUSS_SHIFT : 0,
+                                                            m->d_tc_norm, m->d_tc_unscale, m->d_tc_scale);
     dim3 grid((ncol_pad + 31) / 32, (Kpad + 31) / 32);
     tc::k_tc_pack<<<grid, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad, Kpad, m->d_tc_norm, m->d_tc_scale,
                                        (__half*)m->d_tc_wt_hi, (__half*)m->d_tc_wt_lo);
@@ -765,11 +950,12 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
 {
     if (V <= 0) return cudaSuccess;
     tc::Args a;
-    a.ctab = m->d_ctab32;
+    a.ctab = m->d_ctab_pair;
     a.norm = m->d_tc_norm;
     a.colscale = m->d_tc_unscale;
     a.N = m->N;
     a.Kpad = fd_tc_kpad(m->N);
+    a.Ktot = m->N + m->np;
     a.F = m->F;
     a.ncb = fd_tc_ncb(m->F);
     a.P = P;
@@ -789,9 +975,9 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
     if (a.vec_store_ok && !tc::make_out_map(&mo, P_out, V, m->F)) a.vec_store_ok = 0;
     static long long* d_dbg = nullptr;
     static const bool want_dbg = getenv("FD_TC_DEBUG") != nullptr;
-    if (want_dbg && !d_dbg) { cudaMalloc(&d_dbg, 16 * 8 * sizeof(long long)); cudaMemset(d_dbg, 0, 16 * 8 * sizeof(long long)); }
+    if (want_dbg && !d_dbg) { cudaMalloc(&d_dbg, 256 * sizeof(long long)); cudaMemset(d_dbg, 0, 256 * sizeof(long long)); }
     a.dbg = want_dbg ? d_dbg : nullptr;
-    a.dbg_nostore = want_dbg && atoi(getenv("FD_TC_DEBUG")) == 2;
+    a.dbg_mode = want_dbg ? atoi(getenv("FD_TC_DEBUG")) : 0;
     const int64_t n_units = ((V + tc::TM - 1) / tc::TM) * a.ncb;
     const int grid = (int)(n_units < ctx->sm_count ? n_units : ctx->sm_count);
     const CUtensorMap& mh = *(const CUtensorMap*)m->tc_map_hi;
@@ -799,7 +985,8 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
     const bool tang = a.do_tangent != 0;
 #define FD_TC_LAUNCH(KERNEL, TANG)                                                                                  \
     do {                                                                                                            \
-        auto kfn = tc::k_eval_tc<KERNEL, TANG>;                                                                     \
+        auto kfn = tc::k_eval_tc<KERNEL, TANG, false>;                                                              \
+        if (want_dbg && KERNEL == FD_KERNEL_GAUSSIAN && !TANG) kfn = tc::k_eval_tc<FD_KERNEL_GAUSSIAN, false, true>; \
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC);                     \
         kfn<<<grid, tc::THREADS, tc::SMEM_ALLOC, ctx->stream>>>(a, mh, ml, mo);                                        \
     } while (0)
@@ -816,9 +1003,13 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
     }
 #undef FD_TC_LAUNCH
     if (want_dbg) { // development aid: per-unit phase timestamps of CTA 0 (cycles)
-        long long h[128];
+        long long h[256];
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[fd_tc] CTA 0 waits (cycles): MMA lane total %lld = tmem_empty %lld + full_a %lld + full_b %lld + issue; "
+                        "TMA lane total %lld: cempty %lld, empty %lld; producer w0 total %lld: cfull %lld, empty %lld; "
+                        "producer w8 total %lld: cfull %lld, empty %lld; epilogue w0 total %lld: tmem_full %lld\n",
+                h[200], h[201], h[202], h[203], h[210], h[211], h[212], h[204], h[205], h[206], h[214], h[215], h[216], h[208], h[209]);
         fprintf(stderr, "[fd_tc] chunk: issue-ldtm+bulkwait %lld  ldtm-wait %lld  math+sts %lld  fence %lld  bulk-issue %lld\n",
                 h[121] - h[120], h[122] - h[121], h[123] - h[122], h[124] - h[123], h[125] - h[124]);
         {

@@ -68,6 +68,7 @@ struct fd_model {
     double* d_pivstat; // [min |u_kk|, max |u_kk|]
     // evaluation tables (built by pack)
     float4* d_ctab32;  // N: (cx, cy, cz, kernel parameter)
+    float4* d_ctab_pair; // the same table with pairs of centres interleaved (tensor path, fd_eval_tc.cu)
     float* d_W32;      // n x ldw32 floats
     int ldw32;
     double4* d_ctab64; // N (only when eval64)

@@ -428,12 +428,16 @@ __global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __rest
 // FP64 centre table when the evaluation runs in double.  Flags non-finite weights.
 __global__ void __launch_bounds__(256) k_pack_tables(const float* __restrict__ rest, const double* __restrict__ radii,
                                                      int N, int Npad, int kernel, float4* __restrict__ ctab32,
-                                                     double4* __restrict__ ctab64)
+                                                     float* __restrict__ ctab_pair, double4* __restrict__ ctab64)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Npad) return;
+    // the tensor path reads pairs of centres interleaved as (x0 x1 y0 y1 z0 z1 prm0 prm1) for the packed FP32 pipe
+    float* pr = ctab_pair + (j >> 1) * 8 + (j & 1);
     if (j >= N) { // padding of the centre table (multiquadric parameter 1 keeps the padded basis finite)
-        ctab32[j] = make_float4(0.f, 0.f, 0.f, kernel == FD_KERNEL_MULTIQUADRIC ? 1.f : 0.f);
+        const float pad = kernel == FD_KERNEL_MULTIQUADRIC ? 1.f : 0.f;
+        ctab32[j] = make_float4(0.f, 0.f, 0.f, pad);
+        pr[0] = 0.f, pr[2] = 0.f, pr[4] = 0.f, pr[6] = pad;
         return;
     }
     const double R = radii[j];
@@ -445,6 +449,7 @@ __global__ void __launch_bounds__(256) k_pack_tables(const float* __restrict__ r
     // FP32 Gaussian evaluates ex2(r2 * (-log2(e) / R^2))
     const double prm32 = kernel == FD_KERNEL_GAUSSIAN ? prm * 1.4426950408889634074 : prm;
     ctab32[j] = make_float4(x, y, z, (float)prm32);
+    pr[0] = x, pr[2] = y, pr[4] = z, pr[6] = (float)prm32;
     if (ctab64) ctab64[j] = make_double4((double)x, (double)y, (double)z, prm);
 }
 
@@ -532,7 +537,7 @@ cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
     cudaStream_t s = ctx->stream;
     const int npad = fd_tc_kpad(m->N);
     k_pack_tables<<<(npad + 255) / 256, 256, 0, s>>>(m->d_rest, m->d_radii, m->N, npad, m->prm.kernel, m->d_ctab32,
-                                                    m->eval64 ? m->d_ctab64 : nullptr);
+                                                    reinterpret_cast<float*>(m->d_ctab_pair), m->eval64 ? m->d_ctab64 : nullptr);
     dim3 grid((m->ldw32 + 255) / 256, m->n);
     k_pack_weights<<<grid, 256, 0, s>>>(m->d_W, m->n, m->ldw, 3 * m->F, m->d_W32, m->ldw32, m->d_flags);
     ctx->launches += 2;
