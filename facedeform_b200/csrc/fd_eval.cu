@@ -51,6 +51,38 @@ template <int KERNEL> __device__ __forceinline__ double phi(double r2, double pr
     return r2 > 0.0 ? 0.5 * r2 * log(r2) : 0.0;
 }
 
+// ---- FP64 evaluation of multiquadric / thin plate (FD_EVAL_AUTO for those kernels) ------------------
+// The FP64 pipe is the bound (64 lanes/clk/SM), so the kernel functions are built from few DFMAs instead of libdevice's
+// IEEE sqrt / log (~20 and ~40 FP64 instructions): 2^-40 relative accuracy is ample for a result that is rounded to
+// FP32, the point of FP64 here is the cancellation in sum_j w_j phi_j, not the last bits of phi.
+// sqrt: MUFU.RSQ64H seed (rsqrt.approx.f64, ~2^-20) + one Newton step in FP64 -> ~2^-40 relative, 4 FP64 instructions
+// and no FP32 <-> FP64 conversions (F2F runs at a quarter of the FP64 rate: two of them cost as much as the rest).
+// x > 0 (multiquadric: r^2 + R^2 with R > 0).
+__device__ __forceinline__ double fast_sqrt64(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    return fma(0.5 * t, e, t);
+}
+// 0.5 * ln|x| by a 128-entry table of (1 / c_i, 0.5 ln c_i), c_i = 1 + (i + 0.5) / 128, and a degree-4 series in
+// d = m / c_i - 1, |d| <= 2^-8 (truncation d^5 / 5 < 2^-42); x = 0 gives a finite value (the caller multiplies by x).
+__device__ __forceinline__ double half_log64(double x, const double2* __restrict__ s_tab)
+{
+    const int hi = __double2hiint(x);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x)); // [1, 2)
+    const double2 t = s_tab[(hi >> 13) & 127];
+    const double d = fma(m, t.x, -1.0);
+    double p = fma(d, -0.125, 1.0 / 6.0);
+    p = fma(d, p, -0.25);
+    p = fma(d, p, 0.5);
+    // (double)e without an I2F conversion: 2^52 + 2^31 + e as raw bits, minus the magic constant (exact)
+    const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
+    return fma(ed, 0.34657359027997264, fma(d, p, t.y)); // e * ln2 / 2 + 0.5 ln c + 0.5 ln(1 + d)
+}
+
 __device__ __forceinline__ void normalize3(float a[3])
 {
     const float len = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
@@ -86,6 +118,7 @@ __device__ __forceinline__ void project_to_tangents(const float u[3], const floa
 
 struct EvalArgs {
     const void* ctab;  // float4 / double4 [N]
+    const float* origin; // FP64 multiquadric / thin plate: coordinates are taken relative to this point (centre 0)
     const void* W;     // float / double, n x ldw
     int ldw;
     int N, np, F;
@@ -101,6 +134,65 @@ struct EvalArgs {
     float falloffrate;
     int do_tangent;
 };
+
+// polynomial block + SOP epilogue (gate, tangent projection, falloff, position write), shared by the evaluation kernels
+template <typename T, int FC, int VPT>
+__device__ __forceinline__ void finish_vertices(const EvalArgs& a, const T* __restrict__ W, int f0, int ncol, int64_t vbase,
+                                                const T (&px)[VPT], const T (&py)[VPT], const T (&pz)[VPT],
+                                                const float (&pos)[VPT][3], T (&acc)[VPT][3 * FC])
+{
+    // polynomial block: rows N .. N+np-1 of W hold a0 and the three columns of A (oracle: fdo_calc)
+    if (a.np >= 1) {
+#pragma unroll
+        for (int q = 0; q < 3 * FC; ++q) {
+            if (q < ncol) {
+                const T a0 = W[(size_t)a.N * a.ldw + 3 * f0 + q];
+                T ax = (T)0, ay = (T)0, az = (T)0;
+                if (a.np == 4) {
+                    ax = W[(size_t)(a.N + 1) * a.ldw + 3 * f0 + q];
+                    ay = W[(size_t)(a.N + 2) * a.ldw + 3 * f0 + q];
+                    az = W[(size_t)(a.N + 3) * a.ldw + 3 * f0 + q];
+                }
+#pragma unroll
+                for (int u = 0; u < VPT; ++u) acc[u][q] += a0 + ax * px[u] + ay * py[u] + az * pz[u];
+            }
+        }
+    }
+
+    // epilogue: gate, tangent projection, falloff, position write
+#pragma unroll
+    for (int u = 0; u < VPT; ++u) {
+        const int64_t v = vbase + (int64_t)u * EVAL_THREADS;
+        if (v >= a.V) continue;
+        const float d2 = a.dist2 ? a.dist2[v] : 0.f;
+        const bool skip = d2 > a.radius2;                       // SOP_FaceDeform.cpp:408-410
+        float fo = fminf(d2 / a.radius2, 1.0f);                 // :423
+        fo = powf(1.0f - fo, a.falloffrate);                    // :424
+        if (skip) fo = 0.f;
+        if (a.falloff_out && blockIdx.y == 0) a.falloff_out[v] = fo;
+        float tu[3], tv[3], tn[3];
+        if (a.do_tangent) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                tu[k] = a.tu[3 * v + k];
+                tv[k] = a.tv[3 * v + k];
+                tn[k] = a.nrm[3 * v + k];
+            }
+            normalize3(tu);
+            normalize3(tv);
+            normalize3(tn);
+        }
+#pragma unroll
+        for (int f = 0; f < FC; ++f) {
+            if (f0 + f >= a.F) break;
+            float d[3] = {(float)acc[u][3 * f], (float)acc[u][3 * f + 1], (float)acc[u][3 * f + 2]};
+            if (a.do_tangent) project_to_tangents(tu, tv, tn, d);
+            float* o = a.P_out + ((size_t)(f0 + f) * (size_t)a.V + (size_t)v) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) o[k] = skip ? pos[u][k] : pos[u][k] + d[k] * fo;
+        }
+    }
+}
 
 template <typename T, int KERNEL, int FC, int VPT>
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval_simt(const EvalArgs a)
@@ -173,57 +265,97 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_simt(const EvalArgs a)
         }
     }
 
-    // polynomial block: rows N .. N+np-1 of W hold a0 and the three columns of A (oracle: fdo_calc)
-    if (a.np >= 1) {
-#pragma unroll
-        for (int q = 0; q < 3 * FC; ++q) {
-            if (q < ncol) {
-                const T a0 = W[(size_t)a.N * a.ldw + 3 * f0 + q];
-                T ax = (T)0, ay = (T)0, az = (T)0;
-                if (a.np == 4) {
-                    ax = W[(size_t)(a.N + 1) * a.ldw + 3 * f0 + q];
-                    ay = W[(size_t)(a.N + 2) * a.ldw + 3 * f0 + q];
-                    az = W[(size_t)(a.N + 3) * a.ldw + 3 * f0 + q];
-                }
-#pragma unroll
-                for (int u = 0; u < VPT; ++u) acc[u][q] += a0 + ax * px[u] + ay * py[u] + az * pz[u];
-            }
-        }
-    }
+    finish_vertices<T, FC, VPT>(a, W, f0, ncol, vbase, px, py, pz, pos, acc);
+}
 
-    // epilogue: gate, tangent projection, falloff, position write
+// FP64 multiquadric / thin plate: distance in the expanded form (the centre table holds -2 (c - o) and |c - o|^2 +
+// kernel parameter, o = centre 0; cancellation is harmless at 53 bits), kernel functions from fast_sqrt64 / half_log64:
+// per (vertex, centre) pair 4 + 4 (+ 8 thin plate) + 3 FC FP64 instructions instead of ~26 / ~60 with libdevice.
+template <int KERNEL, int FC, int VPT>
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_f64(const EvalArgs a)
+{
+    constexpr int WPAD = (3 * FC + 1) / 2 * 2; // weights per centre in shared memory, padded for 128-bit reads
+    __shared__ double4 s_c[TJ];
+    __shared__ __align__(16) double s_w[TJ * WPAD];
+    __shared__ double2 s_tab[128];
+
+    if (KERNEL == FD_KERNEL_THINPLATE && threadIdx.x < 128) {
+        const double c = 1.0 + ((double)threadIdx.x + 0.5) / 128.0;
+        s_tab[threadIdx.x] = make_double2(1.0 / c, 0.5 * log(c));
+    }
+    const int f0 = blockIdx.y * FC;
+    const int64_t vbase = (int64_t)blockIdx.x * (EVAL_THREADS * VPT) + threadIdx.x;
+    const double ox = (double)a.origin[0], oy = (double)a.origin[1], oz = (double)a.origin[2];
+    double px[VPT], py[VPT], pz[VPT], pp[VPT], qx[VPT], qy[VPT], qz[VPT];
+    float pos[VPT][3];
 #pragma unroll
     for (int u = 0; u < VPT; ++u) {
         const int64_t v = vbase + (int64_t)u * EVAL_THREADS;
-        if (v >= a.V) continue;
-        const float d2 = a.dist2 ? a.dist2[v] : 0.f;
-        const bool skip = d2 > a.radius2;                       // SOP_FaceDeform.cpp:408-410
-        float fo = fminf(d2 / a.radius2, 1.0f);                 // :423
-        fo = powf(1.0f - fo, a.falloffrate);                    // :424
-        if (skip) fo = 0.f;
-        if (a.falloff_out && blockIdx.y == 0) a.falloff_out[v] = fo;
-        float tu[3], tv[3], tn[3];
-        if (a.do_tangent) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                tu[k] = a.tu[3 * v + k];
-                tv[k] = a.tv[3 * v + k];
-                tn[k] = a.nrm[3 * v + k];
-            }
-            normalize3(tu);
-            normalize3(tv);
-            normalize3(tn);
+        if (v < a.V) {
+            pos[u][0] = a.P[3 * v];
+            pos[u][1] = a.P[3 * v + 1];
+            pos[u][2] = a.P[3 * v + 2];
+        } else {
+            pos[u][0] = pos[u][1] = pos[u][2] = 0.f;
         }
+        px[u] = (double)pos[u][0];
+        py[u] = (double)pos[u][1];
+        pz[u] = (double)pos[u][2];
+        qx[u] = px[u] - ox;
+        qy[u] = py[u] - oy;
+        qz[u] = pz[u] - oz;
+        pp[u] = qx[u] * qx[u] + qy[u] * qy[u] + qz[u] * qz[u];
+    }
+    double acc[VPT][3 * FC];
 #pragma unroll
-        for (int f = 0; f < FC; ++f) {
-            if (f0 + f >= a.F) break;
-            float d[3] = {(float)acc[u][3 * f], (float)acc[u][3 * f + 1], (float)acc[u][3 * f + 2]};
-            if (a.do_tangent) project_to_tangents(tu, tv, tn, d);
-            float* o = a.P_out + ((size_t)(f0 + f) * (size_t)a.V + (size_t)v) * 3;
+    for (int u = 0; u < VPT; ++u)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) o[k] = skip ? pos[u][k] : pos[u][k] + d[k] * fo;
+        for (int c = 0; c < 3 * FC; ++c) acc[u][c] = 0.0;
+
+    const double4* __restrict__ ctab = (const double4*)a.ctab;
+    const double* __restrict__ W = (const double*)a.W;
+    const int ncol = min(3 * FC, 3 * (a.F - f0));
+
+    for (int j0 = 0; j0 < a.N; j0 += TJ) {
+        const int cnt = min(TJ, a.N - j0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < TJ; t += EVAL_THREADS)
+            s_c[t] = t < cnt ? ctab[j0 + t] : make_double4(0.0, 0.0, 0.0, 1.0); // padded centres carry zero weights
+        for (int t = threadIdx.x; t < TJ * WPAD; t += EVAL_THREADS) {
+            const int j = t / WPAD, c = t - j * WPAD;
+            s_w[t] = (j < cnt && c < ncol) ? W[(size_t)(j0 + j) * a.ldw + 3 * f0 + c] : 0.0;
+        }
+        __syncthreads();
+        const int jn = (cnt + 3) & ~3;
+#pragma unroll 4
+        for (int j = 0; j < jn; ++j) {
+            const double4 c = s_c[j];
+            double w[WPAD];
+#pragma unroll
+            for (int q = 0; q < WPAD; q += 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(&s_w[j * WPAD + q]);
+                w[q] = t2.x;
+                w[q + 1] = t2.y;
+            }
+#pragma unroll
+            for (int u = 0; u < VPT; ++u) {
+                const double x = fma(qx[u], c.x, fma(qy[u], c.y, fma(qz[u], c.z, c.w))) + pp[u]; // r^2 (+ R^2)
+                const double ph = KERNEL == FD_KERNEL_MULTIQUADRIC ? fast_sqrt64(x) : x * half_log64(x, s_tab);
+#pragma unroll
+                for (int q = 0; q < 3 * FC; ++q) acc[u][q] = fma(w[q], ph, acc[u][q]);
+            }
         }
     }
+    finish_vertices<double, FC, VPT>(a, W, f0, ncol, vbase, px, py, pz, pos, acc);
+}
+
+template <int KERNEL, int FC, int VPT>
+cudaError_t launch_f64(fd_ctx* ctx, const EvalArgs& a)
+{
+    dim3 grid((unsigned)((a.V + EVAL_THREADS * VPT - 1) / (EVAL_THREADS * VPT)), (unsigned)((a.F + FC - 1) / FC));
+    k_eval_f64<KERNEL, FC, VPT><<<grid, EVAL_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    return cudaGetLastError();
 }
 
 template <typename T, int KERNEL, int FC, int VPT>
@@ -279,11 +411,16 @@ cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64
     a.radius2 = m->prm.radius * m->prm.radius;
     a.falloffrate = m->prm.falloffrate;
     a.do_tangent = (m->prm.tangent && tu && tv && nrm) ? 1 : 0; // SOP_FaceDeform.cpp:293-294
+    a.origin = m->d_rest;
     if (m->eval64) {
         a.ctab = m->d_ctab64;
         a.W = m->d_W;
         a.ldw = m->ldw;
-        return launch_kernel<double>(ctx, m->prm.kernel, a);
+        if (m->prm.kernel == FD_KERNEL_MULTIQUADRIC)
+            return a.F >= 2 ? launch_f64<FD_KERNEL_MULTIQUADRIC, 2, 2>(ctx, a) : launch_f64<FD_KERNEL_MULTIQUADRIC, 1, 4>(ctx, a);
+        if (m->prm.kernel == FD_KERNEL_THINPLATE)
+            return a.F >= 2 ? launch_f64<FD_KERNEL_THINPLATE, 2, 2>(ctx, a) : launch_f64<FD_KERNEL_THINPLATE, 1, 4>(ctx, a);
+        return launch_kernel<double>(ctx, m->prm.kernel, a); // Gaussian in FP64 (forced by eval_precision)
     }
     a.ctab = m->d_ctab32;
     a.W = m->d_W32;

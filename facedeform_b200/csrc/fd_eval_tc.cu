@@ -441,14 +441,15 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                     const uint64_t b_hi = a_hi + (2 * A_SPLIT_BYTES >> 4);
                     const uint64_t b_lo = b_hi + (B_SPLIT_BYTES >> 4);
                     const bool one = DBG && (a.dbg_mode & 8);
-                    // first K=16 step of the stage
-                    umma_f16(d, a_hi, b_hi, idesc, kb != 0);
-                    if (!one) {
-                        umma_f16(d, a_hi, b_lo, idesc, 1);
-                        umma_f16(d, a_lo, b_hi, idesc, 1);
+                    // The last stage holds the tail of the centres + the polynomial rows: its K=16 steps that hold
+                    // nothing but zero padding are skipped (the producers do not write them either).
+                    if (kb != nk - 1 || tail_ksteps > 0) {
+                        umma_f16(d, a_hi, b_hi, idesc, kb != 0);
+                        if (!one) {
+                            umma_f16(d, a_hi, b_lo, idesc, 1);
+                            umma_f16(d, a_lo, b_hi, idesc, 1);
+                        }
                     }
-                    // second step; the last stage holds the tail of the centres + the affine rows and skips it when
-                    // nothing but zero padding lives there
                     if (kb != nk - 1 || tail_ksteps > 1) {
                         umma_f16(d, a_hi + 2, b_hi + 2, idesc, 1);
                         if (!one) {

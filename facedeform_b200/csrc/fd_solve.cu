@@ -450,7 +450,14 @@ __global__ void __launch_bounds__(256) k_pack_tables(const float* __restrict__ r
     const double prm32 = kernel == FD_KERNEL_GAUSSIAN ? prm * 1.4426950408889634074 : prm;
     ctab32[j] = make_float4(x, y, z, (float)prm32);
     pr[0] = x, pr[2] = y, pr[4] = z, pr[6] = (float)prm32;
-    if (ctab64) ctab64[j] = make_double4((double)x, (double)y, (double)z, prm);
+    if (ctab64) {
+        if (kernel == FD_KERNEL_GAUSSIAN) {
+            ctab64[j] = make_double4((double)x, (double)y, (double)z, prm);
+        } else { // expanded-distance form of k_eval_f64: -2 (c - o), |c - o|^2 + kernel parameter, o = centre 0
+            const double cx = (double)x - (double)rest[0], cy = (double)y - (double)rest[1], cz = (double)z - (double)rest[2];
+            ctab64[j] = make_double4(-2.0 * cx, -2.0 * cy, -2.0 * cz, cx * cx + cy * cy + cz * cz + prm);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_pack_weights(const double* __restrict__ W, int n, int ldw, int nrhs,
