@@ -34,7 +34,7 @@ class FdParams(C.Structure):
         ("tangent", C.c_int32), ("maxedges", C.c_int32), ("morphspace", C.c_int32), ("doclampweight", C.c_int32),
         ("weightrange", C.c_float * 2),
         ("dofalloff", C.c_int32), ("falloffradius", C.c_float), ("falloffrate", C.c_float),
-        ("eval_precision", C.c_int32), ("eval_path", C.c_int32),
+        ("eval_precision", C.c_int32), ("eval_path", C.c_int32), ("factor_precision", C.c_int32),
     ]
 
 
@@ -43,6 +43,7 @@ class FdReport(C.Structure):
     _fields_ = [
         ("terminationtype", C.c_int32), ("iterationscount", C.c_int32), ("n", C.c_int32), ("npoly", C.c_int32),
         ("frames", C.c_int32), ("reserved", C.c_int32), ("min_pivot", C.c_double), ("max_pivot", C.c_double),
+        ("residual", C.c_double),
     ]
 
 

@@ -67,6 +67,7 @@ int check_params(fd_ctx* ctx, const fd_params* p)
     if (!(p->radius > 0.f) || !isfinite(p->radius)) { FD_SET_ERR(ctx, "radius must be positive"); return FD_E_INVALID; }
     if (!(p->lambda >= 0.f)) { FD_SET_ERR(ctx, "lambda must be >= 0"); return FD_E_INVALID; }
     if (p->eval_precision < 0 || p->eval_precision > 2 || p->eval_path < 0 || p->eval_path > 2) { FD_SET_ERR(ctx, "bad eval_precision / eval_path"); return FD_E_INVALID; }
+    if (p->factor_precision != FD_FACTOR_FP64 && p->factor_precision != FD_FACTOR_FP32_IR) { FD_SET_ERR(ctx, "bad factor_precision"); return FD_E_INVALID; }
     return FD_OK;
 }
 
@@ -100,6 +101,9 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
         if (st == FD_OK) st = dev_alloc(ctx, &m->d_perm, (size_t)m->n);
         if (st == FD_OK) st = dev_alloc(ctx, &m->d_win, (size_t)132);
         if (st == FD_OK) st = dev_alloc(ctx, &m->d_Tinv, (size_t)((m->n + 31) / 32) * 2 * 32 * 32);
+        m->f32ir = params->factor_precision == FD_FACTOR_FP32_IR;
+        if (st == FD_OK && m->f32ir) st = dev_alloc(ctx, &m->d_A32, (size_t)m->lda * m->n);
+        if (st == FD_OK && m->f32ir) st = dev_alloc(ctx, &m->d_ir_norm, 2);
     }
     if (st != FD_OK) {
         fd_model_destroy(m);
@@ -121,15 +125,18 @@ int model_reserve_frames(fd_model* m, int F)
 {
     fd_ctx* ctx = m->ctx;
     if (F <= m->capF) return FD_OK;
-    void* old[] = {m->d_W, m->d_W32, m->d_tc_scale, m->d_tc_unscale, m->d_tc_wt_hi, m->d_tc_wt_lo};
+    void* old[] = {m->d_W, m->d_W32, m->d_tc_scale, m->d_tc_unscale, m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_B, m->d_R, m->d_D32};
     for (void* b : old)
         if (b) cudaFreeAsync(b, ctx->stream);
     m->d_W = nullptr; m->d_W32 = nullptr; m->d_tc_scale = nullptr; m->d_tc_unscale = nullptr;
-    m->d_tc_wt_hi = nullptr; m->d_tc_wt_lo = nullptr;
+    m->d_tc_wt_hi = nullptr; m->d_tc_wt_lo = nullptr; m->d_B = nullptr; m->d_R = nullptr; m->d_D32 = nullptr;
     m->capF = 0;
     const int ld = fd_round_up(3 * F, 4);
     int st = dev_alloc(ctx, &m->d_W, (size_t)m->n * ld);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_W32, (size_t)m->n * ld);
+    if (st == FD_OK && m->f32ir) st = dev_alloc(ctx, &m->d_B, (size_t)m->n * ld);
+    if (st == FD_OK && m->f32ir) st = dev_alloc(ctx, &m->d_R, (size_t)m->n * ld);
+    if (st == FD_OK && m->f32ir) st = dev_alloc(ctx, &m->d_D32, (size_t)m->n * ld);
     if (st == FD_OK && !m->eval64 && m->prm.eval_path != FD_PATH_SIMT) { // tensor-path tables (used when 3F is wide enough)
         const size_t cols = (size_t)fd_tc_col_pad(F), kpad = (size_t)fd_tc_kpad(m->N);
         unsigned short *hi = nullptr, *lo = nullptr;
@@ -187,6 +194,7 @@ void fd_params_default(fd_params* p)
     p->falloffrate = 1.0f;
     p->eval_precision = FD_EVAL_AUTO;
     p->eval_path = FD_PATH_AUTO;
+    p->factor_precision = FD_FACTOR_FP64;
 }
 
 // SYSmax clamps of cookMySop, SOP_FaceDeform.cpp:249-257
@@ -285,7 +293,8 @@ void fd_model_destroy(fd_model* m)
     cudaStream_t s = m->ctx->stream; // stream-ordered frees: later work on the stream may reuse the blocks safely
     void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
                       m->d_ctab32, m->d_W32, m->d_ctab64, m->d_tc_norm, m->d_tc_scale, m->d_tc_unscale,
-                      m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win, m->d_ctab_pair};
+                      m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win, m->d_ctab_pair, m->d_A32, m->d_B, m->d_R, m->d_D32,
+                      m->d_ir_norm};
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;
@@ -316,7 +325,13 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
     // Gaussian kernel with one radius: K + lambda I is symmetric positive definite -> no pivot search needed
     const bool spd = m->prm.kernel == FD_KERNEL_GAUSSIAN && (m->prm.model == FD_MODEL_ML || m->N == 1) && !getenv("FD_FORCE_PIVOTED_LU");
     const bool unfused = getenv("FD_LU_UNFUSED") != nullptr; // per-block-column launches (kept for comparison)
-    if (e == cudaSuccess) {
+    if (e == cudaSuccess && m->f32ir) {
+        // FP32 factorisation of fl32(A); d_A keeps the FP64 system for the residuals of the refinement (fd_refine.cu)
+        e = fd_launch_to_f32(ctx, m->d_A, m->d_A32, (size_t)m->lda * m->n);
+        if (e == cudaSuccess)
+            e = spd ? fd_launch_lu_nopivot_f32(ctx, m->d_A32, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat)
+                    : fd_launch_lu_f32(ctx, m->d_A32, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_win);
+    } else if (e == cudaSuccess) {
         if (spd && !unfused) {
             e = fd_launch_lu_nopivot_fused(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_Tinv);
         } else {
@@ -365,7 +380,7 @@ int fd_rbf_solve_dev(fd_model* m, const float* deform_ctrl_dev, int32_t n_ctrl, 
     m->ldw32 = m->ldw;
     m->use_tc = model_wants_tc(m, frames);
     phase_begin(ctx, FD_PH_SOLVE);
-    cudaError_t e = fd_launch_solve(ctx, m, deform_ctrl_dev, frames);
+    cudaError_t e = m->f32ir ? fd_refine_solve(ctx, m, deform_ctrl_dev, frames) : fd_launch_solve(ctx, m, deform_ctrl_dev, frames);
     if (e == cudaSuccess) e = fd_launch_pack(ctx, m);
     phase_end(ctx, FD_PH_SOLVE);
     if (e != cudaSuccess) { FD_SET_ERR(ctx, "solve: %s", cudaGetErrorString(e)); return FD_E_CUDA; }
@@ -403,9 +418,11 @@ int fd_model_report(fd_model* m, fd_report* report)
     int term = 1;
     if (flags[FD_FLAG_ZERO_RADIUS]) term = -5;
     else if (flags[FD_FLAG_SINGULAR] || flags[FD_FLAG_NONFINITE]) term = -3;
+    else if (m->f32ir && m->solved && !m->ir_converged) term = -4;
     if (report) {
         report->terminationtype = term;
-        report->iterationscount = 0;
+        report->iterationscount = m->f32ir ? m->ir_sweeps : 0;
+        report->residual = m->f32ir ? m->ir_residual : 0.0;
         report->n = m->N;
         report->npoly = m->np;
         report->frames = m->F;

@@ -9,6 +9,9 @@
 
 #define FD_NUM_FLAGS 8
 #define FD_TMAP_BYTES 128
+#define FD_IR_MAX_SWEEPS 40     // FD_FACTOR_FP32_IR: refinement sweeps at most
+#define FD_IR_TOLERANCE 1e-12   // converged: max |B - A X| <= this * max |B|
+#define FD_IR_FLOOR_OK 1e-9     // a residual that stagnates below this sits at the FP64 floor of the system: accepted
 #define FD_TC_MIN_COLUMNS 48 // FD_PATH_AUTO takes the tensor-core evaluation from 3F >= 48 columns
 // device-side status words (ints): written by kernels, read by fd_model_report
 #define FD_FLAG_ZERO_RADIUS 0 // != 0: a QNN radius was zero (duplicate centres)      -> terminationtype -5
@@ -66,6 +69,16 @@ struct fd_model {
     double* d_W;     // n x ldw weights (solve in place over the right-hand sides)
     int* d_flags;    // FD_NUM_FLAGS
     double* d_pivstat; // [min |u_kk|, max |u_kk|]
+    // FD_FACTOR_FP32_IR (fd_refine.cu): d_A stays the assembled FP64 system, the LU lives in d_A32
+    bool f32ir;
+    float* d_A32;      // lda x n FP32, LU in place
+    double* d_B;       // n x ldw right-hand sides
+    double* d_R;       // n x ldw residual
+    float* d_D32;      // n x ldw correction
+    double* d_ir_norm; // [max |B|, max |R|]
+    int ir_sweeps;
+    double ir_residual;
+    bool ir_converged;
     // evaluation tables (built by pack)
     float4* d_ctab32;  // N: (cx, cy, cz, kernel parameter)
     float4* d_ctab_pair; // the same table with pairs of centres interleaved (tensor path, fd_eval_tc.cu)
@@ -113,6 +126,13 @@ cudaError_t fd_launch_lu_nopivot_fused(fd_ctx* ctx, double* d_A, int lda, int n,
 cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_deform, int F);
 cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_invdiag(fd_ctx* ctx, fd_model* m);
+// fd_refine.cu
+cudaError_t fd_launch_to_f32(fd_ctx* ctx, const double* d_A, float* d_A32, size_t count);
+cudaError_t fd_refine_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int F);
+cudaError_t fd_launch_lu_f32(fd_ctx* ctx, float* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
+                             double* d_pivstat, int* d_win);
+cudaError_t fd_launch_lu_nopivot_f32(fd_ctx* ctx, float* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
+                                     double* d_pivstat);
 // fd_eval.cu
 cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
                            const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out);

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FD_ABI_VERSION 1
+#define FD_ABI_VERSION 2
 
 typedef struct fd_ctx fd_ctx;     /* one GPU + stream + scratch; replaces the node-member state, SOP_FaceDeform.hpp:108-113 */
 typedef struct fd_model fd_model; /* replaces alglib::rbfmodel (SOP_FaceDeform.cpp:332): centres, radii, LU factors, weights */
@@ -67,6 +67,9 @@ typedef enum fd_status {
 #define FD_EVAL_AUTO 0   /* FP32 for the Gaussian, FP64 for multiquadric / thin plate (cancellation) */
 #define FD_EVAL_FP32 1
 #define FD_EVAL_FP64 2
+/* arithmetic of the factorisation (BASELINE.json config 4: "FP64 vs FP32+refinement tolerance study") */
+#define FD_FACTOR_FP64 0    /* FP64 LU + FP64 triangular solves (default) */
+#define FD_FACTOR_FP32_IR 1 /* FP32 LU, solutions refined in FP64 until the residual stops shrinking (fd_report) */
 /* evaluation kernel */
 #define FD_PATH_AUTO 0   /* tensor cores when 3F is wide enough, else FMA/SFU */
 #define FD_PATH_SIMT 1
@@ -92,18 +95,21 @@ typedef struct fd_params {
     float falloffrate;     /* default 1                       :135 */
     int32_t eval_precision;/* FD_EVAL_* */
     int32_t eval_path;     /* FD_PATH_* */
+    int32_t factor_precision; /* FD_FACTOR_* */
 } fd_params;
 
 /* analogue of alglib::rbfreport (SOP_FaceDeform.cpp:333, :365-373) */
 typedef struct fd_report {
-    int32_t terminationtype; /* 1 = ok; -3 = singular / non-finite weights; -5 = zero radius (duplicate centres) */
-    int32_t iterationscount; /* refinement iterations (0: direct FP64 solve) */
+    int32_t terminationtype; /* 1 = ok; -3 = singular / non-finite weights; -4 = refinement did not converge;
+                                -5 = zero radius (duplicate centres) */
+    int32_t iterationscount; /* refinement sweeps of FD_FACTOR_FP32_IR (0: direct FP64 solve) */
     int32_t n;               /* control points */
     int32_t npoly;           /* polynomial terms 4 / 1 / 0 */
     int32_t frames;          /* F of the last solve */
     int32_t reserved;
     double min_pivot;        /* min |u_kk| of the LU */
     double max_pivot;
+    double residual;         /* FD_FACTOR_FP32_IR: max |B - A X| / max |B| after the last sweep (0 otherwise) */
 } fd_report;
 
 int fd_abi_version(void);

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in facedeform_gpu.h but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert L.fd_abi_version() == 1
+    assert L.fd_abi_version() == 2
 
 
 def test_params_defaults_and_clamps_match_the_sop():

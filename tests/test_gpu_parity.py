@@ -268,3 +268,49 @@ def test_receiver_model_matches_root_bit_for_bit(ctx):
         assert e.value.status == 9
         root.close()
         recv.close()
+
+
+# ---- FP32 factorisation + FP64 iterative refinement (fd_params.factor_precision = 1, BASELINE config 4) -------------
+
+@pytest.mark.parametrize("kernel,N,rscale", [(0, 512, 1.5), (0, 1000, 2.0), (1, 300, 1.0), (2, 257, 1.0)])
+def test_fp32_refinement_reaches_the_fp64_solution(ctx, kernel, N, rscale):
+    """FP32 LU (pivoted for multiquadric / thin plate, unpivoted for the SPD Gaussian) + FP64 residual sweeps: the
+    weights agree with the FP64 factorisation and the report carries the sweep count and the final residual."""
+    from facedeform_b200 import make_params
+    rig = synth.control_rig(N)
+    deform = synth.deformed_rig(rig, 3)
+    W = []
+    for fp in (0, 1):
+        p = make_params(model=1, term=0, kernel=kernel, radius=rscale * rig.spacing, factor_precision=fp,
+                        **{"lambda": 0.0})
+        m = ctx.fit(p, rig.rest).solve(deform)
+        rep = m.report()
+        assert rep.terminationtype == 1
+        if fp:
+            assert 1 <= rep.iterationscount <= 40 and 0.0 <= rep.residual <= 1e-9
+        else:
+            assert rep.iterationscount == 0 and rep.residual == 0.0
+        W.append(m.weights()[0])
+        out, _ = m.eval(rig.rest)
+        assert np.abs(out - deform).max() <= 1e-5 * 2.9      # interpolation at the control points
+        m.close()
+    assert np.abs(W[0] - W[1]).max() <= 1e-6 * np.abs(W[0]).max()
+
+
+def test_fp32_refinement_reports_non_convergence(ctx):
+    """a Gaussian system far beyond cond ~ 2^24 cannot be refined from FP32 factors: the solve must say so
+    (terminationtype -4 -> FD_E_SINGULAR, "Can't solve the problem."), never return unconverged weights silently."""
+    from facedeform_b200 import FdError, make_params
+    rig = synth.control_rig(1024)
+    deform = synth.deformed_rig(rig, 1)
+    p = make_params(model=1, term=0, kernel=0, radius=8.0 * rig.spacing, factor_precision=1, **{"lambda": 0.0})
+    m = ctx.fit(p, rig.rest)
+    try:
+        m.solve(deform)
+        rep = m.report()
+        assert rep.terminationtype == 1 and rep.residual <= 1e-9   # it converged after all: then it must be accurate
+    except FdError as e:
+        assert e.status == 4
+        assert m.last_report.terminationtype in (-3, -4)
+    finally:
+        m.close()
