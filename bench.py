@@ -192,6 +192,27 @@ def factor_table(ctx, sizes, cpu=True):
     return out
 
 
+def configs_table(ctx):
+    """phase times of BASELINE.json's other single-GPU configurations (C1, C3 multiquadric / thin plate, the C3 shape
+    with the Gaussian kernel, a slice of C5), device resident -- parity-test cases reported for context, not bench lines."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("configs_probe", os.path.join(ROOT, "profiles", "tools", "configs_probe.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import contextlib
+    import io
+    rows = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        for name, N, V, F, kern in (("C1", 64, 10_000, 1, "gaussian"), ("C3", 2048, 1_000_000, 1, "multiquadric"),
+                                    ("C3_thin_plate", 2048, 1_000_000, 1, "thin_plate"),
+                                    ("C3_shape_gaussian", 2048, 1_000_000, 1, "gaussian"),
+                                    ("C5_slice", 4096, 65_536, 1000, "gaussian")):
+            r = mod.run(ctx, name, N, V, F, kern, 3)
+            rows[name] = {k: r[k] for k in ("N", "V", "F", "kernel", "assemble_ms", "factor_ms", "solve_ms", "eval_ms",
+                                            "eval_vertex_frames_per_s", "eval_alg_tflops")}
+    return rows
+
+
 def describe(cfg):
     return (f"{cfg['N']} control points, {cfg['V']} vertices/GPU, {cfg['F']} frames, {cfg['kernel']} kernel, "
             f"{cfg['term']} term, step = assemble + LU + {3 * cfg['F']}-RHS solve + fused eval")
@@ -207,6 +228,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-path", type=int, default=0)
+    ap.add_argument("--no-configs-table", action="store_true", help="skip the phase times of C1 / C3 / C5-slice")
     ap.add_argument("--factor-sizes", default="256,1024,2048,4096,8192",
                     help="control-point counts for the factor-ms table (second half of the metric); empty to skip")
     args = ap.parse_args()
@@ -365,10 +387,10 @@ def main():
         # DRAM traffic of one launch from the committed `ncu --set full` capture of this command (profiles/), C2 only
         try:
             if args.config == "C2" and tensor_path:
-                with open(os.path.join(ROOT, "profiles", "r1_final_eval_tc_ncu_summary.json")) as f:
+                with open(os.path.join(ROOT, "profiles", "r1d_eval_tc_ncu_summary.json")) as f:
                     nc = json.load(f)
                 roofline["traffic"] = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6
-                roofline["traffic_source"] = "profiles/r1_final_eval_tc_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+                roofline["traffic_source"] = "profiles/r1d_eval_tc_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
                 roofline["algorithmic_bytes"] = alg_bytes
         except Exception:
             pass
@@ -392,6 +414,8 @@ def main():
         if world == 1 and args.factor_sizes:
             line["factor_ms_by_n"] = factor_table(ctx, [int(x) for x in args.factor_sizes.split(",") if x],
                                                   cpu=not args.no_cpu_baseline)
+        if world == 1 and not args.no_configs_table:
+            line["other_configs"] = configs_table(ctx)
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_sample(cfg, rig, deform, radius, seconds_target=args.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
