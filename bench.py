@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-path", type=int, default=0)
+    ap.add_argument("--weights", default="auto", choices=["auto", "broadcast", "replicated"],
+                    help="N > 1: root solves + NCCL broadcast of the weights, or every rank solves the small system itself")
     ap.add_argument("--no-configs-table", action="store_true", help="skip the phase times of C1 / C3 / C5-slice")
     ap.add_argument("--factor-sizes", default="256,1024,2048,4096,8192",
                     help="control-point counts for the factor-ms table (second half of the metric); empty to skip")
@@ -243,11 +245,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    json_fd = None
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its version banner to stdout (C level): route fd 1 to stderr for the run, the JSON line goes to the
+        # saved descriptor at the end, so stdout carries exactly one line
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -271,14 +279,17 @@ def main():
     d_out = torch.empty((F, V, 3), dtype=torch.float32, device=dev)
     d_fall = torch.empty((V,), dtype=torch.float32, device=dev)
 
+    wmode = shard.weights_mode(N, args.weights) if world > 1 else "single"
+
     def step_device():
-        """one pass, everything resident in HBM: fit + solve on rank 0, NCCL broadcast, sharded eval."""
-        if rank == 0:
+        """one pass, everything resident in HBM: fit + solve (on rank 0 + NCCL broadcast, or replicated on every rank
+        for small systems, shard.weights_mode), then the sharded eval."""
+        if rank == 0 or wmode == "replicated":
             m = ctx.fit(params, d_rest)
             m.solve(d_deform)
         else:
             m = ctx.receiver(params, d_rest, F)
-        if world > 1:
+        if wmode == "broadcast":
             shard.broadcast_model(m, 0, shared_stream=True)
         m.eval(d_P, out=d_out, falloff_out=d_fall)
         return m
@@ -328,12 +339,12 @@ def main():
     h_fall = torch.empty((V,), dtype=torch.float32).pin_memory().numpy()
 
     def step_e2e():
-        if rank == 0:
+        if rank == 0 or wmode == "replicated":
             m = ctx.fit(params, h_rest)
             m.solve(h_deform)
         else:
             m = ctx.receiver(params, h_rest, F)
-        if world > 1:
+        if wmode == "broadcast":
             shard.broadcast_model(m, 0, shared_stream=True)
         m.eval(h_P, out=h_out, falloff_out=h_fall)
         m.close()
@@ -402,7 +413,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": describe(cfg), "name": args.config,
                        "l2": "per-step output (F x V x 12 B = %.0f MB) exceeds the 126 MB L2; no explicit flush" % (F * V * 12 / 1e6),
-                       "precision": "FP64 assemble/factor/solve, FP32 evaluation", "parallelism": f"vertex-range x{world}"},
+                       "precision": "FP64 assemble/factor/solve, FP32 evaluation", "parallelism": f"vertex-range x{world}" + ("" if world == 1 else f", weights {wmode}")},
             "phase_ms_last_step": phases, "factor_ms": {"n_ctrl": N, "assemble": phases["assemble"], "factor": phases["factor"],
                                                         "solve": phases["solve"]},
             "roofline": roofline,
@@ -419,7 +430,10 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_sample(cfg, rig, deform, radius, seconds_target=args.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        if json_fd is None:
+            print(json.dumps(line), flush=True)
+        else:
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

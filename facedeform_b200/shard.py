@@ -17,6 +17,24 @@ def vertex_range(n_vtx: int, rank: int, world: int) -> tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+# Up to this many control points every rank factors and solves the (small) system itself instead of waiting for the
+# root's broadcast: the fit costs the same on every rank and runs concurrently, so the step loses nothing and the
+# exchange step (NCCL launch + 1.5 MB over NVLink + the wait for the root) disappears -- SURVEY.md section 8e's
+# "alternative without the broadcast (redundant solve per rank)", valid while 2/3 N^3 << V N 3F / G.
+REPLICATE_MAX_CTRL = 1024
+
+
+def weights_mode(n_ctrl: int, mode: str = "auto") -> str:
+    """how the ranks of a vertex-sharded evaluation get their weights: "broadcast" (root fits and solves, NCCL
+    broadcast of the weight block) or "replicated" (every rank fits and solves; no collective).  Both give bit-identical
+    weights (same deterministic kernels on the same inputs)."""
+    if mode not in ("auto", "broadcast", "replicated"):
+        raise ValueError(mode)
+    if mode != "auto":
+        return mode
+    return "replicated" if int(n_ctrl) <= REPLICATE_MAX_CTRL else "broadcast"
+
+
 class _CudaBlock:
     """zero-copy view of a device allocation owned by libfacedeform_gpu.so (via __cuda_array_interface__)."""
 

@@ -83,3 +83,14 @@ def test_sharded_equals_unsharded_over_gloo():
     out = np.concatenate([g[2] for g in gathered], axis=1)       # concatenation in rank order = vertex order
     fall = np.concatenate([g[3] for g in gathered])
     assert np.array_equal(out, ref) and np.array_equal(fall, rfall)   # bit-identical to the unsharded run
+
+
+def test_weights_mode_policy():
+    """small systems are solved on every rank (no exchange step), large ones by the root + broadcast."""
+    from facedeform_b200 import shard
+    assert shard.weights_mode(256) == "replicated" and shard.weights_mode(1024) == "replicated"
+    assert shard.weights_mode(2048) == "broadcast" and shard.weights_mode(4096) == "broadcast"
+    assert shard.weights_mode(256, "broadcast") == "broadcast" and shard.weights_mode(8192, "replicated") == "replicated"
+    import pytest
+    with pytest.raises(ValueError):
+        shard.weights_mode(10, "gather")
