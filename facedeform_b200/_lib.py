@@ -21,6 +21,8 @@ EXPORTS = [
     "fd_model_create_receiver", "fd_model_weights_dev", "fd_model_radii_dev", "fd_model_commit_weights",
     "fd_model_info", "fd_model_get_weights",
     "fd_capture", "fd_ctx_phase_ms", "fd_ctx_launch_count",
+    "fd_dbse_init", "fd_dbse_compute_weights", "fd_dbse_displace", "fd_dbse_get_weights", "fd_dbse_get_qr", "fd_dbse_info",
+    "fd_dbse_destroy",
     "fd_sop_create", "fd_sop_destroy", "fd_sop_params", "fd_sop_cook", "fd_sop_messages", "fd_sop_fit_count",
 ]
 
@@ -102,6 +104,14 @@ def load() -> C.CDLL:
     L.fd_ctx_phase_ms.restype = C.c_float
     L.fd_ctx_launch_count.argtypes = [vp]
     L.fd_ctx_launch_count.restype = C.c_int64
+    L.fd_dbse_init.argtypes = [vp, fp, C.c_int64, fp, C.c_int32, C.POINTER(vp)]
+    L.fd_dbse_compute_weights.argtypes = [vp, fp, fp, fp]
+    L.fd_dbse_displace.argtypes = [vp, fp, fp, C.c_int32, fp, C.c_int32, C.c_float, fp]
+    L.fd_dbse_get_weights.argtypes = [vp, fp]
+    L.fd_dbse_get_qr.argtypes = [vp, fp, fp]
+    L.fd_dbse_info.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.fd_dbse_destroy.argtypes = [vp]
+    L.fd_dbse_destroy.restype = None
     L.fd_sop_create.argtypes = [C.c_int]
     L.fd_sop_create.restype = vp
     L.fd_sop_destroy.argtypes = [vp]

@@ -171,6 +171,70 @@ class Context:
                     grp_class=gclass[:g].copy(), grp_off=goff[:g + 1].copy(), grp_idx=gidx[:total].copy())
 
 
+class DirectBSEdit:
+    """fd_dbse: the "morph space" post-pass of the SOP (reference src/dbse.{hpp,cpp}, same entry-point names).
+
+    init happens in the constructor (DirectBSEdit::init, dbse.cpp:9-35): `rest` (P, 3) and `shapes` (S, P, 3)."""
+
+    def __init__(self, ctx: Context, rest, shapes):
+        self.ctx, self._L = ctx, ctx._L
+        rest = _host_f32(rest, 3)
+        shapes = np.ascontiguousarray(shapes, dtype=np.float32)
+        if shapes.ndim != 3 or shapes.shape[1:] != rest.shape:
+            raise ValueError("shapes must be (S, P, 3) matching rest (P, 3)")
+        h = C.c_void_p()
+        ctx._check(self._L.fd_dbse_init(ctx._h, _ptr(rest), rest.shape[0], _ptr(shapes), shapes.shape[0], C.byref(h)))
+        self._h, self.n_pts, self.n_shapes = h, rest.shape[0], shapes.shape[0]
+        ctx._models.add(self)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.fd_dbse_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def is_initialized(self) -> bool:                      # DirectBSEdit::isInitialized
+        return bool(self._h)
+
+    def is_computed(self) -> bool:                         # DirectBSEdit::isComputed
+        c = C.c_int32()
+        self._L.fd_dbse_info(self._h, None, None, C.byref(c))
+        return bool(c.value)
+
+    def compute_weights(self, pos, rest):
+        """DirectBSEdit::computeWeights (dbse.cpp:37-58); returns the S weights."""
+        pos, rest = _host_f32(pos, 3), _host_f32(rest, 3)
+        w = np.empty(self.n_shapes, dtype=np.float64)
+        self.ctx._check(self._L.fd_dbse_compute_weights(self._h, _ptr(pos), _ptr(rest), _ptr(w)))
+        return w
+
+    def displace(self, pos, rest, weightrange=None, dofalloff=0, falloffradius=1.0):
+        """displaceVector over all points + the SOP's position write (dbse.cpp:60-75, SOP_FaceDeform.cpp:460-472)."""
+        pos, rest = _host_f32(pos, 3), _host_f32(rest, 3)
+        out = np.empty_like(rest)
+        wr = None if weightrange is None else np.ascontiguousarray(weightrange, dtype=np.float32)
+        self.ctx._check(self._L.fd_dbse_displace(self._h, _ptr(pos), _ptr(rest), 0 if wr is None else 1, _ptr(wr),
+                                                 int(dofalloff), float(falloffradius), _ptr(out)))
+        return out
+
+    def get_weights(self):
+        """DirectBSEdit::getWeights (dbse.cpp:77-87): raises FdError(FD_E_STATE) before compute_weights."""
+        w = np.empty(self.n_shapes, dtype=np.float64)
+        self.ctx._check(self._L.fd_dbse_get_weights(self._h, _ptr(w)))
+        return w
+
+    def packed_qr(self):
+        qr = np.empty((3 * self.n_pts, self.n_shapes), dtype=np.float64, order="F")
+        tau = np.empty(self.n_shapes, dtype=np.float64)
+        self.ctx._check(self._L.fd_dbse_get_qr(self._h, _ptr(qr), _ptr(tau)))
+        return qr, tau
+
+
 class RbfModel:
     """fd_model: centres, radii, LU factors and the weights of the last solve (replaces alglib::rbfmodel)."""
 

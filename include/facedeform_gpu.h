@@ -14,6 +14,8 @@
  *                                                      SOP_FaceDeform.cpp:384-439, SOP_FaceDeform.hpp:28-41
  *   fd_capture        ProximityCapture::init / capture / findIslands
  *                                                      capture.cpp:10-44, :46-105, :107-141 (capture.hpp:21-27)
+ *   fd_dbse_*         DirectBSEdit::init / computeWeights / displaceVector / getWeights (the "morph space" post-pass)
+ *                                                      dbse.cpp:9-87 (dbse.hpp:16-22), SOP_FaceDeform.cpp:444-482
  *   fd_model_report   alglib::rbfreport checked at     SOP_FaceDeform.cpp:365-373
  *   fd_last_error     addError / addWarning strings    SOP_FaceDeform.cpp:231-234, :337-340, :365-368
  *
@@ -87,7 +89,7 @@ typedef struct fd_params {
     float lambda;          /* default 0.1, clamp >= 0.01      :128, :253  (K + lambda I) */
     int32_t tangent;       /* default 0                       :129 */
     int32_t maxedges;      /* default 4, clamp >= 1           :127, :257 */
-    int32_t morphspace;    /* default 0                       :130  (dbse post-pass: carried, not executed) */
+    int32_t morphspace;    /* default 0                       :130  (dbse post-pass: fd_dbse_*, FaceDeformOp::setBlendshapes) */
     int32_t doclampweight; /* default 0                       :131 */
     float weightrange[2];  /* default (0, 1)                  :132 */
     int32_t dofalloff;     /* default 0                       :133 */
@@ -168,6 +170,23 @@ int fd_capture(fd_ctx* ctx, const float* P, int64_t n_vtx, const int32_t* poly_o
                int32_t n_rig_prim, const int32_t* rig_class /* or NULL */, int32_t max_edges, float radius,
                int32_t dofalloff, int32_t* nearest_idx, uint8_t* member, float* dist2, int32_t* n_groups,
                int32_t* grp_class, int64_t* grp_off, int32_t* grp_idx, int32_t grp_cap, int64_t idx_cap);
+
+/* ---- DirectBSEdit: the "morph space" post-pass (dbse.hpp:16-22) ---------------------------------------------------
+ * init: shapes matrix M (3P x S) of FP32 (shape - rest) deltas + its Householder QR (dbse.cpp:9-35); `shapes` is
+ * S x P x 3 floats.  compute_weights: w_s = sum_i (pos - rest)_i * QR(i, s) with the PACKED QR storage, as the
+ * reference does (matrixQR(), dbse.cpp:53-54).  displace: displaceVector for every point + the SOP's write
+ * (dbse.cpp:60-75, SOP_FaceDeform.cpp:460-472): P_out = rest + sum_s M_s * clamp((float)(3 w_s)) [+ (pos - rest) *
+ * falloffradius when dofalloff and falloffradius != 0].  get_weights fails with FD_E_STATE before compute_weights
+ * (getWeights returns false, dbse.cpp:79-81).  get_qr copies the packed QR (3P x S column-major) and tau. */
+typedef struct fd_dbse fd_dbse;
+int fd_dbse_init(fd_ctx* ctx, const float* rest_P, int64_t n_pts, const float* shapes, int32_t n_shapes, fd_dbse** out);
+int fd_dbse_compute_weights(fd_dbse* h, const float* pos, const float* rest, double* weights_out /* S or NULL */);
+int fd_dbse_displace(fd_dbse* h, const float* pos, const float* rest, int32_t doclamp, const float* weightrange /* 2 */,
+                     int32_t dofalloff, float falloffradius, float* P_out /* P x 3 */);
+int fd_dbse_get_weights(fd_dbse* h, double* weights /* S */);
+int fd_dbse_get_qr(fd_dbse* h, double* qr, double* tau);
+int fd_dbse_info(const fd_dbse* h, int64_t* n_pts, int32_t* n_shapes, int32_t* computed);
+void fd_dbse_destroy(fd_dbse* h);
 
 /* timing of the last call on this ctx, measured with CUDA events on the ctx stream (ms); phase: 0 assemble,
  * 1 factor, 2 solve, 3 eval.  Returns < 0 when the phase has not run. */

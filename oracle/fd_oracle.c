@@ -651,3 +651,92 @@ int fdo_capture(const float* P, int64_t V, const int32_t* poly_off, const int32_
     free(adj_off);
     return ngrp;
 }
+
+
+/* ======================================================================================================
+ * DirectBSEdit (reference src/dbse.cpp), see fd_oracle.h
+ * ====================================================================================================== */
+
+/* dbse.cpp:9-35 */
+void fdo_dbse_shapes_matrix(const float* rest, const float* shapes, int64_t P, int32_t S, double* M)
+{
+    const int64_t m = 3 * P;
+    for (int32_t s = 0; s < S; ++s)
+        for (int64_t p = 0; p < P; ++p)
+            for (int k = 0; k < 3; ++k) {
+                const float d = shapes[((int64_t)s * P + p) * 3 + k] - rest[3 * p + k]; /* UT_Vector3 subtraction, :24 */
+                M[(int64_t)s * m + 3 * p + k] = (double)d;                               /* :25-27 */
+            }
+}
+
+/* Eigen::HouseholderQR<MatrixXd> (dbse.cpp:31), unblocked, LAPACK dgeqr2 conventions */
+void fdo_householder_qr(double* A, int64_t m, int32_t n, double* tau)
+{
+    for (int32_t j = 0; j < n && j < m; ++j) {
+        double* x = A + (int64_t)j * m;
+        const double alpha = x[j];
+        double ss = 0.0;
+        for (int64_t i = j + 1; i < m; ++i) ss += x[i] * x[i];
+        if (ss == 0.0) { /* tail is zero: H = I (Eigen: tau = 0, beta = c0) */
+            tau[j] = 0.0;
+            continue;
+        }
+        double beta = sqrt(alpha * alpha + ss);
+        if (alpha >= 0.0) beta = -beta;
+        const double t = (beta - alpha) / beta;
+        const double scale = 1.0 / (alpha - beta);
+        for (int64_t i = j + 1; i < m; ++i) x[i] *= scale;
+        x[j] = beta;
+        tau[j] = t;
+        for (int32_t c = j + 1; c < n; ++c) { /* apply H = I - tau v v^T to the trailing columns */
+            double* y = A + (int64_t)c * m;
+            double w = y[j];
+            for (int64_t i = j + 1; i < m; ++i) w += x[i] * y[i];
+            w *= t;
+            y[j] -= w;
+            for (int64_t i = j + 1; i < m; ++i) y[i] -= w * x[i];
+        }
+    }
+}
+
+/* dbse.cpp:37-58 */
+void fdo_dbse_weights(const double* QR, int64_t P, int32_t S, const float* pos, const float* rest, double* weights)
+{
+    const int64_t m = 3 * P;
+    for (int32_t s = 0; s < S; ++s) {
+        double w = 0.0;
+        for (int64_t i = 0; i < m; ++i) {
+            const float d = pos[i] - rest[i]; /* :46-48 */
+            w += (double)d * QR[(int64_t)s * m + i]; /* (delta.asDiagonal() * matrixQR()).colwise().sum(), :53-54 */
+        }
+        weights[s] = w;
+    }
+}
+
+/* dbse.cpp:60-75 + SOP_FaceDeform.cpp:460-472 */
+void fdo_dbse_displace(const double* M, int64_t P, int32_t S, const double* weights, const float* weightrange,
+                       int32_t dofalloff, float falloffradius, const float* pos, const float* rest, float* P_out)
+{
+    const int64_t m = 3 * P;
+    for (int64_t p = 0; p < P; ++p) {
+        float disp[3] = {0.f, 0.f, 0.f};
+        for (int32_t s = 0; s < S; ++s) {
+            const float w = (float)(weights[s] * 3); /* :69 "magic number" */
+            float cw = w;
+            if (weightrange) cw = w < weightrange[0] ? weightrange[0] : (w > weightrange[1] ? weightrange[1] : w); /* SYSclamp :71 */
+            for (int k = 0; k < 3; ++k) {
+                const float d = (float)M[(int64_t)s * m + 3 * p + k]; /* :65-67 */
+                const float prod = d * cw;
+                disp[k] = disp[k] + prod; /* :72 */
+            }
+        }
+        for (int k = 0; k < 3; ++k) {
+            if (dofalloff && falloffradius != 0.f) { /* SOP_FaceDeform.cpp:467-470 */
+                const float delta = pos[3 * p + k] - rest[3 * p + k];
+                const float prod = delta * falloffradius;
+                disp[k] = disp[k] + prod;
+            }
+            P_out[3 * p + k] = rest[3 * p + k] + disp[k]; /* :471 */
+        }
+    }
+}

@@ -110,6 +110,23 @@ int fdo_capture(const float* P, int64_t V, const int32_t* poly_off, const int32_
 float fdo_point_tri_dist2(const float p[3], const float a[3], const float b[3], const float c[3]);
 float fdo_point_seg_dist2(const float p[3], const float a[3], const float b[3]);
 
+/* ---- DirectBSEdit, the "morph space" post-pass (reference src/dbse.cpp, caller SOP_FaceDeform.cpp:444-482) ----------
+ * Eigen (absent, unpinned) supplies HouseholderQR there; restated here as the unblocked Householder QR with Eigen's /
+ * LAPACK dgeqr2's conventions [recollection for Eigen; pinned against LAPACK through scipy.linalg.qr(mode="raw")]:
+ * beta = -sign(alpha) |x|, v = x / (alpha - beta) with v0 = 1 implied, tau = (beta - alpha) / beta; packed storage =
+ * R in the upper triangle, the essential parts of v below the diagonal (what Eigen's matrixQR() returns). */
+/* dbse.cpp:9-35: M (3P x S, column-major doubles) = shape - rest, subtracted in FP32 (UT_Vector3) and widened */
+void fdo_dbse_shapes_matrix(const float* rest, const float* shapes /* S x P x 3 */, int64_t P, int32_t S, double* M);
+/* in place: A (m x n column-major, lda = m) -> packed QR; tau[n] */
+void fdo_householder_qr(double* A, int64_t m, int32_t n, double* tau);
+/* dbse.cpp:37-58: delta = pos - rest (FP32 subtract, widened); weights[s] = sum_i delta_i * QR(i, s) */
+void fdo_dbse_weights(const double* QR, int64_t P, int32_t S, const float* pos, const float* rest, double* weights);
+/* dbse.cpp:60-75 for every point + the SOP's write SOP_FaceDeform.cpp:460-472 (all FP32, un-fused, columns in order):
+ * disp = sum_s (float)M[3p..3p+2][s] * clamp((float)(w_s * 3)); disp += (pos - rest) * falloffradius when dofalloff
+ * and falloffradius != 0; P_out = rest + disp.  weightrange == NULL: no clamping. */
+void fdo_dbse_displace(const double* M, int64_t P, int32_t S, const double* weights, const float* weightrange,
+                       int32_t dofalloff, float falloffradius, const float* pos, const float* rest, float* P_out);
+
 int fdo_num_threads(void);
 
 #ifdef __cplusplus

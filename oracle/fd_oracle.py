@@ -79,6 +79,10 @@ def lib():
         L.fdo_point_seg_dist2.argtypes = [fp, fp, fp]
         L.fdo_point_seg_dist2.restype = C.c_float
         L.fdo_num_threads.restype = C.c_int
+        L.fdo_dbse_shapes_matrix.argtypes = [fp, fp, C.c_int64, C.c_int32, dp]
+        L.fdo_householder_qr.argtypes = [dp, C.c_int64, C.c_int32, dp]
+        L.fdo_dbse_weights.argtypes = [dp, C.c_int64, C.c_int32, fp, fp, dp]
+        L.fdo_dbse_displace.argtypes = [dp, C.c_int64, C.c_int32, dp, fp, C.c_int32, C.c_float, fp, fp, fp]
         _lib = L
     return _lib
 
@@ -247,3 +251,44 @@ def capture(P, poly_off, poly_vtx, rigP, rig_off, rig_vtx, rig_class, max_edges,
     g = call(gidx, total)
     return dict(ngroups=g, nearest_idx=nearest, member=member.astype(bool), dist2=dist2,
                 grp_class=gclass[:g].copy(), grp_off=goff[:g + 1].copy(), grp_idx=gidx[:total].copy())
+
+
+# ---- DirectBSEdit (reference src/dbse.cpp) --------------------------------------------------------------------------
+
+def dbse_shapes_matrix(rest, shapes):
+    """(3P, S) matrix of FP32 shape deltas widened to FP64 (dbse.cpp:9-35); returned column-major (Fortran order)."""
+    rest = np.ascontiguousarray(rest, dtype=np.float32)
+    shapes = np.ascontiguousarray(shapes, dtype=np.float32)
+    S, P = shapes.shape[0], rest.shape[0]
+    M = np.empty((3 * P, S), dtype=np.float64, order="F")
+    lib().fdo_dbse_shapes_matrix(_f(rest), _f(shapes), P, S, M.ctypes.data_as(C.POINTER(C.c_double)))
+    return M
+
+
+def householder_qr(M):
+    """packed Householder QR (R above, essential reflector parts below the diagonal) and tau, LAPACK conventions."""
+    A = np.array(M, dtype=np.float64, order="F", copy=True)
+    tau = np.zeros(A.shape[1], dtype=np.float64)
+    lib().fdo_householder_qr(A.ctypes.data_as(C.POINTER(C.c_double)), A.shape[0], A.shape[1], _d(tau))
+    return A, tau
+
+
+def dbse_weights(QR, pos, rest):
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    rest = np.ascontiguousarray(rest, dtype=np.float32)
+    QR = np.asfortranarray(QR, dtype=np.float64)
+    w = np.zeros(QR.shape[1], dtype=np.float64)
+    lib().fdo_dbse_weights(QR.ctypes.data_as(C.POINTER(C.c_double)), rest.shape[0], QR.shape[1], _f(pos), _f(rest), _d(w))
+    return w
+
+
+def dbse_displace(M, weights, pos, rest, weightrange=None, dofalloff=0, falloffradius=1.0):
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    rest = np.ascontiguousarray(rest, dtype=np.float32)
+    M = np.asfortranarray(M, dtype=np.float64)
+    weights = np.ascontiguousarray(weights, dtype=np.float64)
+    out = np.empty_like(rest)
+    wr = None if weightrange is None else np.ascontiguousarray(weightrange, dtype=np.float32)
+    lib().fdo_dbse_displace(M.ctypes.data_as(C.POINTER(C.c_double)), rest.shape[0], M.shape[1], _d(weights),
+                            None if wr is None else _f(wr), int(dofalloff), float(falloffradius), _f(pos), _f(rest), _f(out))
+    return out
