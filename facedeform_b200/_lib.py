@@ -24,6 +24,7 @@ EXPORTS = [
     "fd_dbse_init", "fd_dbse_compute_weights", "fd_dbse_displace", "fd_dbse_get_weights", "fd_dbse_get_qr", "fd_dbse_info",
     "fd_dbse_destroy",
     "fd_sop_create", "fd_sop_destroy", "fd_sop_params", "fd_sop_cook", "fd_sop_messages", "fd_sop_fit_count",
+    "fd_sop_set_blendshapes", "fd_sop_blend_weights",
 ]
 
 
@@ -112,6 +113,8 @@ def load() -> C.CDLL:
     L.fd_dbse_info.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.fd_dbse_destroy.argtypes = [vp]
     L.fd_dbse_destroy.restype = None
+    L.fd_sop_set_blendshapes.argtypes = [vp, fp, C.c_int32, C.c_int64, C.c_int64]
+    L.fd_sop_blend_weights.argtypes = [vp, fp, C.c_int32]
     L.fd_sop_create.argtypes = [C.c_int]
     L.fd_sop_create.restype = vp
     L.fd_sop_destroy.argtypes = [vp]

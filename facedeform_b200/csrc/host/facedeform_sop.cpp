@@ -51,6 +51,58 @@ FaceDeformOp::FaceDeformOp(int device) : m_mesh_capture(nullptr)
     fd_params_default(&parms);
     if (fd_ctx_create(&m_ctx, device, nullptr) != FD_OK) m_ctx = nullptr;
     m_mesh_capture = ProximityCapture(m_ctx);
+    m_direct_blends.reset(new DirectBSEdit(m_ctx));
+}
+
+// ---- DirectBSEdit (reference src/dbse.cpp) over fd_dbse_* ----------------------------------------------------------
+DirectBSEdit::~DirectBSEdit()
+{
+    if (m_h) fd_dbse_destroy(m_h);
+}
+
+bool DirectBSEdit::init(const Geo& gdp, const ShapesVector& shapes)
+{
+    if (m_h) {
+        fd_dbse_destroy(m_h);
+        m_h = nullptr;
+    }
+    m_computed = false; // we need to recompute weights (dbse.cpp:33)
+    m_shapes = (int)shapes.size();
+    if (!m_ctx || shapes.empty() || gdp.npoints < 1) return false;
+    // the C ABI takes the S shapes contiguously (S x P x 3)
+    std::vector<float> packed((size_t)shapes.size() * gdp.npoints * 3);
+    for (size_t s = 0; s < shapes.size(); ++s)
+        std::memcpy(packed.data() + s * gdp.npoints * 3, shapes[s], (size_t)gdp.npoints * 3 * sizeof(float));
+    return fd_dbse_init(m_ctx, gdp.P, gdp.npoints, packed.data(), (int32_t)shapes.size(), &m_h) == FD_OK;
+}
+
+bool DirectBSEdit::computeWeights(const float* pos, const float* rest)
+{
+    if (!m_h || !pos || !rest) return false; // rest_h.isInvalid(), dbse.cpp:39-41
+    m_computed = fd_dbse_compute_weights(m_h, pos, rest, nullptr) == FD_OK;
+    return m_computed;
+}
+
+bool DirectBSEdit::displace(const float* pos, const float* rest, const float* clamp, int dofalloff, float falloffradius,
+                            float* P_out)
+{
+    return m_h && m_computed &&
+           fd_dbse_displace(m_h, pos, rest, clamp ? 1 : 0, clamp, dofalloff, falloffradius, P_out) == FD_OK;
+}
+
+bool DirectBSEdit::getWeights(std::vector<double>& weights_array)
+{
+    if (!m_computed) return false; // dbse.cpp:79-81
+    weights_array.resize((size_t)m_shapes);
+    return fd_dbse_get_weights(m_h, weights_array.data()) == FD_OK;
+}
+
+void FaceDeformOp::setBlendshapes(const std::vector<const float*>& shapes, const std::vector<int64_t>& npoints,
+                                  int64_t data_id)
+{
+    m_blend_shapes = shapes;
+    m_blend_npoints = npoints;
+    m_blend_id = data_id;
 }
 
 FaceDeformOp::~FaceDeformOp()
@@ -140,6 +192,37 @@ CookStatus FaceDeformOp::cook(const Geo& mesh, const Geo& rest_rig, const float*
         addError(fd_last_error(m_ctx));
         return COOK_ERROR;
     }
+    // Any inputs above 2 are morph targets: project the deformation onto them (SOP_FaceDeform.cpp:325-329, :444-482)
+    if (p.morphspace && !m_blend_shapes.empty()) {
+        // setupBlends (:175-213): the rest attribute is the undeformed mesh; re-init when the blendshapes changed
+        if (rest_pose_changed || m_blend_built_id != m_blend_id || !m_direct_blends->isInitialized()) {
+            DirectBSEdit::ShapesVector shapes;
+            for (size_t i = 0; i < m_blend_shapes.size(); ++i) {
+                if (i >= m_blend_npoints.size() || m_blend_npoints[i] != mesh.npoints) {
+                    addWarning("Some blendshapes don't match rest pose point count. Ignoring them."); // :201-205
+                    continue;
+                }
+                shapes.push_back(m_blend_shapes[i]);
+            }
+            if (!m_direct_blends->init(mesh, shapes))
+                addWarning("Can't proceed with morph space deformation. Ingoring it."); // :209-211
+            m_blend_built_id = m_blend_id;
+        }
+        if (m_direct_blends->isInitialized()) {
+            const float* clamp = p.doclampweight ? p.weightrange : nullptr; // :455-458
+            for (int f = 0; f < frames; ++f) {
+                float* Pf = P_out + (size_t)f * mesh.npoints * 3;
+                // The reference computes the weights only while !isComputed() and warns otherwise (:448-452), so a
+                // second cook would skip the pass; here they are recomputed for every cooked frame.
+                if (!m_direct_blends->computeWeights(Pf, mesh.P)) {
+                    addWarning("Can't compute weights for morphspace deformation. Ingoring it."); // :451-452
+                    break;
+                }
+                m_direct_blends->displace(Pf, mesh.P, clamp, p.dofalloff, p.falloffradius, Pf); // :460-472
+            }
+            m_direct_blends->getWeights(m_blend_weights); // the "weights" detail attribute, :474-480
+        }
+    }
     return m_warnings.empty() ? COOK_OK : COOK_WARNING;
 }
 
@@ -151,6 +234,7 @@ extern "C" {
 struct fd_sop {
     fd::FaceDeformOp op;
     std::string joined;
+    std::vector<float> blends; // copy of the blendshape inputs (the shim owns what the operator points at)
     explicit fd_sop(int device) : op(device) {}
 };
 
@@ -186,5 +270,28 @@ const char* fd_sop_messages(fd_sop* s, int kind)
 }
 
 int fd_sop_fit_count(const fd_sop* s) { return s ? s->op.fits() : 0; }
+
+int fd_sop_set_blendshapes(fd_sop* s, const float* shapes, int32_t n_shapes, int64_t n_pts, int64_t data_id)
+{
+    if (!s || n_shapes < 0 || (n_shapes > 0 && (!shapes || n_pts < 1))) return FD_E_INVALID;
+    s->blends.assign(shapes, shapes + (size_t)n_shapes * n_pts * 3);
+    std::vector<const float*> ptrs;
+    std::vector<int64_t> np;
+    for (int32_t i = 0; i < n_shapes; ++i) {
+        ptrs.push_back(s->blends.data() + (size_t)i * n_pts * 3);
+        np.push_back(n_pts);
+    }
+    s->op.setBlendshapes(ptrs, np, data_id);
+    return FD_OK;
+}
+
+int fd_sop_blend_weights(fd_sop* s, double* weights, int32_t cap)
+{
+    if (!s) return -1;
+    const std::vector<double>& w = s->op.blendWeights();
+    if (weights)
+        for (size_t i = 0; i < w.size() && (int32_t)i < cap; ++i) weights[i] = w[i];
+    return (int)w.size();
+}
 
 } // extern "C"

@@ -209,6 +209,10 @@ int fd_sop_cook(fd_sop* s, const float* mesh_P, int64_t n_vtx, const int32_t* po
                 float* falloff_out);
 const char* fd_sop_messages(fd_sop* s, int kind); /* 0 errors, 1 warnings, 2 messages */
 int fd_sop_fit_count(const fd_sop* s);
+/* inputs >= 3 of the SOP (blendshapes of the morph-space pass, `morphspace` parm): n_shapes x n_pts x 3 floats, copied */
+int fd_sop_set_blendshapes(fd_sop* s, const float* shapes, int32_t n_shapes, int64_t n_pts, int64_t data_id);
+/* the "weights" detail attribute of the last cook (SOP_FaceDeform.cpp:474-480); returns their count */
+int fd_sop_blend_weights(fd_sop* s, double* weights, int32_t cap);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@
 // (src/capture.{hpp,cpp}).  Houdini's HDK is absent, so geometry arrives as plain arrays (fd::Geo) instead of
 // GU_Detail; everything else keeps the reference's names, argument meaning and error behaviour:
 //   fd::ProximityCapture::{init, capture, isInitialized, isCaptured, getDistanceAttribute}   capture.hpp:21-27
+//   fd::DirectBSEdit::{init, isInitialized, computeWeights, isComputed, displace, getWeights}   dbse.hpp:16-22
 //   fd::FaceDeformOp::cook                                          SOP_FaceDeform::cookMySop, SOP_FaceDeform.cpp:215-489
 //   parameter accessors MODEL/TERM/QCOEF/ZCOEF/RADIUS/LAYERS/LAMBDA/TANGENT/MAXEDGES/DOFALLOFF/FALLOFFRATE
 //                                                                   SOP_FaceDeform.hpp:84-101
@@ -12,6 +13,7 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -57,6 +59,29 @@ private:
     std::vector<int32_t> m_nearest;
 };
 
+// the "morph space" post-pass (reference src/dbse.{hpp,cpp}); blendshapes arrive as plain P x 3 float arrays
+class DirectBSEdit {
+public:
+    typedef std::vector<const float*> ShapesVector;
+    explicit DirectBSEdit(fd_ctx* ctx) : m_ctx(ctx) {}
+    ~DirectBSEdit();
+    DirectBSEdit(const DirectBSEdit&) = delete;
+    DirectBSEdit& operator=(const DirectBSEdit&) = delete;
+    bool init(const Geo& gdp, const ShapesVector& shapes);                               // dbse.cpp:9-35
+    bool isInitialized() const { return m_h != nullptr; }
+    bool computeWeights(const float* pos, const float* rest);                            // dbse.cpp:37-58
+    bool isComputed() const { return m_computed; }
+    // displaceVector for every point + the position write of SOP_FaceDeform.cpp:460-472 (clamp: nullptr = no clamping)
+    bool displace(const float* pos, const float* rest, const float* clamp, int dofalloff, float falloffradius, float* P_out);
+    bool getWeights(std::vector<double>& weights_array);                                 // dbse.cpp:77-87
+
+private:
+    fd_ctx* m_ctx;
+    fd_dbse* m_h = nullptr;
+    bool m_computed = false;
+    int m_shapes = 0;
+};
+
 // status of a cook, the analogue of OP_ERROR + the node's message lists
 enum CookStatus { COOK_OK = 0, COOK_WARNING = 1, COOK_ERROR = 2 };
 
@@ -88,6 +113,11 @@ public:
     CookStatus cook(const Geo& mesh, const Geo& rest_rig, const float* deform_rig_P, int64_t deform_npoints,
                     int frames, float* P_out, float* falloff_out);
 
+    // inputs >= 3 of the SOP: the blendshapes of the morph-space pass (setupBlends, SOP_FaceDeform.cpp:175-213);
+    // npoints[i] != mesh point count => the shape is ignored with the reference's warning.  data_id tracks changes.
+    void setBlendshapes(const std::vector<const float*>& shapes, const std::vector<int64_t>& npoints, int64_t data_id);
+    const std::vector<double>& blendWeights() const { return m_blend_weights; } // the "weights" detail attribute, :474-480
+
     const std::vector<std::string>& errors() const { return m_errors; }
     const std::vector<std::string>& warnings() const { return m_warnings; }
     const std::vector<std::string>& messages() const { return m_messages; }
@@ -103,6 +133,11 @@ private:
     fd_ctx* m_ctx = nullptr;
     fd_model* m_model = nullptr;
     ProximityCapture m_mesh_capture;
+    std::unique_ptr<DirectBSEdit> m_direct_blends;
+    std::vector<const float*> m_blend_shapes;
+    std::vector<int64_t> m_blend_npoints;
+    int64_t m_blend_id = -2, m_blend_built_id = -3;
+    std::vector<double> m_blend_weights;
     // InputGeoID trackers (SOP_FaceDeform.hpp:47-63): mesh, rest rig
     int64_t m_mesh_ids[2] = {-2, -2};
     int64_t m_rig_ids[2] = {-2, -2};

@@ -91,3 +91,41 @@ def test_cook_errors_and_warnings_quote_the_reference():
     st, _, _ = sop.cook(mesh, empty, np.zeros((1, 0, 3), np.float32), rig_ids=(6, 6), cls=np.zeros(0, np.int32))
     assert st == 2 and sop.msgs(0) == "Can't capture geometry with a rig!"             # :318-321
     sop.close()
+
+
+def test_cook_morph_space_pass(oracle):
+    """morphspace = 1 with blendshape inputs: after the RBF evaluation the cook projects the deformation onto the
+    blendshapes (SOP_FaceDeform.cpp:444-482, dbse.cpp) -- same result as the oracle's DirectBSEdit fed the cook's own
+    RBF output, the reference's warnings for mismatched shapes, and the "weights" detail attribute."""
+    mesh = synth.face_mesh(4_000)
+    rig = synth.control_rig(32, prims=True)
+    deform = synth.deformed_rig(rig, 2)
+    rng = np.random.default_rng(4)
+    V, S = mesh.P.shape[0], 5
+    shapes = (mesh.P[None] + 0.05 * rng.standard_normal((S, V, 3))).astype(np.float32)
+    sop = Sop()
+    sop.parms.model, sop.parms.radius, sop.parms.lambda_ = 1, 2 * rig.spacing, 0.0
+    st, plain, _ = sop.cook(mesh, rig, deform)                     # morphspace off: the RBF result
+    assert st == 0
+    sop.parms.morphspace, sop.parms.doclampweight = 1, 1
+    sop.parms.weightrange[0], sop.parms.weightrange[1] = -0.5, 0.75
+    assert sop.L.fd_sop_set_blendshapes(sop.h, shapes.ctypes.data, S, V, 7) == 0
+    st, out, _ = sop.cook(mesh, rig, deform)
+    assert st == 0, sop.msgs(1)
+    M = oracle.dbse_shapes_matrix(mesh.P, shapes)
+    QR, _ = oracle.householder_qr(M)
+    for f in range(2):
+        w = oracle.dbse_weights(QR, plain[f], mesh.P)
+        ref = oracle.dbse_displace(M, w, plain[f], mesh.P, weightrange=(-0.5, 0.75))
+        np.testing.assert_allclose(out[f], ref, rtol=0, atol=3e-6)
+    wts = np.zeros(S)
+    assert sop.L.fd_sop_blend_weights(sop.h, wts.ctypes.data, S) == S
+    np.testing.assert_allclose(wts, w, rtol=0, atol=1e-10 * np.abs(w).max())   # weights of the last cooked frame
+    # a blendshape set with the wrong point count is ignored with the reference's warnings (:201-205, :209-211)
+    bad = shapes[:, :-1].copy()
+    assert sop.L.fd_sop_set_blendshapes(sop.h, bad.ctypes.data, S, V - 1, 8) == 0
+    st, out_bad, _ = sop.cook(mesh, rig, deform)
+    assert st == 1 and "Some blendshapes don't match rest pose point count. Ignoring them." in sop.msgs(1)
+    assert "Can't proceed with morph space deformation. Ingoring it." in sop.msgs(1)
+    np.testing.assert_array_equal(out_bad, plain)
+    sop.close()
