@@ -78,6 +78,7 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
     if (!m) return FD_E_NOMEM;
     memset(m, 0, sizeof(*m));
     m->ctx = ctx;
+    fd_ctx_retain(ctx);
     m->prm = *params;
     m->N = N;
     m->np = fd_poly_terms(params->term);
@@ -250,9 +251,20 @@ int fd_ctx_create(fd_ctx** out, int device, void* stream)
     return FD_OK;
 }
 
+static void ctx_teardown(fd_ctx* ctx);
+
 void fd_ctx_destroy(fd_ctx* ctx)
 {
     if (!ctx) return;
+    if (ctx->refs > 0) { // live models / dbse handles: they finish the teardown (fd_ctx_release)
+        ctx->destroy_requested = true;
+        return;
+    }
+    ctx_teardown(ctx);
+}
+
+static void ctx_teardown(fd_ctx* ctx)
+{
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < FD_NUM_STAGE; ++i)
@@ -289,6 +301,8 @@ int64_t fd_ctx_launch_count(const fd_ctx* ctx) { return ctx ? ctx->launches : 0;
 void fd_model_destroy(fd_model* m)
 {
     if (!m) return;
+    fd_ctx* owner = m->ctx;
+    {
     DeviceGuard g(m->ctx->device);
     cudaStream_t s = m->ctx->stream; // stream-ordered frees: later work on the stream may reuse the blocks safely
     void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
@@ -298,6 +312,8 @@ void fd_model_destroy(fd_model* m)
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;
+    }
+    fd_ctx_release(owner);
 }
 
 // rbfcreate + rbfsetpoints + rbfsetalgo* + rbfset*term + the factorisation half of rbfbuildmodel
@@ -569,6 +585,12 @@ int fd_model_get_weights(fd_model* m, double* weights, double* radii)
 }
 
 } // extern "C"
+
+void fd_ctx_retain(fd_ctx* ctx) { ++ctx->refs; }
+void fd_ctx_release(fd_ctx* ctx)
+{
+    if (--ctx->refs == 0 && ctx->destroy_requested) ctx_teardown(ctx);
+}
 
 // exposed to fd_capture_host.cu
 int fd_stage(fd_ctx* ctx, int slot, size_t bytes, void** out) { return stage(ctx, slot, bytes, out); }

@@ -259,12 +259,16 @@ extern "C" {
 void fd_dbse_destroy(fd_dbse* h)
 {
     if (!h) return;
-    DevGuard g(h->ctx->device);
-    cudaStreamSynchronize(h->ctx->stream);
-    void* blocks[] = {h->d_M32, h->d_QR, h->d_tau, h->d_w, h->d_cw, h->d_part, h->d_hh, h->d_a, h->d_b, h->d_o};
-    for (void* b : blocks)
-        if (b) cudaFree(b);
-    delete h;
+    fd_ctx* owner = h->ctx;
+    {
+        DevGuard g(owner->device);
+        cudaStreamSynchronize(owner->stream);
+        void* blocks[] = {h->d_M32, h->d_QR, h->d_tau, h->d_w, h->d_cw, h->d_part, h->d_hh, h->d_a, h->d_b, h->d_o};
+        for (void* b : blocks)
+            if (b) cudaFree(b);
+        delete h;
+    }
+    fd_ctx_release(owner);
 }
 
 int fd_dbse_init(fd_ctx* ctx, const float* rest_P, int64_t n_pts, const float* shapes, int32_t n_shapes, fd_dbse** out)
@@ -277,6 +281,7 @@ int fd_dbse_init(fd_ctx* ctx, const float* rest_P, int64_t n_pts, const float* s
     if (!h) return FD_E_NOMEM;
     memset(h, 0, sizeof(*h));
     h->ctx = ctx;
+    fd_ctx_retain(ctx);
     h->P = n_pts;
     h->m = 3 * n_pts;
     h->lda = (h->m + 3) / 4 * 4;

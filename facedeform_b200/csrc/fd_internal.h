@@ -43,7 +43,13 @@ struct fd_ctx {
     // grid-barrier counter of the persistent factorisation kernels: monotonic, the host tracks its value (sync_base)
     unsigned* d_sync;
     unsigned sync_base;
+    // handles created from this ctx (fd_model, fd_dbse) keep it alive: fd_ctx_destroy with live handles only marks
+    // the ctx, the teardown happens when the last handle is destroyed (any destruction order is safe for the caller)
+    int refs;
+    bool destroy_requested;
 };
+void fd_ctx_retain(fd_ctx* ctx);
+void fd_ctx_release(fd_ctx* ctx); // fd_api.cu
 
 struct fd_model {
     fd_ctx* ctx;

@@ -75,3 +75,23 @@ def test_face_sized_blendshape_set(ctx, oracle):
     out = b.displace(pos, rest, weightrange=(0.0, 1.0))
     np.testing.assert_array_equal(out, oracle.dbse_displace(M, w, pos, rest, weightrange=(0.0, 1.0)))
     b.close()
+
+
+def test_handles_outlive_their_ctx_safely():
+    """fd_ctx_destroy with live handles defers the teardown to the last handle (any destruction order is safe: a
+    garbage collector may finalise the ctx before the models it created)."""
+    import ctypes as C
+    from facedeform_b200 import _lib, make_params
+    L = _lib.load()
+    ctx = C.c_void_p()
+    assert L.fd_ctx_create(C.byref(ctx), -1, None) == 0
+    rest, shapes, pos = _case(3, 500, 4)
+    h, m = C.c_void_p(), C.c_void_p()
+    assert L.fd_dbse_init(ctx, rest.ctypes.data, 500, shapes.ctypes.data, 4, C.byref(h)) == 0
+    p = make_params(model=1, radius=0.5, **{"lambda": 0.0})
+    assert L.fd_rbf_fit(ctx, C.byref(p), rest.ctypes.data, 40, C.byref(m), None) == 0
+    L.fd_ctx_destroy(ctx)                       # both handles still alive
+    w = np.empty(4)
+    assert L.fd_dbse_compute_weights(h, pos.ctypes.data, rest.ctypes.data, w.ctypes.data) == 0 and np.isfinite(w).all()
+    L.fd_model_destroy(m)
+    L.fd_dbse_destroy(h)                        # the last handle tears the ctx down
