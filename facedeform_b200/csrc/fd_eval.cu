@@ -8,6 +8,8 @@
 // their 3*FC accumulators in registers.  Shared-memory reads are warp-wide broadcasts (LDS.128), so per
 // (vertex, centre) pair the issue slots are 6 (distance) + 1-2 (kernel) + 1 MUFU + 3*FC FMA.
 // The same template instantiates the FP64 variant used for multiquadric / thin-plate accuracy.
+#include <stdlib.h>
+
 #include "fd_internal.h"
 
 namespace {
@@ -36,6 +38,42 @@ __device__ __forceinline__ float sqrt_approx(float x)
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// packed FP32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a): the same arithmetic for two vertices in one issue slot
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
 }
 
 template <int KERNEL> __device__ __forceinline__ float phi(float r2, float prm)
@@ -268,6 +306,123 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_simt(const EvalArgs a)
     finish_vertices<T, FC, VPT>(a, W, f0, ncol, vbase, px, py, pz, pos, acc);
 }
 
+// FP32 FMA/SFU path with packed pairs: a thread owns two vertices and carries them as the two halves of FP32x2
+// registers, so the distance, the kernel argument and the 3 FC accumulations of both take one issue slot each
+// (per vertex-centre pair 3.5 + 1.5 FC packed instructions + 1 MUFU instead of 8 + 3 FC + 1: the scalar kernel was
+// issue-bound at 64 % of the FMA pipe).  Lane-wise identical arithmetic to k_eval_simt<float> (same rounding per op).
+template <int KERNEL, int FC, int VP>
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32x2(const EvalArgs a)
+{
+    constexpr int VPT = 2 * VP; // VP packed pairs of vertices per thread
+    constexpr int WPAD = (3 * FC + 3) / 4 * 4;
+    __shared__ float4 s_c[TJ];
+    __shared__ __align__(16) float s_w[TJ * WPAD];
+
+    const int f0 = blockIdx.y * FC;
+    const int64_t vbase = (int64_t)blockIdx.x * (EVAL_THREADS * VPT) + threadIdx.x;
+    float px[VPT], py[VPT], pz[VPT];
+    float pos[VPT][3];
+#pragma unroll
+    for (int u = 0; u < VPT; ++u) {
+        const int64_t v = vbase + (int64_t)u * EVAL_THREADS;
+        if (v < a.V) {
+            pos[u][0] = a.P[3 * v];
+            pos[u][1] = a.P[3 * v + 1];
+            pos[u][2] = a.P[3 * v + 2];
+        } else {
+            pos[u][0] = pos[u][1] = pos[u][2] = 0.f;
+        }
+        px[u] = pos[u][0];
+        py[u] = pos[u][1];
+        pz[u] = pos[u][2];
+    }
+    uint64_t px2[VP], py2[VP], pz2[VP];
+#pragma unroll
+    for (int g = 0; g < VP; ++g) {
+        px2[g] = pack2(px[2 * g], px[2 * g + 1]);
+        py2[g] = pack2(py[2 * g], py[2 * g + 1]);
+        pz2[g] = pack2(pz[2 * g], pz[2 * g + 1]);
+    }
+    uint64_t acc2[VP][3 * FC];
+#pragma unroll
+    for (int g = 0; g < VP; ++g)
+#pragma unroll
+        for (int c = 0; c < 3 * FC; ++c) acc2[g][c] = pack2(0.f, 0.f);
+
+    const float4* __restrict__ ctab = (const float4*)a.ctab;
+    const float* __restrict__ W = (const float*)a.W;
+    const int ncol = min(3 * FC, 3 * (a.F - f0));
+
+    for (int j0 = 0; j0 < a.N; j0 += TJ) {
+        const int cnt = min(TJ, a.N - j0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < TJ; t += EVAL_THREADS)
+            s_c[t] = t < cnt ? ctab[j0 + t] : make_float4(0.f, 0.f, 0.f, KERNEL == FD_KERNEL_MULTIQUADRIC ? 1.f : 0.f);
+        for (int t = threadIdx.x; t < TJ * WPAD; t += EVAL_THREADS) {
+            const int j = t / WPAD, c = t - j * WPAD;
+            s_w[t] = (j < cnt && c < ncol) ? W[(size_t)(j0 + j) * a.ldw + 3 * f0 + c] : 0.f;
+        }
+        __syncthreads();
+        const int jn = (cnt + 3) & ~3; // padded centres carry zero weights
+#pragma unroll 4
+        for (int j = 0; j < jn; ++j) {
+            const float4 c = s_c[j];
+            float w[WPAD];
+#pragma unroll
+            for (int q = 0; q < WPAD; q += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(&s_w[j * WPAD + q]);
+                w[q] = t4.x; w[q + 1] = t4.y; w[q + 2] = t4.z; w[q + 3] = t4.w;
+            }
+            const uint64_t cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z), cw = pack2(c.w, c.w);
+#pragma unroll
+            for (int g = 0; g < VP; ++g) {
+                const uint64_t dx = sub2(px2[g], cx), dy = sub2(py2[g], cy), dz = sub2(pz2[g], cz);
+                const uint64_t r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                float t0, t1;
+                uint64_t ph2;
+                if (KERNEL == FD_KERNEL_GAUSSIAN) {
+                    unpack2(mul2(r2, cw), t0, t1);
+                    ph2 = pack2(ex2_approx(t0), ex2_approx(t1));
+                } else if (KERNEL == FD_KERNEL_MULTIQUADRIC) {
+                    unpack2(add2(r2, cw), t0, t1);
+                    ph2 = pack2(sqrt_approx(t0), sqrt_approx(t1));
+                } else {
+                    unpack2(r2, t0, t1);
+                    ph2 = pack2(phi<KERNEL>(t0, 0.f), phi<KERNEL>(t1, 0.f));
+                }
+#pragma unroll
+                for (int q = 0; q < 3 * FC; ++q) acc2[g][q] = fma2(pack2(w[q], w[q]), ph2, acc2[g][q]);
+            }
+        }
+    }
+    float acc[VPT][3 * FC];
+#pragma unroll
+    for (int g = 0; g < VP; ++g)
+#pragma unroll
+        for (int q = 0; q < 3 * FC; ++q) unpack2(acc2[g][q], acc[2 * g][q], acc[2 * g + 1][q]);
+    finish_vertices<float, FC, VPT>(a, W, f0, ncol, vbase, px, py, pz, pos, acc);
+}
+
+template <int KERNEL, int FC, int VP>
+cudaError_t launch_f32x2(fd_ctx* ctx, const EvalArgs& a)
+{
+    dim3 grid((unsigned)((a.V + EVAL_THREADS * 2 * VP - 1) / (EVAL_THREADS * 2 * VP)), (unsigned)((a.F + FC - 1) / FC));
+    k_eval_f32x2<KERNEL, FC, VP><<<grid, EVAL_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+template <int KERNEL>
+cudaError_t launch_f32x2_fc(fd_ctx* ctx, const EvalArgs& a)
+{
+    static const int vp_env = getenv("FD_EVAL_VP") ? atoi(getenv("FD_EVAL_VP")) : 0;
+    if (a.F >= 4) return launch_f32x2<KERNEL, 4, 1>(ctx, a);
+    if (a.F >= 2) return launch_f32x2<KERNEL, 2, 1>(ctx, a);
+    // one frame: two packed pairs per thread when there are enough vertices to fill the GPU that way
+    const bool wide = vp_env ? vp_env == 2 : a.V >= (int64_t)ctx->sm_count * EVAL_THREADS * 4 * 4;
+    return wide ? launch_f32x2<KERNEL, 1, 2>(ctx, a) : launch_f32x2<KERNEL, 1, 1>(ctx, a);
+}
+
 // FP64 multiquadric / thin plate: distance in the expanded form (the centre table holds -2 (c - o) and |c - o|^2 +
 // kernel parameter, o = centre 0; cancellation is harmless at 53 bits), kernel functions from fast_sqrt64 / half_log64:
 // per (vertex, centre) pair 4 + 4 (+ 8 thin plate) + 3 FC FP64 instructions instead of ~26 / ~60 with libdevice.
@@ -425,5 +580,11 @@ cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64
     a.ctab = m->d_ctab32;
     a.W = m->d_W32;
     a.ldw = m->ldw32;
-    return launch_kernel<float>(ctx, m->prm.kernel, a);
+    static const bool scalar_f32 = getenv("FD_EVAL_SCALAR_F32") != nullptr; // the un-packed kernel, kept for comparison
+    if (scalar_f32) return launch_kernel<float>(ctx, m->prm.kernel, a);
+    switch (m->prm.kernel) {
+    case FD_KERNEL_GAUSSIAN: return launch_f32x2_fc<FD_KERNEL_GAUSSIAN>(ctx, a);
+    case FD_KERNEL_MULTIQUADRIC: return launch_f32x2_fc<FD_KERNEL_MULTIQUADRIC>(ctx, a);
+    default: return launch_f32x2_fc<FD_KERNEL_THINPLATE>(ctx, a);
+    }
 }
