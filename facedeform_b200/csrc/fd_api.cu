@@ -357,6 +357,7 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
         }
     }
     phase_end(ctx, FD_PH_FACTOR);
+    if (e == cudaSuccess) e = fd_launch_pack_tables(ctx, m); // centre tables: once per fit, not per solve
     if (e != cudaSuccess) {
         FD_SET_ERR(ctx, "fit: %s", cudaGetErrorString(e));
         fd_model_destroy(m);

@@ -818,7 +818,8 @@ __device__ __forceinline__ double tc_weight(const double* __restrict__ W, int ld
 // CTA = 32 columns x 8 row groups, row-major reads stay coalesced
 __global__ void __launch_bounds__(256) k_tc_colscale(const double* __restrict__ W, int ldw, int N, int np, int ncol,
                                                      int ncol_pad, int phi_shift, const float* __restrict__ norm,
-                                                     float* __restrict__ unscale, float* __restrict__ scale)
+                                                     float* __restrict__ unscale, float* __restrict__ scale,
+                                                     int* __restrict__ flags)
 {
     __shared__ double s_mx[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -827,13 +828,23 @@ __global__ void __launch_bounds__(256) k_tc_colscale(const double* __restrict__ 
     if (c < ncol) {
         // four independent running maxima: the loads of consecutive iterations overlap instead of one L2 round trip each
         double m4[4] = {0.0, 0.0, 0.0, 0.0};
+        double chk = 0.0; // 0 * w stays 0 unless w is NaN or Inf (fmax would silently drop a NaN)
         int k = ty;
         for (; k + 24 < N; k += 32) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) m4[u] = fmax(m4[u], fabs(W[(size_t)(k + 8 * u) * ldw + c]));
+            for (int u = 0; u < 4; ++u) {
+                const double w = W[(size_t)(k + 8 * u) * ldw + c];
+                m4[u] = fmax(m4[u], fabs(w));
+                chk = fma(w, 0.0, chk);
+            }
         }
-        for (; k < N + 4; k += 8) m4[0] = fmax(m4[0], fabs(tc_weight(W, ldw, N, np, k, c, norm)));
+        for (; k < N + 4; k += 8) {
+            const double w = tc_weight(W, ldw, N, np, k, c, norm);
+            m4[0] = fmax(m4[0], fabs(w));
+            chk = fma(w, 0.0, chk);
+        }
         mx = fmax(fmax(m4[0], m4[1]), fmax(m4[2], m4[3]));
+        if (chk != 0.0) atomicExch(&flags[FD_FLAG_NONFINITE], 1); // NaN / Inf weights -> terminationtype -3
     }
     s_mx[ty][tx] = mx;
     __syncthreads();
@@ -927,19 +938,26 @@ int fd_tc_kpad(int N) { return fd_round_up(N + 4, tc::BK); }
 int fd_tc_ncb(int F) { return (3 * F + tc::CB - 1) / tc::CB; }
 int fd_tc_col_pad(int F) { return fd_tc_ncb(F) * tc::CB; }
 
+// bounding box of the control points -> normalisation of the affine rows (depends on the centres only)
+cudaError_t fd_launch_tc_norm(fd_ctx* ctx, fd_model* m)
+{
+    tc::k_tc_norm<<<1, 256, 0, ctx->stream>>>(m->d_rest, m->N, m->d_tc_norm);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
 // builds the tensor-path tables for the weights currently in m->d_W (called from fd_launch_pack)
 cudaError_t fd_launch_pack_tc(fd_ctx* ctx, fd_model* m)
 {
     cudaStream_t s = ctx->stream;
     const int ncol = 3 * m->F, ncol_pad = fd_tc_col_pad(m->F), Kpad = fd_tc_kpad(m->N);
-    tc::k_tc_norm<<<1, 256, 0, s>>>(m->d_rest, m->N, m->d_tc_norm);
     tc::k_tc_colscale<<<(ncol_pad + 31) / 32, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad,
                                                             m->prm.kernel == FD_KERNEL_GAUSSIAN ? tc::GAUSS_SHIFT : 0,
-                                                            m->d_tc_norm, m->d_tc_unscale, m->d_tc_scale);
+                                                            m->d_tc_norm, m->d_tc_unscale, m->d_tc_scale, m->d_flags);
     dim3 grid((ncol_pad + 31) / 32, (Kpad + 31) / 32);
     tc::k_tc_pack<<<grid, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad, Kpad, m->d_tc_norm, m->d_tc_scale,
                                        (__half*)m->d_tc_wt_hi, (__half*)m->d_tc_wt_lo);
-    ctx->launches += 3;
+    ctx->launches += 2;
     if (!tc::make_map((CUtensorMap*)m->tc_map_hi, m->d_tc_wt_hi, Kpad, ncol_pad) ||
         !tc::make_map((CUtensorMap*)m->tc_map_lo, m->d_tc_wt_lo, Kpad, ncol_pad))
         return cudaErrorInvalidValue;

@@ -92,6 +92,7 @@ struct fd_model {
     int ldw32;
     double4* d_ctab64; // N (only when eval64)
     // tensor-core evaluation tables (fd_eval_tc.cu), present when use_tc
+    bool tables_packed;  // centre tables / normalisation built for the current centres and radii
     bool use_tc;
     float* d_tc_norm;    // (ox, oy, oz, s)
     float* d_tc_scale;   // per padded column: 2^e
@@ -131,6 +132,7 @@ cudaError_t fd_launch_lu_nopivot_fused(fd_ctx* ctx, double* d_A, int lda, int n,
 // fd_solve.cu
 cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_deform, int F);
 cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);
+cudaError_t fd_launch_pack_tables(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_invdiag(fd_ctx* ctx, fd_model* m);
 // fd_refine.cu
 cudaError_t fd_launch_to_f32(fd_ctx* ctx, const double* d_A, float* d_A32, size_t count);
@@ -147,6 +149,7 @@ int fd_tc_kpad(int N);
 int fd_tc_ncb(int F);
 int fd_tc_col_pad(int F);
 cudaError_t fd_launch_pack_tc(fd_ctx* ctx, fd_model* m);
+cudaError_t fd_launch_tc_norm(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
                               const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out);
 // fd_capture.cu

@@ -539,18 +539,34 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_defor
     return cudaGetLastError();
 }
 
-cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
+// the tables that depend on the centres and radii only (built once per fit; receivers build them when the radii
+// have arrived): centre tables of every evaluation kernel + the bounding-box normalisation of the tensor path
+cudaError_t fd_launch_pack_tables(fd_ctx* ctx, fd_model* m)
 {
     cudaStream_t s = ctx->stream;
     const int npad = fd_tc_kpad(m->N);
     k_pack_tables<<<(npad + 255) / 256, 256, 0, s>>>(m->d_rest, m->d_radii, m->N, npad, m->prm.kernel, m->d_ctab32,
                                                     reinterpret_cast<float*>(m->d_ctab_pair), m->eval64 ? m->d_ctab64 : nullptr);
+    ctx->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = fd_launch_tc_norm(ctx, m);
+    m->tables_packed = e == cudaSuccess;
+    return e;
+}
+
+// per solve: the weight tables of the evaluation kernel that will run (FP32 rows for the FMA/SFU kernel, or the
+// column-scaled FP16 hi/lo tiles of the tensor path; both flag non-finite weights)
+cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
+{
+    cudaStream_t s = ctx->stream;
+    cudaError_t e = cudaSuccess;
+    if (!m->tables_packed || m->receiver) e = fd_launch_pack_tables(ctx, m);
+    if (e != cudaSuccess) return e;
+    if (m->use_tc) return fd_launch_pack_tc(ctx, m);
     dim3 grid((m->ldw32 + 255) / 256, m->n);
     k_pack_weights<<<grid, 256, 0, s>>>(m->d_W, m->n, m->ldw, 3 * m->F, m->d_W32, m->ldw32, m->d_flags);
-    ctx->launches += 2;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && m->use_tc) e = fd_launch_pack_tc(ctx, m);
-    return e;
+    ctx->launches += 1;
+    return cudaGetLastError();
 }
 
 // after the LU: inverted diagonal blocks for the slab solve
