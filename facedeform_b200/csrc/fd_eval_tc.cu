@@ -128,6 +128,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
         : "memory");
 }
 
+// the same load delivered to the same shared-memory offset of every CTA in cta_mask (each CTA's mbarrier at the same
+// offset receives the bytes that landed in that CTA)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
 // 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar)
 {
@@ -149,6 +170,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the arrive lands on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
 // shared-memory matrix descriptor, K-major, SWIZZLE_64B (rows of 64 bytes, 8-row groups 512 bytes apart):
@@ -292,6 +319,7 @@ struct Args {
     int do_tangent;
     int vec_store_ok;       // V % 4 == 0 and P_out 16-byte aligned
     long long* dbg;         // optional per-unit phase timestamps of CTA 0 (FD_TC_DEBUG=1), else NULL
+    int pair;               // 1: CTAs run as clusters of two that share every weight tile (each loads half, multicast)
     int dbg_mode;           // FD_TC_DEBUG bits (debug instantiation only; results are then garbage): 2 skip the epilogue
                             // math + stores, 4 skip the Phi computation, 8 issue one MMA of three, 16 skip the TMA stores only
 };
@@ -341,7 +369,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full_a + 8 * s, PRODUCER_WARPS / 2);
             mbar_init(bar_full_b + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, a.pair ? 2 : 1); // pair: the MMAs of both CTAs must have read the slot
         }
         mbar_init(bar_tmem_full, 1);
         mbar_init(bar_tmem_full + 8, 1);
@@ -359,13 +387,21 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
     }
     tc_fence_before();
     __syncthreads();
+    if (a.pair) cluster_sync_all(); // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    // Unit walk.  Alone: CTA b takes units b, b + grid, ... (unit = vertex tile x column block).  As a pair: both CTAs
+    // of a cluster take the same column block of two neighbouring vertex tiles in lockstep, so one copy of every
+    // weight tile serves both (half of it loaded by each CTA and multicast): half the L2 -> SM stream.
+    const uint32_t crank = a.pair ? cluster_ctarank() : 0;
+    const int64_t unit0 = a.pair ? (blockIdx.x >> 1) : blockIdx.x;
+    const int64_t ustride = a.pair ? (gridDim.x >> 1) : gridDim.x;
     const int nk = a.Kpad / BK;
     const int tail_ksteps = (a.Ktot - (nk - 1) * BK + 15) >> 4; // K=16 steps of the last stage that hold real rows (1 or 2)
     const int64_t n_vt = (a.V + TM - 1) / TM;
-    const int64_t n_units = n_vt * a.ncb;
+    const int64_t n_units = (a.pair ? (n_vt + 1) / 2 : n_vt) * a.ncb;
+#define FD_UNIT_VT(u) (a.pair ? 2 * ((u) / a.ncb) + crank : (u) / a.ncb)
 
     // The two issuing roles run their loops with the whole warp (waits included) and elect one lane only around the
     // issue itself: control flow and addresses stay warp-uniform, so descriptors and barrier addresses live in
@@ -377,17 +413,18 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
         const long long t_begin = DBG ? clock64() : 0;
         uint32_t it = 0, ic = 0;  // weight stages / centre tiles issued so far
         int kc = 0;               // k block of centre tile ic
-        const uint32_t my_units = (uint32_t)((n_units - blockIdx.x + gridDim.x - 1) / gridDim.x);
+        const uint32_t my_units = (uint32_t)((n_units - unit0 + ustride - 1) / ustride);
         const uint32_t total = my_units * (uint32_t)nk;
-        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        for (int64_t u = unit0; u < n_units; u += ustride) {
             const int cb = (int)(u % a.ncb);
             for (int kb = 0; kb < nk; ++kb, ++it) {
-                // centre tiles run up to CDEPTH stages ahead of the weights (waiting here cannot deadlock: the
-                // slot of tile ic frees once the producers finished stage ic - CDEPTH <= it, whose A slot only
-                // needs MMAs on weight tiles this warp has already issued)
+                // Centre tiles run up to CDEPTH stages ahead of the weights.  The refill never blocks: a slot that is
+                // still being read is retried at the next stage, so the weight tile of this stage is issued the moment
+                // its slot frees (a blocking wait here tied every weight load to the producers' progress).  The ring
+                // then holds the CDEPTH oldest unconsumed tiles, which are the ones the producers need next.
                 while (ic < total && ic < it + CDEPTH) {
                     const int c = ic % CDEPTH;
-                    mbar_wait_t<DBG>(bar_cempty + 8 * c, ((ic / CDEPTH) & 1) ^ 1, w_ce);
+                    if (!mbar_try_wait(bar_cempty + 8 * c, ((ic / CDEPTH) & 1) ^ 1)) break;
                     if (elect_one()) {
                         mbar_expect_tx(bar_cfull + 8 * c, C_TILE_BYTES);
                         bulk_load_1d(smem_base + SMEM_CENTRES + c * C_TILE_BYTES, a.ctab + kc * BK, C_TILE_BYTES, bar_cfull + 8 * c);
@@ -401,8 +438,17 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                 if (elect_one()) {
                     const uint32_t sb = smem_base + s * STAGE_BYTES + 2 * A_SPLIT_BYTES;
                     mbar_expect_tx(bar_full_b + 8 * s, 2 * B_SPLIT_BYTES);
-                    tma_load_2d(sb, &map_hi, bar_full_b + 8 * s, kb * BK, cb * CB);
-                    tma_load_2d(sb + B_SPLIT_BYTES, &map_lo, bar_full_b + 8 * s, kb * BK, cb * CB);
+                    constexpr int HB = B_SPLIT_BYTES / 2; // the tensor-map box is half a tile (CB / 2 columns)
+                    if (a.pair) { // this CTA's half of the tile, delivered to both CTAs
+                        tma_load_2d_mc(sb + crank * HB, &map_hi, bar_full_b + 8 * s, kb * BK, cb * CB + crank * (CB / 2), 3);
+                        tma_load_2d_mc(sb + B_SPLIT_BYTES + crank * HB, &map_lo, bar_full_b + 8 * s, kb * BK,
+                                       cb * CB + crank * (CB / 2), 3);
+                    } else {
+                        tma_load_2d(sb, &map_hi, bar_full_b + 8 * s, kb * BK, cb * CB);
+                        tma_load_2d(sb + HB, &map_hi, bar_full_b + 8 * s, kb * BK, cb * CB + CB / 2);
+                        tma_load_2d(sb + B_SPLIT_BYTES, &map_lo, bar_full_b + 8 * s, kb * BK, cb * CB);
+                        tma_load_2d(sb + B_SPLIT_BYTES + HB, &map_lo, bar_full_b + 8 * s, kb * BK, cb * CB + CB / 2);
+                    }
                 }
                 __syncwarp();
             }
@@ -419,7 +465,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
         uint32_t it = 0, unit_iter = 0;
         const uint64_t desc0 = make_desc_sw64(smem_base); // A hi tile of stage 0 (the whole window is < 256 KB: no carry)
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0); // warp-uniform copy
-        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
+        for (int64_t u = unit0; u < n_units; u += ustride, ++unit_iter) {
             const int cb = (int)(u % a.ncb);
             const int ncols = min(CB, (3 * a.F - cb * CB + 15) & ~15);
             const uint32_t idesc = make_idesc(ncols);
@@ -457,7 +503,8 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
                             umma_f16(d, a_lo + 2, b_hi + 2, idesc, 1);
                         }
                     }
-                    umma_commit(bar_empty + 8 * s);                        // frees the stage when these MMAs have read it
+                    // frees the stage when these MMAs have read it (in both CTAs of a pair: the slot is refilled by multicast)
+                    if (a.pair) umma_commit_mc(bar_empty + 8 * s, 3); else umma_commit(bar_empty + 8 * s);
                     if (kb == nk - 1) umma_commit(bar_tmem_full + 8 * ab); // accumulator complete
                 }
                 __syncwarp();
@@ -479,8 +526,8 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
         long long w_c = 0, w_e = 0;
         const long long t_begin = DBG ? clock64() : 0;
         uint32_t it = 0, unit_iter = 0;
-        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
-            const int64_t vt = u / a.ncb;
+        for (int64_t u = unit0; u < n_units; u += ustride, ++unit_iter) {
+            const int64_t vt = FD_UNIT_VT(u);
             const int64_t v = vt * TM + row;
             float px = 0.f, py = 0.f, pz = 0.f;
             if (v < a.V) {
@@ -600,9 +647,9 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
             for (int t = et; t < a.ncb * CB; t += 32 * EPILOGUE_WARPS) s_colscale[t] = a.colscale[t];
             asm volatile("bar.sync 2, 256;" ::: "memory");
         }
-        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_iter) {
+        for (int64_t u = unit0; u < n_units; u += ustride, ++unit_iter) {
             const int cb = (int)(u % a.ncb);
-            const int64_t vt = u / a.ncb;
+            const int64_t vt = FD_UNIT_VT(u);
             const int f_base = cb * (CB / 3);
             const int nframes = min(CB / 3, a.F - f_base);
             const float* s_cs = s_colscale + (resident_cs ? cb * CB : 0); // this unit's 240 column scales
@@ -754,8 +801,10 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
         }
     }
 
+#undef FD_UNIT_VT
     tc_fence_before();
     __syncthreads();
+    if (a.pair) cluster_sync_all(); // no CTA leaves while its peer may still multicast into it or signal its barriers
     if (warp == WARP_TMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
@@ -924,7 +973,7 @@ static bool make_map(CUtensorMap* map, void* ptr, int Kpad, int rows)
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
-    cuuint32_t box[2] = {BK, CB};
+    cuuint32_t box[2] = {BK, CB / 2}; // half a weight tile per load: a pair of CTAs loads one half each
     cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -997,17 +1046,34 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
     if (want_dbg && !d_dbg) { cudaMalloc(&d_dbg, 256 * sizeof(long long)); cudaMemset(d_dbg, 0, 256 * sizeof(long long)); }
     a.dbg = want_dbg ? d_dbg : nullptr;
     a.dbg_mode = want_dbg ? atoi(getenv("FD_TC_DEBUG")) : 0;
-    const int64_t n_units = ((V + tc::TM - 1) / tc::TM) * a.ncb;
-    const int grid = (int)(n_units < ctx->sm_count ? n_units : ctx->sm_count);
+    const int64_t n_vt = (V + tc::TM - 1) / tc::TM;
+    static const bool no_pair = getenv("FD_TC_NOPAIR") != nullptr;
+    a.pair = (!no_pair && n_vt >= 4 && ctx->sm_count >= 2) ? 1 : 0;
+    const int64_t n_units = (a.pair ? (n_vt + 1) / 2 : n_vt) * a.ncb;
+    const int64_t max_ctas = a.pair ? ctx->sm_count / 2 : ctx->sm_count;
+    const int grid = (int)(n_units < max_ctas ? n_units : max_ctas) * (a.pair ? 2 : 1);
     const CUtensorMap& mh = *(const CUtensorMap*)m->tc_map_hi;
     const CUtensorMap& ml = *(const CUtensorMap*)m->tc_map_lo;
     const bool tang = a.do_tangent != 0;
+    cudaError_t launch_err = cudaSuccess;
 #define FD_TC_LAUNCH(KERNEL, TANG)                                                                                  \
     do {                                                                                                            \
         auto kfn = tc::k_eval_tc<KERNEL, TANG, false>;                                                              \
         if (want_dbg && KERNEL == FD_KERNEL_GAUSSIAN && !TANG) kfn = tc::k_eval_tc<FD_KERNEL_GAUSSIAN, false, true>; \
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC);                     \
-        kfn<<<grid, tc::THREADS, tc::SMEM_ALLOC, ctx->stream>>>(a, mh, ml, mo);                                        \
+        cudaLaunchConfig_t cfg = {};                                                                                \
+        cfg.gridDim = dim3(grid);                                                                                   \
+        cfg.blockDim = dim3(tc::THREADS);                                                                           \
+        cfg.dynamicSmemBytes = tc::SMEM_ALLOC;                                                                      \
+        cfg.stream = ctx->stream;                                                                                   \
+        cudaLaunchAttribute attr[1];                                                                                \
+        attr[0].id = cudaLaunchAttributeClusterDimension;                                                           \
+        attr[0].val.clusterDim.x = a.pair ? 2 : 1;                                                                  \
+        attr[0].val.clusterDim.y = 1;                                                                               \
+        attr[0].val.clusterDim.z = 1;                                                                               \
+        cfg.attrs = attr;                                                                                           \
+        cfg.numAttrs = 1;                                                                                           \
+        launch_err = cudaLaunchKernelEx(&cfg, kfn, a, mh, ml, mo);                                                  \
     } while (0)
     switch (m->prm.kernel) {
     case FD_KERNEL_GAUSSIAN:
@@ -1042,5 +1108,5 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
                     h[u * 8 + 1] - h[u * 8], h[u * 8 + 3] - h[u * 8 + 2], h[u * 8 + 4] - h[u * 8 + 3], h[u * 8 + 4] - h[u * 8]);
     }
     ctx->launches += 1;
-    return cudaGetLastError();
+    return launch_err != cudaSuccess ? launch_err : cudaGetLastError();
 }
