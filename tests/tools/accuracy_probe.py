@@ -1,5 +1,5 @@
 """max |P_gpu - P_oracle| / bbox diagonal of the FP32 evaluation paths (tensor-core and FMA/SFU) by control-point count.
-Usage: python profiles/tools/accuracy_probe.py [N ...]   (the oracle fit at N = 4096 takes ~15 s of CPU)"""
+Usage: python tests/tools/accuracy_probe.py [N ...]   (the oracle fit at N = 4096 takes ~15 s of CPU)"""
 import os
 import sys
 

@@ -1,5 +1,5 @@
 """DirectBSEdit timings through the host-pointer C ABI (H2D / D2H included), beside the CPU oracle (1 thread, like Eigen's
-HouseholderQR in the reference).  Usage: python profiles/tools/dbse_probe.py [P S]"""
+HouseholderQR in the reference).  Usage: python tests/tools/dbse_probe.py [P S]"""
 import os
 import sys
 import time
