@@ -995,11 +995,36 @@ cudaError_t fd_launch_tc_norm(fd_ctx* ctx, fd_model* m)
     return cudaGetLastError();
 }
 
-// builds the tensor-path tables for the weights currently in m->d_W (called from fd_launch_pack)
+void fd_tc_pack_args_fill(const fd_model* m, fd_tc_pack_args* pk)
+{
+    pk->enabled = 1;
+    pk->N = m->N;
+    pk->np = m->np;
+    pk->Kpad = fd_tc_kpad(m->N);
+    pk->ncol = 3 * m->F;
+    pk->ncol_pad = fd_tc_col_pad(m->F);
+    pk->phi_shift = m->prm.kernel == FD_KERNEL_GAUSSIAN ? tc::GAUSS_SHIFT : 0;
+    pk->norm = m->d_tc_norm;
+    pk->scale = m->d_tc_scale;
+    pk->unscale = m->d_tc_unscale;
+    pk->wt_hi = m->d_tc_wt_hi;
+    pk->wt_lo = m->d_tc_wt_lo;
+    pk->flags = m->d_flags;
+}
+
+// builds the tensor-path tables for the weights currently in m->d_W (called from fd_launch_pack); when the slab solve
+// has already written them in its epilogue only the tensor maps are (re)encoded
 cudaError_t fd_launch_pack_tc(fd_ctx* ctx, fd_model* m)
 {
     cudaStream_t s = ctx->stream;
     const int ncol = 3 * m->F, ncol_pad = fd_tc_col_pad(m->F), Kpad = fd_tc_kpad(m->N);
+    if (m->tc_packed_by_solve) {
+        m->tc_packed_by_solve = false;
+        if (!tc::make_map((CUtensorMap*)m->tc_map_hi, m->d_tc_wt_hi, Kpad, ncol_pad) ||
+            !tc::make_map((CUtensorMap*)m->tc_map_lo, m->d_tc_wt_lo, Kpad, ncol_pad))
+            return cudaErrorInvalidValue;
+        return cudaSuccess;
+    }
     tc::k_tc_colscale<<<(ncol_pad + 31) / 32, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad,
                                                             m->prm.kernel == FD_KERNEL_GAUSSIAN ? tc::GAUSS_SHIFT : 0,
                                                             m->d_tc_norm, m->d_tc_unscale, m->d_tc_scale, m->d_flags);

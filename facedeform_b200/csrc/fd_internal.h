@@ -92,6 +92,7 @@ struct fd_model {
     int ldw32;
     double4* d_ctab64; // N (only when eval64)
     // tensor-core evaluation tables (fd_eval_tc.cu), present when use_tc
+    bool tc_packed_by_solve; // the slab solve wrote the tensor path's weight tables itself (fused epilogue)
     bool tables_packed;  // centre tables / normalisation built for the current centres and radii
     bool use_tc;
     float* d_tc_norm;    // (ox, oy, oz, s)
@@ -130,7 +131,7 @@ cudaError_t fd_launch_lu_nopivot(fd_ctx* ctx, double* d_A, int lda, int n, int* 
 cudaError_t fd_launch_lu_nopivot_fused(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                                        double* d_pivstat, double* d_Tinv);
 // fd_solve.cu
-cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_deform, int F);
+cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int F);
 cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_pack_tables(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_invdiag(fd_ctx* ctx, fd_model* m);
@@ -149,6 +150,18 @@ int fd_tc_kpad(int N);
 int fd_tc_ncb(int F);
 int fd_tc_col_pad(int F);
 cudaError_t fd_launch_pack_tc(fd_ctx* ctx, fd_model* m);
+// what the fused pack epilogue of the slab solve needs (fd_solve.cu: k_solve_slab8); enabled = 0: plain solve
+struct fd_tc_pack_args {
+    int enabled;
+    int N, np, Kpad, ncol, ncol_pad, phi_shift;
+    const float* norm;  // (ox, oy, oz, s)
+    float* scale;       // per padded column
+    float* unscale;
+    void* wt_hi;        // __half [ncol_pad][Kpad]
+    void* wt_lo;
+    int* flags;
+};
+void fd_tc_pack_args_fill(const fd_model* m, fd_tc_pack_args* pk); // fd_eval_tc.cu
 cudaError_t fd_launch_tc_norm(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
                               const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out);

@@ -5,6 +5,7 @@
 // and the solve inside alglib::rbfbuildmodel (:363).  Right-hand sides / weights live row-major as
 // (N + npoly) x ldw doubles, column 3f + k = frame f, axis k, so one row is one control point's weights for
 // every frame -- the layout the evaluation kernels stage.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "fd_internal.h"
@@ -319,9 +320,12 @@ __device__ __forceinline__ void s8_prefetch_tinv(double* s_T, const double* __re
 __global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __restrict__ A, int lda, int n, int N,
                                                             const int* __restrict__ perm, const float* __restrict__ rest,
                                                             const float* __restrict__ deform, int F,
-                                                            const double* __restrict__ Tinv, double* __restrict__ W, int ldw)
+                                                            const double* __restrict__ Tinv, double* __restrict__ W, int ldw,
+                                                            const fd_tc_pack_args pk)
 {
     extern __shared__ __align__(16) double s8_smem[];
+    __shared__ double s_red[32][S8_RC + 1];
+    __shared__ float s_scale[S8_RC];
     const int nblk = (n + SB - 1) / SB, n_pad = nblk * SB;
     double* s_B = s8_smem;                           // [n_pad][8]
     double* s_P = s_B + (size_t)n_pad * S8_RC;       // [2][32][S8_LDP]
@@ -330,6 +334,21 @@ __global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __rest
     const int fr = lane >> 2, fk = lane & 3;         // fragment coordinates: row (or column) group, k within the k4 step
     const int c0 = blockIdx.x * S8_RC;
     const int nrhs = 3 * F;
+    if (c0 >= ldw) { // only with the fused pack: padded columns of the tensor path's tables (zero weights, unit scale)
+        for (int cc = tid; cc < S8_RC; cc += S8_THREADS)
+            if (c0 + cc < pk.ncol_pad) {
+                pk.scale[c0 + cc] = 1.0f;
+                pk.unscale[c0 + cc] = (float)ldexp(1.0, -pk.phi_shift);
+            }
+        for (int t = tid; t < S8_RC * pk.Kpad; t += S8_THREADS) {
+            const int c = c0 + t / pk.Kpad, k = t % pk.Kpad;
+            if (c < pk.ncol_pad) {
+                ((__half*)pk.wt_hi)[(size_t)c * pk.Kpad + k] = __float2half_rn(0.f);
+                ((__half*)pk.wt_lo)[(size_t)c * pk.Kpad + k] = __float2half_rn(0.f);
+            }
+        }
+        return;
+    }
     s8_prefetch_tinv(s_T, Tinv); // block 0 of L
     cp_async_commit();
     // right-hand sides, permuted: delta subtracted in FP32 then widened (SOP_FaceDeform.cpp:276-284); pad rows are zero
@@ -422,6 +441,69 @@ __global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __rest
         const int i = t / S8_RC, c = c0 + (t % S8_RC);
         if (c < ldw) W[(size_t)i * ldw + c] = s_B[t];
     }
+    if (!pk.enabled) return;
+    // ---- fused pack for the tensor-core evaluation (the arithmetic of tc::k_tc_colscale + tc::k_tc_pack, fd_eval_tc.cu):
+    // this CTA holds its 8 columns for every row, so the per-column power-of-two scale and the transposed FP16 hi/lo
+    // tiles W^T[c][k] come straight out of shared memory -- two launches and a pass over W less per solve.
+    const int N_ = pk.N, np_ = pk.np;
+    const float n0 = pk.norm[0], n1 = pk.norm[1], n2 = pk.norm[2], n3 = pk.norm[3];
+    auto weff = [&](int k, int cc) -> double { // effective weight of row k (affine rows in normalised coordinates)
+        if (k < N_) return s_B[(size_t)k * S8_RC + cc];
+        if (np_ == 0) return 0.0;
+        if (k == N_) {
+            double v = s_B[(size_t)N_ * S8_RC + cc];
+            if (np_ == 4) {
+                v += s_B[(size_t)(N_ + 1) * S8_RC + cc] * (double)n0;
+                v += s_B[(size_t)(N_ + 2) * S8_RC + cc] * (double)n1;
+                v += s_B[(size_t)(N_ + 3) * S8_RC + cc] * (double)n2;
+            }
+            return v;
+        }
+        if (np_ == 4 && k <= N_ + 3) return s_B[(size_t)k * S8_RC + cc] / (double)n3;
+        return 0.0;
+    };
+    {
+        const int cc = tid % S8_RC, kg = tid / S8_RC; // 32 row groups x 8 columns
+        double mx = 0.0, chk = 0.0;
+        if (c0 + cc < pk.ncol)
+            for (int k = kg; k < N_ + 4; k += S8_THREADS / S8_RC) {
+                const double w = weff(k, cc);
+                mx = fmax(mx, fabs(w));
+                chk = fma(w, 0.0, chk);
+            }
+        if (chk != 0.0) atomicExch(&pk.flags[FD_FLAG_NONFINITE], 1); // NaN / Inf weights -> terminationtype -3
+        s_red[kg][cc] = mx;
+    }
+    __syncthreads();
+    if (tid < S8_RC) {
+        double mx = 0.0;
+        for (int g = 0; g < S8_THREADS / S8_RC; ++g) mx = fmax(mx, s_red[g][tid]);
+        int e = 0;
+        if (mx > 0.0 && isfinite(mx)) {
+            frexp(mx, &e);
+            e = max(-60, min(60, 14 - e)); // mx * 2^e in [8192, 16384)
+        }
+        s_scale[tid] = (float)ldexp(1.0, e);
+        if (c0 + tid < pk.ncol_pad) {
+            pk.scale[c0 + tid] = s_scale[tid];
+            pk.unscale[c0 + tid] = (float)ldexp(1.0, -e - pk.phi_shift);
+        }
+    }
+    __syncthreads();
+    for (int cc = 0; cc < S8_RC; ++cc) {
+        const int c = c0 + cc;
+        if (c >= pk.ncol_pad) break;
+        __half* hi = (__half*)pk.wt_hi + (size_t)c * pk.Kpad;
+        __half* lo = (__half*)pk.wt_lo + (size_t)c * pk.Kpad;
+        const double sc = (double)s_scale[cc];
+        for (int k = tid; k < pk.Kpad; k += S8_THREADS) {
+            float v = 0.f;
+            if (c < pk.ncol) v = (float)(weff(k, cc) * sc);
+            const __half h = __float2half_rn(v);
+            hi[k] = h;
+            lo[k] = __float2half_rn(v - __half2float(h));
+        }
+    }
 }
 
 // weights -> evaluation tables.  FP32: centre table (cx, cy, cz, kernel parameter) and weights n x ldw32;
@@ -476,8 +558,9 @@ __global__ void __launch_bounds__(256) k_pack_weights(const double* __restrict__
 
 } // namespace
 
-cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_deform, int F)
+cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int F)
 {
+    m->tc_packed_by_solve = false;
     cudaStream_t s = ctx->stream;
     const int n = m->n, nrhs = 3 * F, ldw = m->ldw;
     {
@@ -490,9 +573,15 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, const fd_model* m, const float* d_defor
                 cudaFuncSetAttribute(k_solve_slab8, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
                 attr8_set = true;
             }
-            k_solve_slab8<<<(ldw + S8_RC - 1) / S8_RC, S8_THREADS, bytes8, s>>>(m->d_A, m->lda, n, m->N, m->d_perm, m->d_rest,
-                                                                               d_deform, F, m->d_Tinv, m->d_W, ldw);
+            fd_tc_pack_args pk;
+            pk.enabled = 0;
+            static const bool no_fused_pack = getenv("FD_NO_FUSED_PACK") != nullptr;
+            if (m->use_tc && !no_fused_pack) fd_tc_pack_args_fill(m, &pk);
+            const int cols = pk.enabled ? max(ldw, pk.ncol_pad) : ldw;
+            k_solve_slab8<<<(cols + S8_RC - 1) / S8_RC, S8_THREADS, bytes8, s>>>(m->d_A, m->lda, n, m->N, m->d_perm, m->d_rest,
+                                                                                d_deform, F, m->d_Tinv, m->d_W, ldw, pk);
             ctx->launches += 1;
+            m->tc_packed_by_solve = pk.enabled != 0;
             return cudaGetLastError();
         }
     }
