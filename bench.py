@@ -398,10 +398,10 @@ def main():
         # DRAM traffic of one launch from the committed `ncu --set full` capture of this command (profiles/), C2 only
         try:
             if args.config == "C2" and tensor_path:
-                with open(os.path.join(ROOT, "profiles", "r1d_eval_tc_ncu_summary.json")) as f:
+                with open(os.path.join(ROOT, "profiles", "r1e_eval_tc_ncu_summary.json")) as f:
                     nc = json.load(f)
                 roofline["traffic"] = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6
-                roofline["traffic_source"] = "profiles/r1d_eval_tc_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+                roofline["traffic_source"] = "profiles/r1e_eval_tc_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
                 roofline["algorithmic_bytes"] = alg_bytes
         except Exception:
             pass
