@@ -66,3 +66,37 @@ def test_no_gpu_fails_loudly():
     with pytest.raises(FdError) as e:
         Context()
     assert e.value.status == 5
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_mirror(tmp_path):
+    """include/facedeform_gpu.h compiles as C (no C++ / torch types in the boundary) and fd_params / fd_report have the
+    size and field offsets the ctypes mirror (facedeform_b200/_lib.py) assumes."""
+    import shutil
+    import subprocess
+    from facedeform_b200._lib import FdParams, FdReport
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    src = tmp_path / "layout.c"
+    fields_p = [f[0] for f in FdParams._fields_]
+    fields_r = [f[0] for f in FdReport._fields_]
+    cname = lambda f: "lambda" if f == "lambda_" else f
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "facedeform_gpu.h"', "int main(void) {",
+             '  printf("%zu %zu\\n", sizeof(fd_params), sizeof(fd_report));']
+    for f in fields_p:
+        lines.append(f'  printf("p {f} %zu\\n", offsetof(fd_params, {cname(f)}));')
+    for f in fields_r:
+        lines.append(f'  printf("r {f} %zu\\n", offsetof(fd_report, {f}));')
+    lines += ["  return 0;", "}"]
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    sp, sr = (int(x) for x in out[0].split())
+    assert sp == ctypes.sizeof(FdParams) and sr == ctypes.sizeof(FdReport)
+    for line in out[1:]:
+        if not line:
+            continue
+        kind, name, off = line.split()
+        struct = FdParams if kind == "p" else FdReport
+        assert getattr(struct, name).offset == int(off), (kind, name)
