@@ -71,13 +71,14 @@ __global__ void __launch_bounds__(128) k_trsm_diag(const double* __restrict__ A,
 
 // B[rows][c] -= T[rows, k0:k0+nb] * X[k0:k0+nb][c]; rows below the block (LOWER) or above it (UPPER).
 // CTA tile: 64 rows x 32 columns, 256 threads, 8 rows per thread.
+// (`n` bounds the rows of the LOWER variant, `row_lo` those of the UPPER one: the blocked sweeps restrict both to a panel.)
 template <bool LOWER>
 __global__ void __launch_bounds__(256) k_trsm_update(const double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                     double* __restrict__ B, int ldw, int nrhs)
+                                                     double* __restrict__ B, int ldw, int nrhs, int row_lo)
 {
     __shared__ double s_t[SB][64 + 1]; // [k][row]
     __shared__ double s_x[SB][32 + 1]; // [k][col]
-    const int row_begin = LOWER ? k0 + nb : 0;
+    const int row_begin = LOWER ? k0 + nb : row_lo;
     const int row_end = LOWER ? n : k0;
     const int r0 = row_begin + blockIdx.y * 64;
     const int c0 = blockIdx.x * 32;
@@ -109,6 +110,108 @@ __global__ void __launch_bounds__(256) k_trsm_update(const double* __restrict__ 
         for (int i = 0; i < 8; ++i) {
             const int r = r0 + rg * 8 + i;
             if (r < row_end) B[(size_t)r * ldw + c0 + cc] = bv[i] - acc[i];
+        }
+    }
+}
+
+// X_k = T_kk^-1 B_k with the pre-inverted diagonal block (fd_model::d_Tinv, column-major 32 x 32): a small dense product
+// of independent FMAs instead of the 32-step dependent substitution of k_trsm_diag; one thread per right-hand side.
+__global__ void __launch_bounds__(128) k_trsm_diag_inv(const double* __restrict__ Tinv_blk, int k0, int nb,
+                                                       double* __restrict__ B, int ldw, int nrhs)
+{
+    __shared__ __align__(16) double s_I[SB * SB]; // s_I[k * 32 + r] = inverse[r][k]
+    for (int t = threadIdx.x; t < SB * SB; t += 128) s_I[t] = Tinv_blk[t];
+    __syncthreads();
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= nrhs) return;
+    double x[SB];
+#pragma unroll
+    for (int r = 0; r < SB; ++r) x[r] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < SB; ++k) {
+        const double b = k < nb ? B[(size_t)(k0 + k) * ldw + c] : 0.0;
+#pragma unroll
+        for (int r = 0; r < SB; r += 2) {
+            const double2 iv = *reinterpret_cast<const double2*>(&s_I[k * SB + r]);
+            x[r] = fma(iv.x, b, x[r]);
+            x[r + 1] = fma(iv.y, b, x[r + 1]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < SB; ++r)
+        if (r < nb) B[(size_t)(k0 + r) * ldw + c] = x[r];
+}
+
+// Panel update of the blocked sweeps: B[r][c] -= sum_k T[r][kb + k] * B[kb + k][c] for r in [r_lo, r_hi), k < K.
+// T column-major (the LU factors), B row-major.  CTA tile 128 rows x 64 columns, 8 x 4 per thread, K in chunks of 16
+// through shared memory; FP64 FMA bound (64 flop per 6 shared-memory reads of 16 bytes).
+constexpr int PG_TM = 128, PG_TN = 64, PG_KC = 16;
+__global__ void __launch_bounds__(256, 2) k_panel_gemm(const double* __restrict__ A, int lda, int r_lo, int r_hi, int kb, int K,
+                                                    double* __restrict__ B, int ldw, int nrhs)
+{
+    __shared__ __align__(16) double s_a[PG_KC][PG_TM + 2];
+    __shared__ __align__(16) double s_x[PG_KC][PG_TN + 2];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int r0 = r_lo + blockIdx.y * PG_TM, c0 = blockIdx.x * PG_TN;
+    double acc[8][4] = {};
+    // the next chunk's operands travel from global memory into registers while the current chunk is multiplied
+    double pa[PG_KC * PG_TM / 256], px[PG_KC * PG_TN / 256];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < PG_KC * PG_TM / 256; ++u) {
+            const int t = tid + 256 * u, k = t / PG_TM, i = t - k * PG_TM;
+            pa[u] = (k0 + k < K && r0 + i < r_hi) ? A[(size_t)(kb + k0 + k) * lda + r0 + i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < PG_KC * PG_TN / 256; ++u) {
+            const int t = tid + 256 * u, k = t / PG_TN, j = t - k * PG_TN;
+            px[u] = (k0 + k < K && c0 + j < nrhs) ? B[(size_t)(kb + k0 + k) * ldw + c0 + j] : 0.0;
+        }
+    };
+    gload(0);
+    for (int k0 = 0; k0 < K; k0 += PG_KC) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PG_KC * PG_TM / 256; ++u) {
+            const int t = tid + 256 * u, k = t / PG_TM, i = t - k * PG_TM;
+            s_a[k][i] = pa[u];
+        }
+#pragma unroll
+        for (int u = 0; u < PG_KC * PG_TN / 256; ++u) {
+            const int t = tid + 256 * u, k = t / PG_TN, j = t - k * PG_TN;
+            s_x[k][j] = px[u];
+        }
+        __syncthreads();
+        if (k0 + PG_KC < K) gload(k0 + PG_KC);
+#pragma unroll
+        for (int k = 0; k < PG_KC; ++k) {
+            double a[8], x[4];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&s_a[k][ty * 8 + i]);
+                a[i] = v.x;
+                a[i + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) { // columns {2 tx, 2 tx + 1} and {32 + 2 tx, 33 + 2 tx}: conflict-free 16-byte reads
+                const double2 v = *reinterpret_cast<const double2*>(&s_x[k][tx * 2 + 16 * j]);
+                x[j] = v.x;
+                x[j + 1] = v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], x[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = r0 + ty * 8 + i;
+        if (r >= r_hi) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + tx * 2 + (j & 1) + 32 * (j >> 1);
+            if (c < nrhs) B[(size_t)r * ldw + c] -= acc[i][j];
         }
     }
 }
@@ -603,25 +706,69 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int
         k_build_rhs<<<grid, 256, 0, s>>>(m->d_rest, d_deform, m->d_perm, m->N, n, F, m->d_W, ldw);
         ctx->launches += 1;
     }
+    // Blocked sweeps for systems whose slab does not fit in shared memory: panels of 256 rows.  Inside a panel the
+    // 32-row block steps touch only the panel's rows (rank-32 updates of <= 224 rows); the rows outside it take one
+    // rank-256 update (k_panel_gemm), so the right-hand sides are re-read n / 256 times instead of n / 32.
+    constexpr int PB = 256;
     const int cblocks = (nrhs + 127) / 128;
-    for (int k0 = 0; k0 < n; k0 += SB) { // L y = P b
-        const int nb = min(SB, n - k0);
-        k_trsm_diag<true><<<cblocks, 128, 0, s>>>(m->d_A, m->lda, k0, nb, m->d_W, ldw, nrhs);
-        ctx->launches += 1;
-        const int rows = n - k0 - nb;
-        if (rows > 0) {
-            dim3 grid((nrhs + 31) / 32, (rows + 63) / 64);
-            k_trsm_update<true><<<grid, 256, 0, s>>>(m->d_A, m->lda, n, k0, nb, m->d_W, ldw, nrhs);
+    if (nrhs < 64) { // a handful of right-hand sides: plain rank-32 sweeps (a GEMM tile would be mostly padding)
+        for (int k0 = 0; k0 < n; k0 += SB) { // L y = P b
+            const int nb = min(SB, n - k0);
+            k_trsm_diag<true><<<cblocks, 128, 0, s>>>(m->d_A, m->lda, k0, nb, m->d_W, ldw, nrhs);
+            ctx->launches += 1;
+            const int rows = n - k0 - nb;
+            if (rows > 0) {
+                dim3 grid((nrhs + 31) / 32, (rows + 63) / 64);
+                k_trsm_update<true><<<grid, 256, 0, s>>>(m->d_A, m->lda, n, k0, nb, m->d_W, ldw, nrhs, 0);
+                ctx->launches += 1;
+            }
+        }
+        for (int k0 = (n - 1) / SB * SB; k0 >= 0; k0 -= SB) { // U x = y
+            const int nb = min(SB, n - k0);
+            k_trsm_diag<false><<<cblocks, 128, 0, s>>>(m->d_A, m->lda, k0, nb, m->d_W, ldw, nrhs);
+            ctx->launches += 1;
+            if (k0 > 0) {
+                dim3 grid((nrhs + 31) / 32, (k0 + 63) / 64);
+                k_trsm_update<false><<<grid, 256, 0, s>>>(m->d_A, m->lda, n, k0, nb, m->d_W, ldw, nrhs, 0);
+                ctx->launches += 1;
+            }
+        }
+        return cudaGetLastError();
+    }
+    for (int p0 = 0; p0 < n; p0 += PB) { // L y = P b
+        const int pe = min(p0 + PB, n);
+        for (int k0 = p0; k0 < pe; k0 += SB) {
+            const int nb = min(SB, pe - k0);
+            k_trsm_diag_inv<<<cblocks, 128, 0, s>>>(m->d_Tinv + (size_t)(k0 / SB) * 2 * SB * SB, k0, nb, m->d_W, ldw, nrhs);
+            ctx->launches += 1;
+            const int rows = pe - k0 - nb;
+            if (rows > 0) {
+                dim3 grid((nrhs + 31) / 32, (rows + 63) / 64);
+                k_trsm_update<true><<<grid, 256, 0, s>>>(m->d_A, m->lda, pe, k0, nb, m->d_W, ldw, nrhs, 0);
+                ctx->launches += 1;
+            }
+        }
+        if (pe < n) {
+            dim3 grid((nrhs + PG_TN - 1) / PG_TN, (n - pe + PG_TM - 1) / PG_TM);
+            k_panel_gemm<<<grid, 256, 0, s>>>(m->d_A, m->lda, pe, n, p0, pe - p0, m->d_W, ldw, nrhs);
             ctx->launches += 1;
         }
     }
-    for (int k0 = (n - 1) / SB * SB; k0 >= 0; k0 -= SB) { // U x = y
-        const int nb = min(SB, n - k0);
-        k_trsm_diag<false><<<cblocks, 128, 0, s>>>(m->d_A, m->lda, k0, nb, m->d_W, ldw, nrhs);
-        ctx->launches += 1;
-        if (k0 > 0) {
-            dim3 grid((nrhs + 31) / 32, (k0 + 63) / 64);
-            k_trsm_update<false><<<grid, 256, 0, s>>>(m->d_A, m->lda, n, k0, nb, m->d_W, ldw, nrhs);
+    for (int p0 = (n - 1) / PB * PB; p0 >= 0; p0 -= PB) { // U x = y
+        const int pe = min(p0 + PB, n);
+        for (int k0 = p0 + (pe - p0 - 1) / SB * SB; k0 >= p0; k0 -= SB) {
+            const int nb = min(SB, pe - k0);
+            k_trsm_diag_inv<<<cblocks, 128, 0, s>>>(m->d_Tinv + ((size_t)(k0 / SB) * 2 + 1) * SB * SB, k0, nb, m->d_W, ldw, nrhs);
+            ctx->launches += 1;
+            if (k0 > p0) {
+                dim3 grid((nrhs + 31) / 32, (k0 - p0 + 63) / 64);
+                k_trsm_update<false><<<grid, 256, 0, s>>>(m->d_A, m->lda, n, k0, nb, m->d_W, ldw, nrhs, p0);
+                ctx->launches += 1;
+            }
+        }
+        if (p0 > 0) {
+            dim3 grid((nrhs + PG_TN - 1) / PG_TN, (p0 + PG_TM - 1) / PG_TM);
+            k_panel_gemm<<<grid, 256, 0, s>>>(m->d_A, m->lda, 0, p0, p0, pe - p0, m->d_W, ldw, nrhs);
             ctx->launches += 1;
         }
     }
