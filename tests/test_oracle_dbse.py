@@ -69,3 +69,30 @@ def test_identity_when_pose_is_rest(oracle):
     w = oracle.dbse_weights(QR, rest, rest)
     assert np.all(w == 0.0)
     np.testing.assert_array_equal(oracle.dbse_displace(M, w, rest, rest), rest)
+
+
+def test_packed_qr_reconstructs_the_shapes_matrix(oracle):
+    """Q R = M with Q = H_0 ... H_{S-1}, H_j = I - tau_j v_j v_j^T read back from the packed storage (v_j has an implied
+    1 on the diagonal and the stored essential part below it): the packed matrix means what dbse.cpp:53 assumes."""
+    rest, shapes, _ = _case(9, 120, 6)
+    M = oracle.dbse_shapes_matrix(rest, shapes)
+    QR, tau = oracle.householder_qr(M)
+    m, n = M.shape
+    X = np.triu(QR[:n]).copy()                       # R, then apply H_{n-1} ... H_0 from the left
+    X = np.vstack([X, np.zeros((m - n, n))])
+    for j in range(n - 1, -1, -1):
+        v = np.zeros(m)
+        v[j] = 1.0
+        v[j + 1:] = QR[j + 1:, j]
+        X -= tau[j] * np.outer(v, v @ X)
+    np.testing.assert_allclose(X, M, rtol=0, atol=1e-12 * np.abs(M).max())
+
+
+def test_weights_are_linear_in_the_pose_delta(oracle):
+    rest, shapes, pos = _case(10, 80, 5)
+    M = oracle.dbse_shapes_matrix(rest, shapes)
+    QR, _ = oracle.householder_qr(M)
+    d = (pos - rest)
+    w1 = oracle.dbse_weights(QR, rest + d, rest)
+    w2 = oracle.dbse_weights(QR, rest + 2 * d, rest)   # 2 * d is exact in FP32, rest + 2 d may round: compare loosely
+    np.testing.assert_allclose(w2, 2 * w1, rtol=0, atol=2e-6 * np.abs(w1).max())
