@@ -1243,7 +1243,8 @@ cudaError_t launch_lu_nopivot_fused(fd_ctx* ctx, REAL* d_A, int lda, int n, int*
     unsigned base = ctx->sync_base;
     if (n <= cluster_max_n) {
         // one cluster: 4 CTAs up to n = 64, 8 up to 128, else 16
-        const int cs = n <= 64 ? 4 : (n <= 128 ? 8 : 16);
+        const char* env_cs = getenv("FD_LU_CLUSTER");
+        const int cs = env_cs ? atoi(env_cs) : (n <= 64 ? 4 : (n <= 128 ? 8 : 16));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cs);
         cfg.blockDim = dim3(FZ_THREADS);
