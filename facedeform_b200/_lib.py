@@ -38,6 +38,7 @@ class FdParams(C.Structure):
         ("weightrange", C.c_float * 2),
         ("dofalloff", C.c_int32), ("falloffradius", C.c_float), ("falloffrate", C.c_float),
         ("eval_precision", C.c_int32), ("eval_path", C.c_int32), ("factor_precision", C.c_int32),
+        ("fidelity", C.c_int32),
     ]
 
 

@@ -68,6 +68,7 @@ int check_params(fd_ctx* ctx, const fd_params* p)
     if (!(p->lambda >= 0.f)) { FD_SET_ERR(ctx, "lambda must be >= 0"); return FD_E_INVALID; }
     if (p->eval_precision < 0 || p->eval_precision > 2 || p->eval_path < 0 || p->eval_path > 2) { FD_SET_ERR(ctx, "bad eval_precision / eval_path"); return FD_E_INVALID; }
     if (p->factor_precision != FD_FACTOR_FP64 && p->factor_precision != FD_FACTOR_FP32_IR) { FD_SET_ERR(ctx, "bad factor_precision"); return FD_E_INVALID; }
+    if (p->fidelity != FD_FIDELITY_DENSE && p->fidelity != FD_FIDELITY_ALGLIB_V1) { FD_SET_ERR(ctx, "bad fidelity"); return FD_E_INVALID; }
     return FD_OK;
 }
 
@@ -153,6 +154,97 @@ int model_reserve_frames(fd_model* m, int F)
     return FD_OK;
 }
 
+// ---- FD_FIDELITY_ALGLIB_V1: two-stage polynomial + Gaussian layers (oracle: fdo_fit_v1) ---------------
+// The parent model owns one ordinary factored sub-model per layer (term = zero: no side conditions) and, after a
+// solve, a stacked evaluation model with N * layers centres that the ordinary evaluation kernels take.
+int v1_fit(fd_ctx* ctx, const fd_params* params, const float* rest_dev, int32_t N, fd_model** out)
+{
+    if (params->kernel != FD_KERNEL_GAUSSIAN) { FD_SET_ERR(ctx, "the ALGLIB v1 formulation is Gaussian only"); return FD_E_UNSUPPORTED; }
+    if (params->factor_precision != FD_FACTOR_FP64) { FD_SET_ERR(ctx, "the ALGLIB v1 formulation factors in FP64"); return FD_E_UNSUPPORTED; }
+    const int L = params->model == FD_MODEL_QNN ? 1 : (params->layers < 1 ? 1 : params->layers);
+    if (L > FD_V1_MAX_LAYERS) { FD_SET_ERR(ctx, "at most %d layers", FD_V1_MAX_LAYERS); return FD_E_INVALID; }
+    fd_model* m = nullptr;
+    int st = model_alloc(ctx, params, N, false, &m);
+    if (st != FD_OK) return st;
+    m->receiver = false;
+    cudaError_t e = cudaMemcpyAsync(m->d_rest, rest_dev, (size_t)N * 3 * sizeof(float), cudaMemcpyDefault, ctx->stream);
+    if (e != cudaSuccess) { FD_SET_ERR(ctx, "fit: %s", cudaGetErrorString(e)); fd_model_destroy(m); return FD_E_CUDA; }
+    for (int k = 0; k < L; ++k) {
+        fd_params pk = *params;
+        pk.fidelity = FD_FIDELITY_DENSE;
+        pk.term = FD_TERM_ZERO;
+        pk.layers = 1;
+        pk.eval_path = FD_PATH_SIMT; // the layers are never evaluated on their own
+        if (params->model != FD_MODEL_QNN) pk.radius = params->radius / (float)(1 << k); // R, R/2, R/4 ...
+        st = fd_rbf_fit_dev(ctx, &pk, m->d_rest, N, &m->v1_layer[k]);
+        if (st != FD_OK) { fd_model_destroy(m); return st; }
+        m->v1_layers = k + 1;
+    }
+    m->fitted = true;
+    *out = m;
+    return FD_OK;
+}
+
+int v1_solve(fd_model* m, const float* deform_dev, int32_t F)
+{
+    fd_ctx* ctx = m->ctx;
+    const int N = m->N, np = m->np, L = m->v1_layers, nrhs = 3 * F, ldw = fd_round_up(3 * F, 4);
+    cudaStream_t s = ctx->stream;
+    int st = FD_OK;
+    if (F > m->capF) {
+        if (m->d_v1_R) cudaFreeAsync(m->d_v1_R, s);
+        if (m->d_v1_V) cudaFreeAsync(m->d_v1_V, s);
+        m->d_v1_R = m->d_v1_V = nullptr;
+        st = dev_alloc(ctx, &m->d_v1_R, (size_t)N * ldw);
+        if (st == FD_OK) st = dev_alloc(ctx, &m->d_v1_V, (size_t)4 * ldw);
+        if (st != FD_OK) return st;
+        m->capF = F;
+    }
+    const int lda = m->v1_layer[0]->lda;
+    if (!m->d_v1_K && (st = dev_alloc(ctx, &m->d_v1_K, (size_t)lda * N)) != FD_OK) return st;
+    if (!m->d_v1_stack && (st = dev_alloc(ctx, &m->d_v1_stack, (size_t)N * L * 3)) != FD_OK) return st;
+    m->F = F;
+    m->ldw = ldw;
+    phase_begin(ctx, FD_PH_SOLVE);
+    cudaError_t e = fd_launch_v1_rhs_poly(ctx, m->d_rest, deform_dev, N, F, np, m->d_v1_R, m->d_v1_V, ldw, m->d_flags);
+    for (int k = 0; k < L && e == cudaSuccess; ++k) {
+        fd_model* l = m->v1_layer[k];
+        st = model_reserve_frames(l, F);
+        if (st != FD_OK) return st;
+        l->F = F;
+        l->ldw = l->ldw32 = ldw;
+        l->use_tc = false;
+        e = fd_launch_v1_gather(ctx, m->d_v1_R, l->d_perm, N, ldw, l->d_W);
+        if (e == cudaSuccess) e = fd_launch_solve_prebuilt(ctx, l, nrhs);
+        fd_params p0 = l->prm;
+        p0.lambda = 0.f; // the fitted function uses the kernel matrix itself, the shift only damps the solve
+        if (e == cudaSuccess) e = fd_launch_assemble(ctx, p0, l->d_rest, l->d_radii, N, 0, m->d_v1_K, lda);
+        if (e == cudaSuccess) e = fd_launch_gemm_sub(ctx, m->d_v1_K, lda, N, N, l->d_W, m->d_v1_R, ldw, nrhs);
+    }
+    if (e != cudaSuccess) { FD_SET_ERR(ctx, "solve: %s", cudaGetErrorString(e)); return FD_E_CUDA; }
+    // the stacked model the evaluation kernels take: layer k's centres, radii and weights at rows [k N, (k + 1) N)
+    if (m->v1_eval) { fd_model_destroy(m->v1_eval); m->v1_eval = nullptr; }
+    for (int k = 0; k < L; ++k)
+        cudaMemcpyAsync(m->d_v1_stack + (size_t)k * N * 3, m->d_rest, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    fd_params pe = m->prm;
+    pe.fidelity = FD_FIDELITY_DENSE;
+    st = fd_model_create_receiver(ctx, &pe, m->d_v1_stack, N * L, F, &m->v1_eval);
+    if (st != FD_OK) return st;
+    fd_model* ev = m->v1_eval;
+    for (int k = 0; k < L; ++k) {
+        fd_model* l = m->v1_layer[k];
+        cudaMemcpyAsync(ev->d_radii + (size_t)k * N, l->d_radii, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(ev->d_W + (size_t)k * N * ldw, l->d_W, (size_t)N * ldw * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    }
+    if (np > 0)
+        cudaMemcpyAsync(ev->d_W + (size_t)N * L * ldw, m->d_v1_V, (size_t)np * ldw * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    st = fd_model_commit_weights(ev);
+    phase_end(ctx, FD_PH_SOLVE);
+    if (st != FD_OK) return st;
+    m->solved = true;
+    return FD_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -196,6 +288,7 @@ void fd_params_default(fd_params* p)
     p->eval_precision = FD_EVAL_AUTO;
     p->eval_path = FD_PATH_AUTO;
     p->factor_precision = FD_FACTOR_FP64;
+    p->fidelity = FD_FIDELITY_DENSE;
 }
 
 // SYSmax clamps of cookMySop, SOP_FaceDeform.cpp:249-257
@@ -302,13 +395,15 @@ void fd_model_destroy(fd_model* m)
 {
     if (!m) return;
     fd_ctx* owner = m->ctx;
+    for (int k = 0; k < m->v1_layers; ++k) fd_model_destroy(m->v1_layer[k]);
+    if (m->v1_eval) fd_model_destroy(m->v1_eval);
     {
     DeviceGuard g(m->ctx->device);
     cudaStream_t s = m->ctx->stream; // stream-ordered frees: later work on the stream may reuse the blocks safely
     void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
                       m->d_ctab32, m->d_W32, m->d_ctab64, m->d_tc_norm, m->d_tc_scale, m->d_tc_unscale,
                       m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win, m->d_ctab_pair, m->d_A32, m->d_B, m->d_R, m->d_D32,
-                      m->d_ir_norm};
+                      m->d_ir_norm, m->d_v1_R, m->d_v1_K, m->d_v1_V, m->d_v1_stack};
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;
@@ -325,6 +420,7 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
     int st = check_params(ctx, params);
     if (st != FD_OK) return st;
     if (n_ctrl < 1 || !rest_ctrl_dev) { FD_SET_ERR(ctx, "Can't build RBF model: no control points"); return FD_E_BUILD; }
+    if (params->fidelity == FD_FIDELITY_ALGLIB_V1) return v1_fit(ctx, params, rest_ctrl_dev, n_ctrl, out);
     if ((size_t)(n_ctrl + 4) * sizeof(int) > 64 * 1024) { FD_SET_ERR(ctx, "more than 16380 control points are not supported"); return FD_E_UNSUPPORTED; }
     fd_model* m = nullptr;
     st = model_alloc(ctx, params, n_ctrl, true, &m);
@@ -390,6 +486,7 @@ int fd_rbf_solve_dev(fd_model* m, const float* deform_ctrl_dev, int32_t n_ctrl, 
     if (m->receiver || !m->fitted) { FD_SET_ERR(ctx, "solve: the model holds no factorisation"); return FD_E_STATE; }
     if (n_ctrl != m->N) { FD_SET_ERR(ctx, "%s", fd_status_string(FD_E_MISMATCH_POINT)); return FD_E_MISMATCH_POINT; } // :231-234
     if (frames < 1) { FD_SET_ERR(ctx, "frames must be >= 1"); return FD_E_INVALID; }
+    if (m->v1_layers) return v1_solve(m, deform_ctrl_dev, frames);
     int st = model_reserve_frames(m, frames);
     if (st != FD_OK) return st;
     m->F = frames;
@@ -427,6 +524,35 @@ int fd_model_report(fd_model* m, fd_report* report)
     if (!m) return FD_E_INVALID;
     fd_ctx* ctx = m->ctx;
     DeviceGuard g(ctx->device);
+    if (m->v1_layers) { // layered fit: every layer's factorisation, then the stacked weights, must be sound
+        for (int k = 0; k < m->v1_layers; ++k) {
+            const int st = fd_model_report(m->v1_layer[k], report);
+            if (st != FD_OK) return st;
+        }
+        fd_report last;
+        if (report) last = *report;
+        if (m->v1_eval) {
+            const int st = fd_model_report(m->v1_eval, report);
+            if (st != FD_OK) return st;
+        }
+        // the parent's own flag: a singular Gram matrix of the polynomial fit
+        int flags[FD_NUM_FLAGS];
+        FD_CUDA_OK(ctx, cudaMemcpyAsync(flags, m->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+        FD_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        const int term = flags[FD_FLAG_SINGULAR] ? -3 : 1;
+        if (report) {
+            *report = last; // pivots of the last layer
+            report->terminationtype = term;
+            report->n = m->N * m->v1_layers;
+            report->npoly = m->np;
+            report->frames = m->F;
+        }
+        if (term != 1) {
+            FD_SET_ERR(ctx, "%s (terminationtype %d)", fd_status_string(FD_E_SINGULAR), term);
+            return FD_E_SINGULAR;
+        }
+        return FD_OK;
+    }
     int flags[FD_NUM_FLAGS];
     double piv[2] = {0, 0};
     FD_CUDA_OK(ctx, cudaMemcpyAsync(flags, m->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
@@ -458,6 +584,7 @@ int fd_rbf_eval_dev(fd_model* m, const float* P, int64_t n_vtx, const float* dis
                     const float* tangentv, const float* normal, float* P_out, float* falloff_out)
 {
     if (!m || (n_vtx > 0 && (!P || !P_out)) || n_vtx < 0) return FD_E_INVALID;
+    if (m->v1_layers && m->solved) m = m->v1_eval; // the stacked model of the layered fit
     fd_ctx* ctx = m->ctx;
     DeviceGuard g(ctx->device);
     if (!m->solved) { FD_SET_ERR(ctx, "eval: no weights (call fd_rbf_solve or fd_model_commit_weights first)"); return FD_E_STATE; }
@@ -472,6 +599,7 @@ int fd_rbf_eval(fd_model* m, const float* P, int64_t n_vtx, const float* dist2, 
                 const float* tangentv, const float* normal, float* P_out, float* falloff_out)
 {
     if (!m || (n_vtx > 0 && (!P || !P_out)) || n_vtx < 0) return FD_E_INVALID;
+    if (m->v1_layers && m->solved) m = m->v1_eval;
     fd_ctx* ctx = m->ctx;
     DeviceGuard g(ctx->device);
     if (!m->solved) { FD_SET_ERR(ctx, "eval: no weights (call fd_rbf_solve or fd_model_commit_weights first)"); return FD_E_STATE; }
@@ -514,6 +642,7 @@ int fd_model_create_receiver(fd_ctx* ctx, const fd_params* params, const float* 
     DeviceGuard g(ctx->device);
     int st = check_params(ctx, params);
     if (st != FD_OK) return st;
+    if (params->fidelity != FD_FIDELITY_DENSE) { FD_SET_ERR(ctx, "receiver models take the dense formulation only"); return FD_E_UNSUPPORTED; }
     fd_model* m = nullptr;
     st = model_alloc(ctx, params, n_ctrl, false, &m);
     if (st != FD_OK) return st;
@@ -534,6 +663,7 @@ int fd_model_create_receiver(fd_ctx* ctx, const fd_params* params, const float* 
 int fd_model_weights_dev(fd_model* m, void** ptr, size_t* bytes)
 {
     if (!m || !ptr || !bytes) return FD_E_INVALID;
+    if (m->v1_layers && m->v1_eval) m = m->v1_eval;
     if (!m->d_W || m->F < 1) { FD_SET_ERR(m->ctx, "weights: nothing solved or reserved yet"); return FD_E_STATE; }
     *ptr = m->d_W;
     *bytes = (size_t)m->n * m->ldw * sizeof(double);
@@ -543,6 +673,7 @@ int fd_model_weights_dev(fd_model* m, void** ptr, size_t* bytes)
 int fd_model_radii_dev(fd_model* m, void** ptr, size_t* bytes)
 {
     if (!m || !ptr || !bytes) return FD_E_INVALID;
+    if (m->v1_layers && m->v1_eval) m = m->v1_eval;
     *ptr = m->d_radii;
     *bytes = (size_t)m->N * sizeof(double);
     return FD_OK;
@@ -563,6 +694,7 @@ int fd_model_commit_weights(fd_model* m)
 int fd_model_info(const fd_model* m, int32_t* n_ctrl, int32_t* npoly, int32_t* frames, int32_t* weights_ld)
 {
     if (!m) return FD_E_INVALID;
+    if (m->v1_layers && m->v1_eval) m = m->v1_eval; // N * layers centres
     if (n_ctrl) *n_ctrl = m->N;
     if (npoly) *npoly = m->np;
     if (frames) *frames = m->F;
@@ -573,6 +705,7 @@ int fd_model_info(const fd_model* m, int32_t* n_ctrl, int32_t* npoly, int32_t* f
 int fd_model_get_weights(fd_model* m, double* weights, double* radii)
 {
     if (!m) return FD_E_INVALID;
+    if (m->v1_layers && m->v1_eval) m = m->v1_eval;
     fd_ctx* ctx = m->ctx;
     DeviceGuard g(ctx->device);
     if (weights) {

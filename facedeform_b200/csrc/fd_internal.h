@@ -9,6 +9,7 @@
 
 #define FD_NUM_FLAGS 8
 #define FD_TMAP_BYTES 128
+#define FD_V1_MAX_LAYERS 16      // FD_FIDELITY_ALGLIB_V1: layers kept per model
 #define FD_IR_MAX_SWEEPS 40     // FD_FACTOR_FP32_IR: refinement sweeps at most
 #define FD_IR_TOLERANCE 1e-12   // converged: max |B - A X| <= this * max |B|
 #define FD_IR_FLOOR_OK 1e-9     // a residual that stagnates below this sits at the FP64 floor of the system: accepted
@@ -75,6 +76,15 @@ struct fd_model {
     double* d_W;     // n x ldw weights (solve in place over the right-hand sides)
     int* d_flags;    // FD_NUM_FLAGS
     double* d_pivstat; // [min |u_kk|, max |u_kk|]
+    // FD_FIDELITY_ALGLIB_V1 (fd_api.cu): the parent holds one factored sub-model per layer and a stacked evaluation
+    // model (N * layers centres); d_v1_* are the residual, a scratch for the layer's kernel matrix and the polynomial
+    int v1_layers;
+    fd_model* v1_layer[FD_V1_MAX_LAYERS];
+    fd_model* v1_eval;
+    double* d_v1_R;
+    double* d_v1_K;
+    double* d_v1_V;
+    float* d_v1_stack;
     // FD_FACTOR_FP32_IR (fd_refine.cu): d_A stays the assembled FP64 system, the LU lives in d_A32
     bool f32ir;
     float* d_A32;      // lda x n FP32, LU in place
@@ -132,6 +142,12 @@ cudaError_t fd_launch_lu_nopivot_fused(fd_ctx* ctx, double* d_A, int lda, int n,
                                        double* d_pivstat, double* d_Tinv);
 // fd_solve.cu
 cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int F);
+cudaError_t fd_launch_solve_prebuilt(fd_ctx* ctx, fd_model* m, int nrhs);
+cudaError_t fd_launch_v1_rhs_poly(fd_ctx* ctx, const float* d_rest, const float* d_deform, int N, int F, int np, double* d_R,
+                                  double* d_V, int ldw, int* d_flags);
+cudaError_t fd_launch_v1_gather(fd_ctx* ctx, const double* d_R, const int* d_perm, int N, int ldw, double* d_W);
+cudaError_t fd_launch_gemm_sub(fd_ctx* ctx, const double* d_A, int lda, int rows, int K, const double* d_X, double* d_C, int ldw,
+                               int nrhs);
 cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_pack_tables(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_invdiag(fd_ctx* ctx, fd_model* m);

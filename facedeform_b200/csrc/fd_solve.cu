@@ -216,6 +216,60 @@ __global__ void __launch_bounds__(256, 2) k_panel_gemm(const double* __restrict_
     }
 }
 
+// C[r][c] -= sum_k A[r][k] X[k][c], r < rows, k < K: A column-major (lda), X and C row-major with the same row stride.
+// (the residual update of the layered fit, fd_api.cu; same tile as k_panel_gemm with separate operands)
+__global__ void __launch_bounds__(256, 2) k_gemm_sub(const double* __restrict__ A, int lda, int rows, int K,
+                                                     const double* __restrict__ X, double* __restrict__ C, int ldw, int nrhs)
+{
+    __shared__ __align__(16) double s_a[PG_KC][PG_TM + 2];
+    __shared__ __align__(16) double s_x[PG_KC][PG_TN + 2];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int r0 = blockIdx.y * PG_TM, c0 = blockIdx.x * PG_TN;
+    double acc[8][4] = {};
+    for (int k0 = 0; k0 < K; k0 += PG_KC) {
+        __syncthreads();
+        for (int t = tid; t < PG_KC * PG_TM; t += 256) {
+            const int k = t / PG_TM, i = t - k * PG_TM;
+            s_a[k][i] = (k0 + k < K && r0 + i < rows) ? A[(size_t)(k0 + k) * lda + r0 + i] : 0.0;
+        }
+        for (int t = tid; t < PG_KC * PG_TN; t += 256) {
+            const int k = t / PG_TN, j = t - k * PG_TN;
+            s_x[k][j] = (k0 + k < K && c0 + j < nrhs) ? X[(size_t)(k0 + k) * ldw + c0 + j] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PG_KC; ++k) {
+            double a[8], x[4];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&s_a[k][ty * 8 + i]);
+                a[i] = v.x;
+                a[i + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&s_x[k][tx * 2 + 16 * j]);
+                x[j] = v.x;
+                x[j + 1] = v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], x[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = r0 + ty * 8 + i;
+        if (r >= rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + tx * 2 + (j & 1) + 32 * (j >> 1);
+            if (c < nrhs) C[(size_t)r * ldw + c] -= acc[i][j];
+        }
+    }
+}
+
 // ---- slab solve: one CTA owns RC right-hand-side columns for the whole forward/backward substitution --------------
 // The slab (n x RC doubles) lives in shared memory, L and U stream once from L2; no inter-CTA dependency, one launch.
 // Warp w owns slab columns {2w, 2w+1}; inside a 32-row diagonal block lane r holds row r, so the triangular solve
@@ -706,6 +760,14 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int
         k_build_rhs<<<grid, 256, 0, s>>>(m->d_rest, d_deform, m->d_perm, m->N, n, F, m->d_W, ldw);
         ctx->launches += 1;
     }
+    return fd_launch_solve_prebuilt(ctx, m, nrhs);
+}
+
+// forward / backward sweeps on right-hand sides that already sit (row-permuted) in m->d_W
+cudaError_t fd_launch_solve_prebuilt(fd_ctx* ctx, fd_model* m, int nrhs)
+{
+    cudaStream_t s = ctx->stream;
+    const int n = m->n, ldw = m->ldw;
     // Blocked sweeps for systems whose slab does not fit in shared memory: panels of 256 rows.  Inside a panel the
     // 32-row block steps touch only the panel's rows (rank-32 updates of <= 224 rows); the rows outside it take one
     // rank-256 update (k_panel_gemm), so the right-hand sides are re-read n / 256 times instead of n / 32.
@@ -810,6 +872,92 @@ cudaError_t fd_launch_invdiag(fd_ctx* ctx, fd_model* m)
 {
     const int nblk = (m->n + SB - 1) / SB;
     k_lu_invdiag<<<nblk, 64, 0, ctx->stream>>>(m->d_A, m->lda, m->n, m->d_Tinv);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+// ---- "ALGLIB v1 like" layered fit (fd_params.fidelity = FD_FIDELITY_ALGLIB_V1; orchestration in fd_api.cu) --------------
+// one thread per right-hand-side column: R = delta - P v with v the least-squares polynomial of the deltas on
+// [1 x y z] (np = 4), their mean (np = 1) or nothing -- rbfsetlinterm / constterm / zeroterm fitted FIRST
+// (SOP_FaceDeform.cpp:351-361 [recollection of ALGLIB v1: two-stage])
+__global__ void __launch_bounds__(128) k_v1_rhs_poly(const float* __restrict__ rest, const float* __restrict__ deform, int N,
+                                                     int F, int np, double* __restrict__ R, double* __restrict__ V, int ldw,
+                                                     int* __restrict__ flags)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= ldw) return;
+    const bool live = c < 3 * F;
+    const int f = c / 3, k = c - 3 * f;
+    auto delta = [&](int i) -> double {
+        return live ? (double)(deform[((size_t)f * N + i) * 3 + k] - rest[3 * i + k]) : 0.0; // FP32 subtract, :276-284
+    };
+    double y[4] = {0, 0, 0, 0}, G[4][4] = {};
+    for (int i = 0; i < N && np > 0; ++i) {
+        const double p[4] = {1.0, (double)rest[3 * i], (double)rest[3 * i + 1], (double)rest[3 * i + 2]};
+        const double d = delta(i);
+        for (int a = 0; a < np; ++a) {
+            y[a] += p[a] * d;
+            for (int b = 0; b < np; ++b) G[a][b] += p[a] * p[b];
+        }
+    }
+    bool bad = false;
+    for (int q = 0; q < np; ++q) { // elimination without pivoting on the Gram matrix (the oracle does the same)
+        const double dg = G[q][q];
+        if (!(dg > 0.0)) { bad = true; break; }
+        for (int r = q + 1; r < np; ++r) {
+            const double l = G[r][q] / dg;
+            for (int t = q; t < np; ++t) G[r][t] -= l * G[q][t];
+            y[r] -= l * y[q];
+        }
+    }
+    if (bad) {
+        atomicExch(&flags[FD_FLAG_SINGULAR], 1);
+        for (int a = 0; a < np; ++a) y[a] = 0.0;
+    } else {
+        for (int q = np - 1; q >= 0; --q) {
+            double sacc = y[q];
+            for (int t = q + 1; t < np; ++t) sacc -= G[q][t] * y[t];
+            y[q] = sacc / G[q][q];
+        }
+    }
+    for (int a = 0; a < np; ++a) V[(size_t)a * ldw + c] = y[a];
+    for (int i = 0; i < N; ++i) {
+        double t = np > 0 ? y[0] : 0.0;
+        if (np == 4) t += y[1] * (double)rest[3 * i] + y[2] * (double)rest[3 * i + 1] + y[3] * (double)rest[3 * i + 2];
+        R[(size_t)i * ldw + c] = delta(i) - t;
+    }
+}
+
+// W[i][c] = R[perm[i]][c]: right-hand sides in the row order of the layer's LU
+__global__ void __launch_bounds__(256) k_v1_gather(const double* __restrict__ R, const int* __restrict__ perm, int ldw,
+                                                   double* __restrict__ W)
+{
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const int i = blockIdx.y;
+    if (c < ldw) W[(size_t)i * ldw + c] = R[(size_t)perm[i] * ldw + c];
+}
+
+cudaError_t fd_launch_v1_rhs_poly(fd_ctx* ctx, const float* d_rest, const float* d_deform, int N, int F, int np, double* d_R,
+                                  double* d_V, int ldw, int* d_flags)
+{
+    k_v1_rhs_poly<<<(ldw + 127) / 128, 128, 0, ctx->stream>>>(d_rest, d_deform, N, F, np, d_R, d_V, ldw, d_flags);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t fd_launch_v1_gather(fd_ctx* ctx, const double* d_R, const int* d_perm, int N, int ldw, double* d_W)
+{
+    dim3 grid((ldw + 255) / 256, N);
+    k_v1_gather<<<grid, 256, 0, ctx->stream>>>(d_R, d_perm, ldw, d_W);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t fd_launch_gemm_sub(fd_ctx* ctx, const double* d_A, int lda, int rows, int K, const double* d_X, double* d_C, int ldw,
+                               int nrhs)
+{
+    dim3 grid((nrhs + PG_TN - 1) / PG_TN, (rows + PG_TM - 1) / PG_TM);
+    k_gemm_sub<<<grid, 256, 0, ctx->stream>>>(d_A, lda, rows, K, d_X, d_C, ldw, nrhs);
     ctx->launches += 1;
     return cudaGetLastError();
 }

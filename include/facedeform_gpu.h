@@ -72,6 +72,12 @@ typedef enum fd_status {
 /* arithmetic of the factorisation (BASELINE.json config 4: "FP64 vs FP32+refinement tolerance study") */
 #define FD_FACTOR_FP64 0    /* FP64 LU + FP64 triangular solves (default) */
 #define FD_FACTOR_FP32_IR 1 /* FP32 LU, solutions refined in FP64 until the residual stops shrinking (fd_report) */
+/* formulation of the fit */
+#define FD_FIDELITY_DENSE 0     /* north_star: the augmented saddle-point system [[K + lambda I, P], [P^T, 0]] (default) */
+#define FD_FIDELITY_ALGLIB_V1 1 /* what the SOP's two rbfsetalgo* calls mean in ALGLIB's v1 unit (SURVEY appendix B,
+                                   unverifiable here): polynomial term fitted first by least squares, then Gaussian layers
+                                   on the residual -- QNN: one layer, per-centre radii; Multilayer: `layers` layers with
+                                   radius R, R/2, R/4 ...  The model then holds N * layers centres (weights, radii). */
 /* evaluation kernel */
 #define FD_PATH_AUTO 0   /* tensor cores when 3F is wide enough, else FMA/SFU */
 #define FD_PATH_SIMT 1
@@ -85,7 +91,7 @@ typedef struct fd_params {
     float qcoef;           /* default 1, clamp >= 0.1         :123, :249 */
     float zcoef;           /* default 5, clamp >= 0.1         :124, :250 */
     float radius;          /* default 1, clamp >= 0.01        :125, :251  (RBF radius AND capture/falloff radius :318, :402) */
-    int32_t layers;        /* default 4, clamp >= 1           :126, :252  (only 1 layer is solved) */
+    int32_t layers;        /* default 4, clamp >= 1           :126, :252  (solved with fidelity = FD_FIDELITY_ALGLIB_V1) */
     float lambda;          /* default 0.1, clamp >= 0.01      :128, :253  (K + lambda I) */
     int32_t tangent;       /* default 0                       :129 */
     int32_t maxedges;      /* default 4, clamp >= 1           :127, :257 */
@@ -98,6 +104,7 @@ typedef struct fd_params {
     int32_t eval_precision;/* FD_EVAL_* */
     int32_t eval_path;     /* FD_PATH_* */
     int32_t factor_precision; /* FD_FACTOR_* */
+    int32_t fidelity;         /* FD_FIDELITY_* */
 } fd_params;
 
 /* analogue of alglib::rbfreport (SOP_FaceDeform.cpp:333, :365-373) */

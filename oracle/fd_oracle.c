@@ -740,3 +740,111 @@ void fdo_dbse_displace(const double* M, int64_t P, int32_t S, const double* weig
         }
     }
 }
+
+
+/* ======================================================================================================
+ * "ALGLIB v1 like" fit, see fd_oracle.h (unverifiable: documentation of SOP_FaceDeform.cpp:342-361)
+ * ====================================================================================================== */
+int fdo_fit_v1(const fdo_params* p, const float* rest, const float* deform, int N, int F,
+               float* centres_out, double* radii_out, double* weights_out)
+{
+    const int np = fdo_poly_terms(p->term);
+    const int nrhs = 3 * F;
+    const int L = p->model == FDO_MODEL_QNN ? 1 : (p->layers < 1 ? 1 : p->layers);
+    const int NL = N * L;
+    int status = 1;
+    double* R = (double*)malloc(sizeof(double) * (size_t)N * nrhs);   /* residual */
+    double* A = (double*)malloc(sizeof(double) * (size_t)N * N);
+    double* K0 = (double*)malloc(sizeof(double) * (size_t)N * N);
+    double* Wk = (double*)malloc(sizeof(double) * (size_t)N * nrhs);
+    int32_t* piv = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+    double* rad = (double*)malloc(sizeof(double) * (size_t)N);
+    /* deltas: FP32 subtract, widened (SOP_FaceDeform.cpp:276-284) */
+    for (int i = 0; i < N; ++i)
+        for (int f = 0; f < F; ++f)
+            for (int k = 0; k < 3; ++k)
+                R[(size_t)i * nrhs + 3 * f + k] = (double)(deform[((size_t)f * N + i) * 3 + k] - rest[3 * i + k]);
+    /* polynomial term first: normal equations of [1 x y z] (np = 4), the mean (np = 1) or nothing */
+    double* v = weights_out + (size_t)NL * nrhs;
+    if (np > 0) {
+        double G[16], piv4[4];
+        (void)piv4;
+        for (int a = 0; a < np; ++a)
+            for (int b = 0; b < np; ++b) {
+                double s = 0.0;
+                for (int i = 0; i < N; ++i) {
+                    const double pa = a == 0 ? 1.0 : (double)rest[3 * i + a - 1], pb = b == 0 ? 1.0 : (double)rest[3 * i + b - 1];
+                    s += pa * pb;
+                }
+                G[a * np + b] = s;
+            }
+        for (int c = 0; c < nrhs; ++c) {
+            double M[16], y[4];
+            for (int a = 0; a < np * np; ++a) M[a] = G[a];
+            for (int a = 0; a < np; ++a) {
+                double s = 0.0;
+                for (int i = 0; i < N; ++i) s += (a == 0 ? 1.0 : (double)rest[3 * i + a - 1]) * R[(size_t)i * nrhs + c];
+                y[a] = s;
+            }
+            /* Gaussian elimination without pivoting on the symmetric positive (semi)definite Gram matrix */
+            for (int k = 0; k < np; ++k) {
+                const double d = M[k * np + k];
+                if (!(d > 0.0)) { status = -3; break; }
+                for (int r = k + 1; r < np; ++r) {
+                    const double l = M[r * np + k] / d;
+                    for (int q = k; q < np; ++q) M[r * np + q] -= l * M[k * np + q];
+                    y[r] -= l * y[k];
+                }
+            }
+            if (status != 1) break;
+            for (int k = np - 1; k >= 0; --k) {
+                double s = y[k];
+                for (int q = k + 1; q < np; ++q) s -= M[k * np + q] * y[q];
+                y[k] = s / M[k * np + k];
+            }
+            for (int a = 0; a < np; ++a) v[(size_t)a * nrhs + c] = y[a];
+        }
+        if (status == 1)
+            for (int i = 0; i < N; ++i)
+                for (int c = 0; c < nrhs; ++c) {
+                    double t = v[c];
+                    if (np == 4)
+                        for (int k = 0; k < 3; ++k) t += v[(size_t)(1 + k) * nrhs + c] * (double)rest[3 * i + k];
+                    R[(size_t)i * nrhs + c] -= t;
+                }
+    }
+    fdo_params q = *p;
+    q.term = FDO_TERM_ZERO; /* the layers carry no side conditions */
+    for (int k = 0; k < L && status == 1; ++k) {
+        if (p->model == FDO_MODEL_QNN) {
+            if (fdo_radii(p, rest, N, rad) != 0) { status = -5; break; }
+        } else {
+            const double Rk = (double)p->radius / (double)(1 << k);
+            for (int i = 0; i < N; ++i) rad[i] = Rk;
+        }
+        for (int i = 0; i < N; ++i) {
+            radii_out[(size_t)k * N + i] = rad[i];
+            for (int c = 0; c < 3; ++c) centres_out[((size_t)k * N + i) * 3 + c] = rest[3 * i + c];
+        }
+        q.lambda = 0.0f;
+        fdo_assemble(&q, rest, rad, N, K0);           /* the layer's kernel matrix */
+        for (size_t t = 0; t < (size_t)N * N; ++t) A[t] = K0[t];
+        for (int i = 0; i < N; ++i) A[(size_t)i * N + i] += (double)p->lambda;
+        if (fdo_lu_factor(A, N, piv) != 0) { status = -3; break; }
+        for (size_t t = 0; t < (size_t)N * nrhs; ++t) Wk[t] = R[t];
+        fdo_lu_solve(A, piv, N, Wk, nrhs);
+        for (size_t t = 0; t < (size_t)N * nrhs; ++t) weights_out[(size_t)k * N * nrhs + t] = Wk[t];
+        for (int i = 0; i < N; ++i)                    /* residual -= K_k w_k */
+            for (int j = 0; j < N; ++j) {
+                const double kij = K0[(size_t)i * N + j];
+                const double* w = Wk + (size_t)j * nrhs;
+                double* r = R + (size_t)i * nrhs;
+                for (int c = 0; c < nrhs; ++c) r[c] -= kij * w[c];
+            }
+    }
+    if (status == 1)
+        for (size_t t = 0; t < (size_t)(NL + np) * nrhs; ++t)
+            if (weights_out[t] != weights_out[t] || isinf(weights_out[t])) { status = -3; break; }
+    free(R); free(A); free(K0); free(Wk); free(piv); free(rad);
+    return status;
+}

@@ -110,6 +110,21 @@ int fdo_capture(const float* P, int64_t V, const int32_t* poly_off, const int32_
 float fdo_point_tri_dist2(const float p[3], const float a[3], const float b[3], const float c[3]);
 float fdo_point_seg_dist2(const float p[3], const float a[3], const float b[3]);
 
+/* ---- "ALGLIB v1 like" fit -- UNVERIFIABLE here: ALGLIB is absent and unpinned,
+ * this documents what the SOP's two algorithm settings mean (SOP_FaceDeform.cpp:342-361), with dense LU in place of
+ * ALGLIB's sparse LSQR [recollection]:
+ *   polynomial term first (rbfsetlinterm / constterm / zeroterm, :351-361): least squares of the deltas on [1 x y z]
+ *   (or their mean / nothing), the RBF part is fitted to the de-trended residual without side conditions;
+ *   model QNN (:344): one Gaussian layer with per-centre radii R_j (fdo_radii);
+ *   model Multilayer (:347): `layers` successive Gaussian layers, radius R, R/2, R/4 ..., each solving
+ *   (K_k + lambda I) w_k = residual and passing residual - K_k w_k on (lambda as a diagonal shift: this repo's
+ *   definition of the damping).
+ * Outputs describe one stacked model the ordinary evaluation takes: centres (N * L x 3, `rest` repeated per layer),
+ * radii (N * L), weights ((N * L + npoly) x 3F, polynomial rows last).  L = layers for Multilayer, 1 for QNN.
+ * Returns 1, -5 (zero QNN radius) or -3 (singular). */
+int fdo_fit_v1(const fdo_params* p, const float* rest, const float* deform, int N, int F,
+               float* centres_out, double* radii_out, double* weights_out);
+
 /* ---- DirectBSEdit, the "morph space" post-pass (reference src/dbse.cpp, caller SOP_FaceDeform.cpp:444-482) ----------
  * Eigen (absent, unpinned) supplies HouseholderQR there; restated here as the unblocked Householder QR with Eigen's /
  * LAPACK dgeqr2's conventions [recollection for Eigen; pinned against LAPACK through scipy.linalg.qr(mode="raw")]:

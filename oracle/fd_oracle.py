@@ -79,6 +79,8 @@ def lib():
         L.fdo_point_seg_dist2.argtypes = [fp, fp, fp]
         L.fdo_point_seg_dist2.restype = C.c_float
         L.fdo_num_threads.restype = C.c_int
+        L.fdo_fit_v1.argtypes = [pp, fp, fp, C.c_int, C.c_int, fp, dp, dp]
+        L.fdo_fit_v1.restype = C.c_int
         L.fdo_dbse_shapes_matrix.argtypes = [fp, fp, C.c_int64, C.c_int32, dp]
         L.fdo_householder_qr.argtypes = [dp, C.c_int64, C.c_int32, dp]
         L.fdo_dbse_weights.argtypes = [dp, C.c_int64, C.c_int32, fp, fp, dp]
@@ -292,3 +294,20 @@ def dbse_displace(M, weights, pos, rest, weightrange=None, dofalloff=0, falloffr
     lib().fdo_dbse_displace(M.ctypes.data_as(C.POINTER(C.c_double)), rest.shape[0], M.shape[1], _d(weights),
                             None if wr is None else _f(wr), int(dofalloff), float(falloffradius), _f(pos), _f(rest), _f(out))
     return out
+
+
+# ---- "ALGLIB v1 like" fit (unverifiable documentation mode, fd_oracle.h) -----------------------------------------------
+
+def fit_v1(p: Params, rest, deform):
+    """two-stage polynomial + QNN single layer / Multilayer `layers` halving radii.
+    returns (status, centres[N*L, 3], radii[N*L], weights[(N*L + npoly), 3F]): a stacked model for evaluate()."""
+    rest, deform = _cf(rest), _cf(deform)
+    if deform.ndim == 2:
+        deform = deform[None]
+    F, N = deform.shape[0], rest.shape[0]
+    L = 1 if p.model == MODEL_QNN else max(1, int(p.layers))
+    cen = np.empty((N * L, 3), np.float32)
+    rad = np.empty(N * L, np.float64)
+    W = np.empty((N * L + poly_terms(p.term), 3 * F), np.float64)
+    st = lib().fdo_fit_v1(C.byref(p), _f(rest), _f(deform), N, F, _f(cen), _d(rad), _d(W))
+    return st, cen, rad, W

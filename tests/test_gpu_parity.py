@@ -314,3 +314,40 @@ def test_fp32_refinement_reports_non_convergence(ctx):
         assert m.last_report.terminationtype in (-3, -4)
     finally:
         m.close()
+
+
+# ---- fidelity = FD_FIDELITY_ALGLIB_V1: two-stage polynomial + Gaussian layers (unverifiable vs ALGLIB) -------
+
+@pytest.mark.parametrize("model,layers,term,F", [(1, 1, 0, 2), (1, 3, 0, 2), (1, 4, 1, 20), (1, 2, 2, 1), (0, 1, 0, 3)])
+def test_alglib_v1_like_mode_matches_the_oracle(ctx, oracle, model, layers, term, F):
+    from facedeform_b200 import make_params
+    rig = synth.control_rig(120)
+    deform = synth.deformed_rig(rig, F)
+    mesh = synth.face_mesh(3000, topology=False)
+    kw = dict(model=model, term=term, kernel=0, radius=3 * rig.spacing, layers=layers, qcoef=1.0, zcoef=5.0)
+    p = make_params(fidelity=1, **kw, **{"lambda": 0.01})
+    m = ctx.fit(p, rig.rest).solve(deform)
+    rep = m.report()
+    L = 1 if model == 0 else layers
+    assert rep.terminationtype == 1 and rep.n == 120 * L
+    out, _ = m.eval(mesh.P)
+    Wg, Rg = m.weights()
+    op = oracle.make_params(**kw, **{"lambda": 0.01})
+    st, cen, rad, W = oracle.fit_v1(op, rig.rest, deform)
+    assert st == 1 and Wg.shape == W.shape
+    np.testing.assert_allclose(Rg, rad, rtol=1e-12)
+    np.testing.assert_allclose(Wg, W, rtol=0, atol=1e-7 * np.abs(W).max())
+    ref, _ = oracle.evaluate(op, cen, rad, W, mesh.P, nthreads=8)
+    assert np.abs(out.astype(np.float64) - ref).max() <= REL_TOL * mesh.bbox_diag
+    m.close()
+
+
+def test_alglib_v1_like_mode_limits(ctx):
+    from facedeform_b200 import FdError, make_params
+    rig = synth.control_rig(30)
+    with pytest.raises(FdError) as e:      # ALGLIB's v1 unit is Gaussian only
+        ctx.fit(make_params(fidelity=1, model=1, kernel=1, radius=0.3), rig.rest)
+    assert e.value.status == 8
+    with pytest.raises(FdError) as e:      # receivers take the dense formulation
+        ctx.receiver(make_params(fidelity=1, model=1, radius=0.3), rig.rest, 2)
+    assert e.value.status == 8
