@@ -642,7 +642,23 @@ int fd_model_create_receiver(fd_ctx* ctx, const fd_params* params, const float* 
     DeviceGuard g(ctx->device);
     int st = check_params(ctx, params);
     if (st != FD_OK) return st;
-    if (params->fidelity != FD_FIDELITY_DENSE) { FD_SET_ERR(ctx, "receiver models take the dense formulation only"); return FD_E_UNSUPPORTED; }
+    if (params->fidelity == FD_FIDELITY_ALGLIB_V1) {
+        // the layered fit's weights describe N * layers stacked centres (v1_solve): the receiver is an ordinary one of
+        // that size, its centres are the control points repeated once per layer
+        if (params->kernel != FD_KERNEL_GAUSSIAN) { FD_SET_ERR(ctx, "the ALGLIB v1 formulation is Gaussian only"); return FD_E_UNSUPPORTED; }
+        const int L = params->model == FD_MODEL_QNN ? 1 : (params->layers < 1 ? 1 : params->layers);
+        if (L > FD_V1_MAX_LAYERS) { FD_SET_ERR(ctx, "at most %d layers", FD_V1_MAX_LAYERS); return FD_E_INVALID; }
+        float* d_stack = nullptr;
+        st = dev_alloc(ctx, &d_stack, (size_t)n_ctrl * L * 3);
+        if (st != FD_OK) return st;
+        for (int k = 0; k < L; ++k)
+            cudaMemcpyAsync(d_stack + (size_t)k * n_ctrl * 3, rest_ctrl, (size_t)n_ctrl * 3 * sizeof(float), cudaMemcpyDefault, ctx->stream);
+        fd_params pe = *params;
+        pe.fidelity = FD_FIDELITY_DENSE;
+        st = fd_model_create_receiver(ctx, &pe, d_stack, n_ctrl * L, frames, out);
+        cudaFreeAsync(d_stack, ctx->stream); // stream-ordered: the receiver's copy of the centres is enqueued before it
+        return st;
+    }
     fd_model* m = nullptr;
     st = model_alloc(ctx, params, n_ctrl, false, &m);
     if (st != FD_OK) return st;

@@ -348,6 +348,28 @@ def test_alglib_v1_like_mode_limits(ctx):
     with pytest.raises(FdError) as e:      # ALGLIB's v1 unit is Gaussian only
         ctx.fit(make_params(fidelity=1, model=1, kernel=1, radius=0.3), rig.rest)
     assert e.value.status == 8
-    with pytest.raises(FdError) as e:      # receivers take the dense formulation
-        ctx.receiver(make_params(fidelity=1, model=1, radius=0.3), rig.rest, 2)
-    assert e.value.status == 8
+
+
+def test_alglib_v1_like_receiver_matches_root_bit_for_bit(ctx):
+    """the layered fit across GPUs: a receiver of N * layers stacked centres fed the root's blocks evaluates identically."""
+    import torch
+    from facedeform_b200 import make_params, shard
+    rig = synth.control_rig(64)
+    deform = synth.deformed_rig(rig, 20)
+    mesh = synth.face_mesh(2000, topology=False)
+    p = make_params(fidelity=1, model=1, term=0, radius=3 * rig.spacing, layers=3, **{"lambda": 0.01})
+    root = ctx.fit(p, rig.rest).solve(deform)
+    want, _ = root.eval(mesh.P)
+    recv = ctx.receiver(p, rig.rest, 20)
+    assert recv.info() == root.info() and recv.info()["n_ctrl"] == 192
+    for get in ("weights_dev", "radii_dev"):
+        (sp, sb), (dp, db) = getattr(root, get)(), getattr(recv, get)()
+        assert sb == db
+        ctx.synchronize()
+        shard.device_view(dp, db).copy_(shard.device_view(sp, sb))
+    torch.cuda.synchronize()
+    recv.commit_weights()
+    got, _ = recv.eval(mesh.P)
+    assert np.array_equal(got, want)
+    root.close()
+    recv.close()
