@@ -403,7 +403,7 @@ void fd_model_destroy(fd_model* m)
     void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
                       m->d_ctab32, m->d_W32, m->d_ctab64, m->d_tc_norm, m->d_tc_scale, m->d_tc_unscale,
                       m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win, m->d_ctab_pair, m->d_A32, m->d_B, m->d_R, m->d_D32,
-                      m->d_ir_norm, m->d_v1_R, m->d_v1_K, m->d_v1_V, m->d_v1_stack};
+                      m->d_ir_norm, m->d_v1_R, m->d_v1_K, m->d_v1_V, m->d_v1_stack, m->d_ns};
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;
@@ -431,13 +431,26 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
     cudaError_t e = cudaMemcpyAsync(m->d_rest, rest_ctrl_dev, (size_t)n_ctrl * 3 * sizeof(float), cudaMemcpyDefault, ctx->stream);
     phase_begin(ctx, FD_PH_ASSEMBLE);
     if (e == cudaSuccess) e = fd_launch_radii(ctx, m->prm, m->d_rest, m->N, m->d_radii, m->d_flags);
-    if (e == cudaSuccess) e = fd_launch_assemble(ctx, m->prm, m->d_rest, m->d_radii, m->N, m->np, m->d_A, m->lda);
+    // Multiquadric / thin plate with a uniform radius and the linear term: the null-space transform makes the system
+    // definite, so it takes the fused no-pivot LU instead of the pivoted one (fd_nullspace.cu).  The multiquadric's
+    // reduced matrix is NEGATIVE definite: a positive diagonal shift would break that, so it needs lambda = 0.
+    m->ns = m->prm.kernel != FD_KERNEL_GAUSSIAN && m->prm.model == FD_MODEL_ML && m->np == 4 && m->N >= 8 &&
+            (m->prm.kernel == FD_KERNEL_THINPLATE || m->prm.lambda == 0.f) && m->prm.factor_precision == FD_FACTOR_FP64 &&
+            !getenv("FD_NO_NULLSPACE") && !getenv("FD_FORCE_PIVOTED_LU");
+    if (m->ns && dev_alloc(ctx, &m->d_ns, (size_t)m->N * 5 + 32) != FD_OK) m->ns = false;
+    if (e == cudaSuccess)
+        e = fd_launch_assemble(ctx, m->prm, m->d_rest, m->d_radii, m->N, m->ns ? 0 : m->np, m->d_A, m->lda);
+    if (e == cudaSuccess && m->ns) e = fd_launch_ns_transform(ctx, m);
     phase_end(ctx, FD_PH_ASSEMBLE);
     phase_begin(ctx, FD_PH_FACTOR);
     // Gaussian kernel with one radius: K + lambda I is symmetric positive definite -> no pivot search needed
     const bool spd = m->prm.kernel == FD_KERNEL_GAUSSIAN && (m->prm.model == FD_MODEL_ML || m->N == 1) && !getenv("FD_FORCE_PIVOTED_LU");
     const bool unfused = getenv("FD_LU_UNFUSED") != nullptr; // per-block-column launches (kept for comparison)
-    if (e == cudaSuccess && m->f32ir) {
+    if (e == cudaSuccess && m->ns) {
+        // the definite (N - 4) x (N - 4) block of Q^T K Q, in place
+        e = fd_launch_lu_nopivot_fused(ctx, m->d_A + (size_t)4 * m->lda + 4, m->lda, m->N - 4, m->d_ipiv, m->d_perm, m->d_flags,
+                                       m->d_pivstat, m->d_Tinv);
+    } else if (e == cudaSuccess && m->f32ir) {
         // FP32 factorisation of fl32(A); d_A keeps the FP64 system for the residuals of the refinement (fd_refine.cu)
         e = fd_launch_to_f32(ctx, m->d_A, m->d_A32, (size_t)m->lda * m->n);
         if (e == cudaSuccess)
@@ -494,7 +507,17 @@ int fd_rbf_solve_dev(fd_model* m, const float* deform_ctrl_dev, int32_t n_ctrl, 
     m->ldw32 = m->ldw;
     m->use_tc = model_wants_tc(m, frames);
     phase_begin(ctx, FD_PH_SOLVE);
-    cudaError_t e = m->f32ir ? fd_refine_solve(ctx, m, deform_ctrl_dev, frames) : fd_launch_solve(ctx, m, deform_ctrl_dev, frames);
+    cudaError_t e;
+    if (m->ns) { // D' = Q^T D, z = S^-1 D'[4:], a = R^-1 (D'[:4] - K'[:4, 4:] z), w = Q [0; z]
+        m->tc_packed_by_solve = false;
+        e = fd_launch_ns_rhs(ctx, m, deform_ctrl_dev, frames);
+        if (e == cudaSuccess)
+            e = fd_launch_solve_sub(ctx, m->d_A + (size_t)4 * m->lda + 4, m->lda, m->N - 4, m->d_perm, m->d_Tinv,
+                                    m->d_W + (size_t)4 * m->ldw, m->ldw, 3 * frames);
+        if (e == cudaSuccess) e = fd_launch_ns_finish(ctx, m, frames);
+    } else {
+        e = m->f32ir ? fd_refine_solve(ctx, m, deform_ctrl_dev, frames) : fd_launch_solve(ctx, m, deform_ctrl_dev, frames);
+    }
     if (e == cudaSuccess) e = fd_launch_pack(ctx, m);
     phase_end(ctx, FD_PH_SOLVE);
     if (e != cudaSuccess) { FD_SET_ERR(ctx, "solve: %s", cudaGetErrorString(e)); return FD_E_CUDA; }

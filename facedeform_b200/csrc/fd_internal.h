@@ -76,6 +76,10 @@ struct fd_model {
     double* d_W;     // n x ldw weights (solve in place over the right-hand sides)
     int* d_flags;    // FD_NUM_FLAGS
     double* d_pivstat; // [min |u_kk|, max |u_kk|]
+    // null-space path of multiquadric / thin plate (fd_nullspace.cu): d_A holds Q^T K Q, its [4:, 4:] block LU-factored;
+    // d_ns = reflectors V (N x 4), tau (4), R (4 x 4), scratch (N)
+    bool ns;
+    double* d_ns;
     // FD_FIDELITY_ALGLIB_V1 (fd_api.cu): the parent holds one factored sub-model per layer and a stacked evaluation
     // model (N * layers centres); d_v1_* are the residual, a scratch for the layer's kernel matrix and the polynomial
     int v1_layers;
@@ -143,6 +147,12 @@ cudaError_t fd_launch_lu_nopivot_fused(fd_ctx* ctx, double* d_A, int lda, int n,
 // fd_solve.cu
 cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int F);
 cudaError_t fd_launch_solve_prebuilt(fd_ctx* ctx, fd_model* m, int nrhs);
+cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, const int* d_perm, const double* d_Tinv,
+                                double* d_W, int ldw, int nrhs);
+// fd_nullspace.cu
+cudaError_t fd_launch_ns_transform(fd_ctx* ctx, fd_model* m);
+cudaError_t fd_launch_ns_rhs(fd_ctx* ctx, fd_model* m, const float* d_deform, int F);
+cudaError_t fd_launch_ns_finish(fd_ctx* ctx, fd_model* m, int F);
 cudaError_t fd_launch_v1_rhs_poly(fd_ctx* ctx, const float* d_rest, const float* d_deform, int N, int F, int np, double* d_R,
                                   double* d_V, int ldw, int* d_flags);
 cudaError_t fd_launch_v1_gather(fd_ctx* ctx, const double* d_R, const int* d_perm, int N, int ldw, double* d_W);

@@ -514,7 +514,9 @@ __global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __rest
         double v = 0.0;
         if (i < n) {
             const int src = perm[i];
-            if (c < nrhs && src < N) {
+            if (!deform) { // right-hand sides prebuilt in W (the null-space path, fd_nullspace.cu)
+                if (c < ldw) v = W[(size_t)src * ldw + c];
+            } else if (c < nrhs && src < N) {
                 const int f = c / 3, k = c - 3 * f;
                 v = (double)(deform[((size_t)f * N + src) * 3 + k] - rest[3 * src + k]);
             }
@@ -766,8 +768,31 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int
 // forward / backward sweeps on right-hand sides that already sit (row-permuted) in m->d_W
 cudaError_t fd_launch_solve_prebuilt(fd_ctx* ctx, fd_model* m, int nrhs)
 {
+    return fd_launch_solve_sub(ctx, m->d_A, m->lda, m->n, nullptr, m->d_Tinv, m->d_W, m->ldw, nrhs);
+}
+
+// the same on an explicit system: LU factors A (n x n, column stride lda), inverted diagonal blocks Tinv, right-hand
+// sides W (row stride ldw) already in the LU's row order.  perm != NULL (an identity for the no-pivot LU) allows the
+// one-launch slab solve when the slab fits.
+cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, const int* d_perm, const double* d_Tinv,
+                                double* d_W, int ldw, int nrhs)
+{
     cudaStream_t s = ctx->stream;
-    const int n = m->n, ldw = m->ldw;
+    if (d_perm) {
+        const int n_pad = fd_round_up(n, SB);
+        const size_t bytes8 = ((size_t)n_pad * S8_RC + 2 * S8_CHUNK_DOUBLES + 2 * S8_TINV_DOUBLES) * sizeof(double);
+        if (bytes8 <= 220 * 1024) {
+            cudaFuncSetAttribute(k_solve_slab8, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            fd_tc_pack_args pk;
+            pk.enabled = 0;
+            k_solve_slab8<<<(ldw + S8_RC - 1) / S8_RC, S8_THREADS, bytes8, s>>>(d_A, lda, n, n, d_perm, nullptr, nullptr,
+                                                                              nrhs / 3, d_Tinv, d_W, ldw, pk);
+            ctx->launches += 1;
+            return cudaGetLastError();
+        }
+    }
+    struct { const double* d_A; int lda; const double* d_Tinv; double* d_W; } mm = {d_A, lda, d_Tinv, d_W};
+    const auto* m = &mm;
     // Blocked sweeps for systems whose slab does not fit in shared memory: panels of 256 rows.  Inside a panel the
     // 32-row block steps touch only the panel's rows (rank-32 updates of <= 224 rows); the rows outside it take one
     // rank-256 update (k_panel_gemm), so the right-hand sides are re-read n / 256 times instead of n / 32.
