@@ -159,9 +159,10 @@ def run_reference(args):
 
 def factor_table(ctx, sizes, cpu=True):
     """factor ms at N control points (assemble + factor, device resident, median of 3 after one warm-up):
-    `gaussian_spd` = Gaussian + uniform radius (symmetric positive definite: LU without pivot search),
-    `multiquadric_pivoted` = the general pivoted LU; `cpu_oracle` = the FP64 oracle's assemble + LU on the host cores
-    (N <= 2048 only: the 8192 case takes minutes on a CPU)."""
+    `gaussian_spd` = Gaussian + uniform radius (symmetric positive definite: fused LU without pivot search),
+    `multiquadric_nullspace` = multiquadric + linear term through the null-space transform onto the same fused LU,
+    `qnn_pivoted` = Gaussian with per-centre QNN radii (non-symmetric: the general pivoted LU);
+    `cpu_oracle` = the FP64 oracle's assemble + LU on the host cores (N <= 2048 only: 8192 takes minutes on a CPU)."""
     import torch
     from facedeform_b200 import make_params, synth
     out = {}
@@ -169,8 +170,9 @@ def factor_table(ctx, sizes, cpu=True):
         rig = synth.control_rig(n)
         d_rest = torch.from_numpy(rig.rest).cuda()
         row = {}
-        for name, kern in (("gaussian_spd", "gaussian"), ("multiquadric_pivoted", "multiquadric")):
-            p = make_params(model=1, term=0, kernel=synth.KERNELS[kern], radius=synth.default_radius(kern, rig.spacing),
+        for name, kern, model in (("gaussian_spd", "gaussian", 1), ("multiquadric_nullspace", "multiquadric", 1),
+                                  ("qnn_pivoted", "gaussian", 0)):
+            p = make_params(model=model, term=0, kernel=synth.KERNELS[kern], radius=synth.default_radius(kern, rig.spacing),
                             **{"lambda": 0.0})
             ts = []
             for i in range(4):
