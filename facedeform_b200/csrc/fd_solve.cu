@@ -142,6 +142,51 @@ __global__ void __launch_bounds__(128) k_trsm_diag_inv(const double* __restrict_
         if (r < nb) B[(size_t)(k0 + r) * ldw + c] = x[r];
 }
 
+// ---- a handful of right-hand sides (one frame per cook, the reference's own usage): one launch per 32-row block step.
+// Every CTA recomputes x_k = T_kk^-1 b_k from the pre-inverted diagonal block (32 x 32 x nrhs FMAs, redundantly: cheaper
+// than a second launch), then updates its own 64 rows outside the block: upd[rows] -= T[rows, k-block] x_k.  Sources and
+// targets are separate buffers (forward: reads B, writes y_k to Y, updates B below; backward: reads Y, writes x_k to X,
+// updates Y above), so no CTA reads rows another one writes in the same launch.
+constexpr int FEW_MAX = 8;
+template <bool LOWER>
+__global__ void __launch_bounds__(256) k_few_step(const double* __restrict__ A, int lda, int n, int k0, int nb,
+                                                  const double* __restrict__ Tinv_blk, const double* src, int lds,
+                                                  double* xout, int ldx, double* upd, int ldu, int nrhs)
+{
+    __shared__ __align__(16) double s_I[SB * SB]; // s_I[j * 32 + r] = inverse[r][j]
+    __shared__ double s_b[SB][FEW_MAX];
+    __shared__ double s_x[SB][FEW_MAX];
+    const int tid = threadIdx.x;
+    for (int t = tid; t < SB * SB; t += 256) s_I[t] = Tinv_blk[t];
+    {
+        const int j = tid & 31, c = tid >> 5;
+        s_b[j][c] = (j < nb && c < nrhs) ? src[(size_t)(k0 + j) * lds + c] : 0.0;
+    }
+    __syncthreads();
+    {
+        const int r = tid & 31, c = tid >> 5;
+        double x = 0.0;
+#pragma unroll 8
+        for (int j = 0; j < SB; ++j) x = fma(s_I[j * SB + r], s_b[j][c], x);
+        s_x[r][c] = x;
+        if (blockIdx.x == 0 && r < nb && c < nrhs) xout[(size_t)(k0 + r) * ldx + c] = x;
+    }
+    __syncthreads();
+    const int row_begin = LOWER ? k0 + nb : 0, row_end = LOWER ? n : k0;
+    const int r = row_begin + blockIdx.x * 64 + (tid & 63);
+    if (r >= row_end) return;
+    const int cg = tid >> 6; // 4 column groups of 2
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < SB; ++k) {
+        const double t = k < nb ? A[(size_t)(k0 + k) * lda + r] : 0.0;
+        a0 = fma(t, s_x[k][2 * cg], a0);
+        a1 = fma(t, s_x[k][2 * cg + 1], a1);
+    }
+    if (2 * cg < nrhs) upd[(size_t)r * ldu + 2 * cg] -= a0;
+    if (2 * cg + 1 < nrhs) upd[(size_t)r * ldu + 2 * cg + 1] -= a1;
+}
+
 // Panel update of the blocked sweeps: B[r][c] -= sum_k T[r][kb + k] * B[kb + k][c] for r in [r_lo, r_hi), k < K.
 // T column-major (the LU factors), B row-major.  CTA tile 128 rows x 64 columns, 8 x 4 per thread, K in chunks of 16
 // through shared memory; FP64 FMA bound (64 flop per 6 shared-memory reads of 16 bytes).
@@ -720,6 +765,7 @@ __global__ void __launch_bounds__(256) k_pack_weights(const double* __restrict__
 cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int F)
 {
     m->tc_packed_by_solve = false;
+
     cudaStream_t s = ctx->stream;
     const int n = m->n, nrhs = 3 * F, ldw = m->ldw;
     {
@@ -790,6 +836,28 @@ cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, 
             ctx->launches += 1;
             return cudaGetLastError();
         }
+    }
+    // beyond the slab: a handful of right-hand sides take one launch per block step (8.0 ms against 9.0 ms for the
+    // two-launch rank-32 sweeps at n = 8196; where the slab fits, its single long-running CTA is still faster)
+    if (nrhs <= FEW_MAX && n >= 512 && !getenv("FD_NO_FEW_RHS")) {
+        double* d_Y = nullptr; // forward-substituted right-hand sides, n x 8
+        cudaError_t e = cudaMallocAsync((void**)&d_Y, (size_t)n * FEW_MAX * sizeof(double), s);
+        if (e != cudaSuccess) return e;
+        for (int k0 = 0; k0 < n; k0 += SB) { // L y = b
+            const int nb = min(SB, n - k0), rows = n - k0 - nb;
+            k_few_step<true><<<max(1, (rows + 63) / 64), 256, 0, s>>>(d_A, lda, n, k0, nb, d_Tinv + (size_t)(k0 / SB) * 2 * SB * SB,
+                                                                      d_W, ldw, d_Y, FEW_MAX, d_W, ldw, nrhs);
+        }
+        for (int k0 = (n - 1) / SB * SB; k0 >= 0; k0 -= SB) { // U x = y
+            const int nb = min(SB, n - k0);
+            k_few_step<false><<<max(1, (k0 + 63) / 64), 256, 0, s>>>(d_A, lda, n, k0, nb,
+                                                                     d_Tinv + ((size_t)(k0 / SB) * 2 + 1) * SB * SB, d_Y, FEW_MAX,
+                                                                     d_W, ldw, d_Y, FEW_MAX, nrhs);
+        }
+        ctx->launches += 2 * ((n + SB - 1) / SB);
+        e = cudaGetLastError();
+        cudaFreeAsync(d_Y, s);
+        return e;
     }
     struct { const double* d_A; int lda; const double* d_Tinv; double* d_W; } mm = {d_A, lda, d_Tinv, d_W};
     const auto* m = &mm;
