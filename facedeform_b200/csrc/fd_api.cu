@@ -433,9 +433,9 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
     if (e == cudaSuccess) e = fd_launch_radii(ctx, m->prm, m->d_rest, m->N, m->d_radii, m->d_flags);
     // Multiquadric / thin plate with a uniform radius and the linear term: the null-space transform makes the system
     // definite, so it takes the fused no-pivot LU instead of the pivoted one (fd_nullspace.cu).  The multiquadric's
-    // reduced matrix is NEGATIVE definite: a positive diagonal shift would break that, so it needs lambda = 0.
+    // reduced matrix is NEGATIVE definite and its smoothing shift is -lambda (k_assemble), which keeps it so.
     m->ns = m->prm.kernel != FD_KERNEL_GAUSSIAN && m->prm.model == FD_MODEL_ML && m->np == 4 && m->N >= 8 &&
-            (m->prm.kernel == FD_KERNEL_THINPLATE || m->prm.lambda == 0.f) && m->prm.factor_precision == FD_FACTOR_FP64 &&
+            m->prm.factor_precision == FD_FACTOR_FP64 &&
             !getenv("FD_NO_NULLSPACE") && !getenv("FD_FORCE_PIVOTED_LU");
     if (m->ns && dev_alloc(ctx, &m->d_ns, (size_t)m->N * 5 + 32) != FD_OK) m->ns = false;
     if (e == cudaSuccess)

@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(kTile* 8) k_assemble(const float* __restrict__
             const double dy = (double)s_ci[threadIdx.x][1] - (double)s_cj[jj][1];
             const double dz = (double)s_ci[threadIdx.x][2] - (double)s_cj[jj][2];
             v = phi64<KERNEL>(dx * dx + dy * dy + dz * dz, s_rj[jj]);
-            if (i == j) v += lambda;
+            // smoothing; the multiquadric is conditionally NEGATIVE definite, its shift carries the opposite sign
+            if (i == j) v += KERNEL == FD_KERNEL_MULTIQUADRIC ? -lambda : lambda;
         } else if (i < N) { // polynomial column j - N of row i
             const int k = j - N;
             v = (k == 0) ? 1.0 : (double)s_ci[threadIdx.x][k - 1];

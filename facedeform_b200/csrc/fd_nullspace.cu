@@ -10,8 +10,8 @@
 //      R a = (Q^T D)[:4] - (Q^T K Q)[:4, 4:] z
 // so S takes the fused no-pivot LU (fd_factor.cu) and its slab solve.  The transform costs 8 passes over K
 // (per reflector: p = tau K v, q = p - (tau/2)(v.p) v, K -= v q^T + q v^T), HBM bound and small beside the LU.
-// Conditions (fd_api.cu): uniform radius (symmetric K), linear term, lambda = 0 for the multiquadric (a positive
-// diagonal shift would make its negative definite S indefinite).
+// Conditions (fd_api.cu): uniform radius (symmetric K), linear term.  Smoothing keeps S definite: + lambda I for the
+// thin plate, - lambda I for the multiquadric (k_assemble).
 #include "fd_internal.h"
 
 namespace {

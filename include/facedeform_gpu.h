@@ -92,7 +92,8 @@ typedef struct fd_params {
     float zcoef;           /* default 5, clamp >= 0.1         :124, :250 */
     float radius;          /* default 1, clamp >= 0.01        :125, :251  (RBF radius AND capture/falloff radius :318, :402) */
     int32_t layers;        /* default 4, clamp >= 1           :126, :252  (solved with fidelity = FD_FIDELITY_ALGLIB_V1) */
-    float lambda;          /* default 0.1, clamp >= 0.01      :128, :253  (K + lambda I) */
+    float lambda;          /* default 0.1, clamp >= 0.01      :128, :253  (K + lambda I; K - lambda I for the conditionally
+                              negative definite multiquadric) */
     int32_t tangent;       /* default 0                       :129 */
     int32_t maxedges;      /* default 4, clamp >= 1           :127, :257 */
     int32_t morphspace;    /* default 0                       :130  (dbse post-pass: fd_dbse_*, FaceDeformOp::setBlendshapes) */

@@ -150,7 +150,9 @@ void fdo_assemble(const fdo_params* p, const float* rest, const double* radii, i
                 const double dx = xi - rest[3 * j], dy = yi - rest[3 * j + 1], dz = zi - rest[3 * j + 2];
                 row[j] = fdo_phi(p->kernel, dx * dx + dy * dy + dz * dz, radii[j]);
             }
-            row[i] += lambda;
+            /* smoothing: the multiquadric +sqrt(r^2 + R^2) is conditionally NEGATIVE definite, so its diagonal shift
+             * carries the opposite sign (the same system scipy solves with kernel -sqrt(1 + (r/R)^2), smoothing lambda/R) */
+            row[i] += p->kernel == FDO_KERNEL_MULTIQUADRIC ? -lambda : lambda;
             if (np >= 1) row[N] = 1.0;
             if (np == 4) {
                 row[N + 1] = xi;

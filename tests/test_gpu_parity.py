@@ -373,3 +373,11 @@ def test_alglib_v1_like_receiver_matches_root_bit_for_bit(ctx):
     assert np.array_equal(got, want)
     root.close()
     recv.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_smoothed_multiquadric_and_thin_plate_take_the_nullspace_path(ctx, oracle, kernel):
+    """lambda > 0 (the SOP clamps it to >= 0.01): -lambda on the multiquadric's diagonal, +lambda on the thin plate's,
+    both keep the reduced matrix definite, so the fused no-pivot LU applies; weights and positions against the oracle."""
+    rel, Wg, W = _run(ctx, oracle, N=300, V=2000, F=2, kernel=kernel, term=0, lam=0.02)
+    np.testing.assert_allclose(Wg, W, rtol=0, atol=1e-5 * np.abs(W).max())

@@ -54,6 +54,26 @@ def test_smoothing_matches_scipy(oracle):
     np.testing.assert_allclose(ours[:, :3], ip(mesh.P.astype(np.float64)), atol=2e-8)
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_smoothing_of_the_conditionally_definite_kernels_matches_scipy(oracle, kernel):
+    """multiquadric: +sqrt(r^2 + R^2) is conditionally negative definite, the shift is -lambda -- the system scipy solves
+    with its kernel -sqrt(1 + (r/R)^2) and smoothing lambda / R; thin plate (conditionally positive): + lambda."""
+    rig, deform, mesh = _problem()
+    R = float(np.float32(1.5 * rig.spacing))
+    lam = float(np.float32(0.02))
+    p = oracle.make_params(model=1, term=0, kernel=kernel, radius=R, **{"lambda": lam})
+    st, rad, W = oracle.fit(p, rig.rest, deform)
+    assert st == 1
+    ours = oracle.evaluate_raw(p, rig.rest, rad, W, mesh.P)
+    delta = (deform - rig.rest[None]).astype(np.float64)
+    if kernel == 1:
+        ip = RBFInterpolator(rig.rest.astype(np.float64), delta[0], kernel="multiquadric", epsilon=1.0 / R, degree=1,
+                             smoothing=lam / R)
+    else:
+        ip = RBFInterpolator(rig.rest.astype(np.float64), delta[0], kernel="thin_plate_spline", degree=1, smoothing=lam)
+    np.testing.assert_allclose(ours[:, :3], ip(mesh.P.astype(np.float64)), atol=5e-8)
+
+
 @pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_interpolates_control_points(oracle, kernel):
     rig, deform, _ = _problem(N=100, F=3)
