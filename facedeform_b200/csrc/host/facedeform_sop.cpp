@@ -142,8 +142,12 @@ CookStatus FaceDeformOp::cook(const Geo& mesh, const Geo& rest_rig, const float*
     m_mesh_ids[1] = mesh.topo_data_id;
     m_rig_ids[0] = rest_rig.p_data_id;
     m_rig_ids[1] = rest_rig.topo_data_id;
-    // Proximity capture (:310-322); the FIXME of :310 (re-capture on radius / max_edges change) is not reproduced
-    if (rest_pose_changed || rest_rig_changed || !m_mesh_capture.isInitialized() || !m_mesh_capture.isCaptured()) {
+    // Proximity capture (:310-322).  The reference re-captures only when the mesh or the rig changed and carries a FIXME
+    // for the parameters the capture depends on (:310: radius, max_edges; also dofalloff); here a change of any of them
+    // re-captures too.
+    const bool capture_parms_changed = m_cap_maxedges != p.maxedges || m_cap_radius != p.radius || m_cap_dofalloff != p.dofalloff;
+    if (rest_pose_changed || rest_rig_changed || capture_parms_changed || !m_mesh_capture.isInitialized() ||
+        !m_mesh_capture.isCaptured()) {
         if (!m_mesh_capture.init(mesh, rest_rig)) {
             addError("Can't initialize geometry to capture with a rig!");
             return COOK_ERROR;
@@ -152,6 +156,9 @@ CookStatus FaceDeformOp::cook(const Geo& mesh, const Geo& rest_rig, const float*
             addError("Can't capture geometry with a rig!");
             return COOK_ERROR;
         }
+        m_cap_maxedges = p.maxedges;
+        m_cap_radius = p.radius;
+        m_cap_dofalloff = p.dofalloff;
     }
     // Create / build the model (:331-368).  The reference rebuilds it every cook; here the factorisation is kept
     // while the rest rig and the fit parameters are unchanged ("once per rest pose").

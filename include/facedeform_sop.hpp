@@ -142,6 +142,8 @@ private:
     int64_t m_mesh_ids[2] = {-2, -2};
     int64_t m_rig_ids[2] = {-2, -2};
     fd_params m_fit_parms{};
+    int m_cap_maxedges = -1, m_cap_dofalloff = -1; // the parameters of the last capture (FIXME of SOP_FaceDeform.cpp:310)
+    float m_cap_radius = -1.f;
     int m_fit_counter = 0;
     std::vector<std::string> m_errors, m_warnings, m_messages;
 };

@@ -129,3 +129,21 @@ def test_cook_morph_space_pass(oracle):
     assert "Can't proceed with morph space deformation. Ingoring it." in sop.msgs(1)
     np.testing.assert_array_equal(out_bad, plain)
     sop.close()
+
+
+def test_cook_recaptures_when_the_capture_parameters_change():
+    """the reference's FIXME (SOP_FaceDeform.cpp:310): radius / max_edges changes did not re-capture; here they do."""
+    mesh = synth.face_mesh(6_000)
+    rig = synth.control_rig(32, prims=True)
+    deform = synth.deformed_rig(rig, 1)
+    sop = Sop()
+    sop.parms.model, sop.parms.radius, sop.parms.dofalloff, sop.parms.maxedges = 1, 2 * rig.spacing, 1, 3
+    st, out_a, fall_a = sop.cook(mesh, rig, deform)
+    assert st == 0
+    sop.parms.maxedges = 12                                  # wider rings: more vertices grouped, more of them fall off
+    st, out_b, fall_b = sop.cook(mesh, rig, deform)
+    assert st == 0 and not np.array_equal(fall_a, fall_b)
+    sop.parms.radius = 4 * rig.spacing                      # also the RBF radius: re-fit and re-capture
+    st, out_c, fall_c = sop.cook(mesh, rig, deform)
+    assert st == 0 and not np.array_equal(fall_b, fall_c) and sop.L.fd_sop_fit_count(sop.h) == 3   # any parm change re-fits
+    sop.close()
