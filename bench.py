@@ -8,9 +8,15 @@ system, solve all 3F right-hand sides, evaluate every vertex for every frame (BA
 256 control points, 100k vertices, 240 frames, Gaussian, linear term).  `value` times it with inputs and
 outputs resident in HBM; `e2e` times the same step through the host-pointer C ABI (pinned host buffers, H2D
 and D2H inside the timed region).  N > 1 (torchrun): weak scaling, every rank owns a 100k-vertex range of an
-N x 100k mesh, rank 0 factors and solves, the weights are broadcast with NCCL, results stay sharded.
+N x 100k mesh, rank 0 factors and solves, the weights are broadcast with NCCL INSIDE the timed region (`comm` in the
+JSON line carries its bytes and device time), results stay sharded.  `--config C5` (BASELINE configs[4]: 16M vertices
+x 4096 control points x 1000 frames) is STRONG scaling: the 16M vertices are split over the ranks, the frames go
+through in chunks (`--frame-chunk`, the 192 GB result cannot be resident at once), every chunk = solve on rank 0 +
+NCCL broadcast + sharded eval.
 `--impl reference` times the CPU oracle (the reference's algorithm restated; the reference itself cannot be
-compiled here: Houdini HDK, ALGLIB and Eigen are absent) on the host cores on a bounded vertex sample.
+compiled here: Houdini HDK, ALGLIB and Eigen are absent) on the host cores on a bounded vertex sample: all cores
+(the line's value; the thread count comes from sched_getaffinity, never from OMP_NUM_THREADS, which torchrun
+overrides) and 1 thread (what the reference does: NO_RBF_THREADS, SOP_FaceDeform.hpp:11).
 """
 from __future__ import annotations
 
@@ -99,11 +105,19 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def host_cores() -> int:
+    """the cores this process may run on -- NOT OMP_NUM_THREADS: torch.distributed.run exports OMP_NUM_THREADS=1"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(cfg, rig, deform, radius, seconds_target=12.0, nthreads=None):
     """the oracle on the host cores over a bounded vertex sample of the same workload (all F frames)."""
     from facedeform_b200 import synth
     from oracle import fd_oracle as o
-    nthreads = nthreads or o.num_threads()
+    nthreads = nthreads or host_cores()
     p = o.make_params(model=o.MODEL_ML, term=synth.TERMS[cfg["term"]], kernel=synth.KERNELS[cfg["kernel"]],
                       radius=radius, **{"lambda": 0.0})
     t0 = time.perf_counter()
@@ -136,25 +150,51 @@ def run_reference(args):
     if rank != 0:
         return 0
     cfg, rig, deform, radius = workload(args.config, 1)
-    vals = []
+    if cfg["F"] > 240:  # C5: the CPU sample covers a 240-frame chunk (the oracle's cost is linear in F)
+        cfg = dict(cfg, F=240)
+        deform = deform[:240]
+    cores = host_cores()
+    vals, vals1 = [], []
     for i in range(args.warmup + args.steps):
-        r = cpu_sample(cfg, rig, deform, radius, seconds_target=args.cpu_seconds)
+        r = cpu_sample(cfg, rig, deform, radius, seconds_target=args.cpu_seconds * 0.6, nthreads=cores)
+        r1 = cpu_sample(cfg, rig, deform, radius, seconds_target=args.cpu_seconds * 0.4, nthreads=1)
         if i >= args.warmup:
             vals.append(r)
+            vals1.append(r1)
     value = float(np.mean([r["value"] for r in vals]))
+    value1 = float(np.mean([r["value"] for r in vals1]))
     ms = cfg["V"] * cfg["F"] / value * 1e3
-    last = vals[-1]
+    last, last1 = vals[-1], vals1[-1]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": describe(cfg), "note": "CPU oracle (restatement of the reference path; the reference needs HDK/ALGLIB/Eigen and cannot be built)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "cpu_baseline_1thread": {"value": value1, "unit": UNIT, "cores": 1, "kind": "port", "sample": last1["sample"],
+                                 "note": "what the reference does: NO_RBF_THREADS (SOP_FaceDeform.hpp:11)"},
+        "host_cores": cores, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def cpu_baseline_subprocess(args):
+    """the CPU leg in its own process: the product process never loads oracle/libfd_oracle.so"""
+    import subprocess
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--config",
+           args.config, "--cpu-seconds", str(args.cpu_seconds)]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            j = json.loads(ln)
+            return j["cpu_baseline"], j.get("cpu_baseline_1thread")
+    raise RuntimeError("cpu baseline subprocess failed: " + r.stderr[-500:])
 
 
 def factor_table(ctx, sizes, cpu=True):
@@ -182,15 +222,26 @@ def factor_table(ctx, sizes, cpu=True):
                     ts.append(ctx.phase_ms("assemble") + ctx.phase_ms("factor"))
                 m.close()
             row[name] = float(np.median(ts))
-        if cpu and n <= 2048:
-            from oracle import fd_oracle as o
-            op = o.make_params(model=1, term=0, kernel=0, radius=synth.default_radius("gaussian", rig.spacing), **{"lambda": 0.0})
-            st, rad = o.radii(op, rig.rest)
-            t0 = time.perf_counter()
-            A = o.assemble(op, rig.rest, rad)
-            o.lu_factor(A)
-            row["cpu_oracle"] = (time.perf_counter() - t0) * 1e3
         out[str(n)] = row
+    if cpu:  # the oracle's assemble + LU, in a subprocess (the product process never loads the oracle)
+        import subprocess
+        code = ("import sys, time, json; sys.path.insert(0, %r)\n"
+                "from oracle import fd_oracle as o\nfrom facedeform_b200 import synth\nres = {}\n"
+                "for n in %r:\n"
+                "    rig = synth.control_rig(n)\n"
+                "    op = o.make_params(model=1, term=0, kernel=0, radius=synth.default_radius('gaussian', rig.spacing), **{'lambda': 0.0})\n"
+                "    st, rad = o.radii(op, rig.rest)\n"
+                "    t0 = time.perf_counter(); A = o.assemble(op, rig.rest, rad); o.lu_factor(A)\n"
+                "    res[str(n)] = (time.perf_counter() - t0) * 1e3\n"
+                "print(json.dumps(res))\n") % (ROOT, [n for n in sizes if n <= 2048])
+        env = dict(os.environ)
+        env.pop("OMP_NUM_THREADS", None)
+        try:
+            r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+            for k, v in json.loads(r.stdout.strip().splitlines()[-1]).items():
+                out[k]["cpu_oracle"] = v
+        except Exception:
+            pass
     return out
 
 
@@ -230,9 +281,12 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-path", type=int, default=0)
+    ap.add_argument("--eval-precision", type=int, default=0, help="0 AUTO (FP32 while the error bound allows, else FP64), 1 FP32, 2 FP64")
     ap.add_argument("--weights", default="auto", choices=["auto", "broadcast", "replicated"],
-                    help="N > 1: root solves + NCCL broadcast of the weights, or every rank solves the small system itself")
+                    help="N > 1: root solves + NCCL broadcast of the weights (default), or every rank solves the small system itself")
+    ap.add_argument("--frame-chunk", type=int, default=0, help="frames per solve + broadcast + eval pass (0: all; C5 defaults to 250)")
     ap.add_argument("--no-configs-table", action="store_true", help="skip the phase times of C1 / C3 / C5-slice")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--factor-sizes", default="256,1024,2048,4096,8192",
                     help="control-point counts for the factor-ms table (second half of the metric); empty to skip")
     args = ap.parse_args()
@@ -262,13 +316,19 @@ def main():
     dev = torch.device("cuda", local)
 
     cfg, rig, deform, radius = workload(args.config, world)
-    N, V, F = cfg["N"], cfg["V"], cfg["F"]
-    # weak scaling: the mesh has world x V vertices, this rank owns the contiguous range of V of them
-    mesh = synth.face_mesh(V * world, topology=False)
-    b, e = shard.vertex_range(V * world, rank, world)
+    N, F = cfg["N"], cfg["F"]
+    strong = args.config == "C5"  # C5 names a total size (16M vertices): strong scaling; the others: V vertices per GPU
+    V_total = cfg["V"] if strong else cfg["V"] * world
+    mesh = synth.face_mesh(V_total, topology=False)
+    b, e = shard.vertex_range(V_total, rank, world)
+    V = e - b
     P_host = np.ascontiguousarray(mesh.P[b:e])
+    del mesh
+    Fc = args.frame_chunk if args.frame_chunk > 0 else (250 if strong else F)
+    Fc = min(Fc, F)
+    chunks = [(f0, min(f0 + Fc, F)) for f0 in range(0, F, Fc)]
     params = make_params(model=1, term=synth.TERMS[cfg["term"]], kernel=synth.KERNELS[cfg["kernel"]], radius=radius,
-                         eval_path=args.eval_path, **{"lambda": 0.0})
+                         eval_path=args.eval_path, eval_precision=args.eval_precision, **{"lambda": 0.0})
 
     # a dedicated (non-default) stream shared by torch and the library, so torch's CUDA events bracket the kernels
     stream = torch.cuda.Stream(device=dev)
@@ -278,22 +338,29 @@ def main():
     d_rest = torch.from_numpy(rig.rest).to(dev)
     d_deform = torch.from_numpy(deform).to(dev)
     d_P = torch.from_numpy(P_host).to(dev)
-    d_out = torch.empty((F, V, 3), dtype=torch.float32, device=dev)
+    d_out = torch.empty((Fc, V, 3), dtype=torch.float32, device=dev)   # one frame chunk; C2: all frames
     d_fall = torch.empty((V,), dtype=torch.float32, device=dev)
 
-    wmode = shard.weights_mode(N, args.weights) if world > 1 else "single"
+    # N > 1: the north_star's exchange step -- rank 0 factors and solves, NCCL broadcast of the weights -- unless asked otherwise
+    wmode = (args.weights if args.weights != "auto" else "broadcast") if world > 1 else "single"
+    receivers = {}
 
     def step_device():
-        """one pass, everything resident in HBM: fit + solve (on rank 0 + NCCL broadcast, or replicated on every rank
-        for small systems, shard.weights_mode), then the sharded eval."""
-        if rank == 0 or wmode == "replicated":
-            m = ctx.fit(params, d_rest)
-            m.solve(d_deform)
-        else:
-            m = ctx.receiver(params, d_rest, F)
-        if wmode == "broadcast":
-            shard.broadcast_model(m, 0, shared_stream=True)
-        m.eval(d_P, out=d_out, falloff_out=d_fall)
+        """one pass, everything resident in HBM: fit on rank 0 (or on every rank: --weights replicated), then per frame
+        chunk solve (+ NCCL broadcast of the weights) + the sharded eval."""
+        root = rank == 0 or wmode == "replicated"
+        m = ctx.fit(params, d_rest) if root else None
+        for (f0, f1) in chunks:
+            if root:
+                m.solve(d_deform[f0:f1])
+                mm = m
+            else:
+                mm = receivers.get(f1 - f0)
+                if mm is None:
+                    mm = receivers[f1 - f0] = ctx.receiver(params, d_rest, f1 - f0)
+            if wmode == "broadcast":
+                shard.broadcast_model(mm, 0, shared_stream=True)
+            mm.eval(d_P, out=d_out[: f1 - f0], falloff_out=d_fall)
         return m
 
     def sync_all():
@@ -303,7 +370,9 @@ def main():
 
     # ---- device-resident timing ---------------------------------------------------------------------------
     for _ in range(args.warmup):
-        step_device().close()
+        m = step_device()
+        if m is not None:
+            m.close()
     sync_all()
     sampler = ClockSampler(local)
     sampler.start()
@@ -322,66 +391,112 @@ def main():
     launches = ctx.launch_count - launches0
     for k in phases:
         phases[k] = ctx.phase_ms(k)
-    prev.close()
-    # the dominant kernel alone (the eval launch), timed with CUDA events on its stream, same resident buffers
+    if prev is not None:
+        prev.close()
+    # the dominant kernel alone (the eval launch of one frame chunk), timed with CUDA events on its stream, same resident buffers
     m = step_device()
+    mm = m if m is not None else receivers[chunks[-1][1] - chunks[-1][0]]
+    rep = mm.report()
     torch.cuda.synchronize()
     eval_ms = []
     for _ in range(max(5, min(args.steps, 20))):
-        m.eval(d_P, out=d_out, falloff_out=d_fall)
+        mm.eval(d_P, out=d_out[: mm.frames], falloff_out=d_fall)
         eval_ms.append(ctx.phase_ms("eval"))
     eval_ms_mean = float(np.mean(eval_ms))
-    m.close()
-
-    # ---- end to end through the host-pointer C ABI ------------------------------------------------------------
-    h_rest = torch.from_numpy(rig.rest).pin_memory().numpy()
-    h_deform = torch.from_numpy(deform).pin_memory().numpy()
-    h_P = torch.from_numpy(P_host).pin_memory().numpy()
-    h_out = torch.empty((F, V, 3), dtype=torch.float32).pin_memory().numpy()
-    h_fall = torch.empty((V,), dtype=torch.float32).pin_memory().numpy()
-
-    def step_e2e():
-        if rank == 0 or wmode == "replicated":
-            m = ctx.fit(params, h_rest)
-            m.solve(h_deform)
-        else:
-            m = ctx.receiver(params, h_rest, F)
-        if wmode == "broadcast":
-            shard.broadcast_model(m, 0, shared_stream=True)
-        m.eval(h_P, out=h_out, falloff_out=h_fall)
+    F_eval = mm.frames
+    eval_kernel = int(rep.eval_kernel)
+    # the exchange step alone: the NCCL broadcast of the weight block + radii (+ the receivers' table build), CUDA events
+    comm_ms = 0.0
+    comm_bytes = 0
+    if wmode == "broadcast":
+        wp, wb = mm.weights_dev()
+        rp, rb = mm.radii_dev()
+        comm_bytes = int(wb + rb)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        c0.record(stream)
+        for _ in range(10):
+            shard.broadcast_model(mm, 0, shared_stream=True)
+        c1.record(stream)
+        sync_all()
+        comm_ms = c0.elapsed_time(c1) / 10
+    if m is not None:
         m.close()
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        step_e2e()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    sync_all()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # ---- end to end through the host-pointer C ABI ------------------------------------------------------------
+    e2e_s = copy_s = float("nan")
+    h2d_bytes = d2h_bytes = 0
+    if not args.no_e2e:
+        h_rest = torch.from_numpy(rig.rest).pin_memory().numpy()
+        h_deform = torch.from_numpy(deform).pin_memory().numpy()
+        h_P = torch.from_numpy(P_host).pin_memory().numpy()
+        h_out_t = torch.empty((Fc, V, 3), dtype=torch.float32).pin_memory()
+        h_out = h_out_t.numpy()
+        h_fall = torch.empty((V,), dtype=torch.float32).pin_memory().numpy()
+        d_def_stage = torch.empty((Fc, N, 3), dtype=torch.float32, device=dev)
+
+        def step_e2e():
+            root = rank == 0 or wmode == "replicated"
+            m = ctx.fit(params, h_rest) if root else None
+            for (f0, f1) in chunks:
+                if root:
+                    m.solve(h_deform[f0:f1])
+                    mm = m
+                else:
+                    mm = receivers[f1 - f0]
+                if wmode == "broadcast":
+                    shard.broadcast_model(mm, 0, shared_stream=True)
+                mm.eval(h_P, out=h_out[: f1 - f0], falloff_out=h_fall)
+            if m is not None:
+                m.close()
+
+        def step_copy_only():
+            """the step's PCIe traffic without any kernel: what bounds e2e (inputs H2D, results D2H, pinned memory)"""
+            for (f0, f1) in chunks:
+                d_def_stage[: f1 - f0].copy_(torch.from_numpy(h_deform[f0:f1]), non_blocking=True)
+                d_P.copy_(torch.from_numpy(h_P), non_blocking=True)
+                h_out_t[: f1 - f0].copy_(d_out[: f1 - f0], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+        e2e_steps = max(3, min(args.steps, 10)) if not strong else max(1, min(args.steps, 2))
+        for _ in range(2 if not strong else 1):
+            step_e2e()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        sync_all()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        step_copy_only()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_copy_only()
+        sync_all()
+        copy_s = (time.perf_counter() - t0) / e2e_steps
+        h2d_bytes = int(h_rest.nbytes + h_deform.nbytes + h_P.nbytes * len(chunks))
+        d2h_bytes = int(V * F * 12 + h_fall.nbytes * len(chunks))
     clocks = sampler.stop()
 
     # max over ranks
-    t = torch.tensor([ms_total, e2e_s, eval_ms_mean], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s, eval_ms_mean, comm_ms, copy_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s, eval_ms_mean = (float(x) for x in t.tolist())
+    ms_total, e2e_s, eval_ms_mean, comm_ms, copy_s = (float(x) for x in t.tolist())
     ms_step = ms_total / args.steps
-    units = float(V) * world * F  # vertex-frames all ranks processed per step
+    units = float(V_total) * F  # vertex-frames all ranks processed per step
     value = units / (ms_step * 1e-3)
-    e2e_value = units / e2e_s
+    e2e_value = units / e2e_s if e2e_s == e2e_s else None
 
     if rank == 0:
         peaks = load_peaks()
         pairs = float(V) * N
         # SURVEY 8d: algorithmic work of one eval launch = the contraction Phi[V x N] . W[N x 3F] (2 flop per MAC)
-        # plus 8 + 2 FP32 flop per (vertex, centre) pair for the distance and the kernel
-        alg_flops = pairs * (2.0 * 3 * F + 8.0 + 2.0)
+        # plus 8 + 2 flop per (vertex, centre) pair for the distance and the kernel
+        alg_flops = pairs * (2.0 * 3 * F_eval + 8.0 + 2.0)
         achieved_tf = alg_flops / (eval_ms_mean * 1e-3) / 1e12
-        alg_bytes = V * 12.0 + V * F * 12.0 + V * 4.0
-        tensor_path = args.eval_path != 1 and 3 * F >= 48
-        if tensor_path:
+        alg_bytes = V * 12.0 + V * F_eval * 12.0 + V * 4.0
+        if eval_kernel == 2:
             roofline = {
                 "kernel": "tc::k_eval_tc (tcgen05.mma kind::f16, FP16 hi/lo splits: 3 MMAs per algorithmic MAC)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16"], "unit": "TFLOP/s",
@@ -389,49 +504,79 @@ def main():
                 "note": "algorithmic flops; the split-precision scheme issues 3x that on the tensor pipe, so 1/3 is the ceiling of this fraction",
                 "traffic": None, "launch_ms": eval_ms_mean,
             }
+        elif eval_kernel == 3:
+            fp64_peak_tf = 148 * 64 * 2 * peaks["sm_max"] * 1e6 / 1e12
+            roofline = {
+                "kernel": "k_eval64_mma (mma.sync.m8n8k4.f64: FD_EVAL_AUTO chose FP64, the FP32 error bound exceeded the tolerance)"
+                          if 3 * F_eval >= 48 else "k_eval_f64 / k_eval_simt<double>",
+                "bound": "tensor", "achieved": achieved_tf, "peak": fp64_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak_tf,
+                "peak_source": "derived: 148 SM x 64 FP64 lanes x 2 flop x clocks.max.sm (the FP64 pipe, DMMA and DFMA alike; "
+                               "MEASURED_PEAKS.json holds no FP64 figure)",
+                "traffic": None, "launch_ms": eval_ms_mean,
+            }
         else:
             fp32_peak_tf = 148 * 128 * 2 * peaks["sm_max"] * 1e6 / 1e12
             roofline = {
-                "kernel": "k_eval_simt", "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s",
+                "kernel": "k_eval_f32x2", "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp32_peak_tf,
                 "peak_source": "derived: 148 SM x 128 FP32 lanes x 2 flop x clocks.max.sm (FP32 FMA issue is not in MEASURED_PEAKS.json)",
                 "traffic": None, "launch_ms": eval_ms_mean,
             }
         # DRAM traffic of one launch from the committed `ncu --set full` capture of this command (profiles/), C2 only
         try:
-            if args.config == "C2" and tensor_path:
-                with open(os.path.join(ROOT, "profiles", "r1e_eval_tc_ncu_summary.json")) as f:
+            if args.config == "C2" and eval_kernel == 2:
+                src = "r2_eval_tc_ncu_summary.json"
+                if not os.path.exists(os.path.join(ROOT, "profiles", src)):
+                    src = "r1e_eval_tc_ncu_summary.json"
+                with open(os.path.join(ROOT, "profiles", src)) as f:
                     nc = json.load(f)
                 roofline["traffic"] = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6
-                roofline["traffic_source"] = "profiles/r1e_eval_tc_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+                roofline["traffic_source"] = f"profiles/{src} (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
                 roofline["algorithmic_bytes"] = alg_bytes
         except Exception:
             pass
         roofline["hbm"] = {"achieved": alg_bytes / (eval_ms_mean * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                            "frac": alg_bytes / (eval_ms_mean * 1e-3) / 1e9 / peaks["hbm"], "peak_source": peaks["source"]}
+        dtype = "f64" if eval_kernel == 3 else "f32"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": describe(cfg), "name": args.config,
-                       "l2": "per-step output (F x V x 12 B = %.0f MB) exceeds the 126 MB L2; no explicit flush" % (F * V * 12 / 1e6),
-                       "precision": "FP64 assemble/factor/solve, FP32 evaluation", "parallelism": f"vertex-range x{world}" + ("" if world == 1 else f", weights {wmode}")},
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic",
+            "config": {"workload": describe(cfg) if not strong else describe_c5(cfg, V_total, world, Fc), "name": args.config,
+                       "l2": "per-pass output (%d frames x V x 12 B = %.0f MB) exceeds the 126 MB L2; no explicit flush" % (Fc, Fc * V * 12 / 1e6),
+                       "precision": "FP64 assemble/factor/solve, %s evaluation (eval_precision %s)" % (
+                           "FP64" if eval_kernel == 3 else "FP32", ["AUTO", "FP32", "FP64"][args.eval_precision]),
+                       "eval_kernel": {1: "FMA/SFU FP32", 2: "tensor cores (FP16 hi/lo)", 3: "FP64"}.get(eval_kernel),
+                       "cancellation": float(rep.cancellation),
+                       "parallelism": f"vertex-range x{world}" + ("" if world == 1 else f", weights {wmode}")},
             "phase_ms_last_step": phases, "factor_ms": {"n_ctrl": N, "assemble": phases["assemble"], "factor": phases["factor"],
                                                         "solve": phases["solve"]},
             "roofline": roofline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
-                    "h2d_bytes_per_step": int(h_rest.nbytes + h_deform.nbytes + h_P.nbytes),
-                    "d2h_bytes_per_step": int(h_out.nbytes + h_fall.nbytes)},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if world > 1:
+            line["comm"] = {"collective": "ncclBroadcast (weights FP64 block + radii), root = rank 0" if wmode == "broadcast" else None,
+                            "in_timed_region": wmode == "broadcast", "bytes_per_pass": comm_bytes, "passes_per_step": len(chunks),
+                            "ms_per_pass": comm_ms, "share_of_step": comm_ms * len(chunks) / ms_step if ms_step > 0 else None,
+                            "note": "ms_per_pass = broadcast + the receivers' table build, CUDA events, max over ranks, measured alone after the timed steps"}
+        if e2e_value is not None:
+            line["e2e"] = {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d_bytes,
+                           "d2h_bytes_per_step": d2h_bytes, "copy_only_ms_per_step": copy_s * 1e3,
+                           "frac_of_copy_only": copy_s / e2e_s if e2e_s > 0 else None,
+                           "note": "copy_only = the same H2D + D2H traffic (pinned) with no kernel: the PCIe / host-memory ceiling of e2e, max over ranks"}
         if world == 1 and args.factor_sizes:
             line["factor_ms_by_n"] = factor_table(ctx, [int(x) for x in args.factor_sizes.split(",") if x],
                                                   cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_configs_table:
             line["other_configs"] = configs_table(ctx)
         if not args.no_cpu_baseline and world == 1:
-            cb = cpu_sample(cfg, rig, deform, radius, seconds_target=args.cpu_seconds)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:
+                cb, cb1 = cpu_baseline_subprocess(args)
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                if cb1:
+                    line["cpu_baseline_1thread"] = cb1
+            except Exception as ex:  # the bench line must not die with the CPU leg
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": f"failed: {ex}"}
         if json_fd is None:
             print(json.dumps(line), flush=True)
         else:
@@ -439,8 +584,15 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    for r in receivers.values():
+        r.close()
     ctx.close()
     return 0
+
+
+def describe_c5(cfg, V_total, world, Fc):
+    return (f"{cfg['N']} control points, {V_total} vertices split over {world} GPU(s), {cfg['F']} frames in chunks of {Fc}, "
+            f"{cfg['kernel']} kernel, {cfg['term']} term, step = assemble + LU, then per chunk {3 * Fc}-RHS solve + weight broadcast + fused eval")
 
 
 if __name__ == "__main__":

@@ -13,17 +13,19 @@ LIB_PATH = os.path.join(_HERE, "libfacedeform_gpu.so")
 
 # every symbol include/facedeform_gpu.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
-    "fd_abi_version", "fd_status_string", "fd_params_default", "fd_params_clamp",
+    "fd_abi_version", "fd_status_string", "fd_params_default", "fd_params_clamp", "fd_params_fit_equal",
     "fd_ctx_create", "fd_ctx_destroy", "fd_ctx_synchronize", "fd_last_error",
     "fd_rbf_fit", "fd_rbf_fit_dev", "fd_model_destroy",
-    "fd_rbf_solve", "fd_rbf_solve_dev", "fd_model_report",
+    "fd_rbf_solve", "fd_rbf_solve_dev", "fd_model_report", "fd_model_set_epilogue", "fd_model_save", "fd_model_load",
+    "fd_mgpu_create", "fd_mgpu_destroy", "fd_mgpu_fit", "fd_mgpu_solve", "fd_mgpu_eval", "fd_mgpu_info", "fd_mgpu_range",
+    "fd_mgpu_ctx", "fd_mgpu_last_error",
     "fd_rbf_eval", "fd_rbf_eval_dev",
     "fd_model_create_receiver", "fd_model_weights_dev", "fd_model_radii_dev", "fd_model_commit_weights",
     "fd_model_info", "fd_model_get_weights",
     "fd_capture", "fd_ctx_phase_ms", "fd_ctx_launch_count",
     "fd_dbse_init", "fd_dbse_compute_weights", "fd_dbse_displace", "fd_dbse_get_weights", "fd_dbse_get_qr", "fd_dbse_info",
     "fd_dbse_destroy",
-    "fd_sop_create", "fd_sop_destroy", "fd_sop_params", "fd_sop_cook", "fd_sop_messages", "fd_sop_fit_count",
+    "fd_sop_create", "fd_sop_destroy", "fd_sop_params", "fd_sop_cook", "fd_sop_messages", "fd_sop_fit_count", "fd_sop_positions_bumped",
     "fd_sop_set_blendshapes", "fd_sop_blend_weights",
 ]
 
@@ -38,7 +40,7 @@ class FdParams(C.Structure):
         ("weightrange", C.c_float * 2),
         ("dofalloff", C.c_int32), ("falloffradius", C.c_float), ("falloffrate", C.c_float),
         ("eval_precision", C.c_int32), ("eval_path", C.c_int32), ("factor_precision", C.c_int32),
-        ("fidelity", C.c_int32),
+        ("fidelity", C.c_int32), ("strict_reference", C.c_int32), ("eval_tolerance", C.c_float), ("group", C.c_char * 64),
     ]
 
 
@@ -47,7 +49,7 @@ class FdReport(C.Structure):
     _fields_ = [
         ("terminationtype", C.c_int32), ("iterationscount", C.c_int32), ("n", C.c_int32), ("npoly", C.c_int32),
         ("frames", C.c_int32), ("reserved", C.c_int32), ("min_pivot", C.c_double), ("max_pivot", C.c_double),
-        ("residual", C.c_double),
+        ("residual", C.c_double), ("cancellation", C.c_double), ("eval_kernel", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -79,6 +81,22 @@ def load() -> C.CDLL:
     L.fd_params_default.restype = None
     L.fd_params_clamp.argtypes = [pp]
     L.fd_params_clamp.restype = None
+    L.fd_params_fit_equal.argtypes = [pp, pp]
+    L.fd_model_set_epilogue.argtypes = [vp, pp]
+    L.fd_model_save.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.fd_model_load.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp)]
+    L.fd_mgpu_create.argtypes = [C.POINTER(vp), ip, C.c_int32, C.c_int32]
+    L.fd_mgpu_destroy.argtypes = [vp]
+    L.fd_mgpu_destroy.restype = None
+    L.fd_mgpu_fit.argtypes = [vp, pp, fp, C.c_int32, rp]
+    L.fd_mgpu_solve.argtypes = [vp, fp, C.c_int32, C.c_int32, rp]
+    L.fd_mgpu_eval.argtypes = [vp, fp, C.c_int64, fp, fp, fp, fp, fp, fp]
+    L.fd_mgpu_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
+    L.fd_mgpu_range.argtypes = [vp, C.c_int32, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.fd_mgpu_ctx.argtypes = [vp, C.c_int32]
+    L.fd_mgpu_ctx.restype = vp
+    L.fd_mgpu_last_error.argtypes = [vp]
+    L.fd_mgpu_last_error.restype = C.c_char_p
     L.fd_ctx_create.argtypes = [C.POINTER(vp), C.c_int, vp]
     L.fd_ctx_destroy.argtypes = [vp]
     L.fd_ctx_destroy.restype = None
@@ -127,5 +145,6 @@ def load() -> C.CDLL:
     L.fd_sop_messages.argtypes = [vp, C.c_int]
     L.fd_sop_messages.restype = C.c_char_p
     L.fd_sop_fit_count.argtypes = [vp]
+    L.fd_sop_positions_bumped.argtypes = [vp]
     _lib = L
     return L

@@ -43,6 +43,9 @@ def make_params(clamp: bool = False, **kw) -> FdParams:
         if k == "weightrange":
             p.weightrange[0], p.weightrange[1] = v
             continue
+        if k == "group":
+            p.group = v.encode() if isinstance(v, str) else v
+            continue
         if not hasattr(p, k):
             raise AttributeError(k)
         setattr(p, k, v)
@@ -125,6 +128,18 @@ class Context:
         self._check(self._L.fd_rbf_fit(self._h, C.byref(params), _ptr(rest), rest.shape[0], C.byref(h), C.byref(rep)))
         m = RbfModel(self, h, rest.shape[0], params)
         m.last_report = rep
+        return m
+
+    def load_model(self, blob) -> "RbfModel":
+        """fd_model_load: a model saved with RbfModel.save (alglib::rbfunserialize in the reference's dead threaded path,
+        SOP_FaceDeform.hpp:150-152)."""
+        buf = np.frombuffer(bytes(blob), dtype=np.uint8)
+        h = C.c_void_p()
+        self._check(self._L.fd_model_load(self._h, buf.ctypes.data, buf.size, C.byref(h)))
+        n, f = C.c_int32(), C.c_int32()
+        self._L.fd_model_info(h, C.byref(n), None, C.byref(f), None)
+        m = RbfModel(self, h, n.value, None)
+        m.frames = f.value
         return m
 
     def receiver(self, params: FdParams, rest_ctrl, frames: int) -> "RbfModel":
@@ -338,3 +353,92 @@ class RbfModel:
     def commit_weights(self):
         self.ctx._check(self._L.fd_model_commit_weights(self._h))
         return self
+
+    def set_epilogue(self, params: FdParams):
+        """epilogue-only parameter changes (tangent, falloff ...) without a refit; raises when `params` needs one."""
+        self.ctx._check(self._L.fd_model_set_epilogue(self._h, C.byref(params)))
+        self.params = params
+        return self
+
+    def save(self) -> bytes:
+        """fd_model_save: parameters, centres, radii, factorisation and weights (the reference's rbfserialize, :377)."""
+        n = C.c_size_t()
+        self.ctx._check(self._L.fd_model_save(self._h, None, 0, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        self.ctx._check(self._L.fd_model_save(self._h, buf.ctypes.data, buf.size, C.byref(n)))
+        return buf.tobytes()
+
+
+MGPU_AUTO, MGPU_NCCL, MGPU_P2P = 0, 1, 2
+
+
+class MultiGpu:
+    """fd_mgpu: several GPUs of one box behind one handle (single process); vertex ranges per device, the root's weights
+    cross NVLink once per solve (transport "p2p": tables built through peer loads; "nccl": ncclBroadcast)."""
+
+    def __init__(self, devices=None, transport: int = MGPU_AUTO):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        if devices is None:
+            import torch
+            devices = list(range(torch.cuda.device_count()))
+        arr = np.ascontiguousarray(devices, dtype=np.int32)
+        st = self._L.fd_mgpu_create(C.byref(h), arr.ctypes.data, len(arr), int(transport))
+        if st != FD_OK:
+            raise FdError(st, f"fd_mgpu_create({list(devices)}, transport={transport}) failed")
+        self._h, self.devices, self.frames = h, list(devices), 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.fd_mgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != FD_OK:
+            raise FdError(st, self._L.fd_mgpu_last_error(self._h).decode(errors="replace"))
+
+    def fit(self, params: FdParams, rest_ctrl):
+        rest = _host_f32(rest_ctrl, 3)
+        rep = FdReport()
+        self._check(self._L.fd_mgpu_fit(self._h, C.byref(params), _ptr(rest), rest.shape[0], C.byref(rep)))
+        self.last_report = rep
+        return self
+
+    def solve(self, deform_ctrl):
+        d = _host_f32(deform_ctrl, 3)
+        if d.ndim == 2:
+            d = d[None]
+        rep = FdReport()
+        self._check(self._L.fd_mgpu_solve(self._h, _ptr(d), d.shape[1], d.shape[0], C.byref(rep)))
+        self.last_report, self.frames = rep, d.shape[0]
+        return self
+
+    def eval(self, P, dist2=None, tangentu=None, tangentv=None, normal=None, out=None, falloff_out=None):
+        P = _host_f32(P, 3)
+        V = P.shape[0]
+        dist2 = _host_f32(dist2)
+        tangentu, tangentv, normal = _host_f32(tangentu, 3), _host_f32(tangentv, 3), _host_f32(normal, 3)
+        if out is None:
+            out = np.empty((self.frames, V, 3), np.float32)
+        if falloff_out is None:
+            falloff_out = np.empty(V, np.float32)
+        self._check(self._L.fd_mgpu_eval(self._h, _ptr(P), V, _ptr(dist2), _ptr(tangentu), _ptr(tangentv), _ptr(normal),
+                                         _ptr(out), _ptr(falloff_out)))
+        return out, falloff_out
+
+    def info(self):
+        n, t, b, ms = C.c_int32(), C.c_int32(), C.c_int64(), C.c_float()
+        self._check(self._L.fd_mgpu_info(self._h, C.byref(n), C.byref(t), C.byref(b), C.byref(ms)))
+        return dict(ndev=n.value, transport={MGPU_NCCL: "nccl", MGPU_P2P: "p2p"}.get(t.value, "?"), bcast_bytes=b.value,
+                    bcast_ms=ms.value)
+
+    def vertex_range(self, i: int, n_vtx: int):
+        b, e = C.c_int64(), C.c_int64()
+        self._check(self._L.fd_mgpu_range(self._h, i, n_vtx, C.byref(b), C.byref(e)))
+        return b.value, e.value

@@ -13,11 +13,7 @@ namespace {
 
 #define FD_SET_ERR(ctx, ...) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__)
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
+using DeviceGuard = fd_device_guard;
 
 int stage(fd_ctx* ctx, int slot, size_t bytes, void** out)
 {
@@ -59,6 +55,32 @@ template <typename T> int dev_alloc(fd_ctx* ctx, T** p, size_t count)
     return FD_OK;
 }
 
+// the development knobs of fd_debug_opts: the only place the library reads the environment
+void read_debug_opts(fd_debug_opts* o)
+{
+    auto flag = [](const char* name) { return getenv(name) != nullptr; };
+    auto num = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
+    memset(o, 0, sizeof(*o));
+    o->no_nullspace = flag("FD_NO_NULLSPACE");
+    o->force_pivoted_lu = flag("FD_FORCE_PIVOTED_LU");
+    o->lu_unfused = flag("FD_LU_UNFUSED");
+    o->solve_dfma = flag("FD_SOLVE_DFMA");
+    o->no_fused_pack = flag("FD_NO_FUSED_PACK");
+    o->no_few_rhs = flag("FD_NO_FEW_RHS");
+    o->no_inverse = flag("FD_NO_INVERSE");
+    o->eval_scalar_f32 = flag("FD_EVAL_SCALAR_F32");
+    o->tc_nopair = flag("FD_TC_NOPAIR");
+    o->has_tc_debug = flag("FD_TC_DEBUG");
+    o->lu_sym_off = flag("FD_LU_NOSYM");
+    o->lu_dfma = flag("FD_LU_DFMA");
+    o->eval_vp = num("FD_EVAL_VP");
+    o->tc_debug = num("FD_TC_DEBUG");
+    o->lu_debug = num("FD_LU_DEBUG");
+    o->lu_nbo = num("FD_LU_NBO");
+    o->lu_cluster_max_n = num("FD_LU_CLUSTER_MAX_N");
+    o->lu_cluster = num("FD_LU_CLUSTER");
+}
+
 int check_params(fd_ctx* ctx, const fd_params* p)
 {
     if (p->model != FD_MODEL_QNN && p->model != FD_MODEL_ML) { FD_SET_ERR(ctx, "model must be 0 (QNN) or 1 (Multilayer)"); return FD_E_INVALID; }
@@ -88,6 +110,8 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
     m->receiver = !with_factor;
     m->eval64 = params->eval_precision == FD_EVAL_FP64 ||
                 (params->eval_precision == FD_EVAL_AUTO && params->kernel != FD_KERNEL_GAUSSIAN);
+    // Gaussian under FD_EVAL_AUTO: FP32 while the measured cancellation allows it, FP64 beyond (fd_eval64.cu)
+    m->auto_sel = params->eval_precision == FD_EVAL_AUTO && params->kernel == FD_KERNEL_GAUSSIAN;
     int st = FD_OK;
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_rest, (size_t)N * 3);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_radii, (size_t)N);
@@ -95,8 +119,11 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_pivstat, 2);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_ctab32, (size_t)fd_tc_kpad(N)); // padded: the tensor path bulk-copies 32-centre tiles
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_ctab_pair, (size_t)fd_tc_kpad(N));
-    if (st == FD_OK && m->eval64) st = dev_alloc(ctx, &m->d_ctab64, (size_t)N);
-    if (st == FD_OK) st = dev_alloc(ctx, &m->d_tc_norm, 4);
+    if (st == FD_OK && (m->eval64 || m->auto_sel)) st = dev_alloc(ctx, &m->d_ctab64, (size_t)N);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_tc_norm, 8);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_sel, 2);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_est, 4);
+    if (st == FD_OK) st = dev_alloc(ctx, &m->d_wmax, (size_t)N);
     if (st == FD_OK && with_factor) {
         st = dev_alloc(ctx, &m->d_A, (size_t)m->lda * m->n);
         if (st == FD_OK) st = dev_alloc(ctx, &m->d_ipiv, (size_t)m->n);
@@ -112,6 +139,8 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
         return st;
     }
     cudaMemsetAsync(m->d_flags, 0, FD_NUM_FLAGS * sizeof(int), ctx->stream);
+    cudaMemsetAsync(m->d_sel, 0, 2 * sizeof(int), ctx->stream);
+    cudaMemsetAsync(m->d_est, 0, 4 * sizeof(double), ctx->stream);
     *out = m;
     return FD_OK;
 }
@@ -289,6 +318,26 @@ void fd_params_default(fd_params* p)
     p->eval_path = FD_PATH_AUTO;
     p->factor_precision = FD_FACTOR_FP64;
     p->fidelity = FD_FIDELITY_DENSE;
+    p->strict_reference = 0;
+    p->eval_tolerance = 1e-5f;
+    p->group[0] = 0;
+}
+
+// the fields a fit depends on (everything else is consumed by the evaluation epilogue, the capture or the host mirror)
+int fd_params_fit_equal(const fd_params* a, const fd_params* b)
+{
+    if (!a || !b) return 0;
+    if (a->model != b->model || a->term != b->term || a->kernel != b->kernel || a->lambda != b->lambda ||
+        a->eval_precision != b->eval_precision || a->eval_path != b->eval_path || a->factor_precision != b->factor_precision ||
+        a->fidelity != b->fidelity || a->eval_tolerance != b->eval_tolerance)
+        return 0;
+    if (a->model == FD_MODEL_QNN) {
+        if (a->qcoef != b->qcoef || a->zcoef != b->zcoef) return 0; // `radius` is only the capture / falloff radius here
+    } else if (a->radius != b->radius) {
+        return 0;
+    }
+    if (a->fidelity == FD_FIDELITY_ALGLIB_V1 && a->model == FD_MODEL_ML && a->layers != b->layers) return 0;
+    return 1;
 }
 
 // SYSmax clamps of cookMySop, SOP_FaceDeform.cpp:249-257
@@ -310,7 +359,7 @@ int fd_ctx_create(fd_ctx** out, int device, void* stream)
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return FD_E_CUDA; // no GPU: fail loudly, no fallback
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return FD_E_CUDA;
     if (device >= count) return FD_E_INVALID;
-    if (cudaSetDevice(device) != cudaSuccess) return FD_E_CUDA;
+    DeviceGuard g(device); // the caller's current device is restored on every return path
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FD_E_CUDA;
     if (prop.major != 10) return FD_E_UNSUPPORTED; // built for sm_100a only
@@ -319,6 +368,7 @@ int fd_ctx_create(fd_ctx** out, int device, void* stream)
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    read_debug_opts(&ctx->dbg);
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -333,6 +383,16 @@ int fd_ctx_create(fd_ctx** out, int device, void* stream)
         fd_ctx_destroy(ctx);
         return FD_E_CUDA;
     }
+    // function attributes are per device: every ctx sets them for its own (one process may hold one ctx per GPU)
+    if (fd_solve_setup(ctx) != cudaSuccess || fd_factor_setup(ctx) != cudaSuccess || fd_eval_tc_setup(ctx) != cudaSuccess ||
+        fd_eval64_setup(ctx) != cudaSuccess) {
+        fd_ctx_destroy(ctx);
+        return FD_E_CUDA;
+    }
+    if (ctx->dbg.has_tc_debug && (cudaMalloc(&ctx->d_tc_dbg, 256 * sizeof(long long)) != cudaSuccess ||
+                                  cudaMemset(ctx->d_tc_dbg, 0, 256 * sizeof(long long)) != cudaSuccess))
+        ctx->d_tc_dbg = nullptr;
+    if (ctx->dbg.lu_debug && cudaMalloc(&ctx->d_lu_dbg, 64) != cudaSuccess) ctx->d_lu_dbg = nullptr;
     { // keep freed blocks cached in the device's default pool instead of returning them to the driver
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -349,7 +409,7 @@ static void ctx_teardown(fd_ctx* ctx);
 void fd_ctx_destroy(fd_ctx* ctx)
 {
     if (!ctx) return;
-    if (ctx->refs > 0) { // live models / dbse handles: they finish the teardown (fd_ctx_release)
+    if (__atomic_load_n(&ctx->refs, __ATOMIC_ACQUIRE) > 0) { // live models / dbse handles: they finish the teardown (fd_ctx_release)
         ctx->destroy_requested = true;
         return;
     }
@@ -363,6 +423,8 @@ static void ctx_teardown(fd_ctx* ctx)
     for (int i = 0; i < FD_NUM_STAGE; ++i)
         if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
     if (ctx->d_sync) cudaFree(ctx->d_sync);
+    if (ctx->d_tc_dbg) cudaFree(ctx->d_tc_dbg);
+    if (ctx->d_lu_dbg) cudaFree(ctx->d_lu_dbg);
     for (int i = 0; i < FD_PH_COUNT; ++i) {
         cudaEventDestroy(ctx->ev_begin[i]);
         cudaEventDestroy(ctx->ev_end[i]);
@@ -403,7 +465,7 @@ void fd_model_destroy(fd_model* m)
     void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
                       m->d_ctab32, m->d_W32, m->d_ctab64, m->d_tc_norm, m->d_tc_scale, m->d_tc_unscale,
                       m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win, m->d_ctab_pair, m->d_A32, m->d_B, m->d_R, m->d_D32,
-                      m->d_ir_norm, m->d_v1_R, m->d_v1_K, m->d_v1_V, m->d_v1_stack, m->d_ns};
+                      m->d_ir_norm, m->d_v1_R, m->d_v1_K, m->d_v1_V, m->d_v1_stack, m->d_ns, m->d_sel, m->d_est, m->d_wmax};
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;
@@ -435,8 +497,7 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
     // definite, so it takes the fused no-pivot LU instead of the pivoted one (fd_nullspace.cu).  The multiquadric's
     // reduced matrix is NEGATIVE definite and its smoothing shift is -lambda (k_assemble), which keeps it so.
     m->ns = m->prm.kernel != FD_KERNEL_GAUSSIAN && m->prm.model == FD_MODEL_ML && m->np == 4 && m->N >= 8 &&
-            m->prm.factor_precision == FD_FACTOR_FP64 &&
-            !getenv("FD_NO_NULLSPACE") && !getenv("FD_FORCE_PIVOTED_LU");
+            m->prm.factor_precision == FD_FACTOR_FP64 && !ctx->dbg.no_nullspace && !ctx->dbg.force_pivoted_lu;
     if (m->ns && dev_alloc(ctx, &m->d_ns, (size_t)m->N * 5 + 32) != FD_OK) m->ns = false;
     if (e == cudaSuccess)
         e = fd_launch_assemble(ctx, m->prm, m->d_rest, m->d_radii, m->N, m->ns ? 0 : m->np, m->d_A, m->lda);
@@ -444,8 +505,8 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
     phase_end(ctx, FD_PH_ASSEMBLE);
     phase_begin(ctx, FD_PH_FACTOR);
     // Gaussian kernel with one radius: K + lambda I is symmetric positive definite -> no pivot search needed
-    const bool spd = m->prm.kernel == FD_KERNEL_GAUSSIAN && (m->prm.model == FD_MODEL_ML || m->N == 1) && !getenv("FD_FORCE_PIVOTED_LU");
-    const bool unfused = getenv("FD_LU_UNFUSED") != nullptr; // per-block-column launches (kept for comparison)
+    const bool spd = m->prm.kernel == FD_KERNEL_GAUSSIAN && (m->prm.model == FD_MODEL_ML || m->N == 1) && !ctx->dbg.force_pivoted_lu;
+    const bool unfused = ctx->dbg.lu_unfused; // per-block-column launches (kept for comparison)
     if (e == cudaSuccess && m->ns) {
         // the definite (N - 4) x (N - 4) block of Q^T K Q, in place
         e = fd_launch_lu_nopivot_fused(ctx, m->d_A + (size_t)4 * m->lda + 4, m->lda, m->N - 4, m->d_ipiv, m->d_perm, m->d_flags,
@@ -507,7 +568,10 @@ int fd_rbf_solve_dev(fd_model* m, const float* deform_ctrl_dev, int32_t n_ctrl, 
     m->ldw32 = m->ldw;
     m->use_tc = model_wants_tc(m, frames);
     phase_begin(ctx, FD_PH_SOLVE);
-    cudaError_t e;
+    // FD_FLAG_NONFINITE describes the weights of THIS solve (a NaN in one frame's rig must not poison later cooks of a
+    // cached model); singular / zero-radius are properties of the fit and stay
+    cudaError_t e = cudaMemsetAsync(m->d_flags + FD_FLAG_NONFINITE, 0, sizeof(int), ctx->stream);
+    if (e != cudaSuccess) { FD_SET_ERR(ctx, "solve: %s", cudaGetErrorString(e)); return FD_E_CUDA; }
     if (m->ns) { // D' = Q^T D, z = S^-1 D'[4:], a = R^-1 (D'[:4] - K'[:4, 4:] z), w = Q [0; z]
         m->tc_packed_by_solve = false;
         e = fd_launch_ns_rhs(ctx, m, deform_ctrl_dev, frames);
@@ -542,6 +606,29 @@ int fd_rbf_solve(fd_model* m, const float* deform_ctrl, int32_t n_ctrl, int32_t 
     return fd_model_report(m, report);
 }
 
+int fd_model_set_epilogue(fd_model* m, const fd_params* p)
+{
+    if (!m || !p) return FD_E_INVALID;
+    if (!fd_params_fit_equal(&m->prm, p)) { FD_SET_ERR(m->ctx, "set_epilogue: the parameters differ in a field the fit depends on"); return FD_E_INVALID; }
+    auto apply = [&](fd_model* t) {
+        t->prm.tangent = p->tangent;
+        t->prm.dofalloff = p->dofalloff;
+        t->prm.falloffrate = p->falloffrate;
+        t->prm.falloffradius = p->falloffradius;
+        t->prm.maxedges = p->maxedges;
+        t->prm.morphspace = p->morphspace;
+        t->prm.doclampweight = p->doclampweight;
+        t->prm.weightrange[0] = p->weightrange[0];
+        t->prm.weightrange[1] = p->weightrange[1];
+        t->prm.strict_reference = p->strict_reference;
+        memcpy(t->prm.group, p->group, sizeof(t->prm.group));
+        t->prm.radius = p->radius; // equal already unless model = QNN, where it is the capture / falloff radius only
+    };
+    apply(m);
+    if (m->v1_eval) apply(m->v1_eval);
+    return FD_OK;
+}
+
 int fd_model_report(fd_model* m, fd_report* report)
 {
     if (!m) return FD_E_INVALID;
@@ -564,7 +651,10 @@ int fd_model_report(fd_model* m, fd_report* report)
         FD_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         const int term = flags[FD_FLAG_SINGULAR] ? -3 : 1;
         if (report) {
+            const double canc = report->cancellation; // of the stacked evaluation model
+            const int ek = report->eval_kernel;
             *report = last; // pivots of the last layer
+            if (m->v1_eval) { report->cancellation = canc; report->eval_kernel = ek; }
             report->terminationtype = term;
             report->n = m->N * m->v1_layers;
             report->npoly = m->np;
@@ -577,9 +667,12 @@ int fd_model_report(fd_model* m, fd_report* report)
         return FD_OK;
     }
     int flags[FD_NUM_FLAGS];
-    double piv[2] = {0, 0};
+    double piv[2] = {0, 0}, est[2] = {0, 0};
+    int sel = 0;
     FD_CUDA_OK(ctx, cudaMemcpyAsync(flags, m->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA_OK(ctx, cudaMemcpyAsync(piv, m->d_pivstat, sizeof(piv), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA_OK(ctx, cudaMemcpyAsync(est, m->d_est, sizeof(est), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA_OK(ctx, cudaMemcpyAsync(&sel, m->d_sel, sizeof(sel), cudaMemcpyDeviceToHost, ctx->stream));
     FD_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     int term = 1;
     if (flags[FD_FLAG_ZERO_RADIUS]) term = -5;
@@ -595,6 +688,9 @@ int fd_model_report(fd_model* m, fd_report* report)
         report->reserved = flags[FD_FLAG_SINGULAR];
         report->min_pivot = piv[0];
         report->max_pivot = piv[1];
+        report->cancellation = est[0];
+        report->eval_kernel = m->solved ? (m->eval64 ? FD_SEL_FP64 : (sel ? sel : (m->use_tc ? FD_SEL_TENSOR : FD_SEL_SIMT))) : 0;
+        report->reserved2 = 0;
     }
     if (term != 1) { // SOP_FaceDeform.cpp:365-368
         FD_SET_ERR(ctx, "%s (terminationtype %d)", fd_status_string(FD_E_SINGULAR), term);
@@ -621,38 +717,8 @@ int fd_rbf_eval_dev(fd_model* m, const float* P, int64_t n_vtx, const float* dis
 int fd_rbf_eval(fd_model* m, const float* P, int64_t n_vtx, const float* dist2, const float* tangentu,
                 const float* tangentv, const float* normal, float* P_out, float* falloff_out)
 {
-    if (!m || (n_vtx > 0 && (!P || !P_out)) || n_vtx < 0) return FD_E_INVALID;
-    if (m->v1_layers && m->solved) m = m->v1_eval;
-    fd_ctx* ctx = m->ctx;
-    DeviceGuard g(ctx->device);
-    if (!m->solved) { FD_SET_ERR(ctx, "eval: no weights (call fd_rbf_solve or fd_model_commit_weights first)"); return FD_E_STATE; }
-    if (n_vtx == 0) return FD_OK;
-    const size_t v3 = (size_t)n_vtx * 3 * sizeof(float), v1 = (size_t)n_vtx * sizeof(float);
-    void *dP = nullptr, *dD = nullptr, *dU = nullptr, *dV = nullptr, *dN = nullptr, *dO = nullptr, *dF = nullptr;
-    int st = stage(ctx, FD_STAGE_P, v3, &dP);
-    if (st == FD_OK && dist2) st = stage(ctx, FD_STAGE_DIST, v1, &dD);
-    const bool tang = m->prm.tangent && tangentu && tangentv && normal;
-    if (st == FD_OK && tang) st = stage(ctx, FD_STAGE_TU, v3, &dU);
-    if (st == FD_OK && tang) st = stage(ctx, FD_STAGE_TV, v3, &dV);
-    if (st == FD_OK && tang) st = stage(ctx, FD_STAGE_N, v3, &dN);
-    if (st == FD_OK) st = stage(ctx, FD_STAGE_OUT, v3 * (size_t)m->F, &dO);
-    if (st == FD_OK && falloff_out) st = stage(ctx, FD_STAGE_FALLOFF, v1, &dF);
-    if (st != FD_OK) return st;
-    cudaStream_t s = ctx->stream;
-    FD_CUDA_OK(ctx, cudaMemcpyAsync(dP, P, v3, cudaMemcpyHostToDevice, s));
-    if (dD) FD_CUDA_OK(ctx, cudaMemcpyAsync(dD, dist2, v1, cudaMemcpyHostToDevice, s));
-    if (tang) {
-        FD_CUDA_OK(ctx, cudaMemcpyAsync(dU, tangentu, v3, cudaMemcpyHostToDevice, s));
-        FD_CUDA_OK(ctx, cudaMemcpyAsync(dV, tangentv, v3, cudaMemcpyHostToDevice, s));
-        FD_CUDA_OK(ctx, cudaMemcpyAsync(dN, normal, v3, cudaMemcpyHostToDevice, s));
-    }
-    st = fd_rbf_eval_dev(m, (const float*)dP, n_vtx, (const float*)dD, (const float*)dU, (const float*)dV,
-                         (const float*)dN, (float*)dO, (float*)dF);
-    if (st != FD_OK) return st;
-    FD_CUDA_OK(ctx, cudaMemcpyAsync(P_out, dO, v3 * (size_t)m->F, cudaMemcpyDeviceToHost, s));
-    if (dF) FD_CUDA_OK(ctx, cudaMemcpyAsync(falloff_out, dF, v1, cudaMemcpyDeviceToHost, s));
-    FD_CUDA_OK(ctx, cudaStreamSynchronize(s));
-    return FD_OK;
+    return fd_eval_host_strided(m, P, n_vtx, dist2, tangentu, tangentv, normal, P_out, (size_t)n_vtx * 3 * sizeof(float),
+                                falloff_out);
 }
 
 // ---- multi-GPU plumbing ------------------------------------------------------------------------------------
@@ -724,7 +790,8 @@ int fd_model_commit_weights(fd_model* m)
     fd_ctx* ctx = m->ctx;
     DeviceGuard g(ctx->device);
     if (!m->d_W || m->F < 1) { FD_SET_ERR(ctx, "commit: no weight block reserved"); return FD_E_STATE; }
-    cudaError_t e = fd_launch_pack(ctx, m);
+    cudaError_t e = cudaMemsetAsync(m->d_flags + FD_FLAG_NONFINITE, 0, sizeof(int), ctx->stream); // per commit, like a solve
+    if (e == cudaSuccess) e = fd_launch_pack(ctx, m);
     if (e != cudaSuccess) { FD_SET_ERR(ctx, "commit: %s", cudaGetErrorString(e)); return FD_E_CUDA; }
     m->solved = true;
     return FD_OK;
@@ -759,10 +826,209 @@ int fd_model_get_weights(fd_model* m, double* weights, double* radii)
 
 } // extern "C"
 
-void fd_ctx_retain(fd_ctx* ctx) { ++ctx->refs; }
+// handles may be created / destroyed from different host threads (one ctx per node): the count is atomic
+void fd_ctx_retain(fd_ctx* ctx) { __atomic_add_fetch(&ctx->refs, 1, __ATOMIC_ACQ_REL); }
 void fd_ctx_release(fd_ctx* ctx)
 {
-    if (--ctx->refs == 0 && ctx->destroy_requested) ctx_teardown(ctx);
+    if (__atomic_sub_fetch(&ctx->refs, 1, __ATOMIC_ACQ_REL) == 0 && ctx->destroy_requested) ctx_teardown(ctx);
+}
+
+// host-pointer evaluation; frame f of the result lands at P_out + f * out_pitch_bytes (fd_rbf_eval: the frames are
+// contiguous; fd_mgpu_eval: every device writes its vertex range into the caller's F x V x 3 array)
+int fd_eval_host_strided(fd_model* m, const float* P, int64_t n_vtx, const float* dist2, const float* tangentu,
+                         const float* tangentv, const float* normal, float* P_out, size_t out_pitch_bytes, float* falloff_out)
+{
+    if (!m || (n_vtx > 0 && (!P || !P_out)) || n_vtx < 0) return FD_E_INVALID;
+    if (m->v1_layers && m->solved) m = m->v1_eval;
+    fd_ctx* ctx = m->ctx;
+    DeviceGuard g(ctx->device);
+    if (!m->solved) { FD_SET_ERR(ctx, "eval: no weights (call fd_rbf_solve or fd_model_commit_weights first)"); return FD_E_STATE; }
+    if (n_vtx == 0) return FD_OK;
+    const size_t v3 = (size_t)n_vtx * 3 * sizeof(float), v1 = (size_t)n_vtx * sizeof(float);
+    if (out_pitch_bytes < v3) { FD_SET_ERR(ctx, "eval: output pitch smaller than a frame"); return FD_E_INVALID; }
+    void *dP = nullptr, *dD = nullptr, *dU = nullptr, *dV = nullptr, *dN = nullptr, *dO = nullptr, *dF = nullptr;
+    int st = stage(ctx, FD_STAGE_P, v3, &dP);
+    if (st == FD_OK && dist2) st = stage(ctx, FD_STAGE_DIST, v1, &dD);
+    const bool tang = m->prm.tangent && tangentu && tangentv && normal;
+    if (st == FD_OK && tang) st = stage(ctx, FD_STAGE_TU, v3, &dU);
+    if (st == FD_OK && tang) st = stage(ctx, FD_STAGE_TV, v3, &dV);
+    if (st == FD_OK && tang) st = stage(ctx, FD_STAGE_N, v3, &dN);
+    if (st == FD_OK) st = stage(ctx, FD_STAGE_OUT, v3 * (size_t)m->F, &dO);
+    if (st == FD_OK && falloff_out) st = stage(ctx, FD_STAGE_FALLOFF, v1, &dF);
+    if (st != FD_OK) return st;
+    cudaStream_t s = ctx->stream;
+    FD_CUDA_OK(ctx, cudaMemcpyAsync(dP, P, v3, cudaMemcpyHostToDevice, s));
+    if (dD) FD_CUDA_OK(ctx, cudaMemcpyAsync(dD, dist2, v1, cudaMemcpyHostToDevice, s));
+    if (tang) {
+        FD_CUDA_OK(ctx, cudaMemcpyAsync(dU, tangentu, v3, cudaMemcpyHostToDevice, s));
+        FD_CUDA_OK(ctx, cudaMemcpyAsync(dV, tangentv, v3, cudaMemcpyHostToDevice, s));
+        FD_CUDA_OK(ctx, cudaMemcpyAsync(dN, normal, v3, cudaMemcpyHostToDevice, s));
+    }
+    st = fd_rbf_eval_dev(m, (const float*)dP, n_vtx, (const float*)dD, (const float*)dU, (const float*)dV,
+                         (const float*)dN, (float*)dO, (float*)dF);
+    if (st != FD_OK) return st;
+    if (out_pitch_bytes == v3)
+        FD_CUDA_OK(ctx, cudaMemcpyAsync(P_out, dO, v3 * (size_t)m->F, cudaMemcpyDeviceToHost, s));
+    else
+        FD_CUDA_OK(ctx, cudaMemcpy2DAsync(P_out, out_pitch_bytes, dO, v3, v3, (size_t)m->F, cudaMemcpyDeviceToHost, s));
+    if (dF) FD_CUDA_OK(ctx, cudaMemcpyAsync(falloff_out, dF, v1, cudaMemcpyDeviceToHost, s));
+    FD_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    return FD_OK;
+}
+
+// fd_mgpu's p2p transport: this (receiver) model builds its evaluation tables straight from the weight block of the root
+// device -- the table builders read it through peer loads over NVLink, so the broadcast and the pack are one pass -- and
+// pulls the FP64 block itself only when the FP64 evaluation will run.  Enqueued on this model's stream; the caller has
+// ordered it after the root's solve (event).
+int fd_model_commit_from_peer(fd_model* m, const double* peer_W, const double* peer_radii, int peer_device)
+{
+    if (!m || !peer_W || !peer_radii) return FD_E_INVALID;
+    fd_ctx* ctx = m->ctx;
+    DeviceGuard g(ctx->device);
+    if (!m->d_W || m->F < 1) { FD_SET_ERR(ctx, "commit: no weight block reserved"); return FD_E_STATE; }
+    cudaError_t e = cudaMemcpyPeerAsync(m->d_radii, ctx->device, peer_radii, peer_device, (size_t)m->N * sizeof(double), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_flags + FD_FLAG_NONFINITE, 0, sizeof(int), ctx->stream);
+    m->d_W_src = peer_W;
+    if (e == cudaSuccess) e = fd_launch_pack(ctx, m);
+    if (e == cudaSuccess) e = fd_launch_pull_weights(ctx, m);
+    m->d_W_src = nullptr;
+    if (e != cudaSuccess) { FD_SET_ERR(ctx, "commit (p2p): %s", cudaGetErrorString(e)); return FD_E_CUDA; }
+    m->solved = true;
+    return FD_OK;
+}
+
+// ---- serialise (the reference's intent: alglib::rbfserialize, SOP_FaceDeform.cpp:377) --------------------------------------
+namespace {
+struct SaveHeader {
+    char magic[8];          // "FDMODEL"
+    uint32_t abi, header_bytes;
+    fd_params prm;
+    int32_t N, np, n, lda, F, ldw;
+    int32_t has_factor, ns, reserved0, reserved1;
+    uint64_t total_bytes;
+};
+struct Section { void** dev; size_t bytes; };
+
+// the device blocks a saved model consists of, in file order
+int save_sections(fd_model* m, bool has_factor, Section* sec)
+{
+    int k = 0;
+    sec[k++] = {(void**)&m->d_rest, (size_t)m->N * 3 * sizeof(float)};
+    sec[k++] = {(void**)&m->d_radii, (size_t)m->N * sizeof(double)};
+    if (m->F > 0) sec[k++] = {(void**)&m->d_W, (size_t)m->n * m->ldw * sizeof(double)};
+    if (has_factor) {
+        sec[k++] = {(void**)&m->d_A, (size_t)m->lda * m->n * sizeof(double)};
+        sec[k++] = {(void**)&m->d_ipiv, (size_t)m->n * sizeof(int)};
+        sec[k++] = {(void**)&m->d_perm, (size_t)m->n * sizeof(int)};
+        sec[k++] = {(void**)&m->d_Tinv, (size_t)((m->n + 31) / 32) * 2 * 32 * 32 * sizeof(double)};
+        sec[k++] = {(void**)&m->d_pivstat, 2 * sizeof(double)};
+        sec[k++] = {(void**)&m->d_flags, FD_NUM_FLAGS * sizeof(int)};
+        if (m->ns) sec[k++] = {(void**)&m->d_ns, ((size_t)m->N * 5 + 32) * sizeof(double)};
+    }
+    return k;
+}
+} // namespace
+
+extern "C" int fd_model_save(fd_model* m, void* buf, size_t cap, size_t* bytes)
+{
+    if (!m || !bytes) return FD_E_INVALID;
+    if (m->v1_layers) { // the layered fit is saved as what evaluates it: the stacked model of its last solve
+        if (!m->v1_eval) { FD_SET_ERR(m->ctx, "save: a layered (ALGLIB v1) model is saved after a solve"); return FD_E_STATE; }
+        m = m->v1_eval;
+    }
+    fd_ctx* ctx = m->ctx;
+    DeviceGuard g(ctx->device);
+    const bool has_factor = m->fitted && !m->receiver && !m->f32ir && m->d_A;
+    if (!has_factor && !(m->solved && m->F > 0)) { FD_SET_ERR(ctx, "save: the model holds neither a factorisation nor weights"); return FD_E_STATE; }
+    SaveHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "FDMODEL", 8);
+    h.abi = FD_ABI_VERSION;
+    h.header_bytes = sizeof(h);
+    h.prm = m->prm;
+    h.N = m->N, h.np = m->np, h.n = m->n, h.lda = m->lda;
+    h.F = m->solved ? m->F : 0;
+    h.ldw = m->solved ? m->ldw : 0;
+    h.has_factor = has_factor ? 1 : 0;
+    h.ns = (has_factor && m->ns) ? 1 : 0;
+    const int keepF = m->F;
+    if (!m->solved) m->F = 0;
+    Section sec[12];
+    const int nsec = save_sections(m, has_factor, sec);
+    m->F = keepF;
+    size_t total = sizeof(h);
+    for (int k = 0; k < nsec; ++k) total += (sec[k].bytes + 15) & ~(size_t)15;
+    h.total_bytes = total;
+    *bytes = total;
+    if (!buf) return FD_OK;
+    if (cap < total) { FD_SET_ERR(ctx, "save: buffer of %zu bytes, %zu needed", cap, total); return FD_E_INVALID; }
+    unsigned char* p = (unsigned char*)buf;
+    memcpy(p, &h, sizeof(h));
+    p += sizeof(h);
+    for (int k = 0; k < nsec; ++k) {
+        FD_CUDA_OK(ctx, cudaMemcpyAsync(p, *sec[k].dev, sec[k].bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        p += (sec[k].bytes + 15) & ~(size_t)15;
+    }
+    FD_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+extern "C" int fd_model_load(fd_ctx* ctx, const void* buf, size_t bytes, fd_model** out)
+{
+    if (!ctx || !buf || !out) return FD_E_INVALID;
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    SaveHeader h;
+    if (bytes < sizeof(h)) { FD_SET_ERR(ctx, "load: truncated header"); return FD_E_INVALID; }
+    memcpy(&h, buf, sizeof(h));
+    if (memcmp(h.magic, "FDMODEL", 8) != 0 || h.abi != FD_ABI_VERSION || h.header_bytes != sizeof(h) || h.total_bytes > bytes) {
+        FD_SET_ERR(ctx, "load: not a model saved by this ABI version (%d)", FD_ABI_VERSION);
+        return FD_E_INVALID;
+    }
+    int st = check_params(ctx, &h.prm);
+    if (st != FD_OK) return st;
+    if (h.N < 1 || h.np != fd_poly_terms(h.prm.term) || h.n != h.N + h.np || h.lda != fd_round_up(h.n, 32) || h.F < 0 ||
+        (h.F > 0 && h.ldw != fd_round_up(3 * h.F, 4)) || h.prm.fidelity != FD_FIDELITY_DENSE) {
+        FD_SET_ERR(ctx, "load: inconsistent header");
+        return FD_E_INVALID;
+    }
+    fd_model* m = nullptr;
+    st = model_alloc(ctx, &h.prm, h.N, h.has_factor != 0, &m);
+    if (st != FD_OK) return st;
+    m->f32ir = false;
+    m->ns = h.ns != 0;
+    if (m->ns && (st = dev_alloc(ctx, &m->d_ns, (size_t)m->N * 5 + 32)) != FD_OK) { fd_model_destroy(m); return st; }
+    if (h.F > 0) {
+        st = model_reserve_frames(m, h.F);
+        if (st != FD_OK) { fd_model_destroy(m); return st; }
+        m->F = h.F;
+        m->ldw = m->ldw32 = h.ldw;
+        m->use_tc = model_wants_tc(m, h.F);
+    }
+    Section sec[12];
+    const int nsec = save_sections(m, h.has_factor != 0, sec);
+    size_t need = sizeof(h);
+    for (int k = 0; k < nsec; ++k) need += (sec[k].bytes + 15) & ~(size_t)15;
+    if (need != h.total_bytes) { FD_SET_ERR(ctx, "load: size mismatch (%zu expected, %llu stored)", need, (unsigned long long)h.total_bytes); fd_model_destroy(m); return FD_E_INVALID; }
+    const unsigned char* p = (const unsigned char*)buf + sizeof(h);
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < nsec && e == cudaSuccess; ++k) {
+        e = cudaMemcpyAsync(*sec[k].dev, p, sec[k].bytes, cudaMemcpyHostToDevice, ctx->stream);
+        p += (sec[k].bytes + 15) & ~(size_t)15;
+    }
+    m->fitted = h.has_factor != 0;
+    m->receiver = !m->fitted;
+    if (e == cudaSuccess && h.F > 0) {
+        m->tc_packed_by_solve = false;
+        e = fd_launch_pack(ctx, m);
+        m->solved = e == cudaSuccess;
+    } else if (e == cudaSuccess) {
+        e = fd_launch_pack_tables(ctx, m);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // `buf` may be pageable and freed by the caller on return
+    if (e != cudaSuccess) { FD_SET_ERR(ctx, "load: %s", cudaGetErrorString(e)); fd_model_destroy(m); return FD_E_CUDA; }
+    *out = m;
+    return FD_OK;
 }
 
 // exposed to fd_capture_host.cu

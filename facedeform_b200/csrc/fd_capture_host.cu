@@ -25,12 +25,27 @@ extern "C" int fd_capture(fd_ctx* ctx, const float* P, int64_t n_vtx, const int3
         (n_rig_prim > 0 && (!rig_off || !rig_vtx)) || !grp_class || !grp_off)
         return FD_E_INVALID;
     if (n_vtx > 0x7fffffff) { snprintf(ctx->err, sizeof(ctx->err), "capture: more than 2^31 vertices"); return FD_E_UNSUPPORTED; }
-    int prev = -1;
-    cudaGetDevice(&prev);
-    cudaSetDevice(ctx->device);
     const int64_t V = n_vtx;
     const int N = n_rig;
     if (max_edges < 1) max_edges = 1; // SOP_FaceDeform.cpp:257
+    // The topology comes from the caller: every offset array must be non-decreasing from 0 and every vertex index in
+    // range before anything is indexed with it (host adjacency lists below, rig[] on the device).
+    auto bad = [&](const char* what, long long where, long long value) {
+        snprintf(ctx->err, sizeof(ctx->err), "capture: %s[%lld] = %lld is out of range", what, where, value);
+        return FD_E_INVALID;
+    };
+    if (n_poly < 0 || n_rig_prim < 0 || grp_cap < 0 || idx_cap < 0) return bad("count", 0, -1);
+    if (n_poly > 0 && poly_off[0] != 0) return bad("poly_off", 0, poly_off[0]);
+    for (int32_t f = 0; f < n_poly; ++f)
+        if (poly_off[f + 1] < poly_off[f]) return bad("poly_off", f + 1, poly_off[f + 1]);
+    for (int64_t t = 0, e = n_poly > 0 ? poly_off[n_poly] : 0; t < e; ++t)
+        if (poly_vtx[t] < 0 || poly_vtx[t] >= V) return bad("poly_vtx", t, poly_vtx[t]);
+    if (n_rig_prim > 0 && rig_off[0] != 0) return bad("rig_off", 0, rig_off[0]);
+    for (int32_t f = 0; f < n_rig_prim; ++f)
+        if (rig_off[f + 1] < rig_off[f]) return bad("rig_off", f + 1, rig_off[f + 1]);
+    for (int64_t t = 0, e = n_rig_prim > 0 ? rig_off[n_rig_prim] : 0; t < e; ++t)
+        if (rig_vtx[t] < 0 || rig_vtx[t] >= N) return bad("rig_vtx", t, rig_vtx[t]);
+    fd_device_guard guard(ctx->device); // restores the caller's device on every return below
     cudaStream_t s = ctx->stream;
     int st = FD_OK;
 
@@ -138,7 +153,6 @@ extern "C" int fd_capture(fd_ctx* ctx, const float* P, int64_t n_vtx, const int3
     if (G == 0) { // capture.cpp:54-56
         std::fill(dist2, dist2 + V, 0.0f);
         snprintf(ctx->err, sizeof(ctx->err), "%s", fd_status_string(FD_E_CAPTURE));
-        if (prev >= 0) cudaSetDevice(prev);
         return FD_E_CAPTURE;
     }
 
@@ -166,6 +180,5 @@ extern "C" int fd_capture(fd_ctx* ctx, const float* P, int64_t n_vtx, const int3
         FD_CUDA_OK(ctx, cudaMemcpyAsync(dist2, dDist, (size_t)V * 4, cudaMemcpyDeviceToHost, s));
     }
     FD_CUDA_OK(ctx, cudaStreamSynchronize(s));
-    if (prev >= 0) cudaSetDevice(prev);
     return FD_OK;
 }

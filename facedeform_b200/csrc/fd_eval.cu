@@ -10,7 +10,7 @@
 // The same template instantiates the FP64 variant used for multiquadric / thin-plate accuracy.
 #include <stdlib.h>
 
-#include "fd_internal.h"
+#include "fd_eval_common.cuh"
 
 namespace {
 
@@ -89,70 +89,7 @@ template <int KERNEL> __device__ __forceinline__ double phi(double r2, double pr
     return r2 > 0.0 ? 0.5 * r2 * log(r2) : 0.0;
 }
 
-// ---- FP64 evaluation of multiquadric / thin plate (FD_EVAL_AUTO for those kernels) ------------------
-// The FP64 pipe is the bound (64 lanes/clk/SM), so the kernel functions are built from few DFMAs instead of libdevice's
-// IEEE sqrt / log (~20 and ~40 FP64 instructions): 2^-40 relative accuracy is ample for a result that is rounded to
-// FP32, the point of FP64 here is the cancellation in sum_j w_j phi_j, not the last bits of phi.
-// sqrt: MUFU.RSQ64H seed (rsqrt.approx.f64, ~2^-20) + one Newton step in FP64 -> ~2^-40 relative, 4 FP64 instructions
-// and no FP32 <-> FP64 conversions (F2F runs at a quarter of the FP64 rate: two of them cost as much as the rest).
-// x > 0 (multiquadric: r^2 + R^2 with R > 0).
-__device__ __forceinline__ double fast_sqrt64(double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double t = x * y;
-    const double e = fma(-t, y, 1.0);
-    return fma(0.5 * t, e, t);
-}
-// 0.5 * ln|x| by a 128-entry table of (1 / c_i, 0.5 ln c_i), c_i = 1 + (i + 0.5) / 128, and a degree-4 series in
-// d = m / c_i - 1, |d| <= 2^-8 (truncation d^5 / 5 < 2^-42); x = 0 gives a finite value (the caller multiplies by x).
-__device__ __forceinline__ double half_log64(double x, const double2* __restrict__ s_tab)
-{
-    const int hi = __double2hiint(x);
-    const int e = ((hi >> 20) & 0x7ff) - 1023;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x)); // [1, 2)
-    const double2 t = s_tab[(hi >> 13) & 127];
-    const double d = fma(m, t.x, -1.0);
-    double p = fma(d, -0.125, 1.0 / 6.0);
-    p = fma(d, p, -0.25);
-    p = fma(d, p, 0.5);
-    // (double)e without an I2F conversion: 2^52 + 2^31 + e as raw bits, minus the magic constant (exact)
-    const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
-    return fma(ed, 0.34657359027997264, fma(d, p, t.y)); // e * ln2 / 2 + 0.5 ln c + 0.5 ln(1 + d)
-}
-
-__device__ __forceinline__ void normalize3(float a[3])
-{
-    const float len = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-    if (len > 0.0f) {
-        const float inv = 1.0f / len;
-        a[0] *= inv;
-        a[1] *= inv;
-        a[2] *= inv;
-    }
-}
-
-// SOP_FaceDeform.hpp:28-41, FP32, row-vector convention (see the oracle for the derivation)
-__device__ __forceinline__ void project_to_tangents(const float u[3], const float v[3], const float n[3], float d[3])
-{
-    float B[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) B[i][j] = u[i] * u[j] + v[i] * v[j] + n[i] * n[j];
-    float a1[3], a2[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        a1[j] = u[0] * B[0][j] + u[1] * B[1][j] + u[2] * B[2][j];
-        a2[j] = v[0] * B[0][j] + v[1] * B[1][j] + v[2] * B[2][j];
-    }
-    normalize3(a1);
-    normalize3(a2);
-    const float da1 = d[0] * a1[0] + d[1] * a1[1] + d[2] * a1[2];
-    const float da2 = d[0] * a2[0] + d[1] * a2[1] + d[2] * a2[2];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) d[k] = a1[k] * da1 + a2[k] * da2;
-}
+// (the FP64 kernel functions fd_fast_sqrt64 / fd_half_log64 and the tangent projection live in fd_eval_common.cuh)
 
 struct EvalArgs {
     const void* ctab;  // float4 / double4 [N]
@@ -171,6 +108,8 @@ struct EvalArgs {
     float radius2;     // radius * radius in FP32 (SOP_FaceDeform.cpp:402)
     float falloffrate;
     int do_tangent;
+    const int* sel; // device word holding the evaluation kernel FD_EVAL_AUTO chose, or NULL (no choice to make);
+    int sel_id;     // this launch's id: the kernel returns at once when *sel differs
 };
 
 // polynomial block + SOP epilogue (gate, tangent projection, falloff, position write), shared by the evaluation kernels
@@ -216,15 +155,15 @@ __device__ __forceinline__ void finish_vertices(const EvalArgs& a, const T* __re
                 tv[k] = a.tv[3 * v + k];
                 tn[k] = a.nrm[3 * v + k];
             }
-            normalize3(tu);
-            normalize3(tv);
-            normalize3(tn);
+            fd_normalize3(tu);
+            fd_normalize3(tv);
+            fd_normalize3(tn);
         }
 #pragma unroll
         for (int f = 0; f < FC; ++f) {
             if (f0 + f >= a.F) break;
             float d[3] = {(float)acc[u][3 * f], (float)acc[u][3 * f + 1], (float)acc[u][3 * f + 2]};
-            if (a.do_tangent) project_to_tangents(tu, tv, tn, d);
+            if (a.do_tangent) fd_project_to_tangents(tu, tv, tn, d);
             float* o = a.P_out + ((size_t)(f0 + f) * (size_t)a.V + (size_t)v) * 3;
 #pragma unroll
             for (int k = 0; k < 3; ++k) o[k] = skip ? pos[u][k] : pos[u][k] + d[k] * fo;
@@ -240,6 +179,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_simt(const EvalArgs a)
     __shared__ V4 s_c[TJ];
     __shared__ __align__(16) T s_w[TJ * WPAD];
 
+    if (a.sel && *a.sel != a.sel_id) return;
     const int f0 = blockIdx.y * FC;
     const int64_t vbase = (int64_t)blockIdx.x * (EVAL_THREADS * VPT) + threadIdx.x;
     T px[VPT], py[VPT], pz[VPT];
@@ -318,6 +258,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32x2(const EvalArgs a)
     __shared__ float4 s_c[TJ];
     __shared__ __align__(16) float s_w[TJ * WPAD];
 
+    if (a.sel && *a.sel != a.sel_id) return;
     const int f0 = blockIdx.y * FC;
     const int64_t vbase = (int64_t)blockIdx.x * (EVAL_THREADS * VPT) + threadIdx.x;
     float px[VPT], py[VPT], pz[VPT];
@@ -415,7 +356,7 @@ cudaError_t launch_f32x2(fd_ctx* ctx, const EvalArgs& a)
 template <int KERNEL>
 cudaError_t launch_f32x2_fc(fd_ctx* ctx, const EvalArgs& a)
 {
-    static const int vp_env = getenv("FD_EVAL_VP") ? atoi(getenv("FD_EVAL_VP")) : 0;
+    const int vp_env = ctx->dbg.eval_vp;
     if (a.F >= 4) return launch_f32x2<KERNEL, 4, 1>(ctx, a);
     if (a.F >= 2) return launch_f32x2<KERNEL, 2, 1>(ctx, a);
     // one frame: two packed pairs per thread when there are enough vertices to fill the GPU that way
@@ -434,10 +375,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f64(const EvalArgs a)
     __shared__ __align__(16) double s_w[TJ * WPAD];
     __shared__ double2 s_tab[128];
 
-    if (KERNEL == FD_KERNEL_THINPLATE && threadIdx.x < 128) {
-        const double c = 1.0 + ((double)threadIdx.x + 0.5) / 128.0;
-        s_tab[threadIdx.x] = make_double2(1.0 / c, 0.5 * log(c));
-    }
+    if (a.sel && *a.sel != a.sel_id) return; // FD_EVAL_AUTO settled on another kernel (fd_eval64.cu: k_cancel_select)
+    if (KERNEL == FD_KERNEL_THINPLATE && threadIdx.x < 128) fd_half_log64_table(s_tab, threadIdx.x);
     const int f0 = blockIdx.y * FC;
     const int64_t vbase = (int64_t)blockIdx.x * (EVAL_THREADS * VPT) + threadIdx.x;
     const double ox = (double)a.origin[0], oy = (double)a.origin[1], oz = (double)a.origin[2];
@@ -495,7 +434,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f64(const EvalArgs a)
 #pragma unroll
             for (int u = 0; u < VPT; ++u) {
                 const double x = fma(qx[u], c.x, fma(qy[u], c.y, fma(qz[u], c.z, c.w))) + pp[u]; // r^2 (+ R^2)
-                const double ph = KERNEL == FD_KERNEL_MULTIQUADRIC ? fast_sqrt64(x) : x * half_log64(x, s_tab);
+                const double ph = KERNEL == FD_KERNEL_MULTIQUADRIC ? fd_fast_sqrt64(x) : x * fd_half_log64(x, s_tab);
 #pragma unroll
                 for (int q = 0; q < 3 * FC; ++q) acc[u][q] = fma(w[q], ph, acc[u][q]);
             }
@@ -550,7 +489,14 @@ cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64
                            const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out)
 {
     if (V <= 0) return cudaSuccess;
-    if (m->use_tc) return fd_launch_eval_tc(ctx, m, P, V, dist2, tu, tv, nrm, P_out, falloff_out);
+    // FD_EVAL_AUTO with the Gaussian: the FP32 candidate and the FP64 kernel are both launched, the device word d_sel
+    // (written after the solve, fd_eval64.cu) lets exactly one of them run -- no host synchronisation in between
+    const int* sel = (!m->eval64 && m->auto_sel) ? m->d_sel : nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!m->eval64 && m->use_tc) {
+        e = fd_launch_eval_tc(ctx, m, P, V, dist2, tu, tv, nrm, P_out, falloff_out, sel, FD_SEL_TENSOR);
+        if (!sel || e != cudaSuccess) return e;
+    }
     EvalArgs a;
     a.N = m->N;
     a.np = m->np;
@@ -567,24 +513,33 @@ cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64
     a.falloffrate = m->prm.falloffrate;
     a.do_tangent = (m->prm.tangent && tu && tv && nrm) ? 1 : 0; // SOP_FaceDeform.cpp:293-294
     a.origin = m->d_rest;
-    if (m->eval64) {
-        a.ctab = m->d_ctab64;
-        a.W = m->d_W;
-        a.ldw = m->ldw;
-        if (m->prm.kernel == FD_KERNEL_MULTIQUADRIC)
-            return a.F >= 2 ? launch_f64<FD_KERNEL_MULTIQUADRIC, 2, 2>(ctx, a) : launch_f64<FD_KERNEL_MULTIQUADRIC, 1, 4>(ctx, a);
-        if (m->prm.kernel == FD_KERNEL_THINPLATE)
-            return a.F >= 2 ? launch_f64<FD_KERNEL_THINPLATE, 2, 2>(ctx, a) : launch_f64<FD_KERNEL_THINPLATE, 1, 4>(ctx, a);
-        return launch_kernel<double>(ctx, m->prm.kernel, a); // Gaussian in FP64 (forced by eval_precision)
+    a.sel = sel;
+    if (!m->eval64 && !m->use_tc) { // FP32 FMA/SFU
+        a.sel_id = FD_SEL_SIMT;
+        a.ctab = m->d_ctab32;
+        a.W = m->d_W32;
+        a.ldw = m->ldw32;
+        if (ctx->dbg.eval_scalar_f32) { // the un-packed kernel, kept for comparison
+            e = launch_kernel<float>(ctx, m->prm.kernel, a);
+        } else {
+            switch (m->prm.kernel) {
+            case FD_KERNEL_GAUSSIAN: e = launch_f32x2_fc<FD_KERNEL_GAUSSIAN>(ctx, a); break;
+            case FD_KERNEL_MULTIQUADRIC: e = launch_f32x2_fc<FD_KERNEL_MULTIQUADRIC>(ctx, a); break;
+            default: e = launch_f32x2_fc<FD_KERNEL_THINPLATE>(ctx, a); break;
+            }
+        }
+        if (!sel || e != cudaSuccess) return e;
     }
-    a.ctab = m->d_ctab32;
-    a.W = m->d_W32;
-    a.ldw = m->ldw32;
-    static const bool scalar_f32 = getenv("FD_EVAL_SCALAR_F32") != nullptr; // the un-packed kernel, kept for comparison
-    if (scalar_f32) return launch_kernel<float>(ctx, m->prm.kernel, a);
-    switch (m->prm.kernel) {
-    case FD_KERNEL_GAUSSIAN: return launch_f32x2_fc<FD_KERNEL_GAUSSIAN>(ctx, a);
-    case FD_KERNEL_MULTIQUADRIC: return launch_f32x2_fc<FD_KERNEL_MULTIQUADRIC>(ctx, a);
-    default: return launch_f32x2_fc<FD_KERNEL_THINPLATE>(ctx, a);
-    }
+    // FP64: the DMMA kernel for wide 3F, else one thread per vertex
+    a.sel_id = FD_SEL_FP64;
+    if (3 * m->F >= FD_MMA64_MIN_COLUMNS)
+        return fd_launch_eval64_mma(ctx, m, P, V, dist2, tu, tv, nrm, P_out, falloff_out, sel, FD_SEL_FP64);
+    a.ctab = m->d_ctab64;
+    a.W = m->d_W;
+    a.ldw = m->ldw;
+    if (m->prm.kernel == FD_KERNEL_MULTIQUADRIC)
+        return a.F >= 2 ? launch_f64<FD_KERNEL_MULTIQUADRIC, 2, 2>(ctx, a) : launch_f64<FD_KERNEL_MULTIQUADRIC, 1, 4>(ctx, a);
+    if (m->prm.kernel == FD_KERNEL_THINPLATE)
+        return a.F >= 2 ? launch_f64<FD_KERNEL_THINPLATE, 2, 2>(ctx, a) : launch_f64<FD_KERNEL_THINPLATE, 1, 4>(ctx, a);
+    return launch_kernel<double>(ctx, m->prm.kernel, a); // Gaussian in FP64
 }

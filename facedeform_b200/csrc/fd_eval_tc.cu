@@ -5,18 +5,23 @@
 //   that carry the affine block), followed by the SOP epilogue (gate, tangent projection, falloff, P += disp):
 //   reference SOP_FaceDeform.cpp:404-439 and SOP_FaceDeform.hpp:28-41, for all F frames at once.
 //
-// Phi never exists in HBM.  One persistent CTA per SM walks "units" of 256 vertices x 240 columns (80 frames):
-//   warp 0      TMA producer: streams the weight tile W^T[240 cols][32 k] (FP16 hi and lo parts, SWIZZLE_64B)
-//   warp 1      MMA issuer  : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=240, K=16),
-//                             FP32 accumulators in TMEM (two M tiles x 240 columns)
-//   warps 2..9  Phi producers: thread t owns vertex row t; per stage it evaluates 32 basis functions on the FMA /
-//                             MUFU pipes, splits each value into FP16 hi + lo and writes both into the canonical
-//                             K-major SWIZZLE_64B shared-memory layout the UMMA descriptor expects;
-//                             after the last stage the same warps drain TMEM (tcgen05.ld), run the epilogue and
-//                             store coalesced float4 rows through a shared-memory transpose.
+// Phi never exists in HBM.  One persistent CTA per SM (26 warps) walks "units" of 128 vertices x 240 columns (80 frames):
+//   warps 0..15  Phi producers: two groups of 8 warps alternate pipeline stages; inside a group two threads share a
+//                              vertex row and evaluate 16 basis functions each per stage on the FMA / MUFU pipes
+//                              (packed FP32 pairs), split each value into FP16 hi + lo and write both into the K-major
+//                              SWIZZLE_64B shared-memory layout the UMMA descriptor expects
+//   warps 16..23 epilogue    : drain one of the two ping-pong TMEM accumulators (tcgen05.ld) while the MMAs of the
+//                              next unit fill the other, un-scale, apply falloff, add P, transpose through shared
+//                              memory and hand [8 frames x 32 vertices x 3] tiles to TMA stores
+//   warp 24      TMA producer: streams the weight tiles W^T[240 cols][32 k] (FP16 hi and lo, SWIZZLE_64B, 4-stage ring;
+//                              CTA pairs load half a tile each and multicast it) and, in a 16-deep ring of their own,
+//                              the 32-centre tiles
+//   warp 25      MMA issuer  : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=240, K=16),
+//                              FP32 accumulators in TMEM (2 x 240 of 512 columns)
 // Precision: hi*hi + hi*lo + lo*hi with FP16 splits keeps ~22 bits per factor (weights are pre-scaled per column by
 // a power of two into FP16 range and un-scaled in the epilogue; coordinates of the affine rows are normalised to the
-// control rig's bounding box), which holds the 1e-5 x bbox-diagonal tolerance of the FP32 path.
+// control rig's bounding box).  The error of any FP32 evaluation scales with the cancellation in sum_j w_j phi_j; the
+// bound and the rule by which FD_EVAL_AUTO leaves this kernel for the FP64 one are in DESIGN.md section 2.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -320,6 +325,8 @@ struct Args {
     int vec_store_ok;       // V % 4 == 0 and P_out 16-byte aligned
     long long* dbg;         // optional per-unit phase timestamps of CTA 0 (FD_TC_DEBUG=1), else NULL
     int pair;               // 1: CTAs run as clusters of two that share every weight tile (each loads half, multicast)
+    const int* sel;         // FD_EVAL_AUTO: the chosen evaluation kernel (device word) or NULL; the launch returns at once
+    int sel_id;             // when *sel != sel_id
     int dbg_mode;           // FD_TC_DEBUG bits (debug instantiation only; results are then garbage): 2 skip the epilogue
                             // math + stores, 4 skip the Phi computation, 8 issue one MMA of three, 16 skip the TMA stores only
 };
@@ -349,6 +356,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
           const __grid_constant__ CUtensorMap map_out)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (a.sel && *a.sel != a.sel_id) return; // uniform over the grid (and the cluster): nothing has been set up yet
     // align inside the shared window with pointer arithmetic only: a uintptr_t round trip would demote every
     // access below to generic LD/ST (long-scoreboard) instead of LDS/STS
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -814,7 +822,7 @@ k_eval_tc(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid
 // pack: FP64 weights -> transposed, column-scaled FP16 hi/lo tables W^T[c][k] the TMA streams
 // ------------------------------------------------------------------------------------------------------------
 
-// bounding box of the control points -> (centre, 2 / largest extent)
+// bounding box of the control points -> (centre, 2 / largest extent, diagonal)
 __global__ void __launch_bounds__(256) k_tc_norm(const float* __restrict__ rest, int N, float* __restrict__ norm)
 {
     __shared__ float s_lo[3][256], s_hi[3][256];
@@ -838,12 +846,14 @@ __global__ void __launch_bounds__(256) k_tc_norm(const float* __restrict__ rest,
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        float ext = 0.f;
+        float ext = 0.f, d2 = 0.f;
         for (int k = 0; k < 3; ++k) {
             norm[k] = 0.5f * (s_lo[k][0] + s_hi[k][0]);
             ext = fmaxf(ext, s_hi[k][0] - s_lo[k][0]);
+            d2 += (s_hi[k][0] - s_lo[k][0]) * (s_hi[k][0] - s_lo[k][0]);
         }
         norm[3] = ext > 0.f ? 2.0f / ext : 1.0f;
+        norm[4] = sqrtf(d2); // the rig's bounding-box diagonal: the length FD_EVAL_AUTO's tolerance is relative to
     }
 }
 
@@ -1025,11 +1035,11 @@ cudaError_t fd_launch_pack_tc(fd_ctx* ctx, fd_model* m)
             return cudaErrorInvalidValue;
         return cudaSuccess;
     }
-    tc::k_tc_colscale<<<(ncol_pad + 31) / 32, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad,
+    tc::k_tc_colscale<<<(ncol_pad + 31) / 32, 256, 0, s>>>(fd_w_src(m), m->ldw, m->N, m->np, ncol, ncol_pad,
                                                             m->prm.kernel == FD_KERNEL_GAUSSIAN ? tc::GAUSS_SHIFT : 0,
                                                             m->d_tc_norm, m->d_tc_unscale, m->d_tc_scale, m->d_flags);
     dim3 grid((ncol_pad + 31) / 32, (Kpad + 31) / 32);
-    tc::k_tc_pack<<<grid, 256, 0, s>>>(m->d_W, m->ldw, m->N, m->np, ncol, ncol_pad, Kpad, m->d_tc_norm, m->d_tc_scale,
+    tc::k_tc_pack<<<grid, 256, 0, s>>>(fd_w_src(m), m->ldw, m->N, m->np, ncol, ncol_pad, Kpad, m->d_tc_norm, m->d_tc_scale,
                                        (__half*)m->d_tc_wt_hi, (__half*)m->d_tc_wt_lo);
     ctx->launches += 2;
     if (!tc::make_map((CUtensorMap*)m->tc_map_hi, m->d_tc_wt_hi, Kpad, ncol_pad) ||
@@ -1038,11 +1048,32 @@ cudaError_t fd_launch_pack_tc(fd_ctx* ctx, fd_model* m)
     return cudaGetLastError();
 }
 
+// per-device function attributes of every instantiation (fd_ctx_create)
+cudaError_t fd_eval_tc_setup(fd_ctx* ctx)
+{
+    (void)ctx;
+    cudaError_t e = cudaSuccess;
+#define FD_TC_ATTR(...)                                                                                                   \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::k_eval_tc<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC)
+    FD_TC_ATTR(FD_KERNEL_GAUSSIAN, false, false);
+    FD_TC_ATTR(FD_KERNEL_GAUSSIAN, true, false);
+    FD_TC_ATTR(FD_KERNEL_MULTIQUADRIC, false, false);
+    FD_TC_ATTR(FD_KERNEL_MULTIQUADRIC, true, false);
+    FD_TC_ATTR(FD_KERNEL_THINPLATE, false, false);
+    FD_TC_ATTR(FD_KERNEL_THINPLATE, true, false);
+    FD_TC_ATTR(FD_KERNEL_GAUSSIAN, false, true); // the debug instantiation (FD_TC_DEBUG)
+#undef FD_TC_ATTR
+    return e;
+}
+
 cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
-                              const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out)
+                              const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out,
+                              const int* sel, int sel_id)
 {
     if (V <= 0) return cudaSuccess;
     tc::Args a;
+    a.sel = sel;
+    a.sel_id = sel_id;
     a.ctab = m->d_ctab_pair;
     a.norm = m->d_tc_norm;
     a.colscale = m->d_tc_unscale;
@@ -1063,16 +1094,24 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
     a.falloffrate = m->prm.falloffrate;
     a.do_tangent = (m->prm.tangent && tu && tv && nrm) ? 1 : 0;
     a.vec_store_ok = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(P_out) & 15) == 0) && !a.do_tangent;
-    alignas(64) CUtensorMap mo;
-    memset(&mo, 0, sizeof(mo));
-    if (a.vec_store_ok && !tc::make_out_map(&mo, P_out, V, m->F)) a.vec_store_ok = 0;
-    static long long* d_dbg = nullptr;
-    static const bool want_dbg = getenv("FD_TC_DEBUG") != nullptr;
-    if (want_dbg && !d_dbg) { cudaMalloc(&d_dbg, 256 * sizeof(long long)); cudaMemset(d_dbg, 0, 256 * sizeof(long long)); }
+    // the tensor map of the output depends on (P_out, V, F) only: cooks that write into the same buffer reuse it
+    if (a.vec_store_ok && !(ctx->tc_out_ptr == P_out && ctx->tc_out_V == V && ctx->tc_out_F == m->F)) {
+        ctx->tc_out_ptr = nullptr;
+        if (tc::make_out_map((CUtensorMap*)ctx->tc_out_map, P_out, V, m->F)) {
+            ctx->tc_out_ptr = P_out;
+            ctx->tc_out_V = V;
+            ctx->tc_out_F = m->F;
+        } else {
+            a.vec_store_ok = 0;
+        }
+    }
+    const CUtensorMap& mo = *(const CUtensorMap*)ctx->tc_out_map;
+    const bool want_dbg = ctx->dbg.has_tc_debug && ctx->d_tc_dbg;
+    long long* d_dbg = ctx->d_tc_dbg;
     a.dbg = want_dbg ? d_dbg : nullptr;
-    a.dbg_mode = want_dbg ? atoi(getenv("FD_TC_DEBUG")) : 0;
+    a.dbg_mode = want_dbg ? ctx->dbg.tc_debug : 0;
     const int64_t n_vt = (V + tc::TM - 1) / tc::TM;
-    static const bool no_pair = getenv("FD_TC_NOPAIR") != nullptr;
+    const bool no_pair = ctx->dbg.tc_nopair;
     a.pair = (!no_pair && n_vt >= 4 && ctx->sm_count >= 2) ? 1 : 0;
     const int64_t n_units = (a.pair ? (n_vt + 1) / 2 : n_vt) * a.ncb;
     const int64_t max_ctas = a.pair ? ctx->sm_count / 2 : ctx->sm_count;
@@ -1085,7 +1124,6 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
     do {                                                                                                            \
         auto kfn = tc::k_eval_tc<KERNEL, TANG, false>;                                                              \
         if (want_dbg && KERNEL == FD_KERNEL_GAUSSIAN && !TANG) kfn = tc::k_eval_tc<FD_KERNEL_GAUSSIAN, false, true>; \
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC);                     \
         cudaLaunchConfig_t cfg = {};                                                                                \
         cfg.gridDim = dim3(grid);                                                                                   \
         cfg.blockDim = dim3(tc::THREADS);                                                                           \

@@ -48,6 +48,14 @@ __device__ __forceinline__ float2 fd_make2(float a, float b) { return make_float
 #undef REAL2
 #undef FD_LU_NS
 
+cudaError_t fd_factor_setup(fd_ctx* ctx)
+{
+    (void)ctx; // the current device is the ctx's (fd_ctx_create)
+    cudaError_t e = lu_f64::setup_attributes();
+    if (e == cudaSuccess) e = lu_f32::setup_attributes();
+    return e;
+}
+
 cudaError_t fd_launch_lu(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                          double* d_pivstat, int* d_win)
 {

@@ -719,19 +719,9 @@ __global__ void __launch_bounds__(32) k_lu_window(const int* __restrict__ ipiv, 
 cudaError_t launch_lu(fd_ctx* ctx, REAL* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                          double* d_pivstat, int* d_win)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_lu_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_MAX);
-        cudaFuncSetAttribute(k_lu_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(k_lu_panel_cluster<1, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        cudaFuncSetAttribute(k_lu_panel_cluster<2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        cudaFuncSetAttribute(k_lu_panel_cluster<3, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        attr_set = true;
-    }
     cudaStream_t s = ctx->stream;
-    static long long* d_dbg = nullptr;
-    static const bool want_dbg = getenv("FD_LU_DEBUG") != nullptr;
-    if (want_dbg && !d_dbg) cudaMalloc(&d_dbg, 64);
+    long long* d_dbg = ctx->d_lu_dbg;
+    const bool want_dbg = d_dbg != nullptr;
     k_lu_init<<<1, 32, 0, s>>>(d_flags, d_pivstat);
     ctx->launches += 1;
     cudaError_t e = cudaSuccess;
@@ -1224,27 +1214,17 @@ static unsigned fz_barrier_count(int n, int nbo)
 cudaError_t launch_lu_nopivot_fused(fd_ctx* ctx, REAL* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                                     double* d_pivstat, double* d_Tinv)
 {
-    static bool attr_set = false;
     const size_t smem = (size_t)FZ_SMEM_REALS * sizeof(REAL);
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_lu_nopiv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_lu_nopiv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_lu_nopiv_fused<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        attr_set = true;
-    }
-    const char* env_dbg = getenv("FD_LU_DEBUG");
-    int dbg = env_dbg ? atoi(env_dbg) : 0;
-    const char* env_nbo = getenv("FD_LU_NBO");
-    const char* env_cluster_max = getenv("FD_LU_CLUSTER_MAX_N");
-    const int cluster_max_n = env_cluster_max ? atoi(env_cluster_max) : 512;
-    int nbo = env_nbo ? atoi(env_nbo) : (n <= 1536 ? 32 : (n <= 3072 ? 128 : 256));
+    const fd_debug_opts& o = ctx->dbg;
+    int dbg = o.lu_debug;
+    const int cluster_max_n = o.lu_cluster_max_n ? o.lu_cluster_max_n : 512;
+    int nbo = o.lu_nbo ? o.lu_nbo : (n <= 1536 ? 32 : (n <= 3072 ? 128 : 256));
     nbo = max(NB, nbo / NB * NB);
     cudaStream_t s = ctx->stream;
     unsigned base = ctx->sync_base;
     if (n <= cluster_max_n) {
         // one cluster: 4 CTAs up to n = 64, 8 up to 128, else 16
-        const char* env_cs = getenv("FD_LU_CLUSTER");
-        const int cs = env_cs ? atoi(env_cs) : (n <= 64 ? 4 : (n <= 128 ? 8 : 16));
+        const int cs = o.lu_cluster ? o.lu_cluster : (n <= 64 ? 4 : (n <= 128 ? 8 : 16));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cs);
         cfg.blockDim = dim3(FZ_THREADS);
@@ -1262,10 +1242,28 @@ cudaError_t launch_lu_nopivot_fused(fd_ctx* ctx, REAL* d_A, int lda, int n, int*
                                   ctx->d_sync, base, dbg);
     }
     const int G = ctx->sm_count;
-    ctx->sync_base = base + (unsigned)G * fz_barrier_count(n, nbo);
     void* args[] = {&d_A, &lda, &n, &nbo, &d_ipiv, &d_perm, &d_flags, &d_pivstat, &d_Tinv, &ctx->d_sync, &base, &dbg};
-    ctx->launches += 1;
-    return cudaLaunchCooperativeKernel((const void*)k_lu_nopiv_fused<false>, dim3(G), dim3(FZ_THREADS), args, smem, s);
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_lu_nopiv_fused<false>, dim3(G), dim3(FZ_THREADS), args, smem, s);
+    if (e == cudaSuccess) { // the counter only moves when the kernel that advances it was really enqueued
+        ctx->sync_base = base + (unsigned)G * fz_barrier_count(n, nbo);
+        ctx->launches += 1;
+    }
+    return e;
+}
+
+// per-device function attributes of this instantiation's kernels (called from fd_ctx_create through fd_factor_setup)
+cudaError_t setup_attributes()
+{
+    cudaError_t e = cudaFuncSetAttribute(k_lu_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_panel_cluster<1, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_panel_cluster<2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_panel_cluster<3, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    const int smem = (int)((size_t)FZ_SMEM_REALS * sizeof(REAL));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_nopiv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_nopiv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_nopiv_fused<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    return e;
 }
 
 // LU without pivoting for the symmetric positive definite case (see k_lu_nopiv_panel)

@@ -28,6 +28,30 @@ int fd_stage(struct fd_ctx* ctx, int slot, size_t bytes, void** out); // grows t
 
 enum fd_phase { FD_PH_ASSEMBLE = 0, FD_PH_FACTOR = 1, FD_PH_SOLVE = 2, FD_PH_EVAL = 3, FD_PH_COUNT = 4 };
 
+// Development knobs.  The environment is read ONCE, by fd_ctx_create (fd_api.cu: read_debug_opts); no entry point on
+// a cook's path calls getenv.  They select older kernels for comparison or switch on the cycle probes of the debug
+// instantiations; none of them changes a result of the default path.
+struct fd_debug_opts {
+    bool no_nullspace;      // FD_NO_NULLSPACE: multiquadric / thin plate take the pivoted LU
+    bool force_pivoted_lu;  // FD_FORCE_PIVOTED_LU
+    bool lu_unfused;        // FD_LU_UNFUSED: per-block-column launches instead of the fused LU
+    bool solve_dfma;        // FD_SOLVE_DFMA: the DFMA slab solve instead of the DMMA one
+    bool no_fused_pack;     // FD_NO_FUSED_PACK: separate tensor-table pack kernels after the slab solve
+    bool no_few_rhs;        // FD_NO_FEW_RHS
+    bool no_inverse;        // FD_NO_INVERSE: per-cook solves never build / use the explicit inverse
+    bool eval_scalar_f32;   // FD_EVAL_SCALAR_F32: the un-packed FP32 evaluation kernel
+    bool tc_nopair;         // FD_TC_NOPAIR: no CTA pairs in the tensor evaluation
+    bool has_tc_debug;      // FD_TC_DEBUG set
+    bool lu_sym_off;        // FD_LU_NOSYM: the fused LU ignores symmetry
+    bool lu_dfma;           // FD_LU_DFMA: DFMA tile product in the fused LU instead of DMMA
+    int eval_vp;            // FD_EVAL_VP
+    int tc_debug;           // FD_TC_DEBUG bits
+    int lu_debug;           // FD_LU_DEBUG step
+    int lu_nbo;             // FD_LU_NBO
+    int lu_cluster_max_n;   // FD_LU_CLUSTER_MAX_N
+    int lu_cluster;         // FD_LU_CLUSTER
+};
+
 struct fd_ctx {
     int device;
     int sm_count;
@@ -48,7 +72,21 @@ struct fd_ctx {
     // the ctx, the teardown happens when the last handle is destroyed (any destruction order is safe for the caller)
     int refs;
     bool destroy_requested;
+    fd_debug_opts dbg;       // environment knobs, read once at creation
+    long long* d_tc_dbg;     // cycle probes of the debug instantiations (allocated at creation when the knob is set)
+    long long* d_lu_dbg;
+    // tensor map of the last output buffer the tensor evaluation wrote (fd_eval_tc.cu): re-encoded only when it changes
+    alignas(64) unsigned char tc_out_map[FD_TMAP_BYTES];
+    const void* tc_out_ptr;
+    int64_t tc_out_V;
+    int tc_out_F;
 };
+// per-device kernel attributes (dynamic shared-memory limits, non-portable cluster sizes): function attributes are per
+// device, so every ctx sets them for its own device at creation (never behind a process-wide flag)
+cudaError_t fd_solve_setup(fd_ctx* ctx);     // fd_solve.cu
+cudaError_t fd_factor_setup(fd_ctx* ctx);    // fd_factor.cu
+cudaError_t fd_eval_tc_setup(fd_ctx* ctx);   // fd_eval_tc.cu
+cudaError_t fd_eval64_setup(fd_ctx* ctx);    // fd_eval64.cu
 void fd_ctx_retain(fd_ctx* ctx);
 void fd_ctx_release(fd_ctx* ctx); // fd_api.cu
 
@@ -65,7 +103,11 @@ struct fd_model {
     bool receiver;
     bool fitted;
     bool solved;
-    bool eval64;     // resolved evaluation precision
+    bool eval64;     // the evaluation is FP64 whatever the weights (eval_precision FP64; AUTO with multiquadric / thin plate)
+    bool auto_sel;   // Gaussian + FD_EVAL_AUTO: FP32 or FP64 is settled per solve on the device (d_sel, fd_eval64.cu)
+    int* d_sel;      // the evaluation kernel chosen for the current weights: 1 FMA/SFU, 2 tensor cores, 3 FP64
+    double* d_est;   // [0] cancellation S, [1] bounding-box diagonal of the rig, [2], [3] scratch of the estimate
+    float* d_wmax;   // N: max_c |w_jc|
     float* d_rest;   // N x 3
     double* d_radii; // N
     double* d_A;     // lda x n, LU in place
@@ -74,6 +116,8 @@ struct fd_model {
     int* d_win;      // 1 + 4*32 ints: the rows the current panel's interchanges touch and their composition
     double* d_Tinv;  // [ceil(n/32)][2][32x32]: inverses of the diagonal blocks of L and U
     double* d_W;     // n x ldw weights (solve in place over the right-hand sides)
+    const double* d_W_src; // where the table builders read the weights from: NULL = d_W; fd_mgpu's p2p transport points it
+                           // at the ROOT device's weight block, so the tables are built through peer loads over NVLink
     int* d_flags;    // FD_NUM_FLAGS
     double* d_pivstat; // [min |u_kk|, max |u_kk|]
     // null-space path of multiquadric / thin plate (fd_nullspace.cu): d_A holds Q^T K Q, its [4:, 4:] block LU-factored;
@@ -128,6 +172,15 @@ struct fd_model {
         }                                                                                          \
     } while (0)
 
+// makes `dev` current for the scope and restores the caller's device on every exit path
+struct fd_device_guard {
+    int prev = -1;
+    explicit fd_device_guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~fd_device_guard() { if (prev >= 0) cudaSetDevice(prev); }
+    fd_device_guard(const fd_device_guard&) = delete;
+    fd_device_guard& operator=(const fd_device_guard&) = delete;
+};
+
 static inline int fd_poly_terms(int term) { return term == FD_TERM_LINEAR ? 4 : (term == FD_TERM_CONST ? 1 : 0); }
 static inline int fd_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -159,6 +212,13 @@ cudaError_t fd_launch_v1_gather(fd_ctx* ctx, const double* d_R, const int* d_per
 cudaError_t fd_launch_gemm_sub(fd_ctx* ctx, const double* d_A, int lda, int rows, int K, const double* d_X, double* d_C, int ldw,
                                int nrhs);
 cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m);
+static inline const double* fd_w_src(const fd_model* m) { return m->d_W_src ? m->d_W_src : m->d_W; }
+// d_W <- d_W_src when the evaluation needs the FP64 block locally (eval64, or FD_EVAL_AUTO chose FP64 on the device)
+cudaError_t fd_launch_pull_weights(fd_ctx* ctx, fd_model* m);
+// internals shared with fd_mgpu.cu / the serialiser (fd_api.cu)
+int fd_model_commit_from_peer(fd_model* m, const double* peer_W, const double* peer_radii, int peer_device);
+int fd_eval_host_strided(fd_model* m, const float* P, int64_t n_vtx, const float* dist2, const float* tangentu,
+                         const float* tangentv, const float* normal, float* P_out, size_t out_pitch_bytes, float* falloff_out);
 cudaError_t fd_launch_pack_tables(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_invdiag(fd_ctx* ctx, fd_model* m);
 // fd_refine.cu
@@ -190,7 +250,16 @@ struct fd_tc_pack_args {
 void fd_tc_pack_args_fill(const fd_model* m, fd_tc_pack_args* pk); // fd_eval_tc.cu
 cudaError_t fd_launch_tc_norm(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
-                              const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out);
+                              const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out,
+                              const int* sel, int sel_id);
+// fd_eval64.cu
+#define FD_SEL_SIMT 1
+#define FD_SEL_TENSOR 2
+#define FD_SEL_FP64 3
+#define FD_MMA64_MIN_COLUMNS 48 // the FP64 evaluation takes the DMMA kernel from 3F >= 48 columns
+cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int cand32, int want);
+cudaError_t fd_launch_eval64_mma(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2, const float* tu,
+                                 const float* tv, const float* nrm, float* P_out, float* falloff_out, const int* sel, int sel_id);
 // fd_capture.cu
 cudaError_t fd_launch_nearest(fd_ctx* ctx, const float* d_P, int64_t V, const float* d_rig, int N,
                               unsigned long long* d_keys /* N scratch */, int32_t* d_nearest);

@@ -762,6 +762,15 @@ __global__ void __launch_bounds__(256) k_pack_weights(const double* __restrict__
 
 } // namespace
 
+// per-device function attributes (fd_ctx_create)
+cudaError_t fd_solve_setup(fd_ctx* ctx)
+{
+    (void)ctx;
+    cudaError_t e = cudaFuncSetAttribute(k_solve_slab8, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_solve_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return e;
+}
+
 cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int F)
 {
     m->tc_packed_by_solve = false;
@@ -772,16 +781,10 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int
         // FP64 tensor-pipe slab solve: 8 right-hand sides per CTA
         const int n_pad = fd_round_up(n, SB);
         const size_t bytes8 = ((size_t)n_pad * S8_RC + 2 * S8_CHUNK_DOUBLES + 2 * S8_TINV_DOUBLES) * sizeof(double);
-        if (bytes8 <= 220 * 1024 && !getenv("FD_SOLVE_DFMA")) {
-            static bool attr8_set = false;
-            if (!attr8_set) {
-                cudaFuncSetAttribute(k_solve_slab8, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-                attr8_set = true;
-            }
+        if (bytes8 <= 220 * 1024 && !ctx->dbg.solve_dfma) {
             fd_tc_pack_args pk;
             pk.enabled = 0;
-            static const bool no_fused_pack = getenv("FD_NO_FUSED_PACK") != nullptr;
-            if (m->use_tc && !no_fused_pack) fd_tc_pack_args_fill(m, &pk);
+            if (m->use_tc && !ctx->dbg.no_fused_pack) fd_tc_pack_args_fill(m, &pk);
             const int cols = pk.enabled ? max(ldw, pk.ncol_pad) : ldw;
             k_solve_slab8<<<(cols + S8_RC - 1) / S8_RC, S8_THREADS, bytes8, s>>>(m->d_A, m->lda, n, m->N, m->d_perm, m->d_rest,
                                                                                 d_deform, F, m->d_Tinv, m->d_W, ldw, pk);
@@ -793,11 +796,6 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int
     const size_t slab_bytes = (size_t)n * RC * sizeof(double);
     if (slab_bytes <= 200 * 1024 && (nrhs >= 2 * RC || n <= 1024)) {
         // one launch: every CTA solves its 16 right-hand sides start to finish out of shared memory
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_solve_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
-        }
         k_solve_slab<<<(ldw + RC - 1) / RC, SLAB_THREADS, slab_bytes, s>>>(m->d_A, m->lda, n, m->N, m->d_perm, m->d_rest,
                                                                           d_deform, F, m->d_Tinv, m->d_W, ldw);
         ctx->launches += 1;
@@ -828,7 +826,6 @@ cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, 
         const int n_pad = fd_round_up(n, SB);
         const size_t bytes8 = ((size_t)n_pad * S8_RC + 2 * S8_CHUNK_DOUBLES + 2 * S8_TINV_DOUBLES) * sizeof(double);
         if (bytes8 <= 220 * 1024) {
-            cudaFuncSetAttribute(k_solve_slab8, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
             fd_tc_pack_args pk;
             pk.enabled = 0;
             k_solve_slab8<<<(ldw + S8_RC - 1) / S8_RC, S8_THREADS, bytes8, s>>>(d_A, lda, n, n, d_perm, nullptr, nullptr,
@@ -839,7 +836,7 @@ cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, 
     }
     // beyond the slab: a handful of right-hand sides take one launch per block step (8.0 ms against 9.0 ms for the
     // two-launch rank-32 sweeps at n = 8196; where the slab fits, its single long-running CTA is still faster)
-    if (nrhs <= FEW_MAX && n >= 512 && !getenv("FD_NO_FEW_RHS")) {
+    if (nrhs <= FEW_MAX && n >= 512 && !ctx->dbg.no_few_rhs) {
         double* d_Y = nullptr; // forward-substituted right-hand sides, n x 8
         cudaError_t e = cudaMallocAsync((void**)&d_Y, (size_t)n * FEW_MAX * sizeof(double), s);
         if (e != cudaSuccess) return e;
@@ -937,7 +934,7 @@ cudaError_t fd_launch_pack_tables(fd_ctx* ctx, fd_model* m)
     cudaStream_t s = ctx->stream;
     const int npad = fd_tc_kpad(m->N);
     k_pack_tables<<<(npad + 255) / 256, 256, 0, s>>>(m->d_rest, m->d_radii, m->N, npad, m->prm.kernel, m->d_ctab32,
-                                                    reinterpret_cast<float*>(m->d_ctab_pair), m->eval64 ? m->d_ctab64 : nullptr);
+                                                    reinterpret_cast<float*>(m->d_ctab_pair), m->d_ctab64);
     ctx->launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = fd_launch_tc_norm(ctx, m);
@@ -953,9 +950,38 @@ cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
     cudaError_t e = cudaSuccess;
     if (!m->tables_packed || m->receiver) e = fd_launch_pack_tables(ctx, m);
     if (e != cudaSuccess) return e;
-    if (m->use_tc) return fd_launch_pack_tc(ctx, m);
-    dim3 grid((m->ldw32 + 255) / 256, m->n);
-    k_pack_weights<<<grid, 256, 0, s>>>(m->d_W, m->n, m->ldw, 3 * m->F, m->d_W32, m->ldw32, m->d_flags);
+    if (m->use_tc) {
+        e = fd_launch_pack_tc(ctx, m);
+    } else {
+        dim3 grid((m->ldw32 + 255) / 256, m->n);
+        k_pack_weights<<<grid, 256, 0, s>>>(fd_w_src(m), m->n, m->ldw, 3 * m->F, m->d_W32, m->ldw32, m->d_flags);
+        ctx->launches += 1;
+        e = cudaGetLastError();
+    }
+    // the cancellation of these weights, and with it the evaluation kernel of FD_EVAL_AUTO (Gaussian; fd_eval64.cu)
+    if (e == cudaSuccess && !m->eval64 && m->prm.kernel == FD_KERNEL_GAUSSIAN)
+        e = fd_launch_cancel_select(ctx, m, m->use_tc ? FD_SEL_TENSOR : FD_SEL_SIMT,
+                                    m->auto_sel ? 0 : (m->use_tc ? FD_SEL_TENSOR : FD_SEL_SIMT));
+    return e;
+}
+
+// d_W <- d_W_src (peer memory), only when the FP64 evaluation will run: statically (eval64) or by the device-side choice
+__global__ void __launch_bounds__(256) k_pull_weights(const double2* __restrict__ src, double2* __restrict__ dst, size_t count2,
+                                                      const int* __restrict__ sel)
+{
+    if (sel && *sel != FD_SEL_FP64) return;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < count2; i += (size_t)gridDim.x * 256) dst[i] = src[i];
+}
+
+cudaError_t fd_launch_pull_weights(fd_ctx* ctx, fd_model* m)
+{
+    if (!m->d_W_src || m->d_W_src == m->d_W) return cudaSuccess;
+    if (!m->eval64 && !m->auto_sel) return cudaSuccess; // FP32 evaluation only: the local tables are all it reads
+    const size_t count2 = (size_t)m->n * m->ldw / 2;    // ldw is a multiple of 4
+    const int grid = (int)((count2 + 255) / 256 < (size_t)ctx->sm_count * 4 ? (count2 + 255) / 256 : (size_t)ctx->sm_count * 4);
+    k_pull_weights<<<grid > 0 ? grid : 1, 256, 0, ctx->stream>>>(reinterpret_cast<const double2*>(m->d_W_src),
+                                                               reinterpret_cast<double2*>(m->d_W), count2,
+                                                               m->eval64 ? nullptr : m->d_sel);
     ctx->launches += 1;
     return cudaGetLastError();
 }

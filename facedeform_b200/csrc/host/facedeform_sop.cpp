@@ -2,10 +2,56 @@
 // (see include/facedeform_sop.hpp).  Pure host code: every number comes from libfacedeform_gpu's kernels.
 #include "facedeform_sop.hpp"
 
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace fd {
+
+// Point-group pattern of the `group` parm (SOP_FaceDeform.cpp:119-120, resolved by cookInputPointGroups :155-173 in
+// Houdini).  The numeric subset of Houdini's syntax: space separated tokens "*", "n", "a-b", "a-b:step", each optionally
+// prefixed by "^" (remove from what was selected so far; a pattern that starts with "^" starts from all points).
+bool resolvePointGroup(const char* pattern, int64_t npoints, std::vector<uint8_t>& mask)
+{
+    mask.assign((size_t)npoints, 0);
+    const char* s = pattern;
+    bool first = true;
+    while (*s) {
+        while (*s == ' ' || *s == '\t' || *s == ',') ++s;
+        if (!*s) break;
+        bool remove = false;
+        if (*s == '^') { remove = true; ++s; }
+        if (first && remove) mask.assign((size_t)npoints, 1);
+        first = false;
+        int64_t a = 0, b = 0, step = 1;
+        if (*s == '*') {
+            a = 0, b = npoints - 1;
+            ++s;
+        } else {
+            char* end = nullptr;
+            a = std::strtoll(s, &end, 10);
+            if (end == s || a < 0) return false;
+            s = end;
+            b = a;
+            if (*s == '-') {
+                ++s;
+                b = std::strtoll(s, &end, 10);
+                if (end == s || b < a) return false;
+                s = end;
+                if (*s == ':') {
+                    ++s;
+                    step = std::strtoll(s, &end, 10);
+                    if (end == s || step < 1) return false;
+                    s = end;
+                }
+            }
+        }
+        if (*s && *s != ' ' && *s != '\t' && *s != ',') return false;
+        for (int64_t i = a; i <= b && i < npoints; i += step) mask[(size_t)i] = remove ? 0 : 1;
+    }
+    return true;
+}
 
 bool ProximityCapture::init(const Geo& mesh, const Geo& rig)
 {
@@ -162,7 +208,8 @@ CookStatus FaceDeformOp::cook(const Geo& mesh, const Geo& rest_rig, const float*
     }
     // Create / build the model (:331-368).  The reference rebuilds it every cook; here the factorisation is kept
     // while the rest rig and the fit parameters are unchanged ("once per rest pose").
-    const bool refit = !m_model || rest_rig_changed || std::memcmp(&m_fit_parms, &p, sizeof(p)) != 0;
+    // A parameter the fit does not depend on (tangent, falloff, maxedges, morph space, group ...) keeps the factorisation.
+    const bool refit = !m_model || rest_rig_changed || !fd_params_fit_equal(&m_fit_parms, &p);
     if (refit) {
         if (m_model) {
             fd_model_destroy(m_model);
@@ -178,9 +225,12 @@ CookStatus FaceDeformOp::cook(const Geo& mesh, const Geo& rest_rig, const float*
             addError("Can't build RBF model."); // :337-340
             return COOK_ERROR;
         }
-        m_fit_parms = p;
         ++m_fit_counter;
+    } else if (fd_model_set_epilogue(m_model, &p) != FD_OK) {
+        addError(fd_last_error(m_ctx));
+        return COOK_ERROR;
     }
+    m_fit_parms = p;
     fd_report rep;
     int st = fd_rbf_solve(m_model, deform_rig_P, (int32_t)deform_npoints, frames, &rep);
     if (st != FD_OK) {
@@ -191,8 +241,26 @@ CookStatus FaceDeformOp::cook(const Geo& mesh, const Geo& rest_rig, const float*
     std::snprintf(info_buffer, sizeof(info_buffer), "Termination type: %d, Iterations: %d", rep.terminationtype,
                   rep.iterationscount); // :370-373
     addMessage(info_buffer);
+    // Here we determine which groups we have to work on (cookInputGroups, :380-381).  The reference resolves the group
+    // and then never consults it inside the loop (:404-439): it only gates the data-ID bump (:485-486).
+    // strict_reference = 1 reproduces that; otherwise the points outside the group are left where they are.
+    std::vector<uint8_t> gmask;
+    const bool have_group = p.group[0] != 0;
+    if (have_group && !resolvePointGroup(p.group, mesh.npoints, gmask)) {
+        addError("Invalid point group pattern.");
+        return COOK_ERROR;
+    }
+    bool group_empty = have_group;
+    for (size_t i = 0; i < gmask.size() && group_empty; ++i) group_empty = gmask[i] == 0;
+    m_p_bumped = !have_group || !group_empty;
     const float* dist = m_mesh_capture.getDistanceAttribute();
     if (!dist) addWarning("Can't find distance capture attribute. Won't apply radius nor falloff."); // :396-398
+    if (have_group && !p.strict_reference) {
+        // outside the group: a distance beyond every radius, which the gate of :408-410 skips (P stays, falloff 0)
+        m_group_dist.resize((size_t)mesh.npoints);
+        for (int64_t i = 0; i < mesh.npoints; ++i) m_group_dist[(size_t)i] = gmask[(size_t)i] ? (dist ? dist[i] : 0.0f) : INFINITY;
+        dist = m_group_dist.data();
+    }
     st = fd_rbf_eval(m_model, mesh.P, mesh.npoints, dist, do_tangent_disp ? mesh.tangentu : nullptr,
                      do_tangent_disp ? mesh.tangentv : nullptr, do_tangent_disp ? mesh.N : nullptr, P_out, falloff_out);
     if (st != FD_OK) {
@@ -219,9 +287,12 @@ CookStatus FaceDeformOp::cook(const Geo& mesh, const Geo& rest_rig, const float*
             const float* clamp = p.doclampweight ? p.weightrange : nullptr; // :455-458
             for (int f = 0; f < frames; ++f) {
                 float* Pf = P_out + (size_t)f * mesh.npoints * 3;
-                // The reference computes the weights only while !isComputed() and warns otherwise (:448-452), so a
-                // second cook would skip the pass; here they are recomputed for every cooked frame.
-                if (!m_direct_blends->computeWeights(Pf, mesh.P)) {
+                // The reference computes the weights only while !isComputed() and warns otherwise (:446-452): after the
+                // first cook that followed an init() the pass is skipped.  strict_reference = 1 reproduces that; the
+                // default recomputes the weights for every cooked frame.
+                bool weights_done = false;
+                if (!p.strict_reference || !m_direct_blends->isComputed()) weights_done = m_direct_blends->computeWeights(Pf, mesh.P);
+                if (!weights_done) {
                     addWarning("Can't compute weights for morphspace deformation. Ingoring it."); // :451-452
                     break;
                 }
@@ -277,6 +348,7 @@ const char* fd_sop_messages(fd_sop* s, int kind)
 }
 
 int fd_sop_fit_count(const fd_sop* s) { return s ? s->op.fits() : 0; }
+int fd_sop_positions_bumped(const fd_sop* s) { return (s && s->op.positionsBumped()) ? 1 : 0; }
 
 int fd_sop_set_blendshapes(fd_sop* s, const float* shapes, int32_t n_shapes, int64_t n_pts, int64_t data_id)
 {

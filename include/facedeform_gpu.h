@@ -22,8 +22,9 @@
  * Conventions: plain pointers and sizes only; the caller owns every host pointer, the
  * library owns device memory; every function returns an fd_status and never throws or aborts; handles carry all
  * state (no globals), so different handles may be used from different host threads.  One fd_ctx drives one GPU:
- * multi-GPU runs use one process (or thread) and one ctx per GPU, vertex ranges sharded by the caller, weights
- * moved with fd_model_weights_dev + fd_model_commit_weights around the caller's broadcast.
+ * multi-GPU runs use either fd_mgpu_* (one process, the library owns the devices and the weight broadcast) or one
+ * process / thread and one ctx per GPU, vertex ranges sharded by the caller, weights moved with fd_model_weights_dev +
+ * fd_model_commit_weights around the caller's broadcast (torch.distributed in facedeform_b200/shard.py).
  *
  * The `*_dev` variants take device pointers, enqueue on the ctx stream and return without synchronising.
  */
@@ -37,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FD_ABI_VERSION 2
+#define FD_ABI_VERSION 3
 
 typedef struct fd_ctx fd_ctx;     /* one GPU + stream + scratch; replaces the node-member state, SOP_FaceDeform.hpp:108-113 */
 typedef struct fd_model fd_model; /* replaces alglib::rbfmodel (SOP_FaceDeform.cpp:332): centres, radii, LU factors, weights */
@@ -106,6 +107,16 @@ typedef struct fd_params {
     int32_t eval_path;     /* FD_PATH_* */
     int32_t factor_precision; /* FD_FACTOR_* */
     int32_t fidelity;         /* FD_FIDELITY_* */
+    int32_t strict_reference; /* default 0.  1: reproduce the reference's quirks that this library otherwise normalises:
+                                 the point `group` never restricts the loop (it only gates the data-ID bump, :380-381,
+                                 :485-486) and the morph-space weights are computed only while !isComputed(), later cooks
+                                 skip the pass with the reference's warning (:446-452).  0: the group restricts the
+                                 deformation, the weights follow every cooked frame. */
+    float eval_tolerance;     /* default 1e-5: FD_EVAL_AUTO keeps the FP32 evaluation (FMA/SFU or tensor cores) only while
+                                 its predicted error stays below HALF of eval_tolerance x the control rig's bounding-box
+                                 diagonal, and switches to the FP64 evaluation otherwise */
+    char group[64];           /* "group"  default ""  (all points)  :119-120  point-group pattern: "*", "7", "3-40",
+                                 "0-100:2", "^5" (remove), space separated; resolved by the host mirror (facedeform_sop.hpp) */
 } fd_params;
 
 /* analogue of alglib::rbfreport (SOP_FaceDeform.cpp:333, :365-373) */
@@ -120,6 +131,11 @@ typedef struct fd_report {
     double min_pivot;        /* min |u_kk| of the LU */
     double max_pivot;
     double residual;         /* FD_FACTOR_FP32_IR: max |B - A X| / max |B| after the last sweep (0 otherwise) */
+    double cancellation;     /* after a solve: S = max_i sum_j max_c |w_jc| phi_j(c_i), the size of the terms that cancel in
+                                the evaluation sum; an FP32 evaluation errs by about 2^-24 S */
+    int32_t eval_kernel;     /* after a solve: the evaluation FD_EVAL_AUTO / FD_PATH_AUTO settled on: 1 FMA/SFU FP32,
+                                2 tensor cores (FP16 hi/lo splits), 3 FP64 */
+    int32_t reserved2;
 } fd_report;
 
 int fd_abi_version(void);
@@ -127,6 +143,10 @@ const char* fd_status_string(int status);
 
 void fd_params_default(fd_params* p);
 void fd_params_clamp(fd_params* p); /* SOP_FaceDeform.cpp:249-257 */
+/* 1 when a model fitted with `a` serves a cook with `b` without a refit: only epilogue parameters differ (tangent,
+ * dofalloff, falloffrate, falloffradius, maxedges, the morph-space and group parameters, and `radius` when it is only
+ * the capture / falloff radius, i.e. model = QNN).  The reference refits every cook (SOP_FaceDeform.cpp:331-363). */
+int fd_params_fit_equal(const fd_params* a, const fd_params* b);
 
 /* device < 0: current CUDA device.  stream: a cudaStream_t (NULL = the ctx creates its own). */
 int fd_ctx_create(fd_ctx** out, int device, void* stream);
@@ -144,6 +164,9 @@ void fd_model_destroy(fd_model* m);
 int fd_rbf_solve(fd_model* m, const float* deform_ctrl /* F x N x 3 host */, int32_t n_ctrl, int32_t frames,
                  fd_report* report /* may be NULL */);
 int fd_rbf_solve_dev(fd_model* m, const float* deform_ctrl_dev, int32_t n_ctrl, int32_t frames);
+
+/* the epilogue parameters of later fd_rbf_eval calls (see fd_params_fit_equal); FD_E_INVALID when `p` needs a refit */
+int fd_model_set_epilogue(fd_model* m, const fd_params* p);
 
 /* synchronises the ctx stream and reads the status flags of the last fit/solve; returns FD_OK or FD_E_SINGULAR */
 int fd_model_report(fd_model* m, fd_report* report);
@@ -167,6 +190,38 @@ int fd_model_commit_weights(fd_model* m);
 int fd_model_info(const fd_model* m, int32_t* n_ctrl, int32_t* npoly, int32_t* frames, int32_t* weights_ld);
 /* copies weights to the host as (N + npoly) x 3F row-major doubles, radii as N doubles (either may be NULL) */
 int fd_model_get_weights(fd_model* m, double* weights, double* radii);
+
+/* ---- serialise: the reference's intent at SOP_FaceDeform.cpp:377 (alglib::rbfserialize, commented out) ------
+ * fd_model_save writes parameters, centres, radii, the factorisation (FP64 dense fits) and the weights of the last
+ * solve into `buf`; buf == NULL queries the size.  fd_model_load rebuilds a model on `ctx` that solves (when the
+ * factorisation was saved) and evaluates bit-identically to the saved one. */
+int fd_model_save(fd_model* m, void* buf, size_t cap, size_t* bytes);
+int fd_model_load(fd_ctx* ctx, const void* buf, size_t bytes, fd_model** out);
+
+/* ---- several GPUs of one box behind one handle (single process) -------------------------------------
+ * The evaluation loop SOP_FaceDeform.cpp:404-439 has no cross-vertex dependence, so it is partitioned by contiguous
+ * vertex range over the devices; device devices[0] assembles, factors and solves, then the weights cross NVLink once:
+ * transport "nccl" (ncclBroadcast of the FP64 weight block, libnccl.so.2 loaded at run time), or "p2p" (each device
+ * builds its evaluation tables straight from the root's weight block through peer loads -- broadcast and pack in one
+ * kernel -- falling back to cudaMemcpyPeerAsync where the evaluation needs the FP64 block itself).
+ * Host buffers in, host buffers out (each device copies its vertex range), results in the caller's vertex order. */
+typedef struct fd_mgpu fd_mgpu;
+#define FD_MGPU_AUTO 0 /* p2p when every device reaches the root by peer access, else nccl */
+#define FD_MGPU_NCCL 1
+#define FD_MGPU_P2P 2
+int fd_mgpu_create(fd_mgpu** out, const int* devices, int32_t ndev, int32_t transport);
+void fd_mgpu_destroy(fd_mgpu* g);
+int fd_mgpu_fit(fd_mgpu* g, const fd_params* params, const float* rest_ctrl, int32_t n_ctrl, fd_report* report);
+int fd_mgpu_solve(fd_mgpu* g, const float* deform_ctrl, int32_t n_ctrl, int32_t frames, fd_report* report);
+int fd_mgpu_eval(fd_mgpu* g, const float* P, int64_t n_vtx, const float* dist2, const float* tangentu,
+                 const float* tangentv, const float* normal, float* P_out, float* falloff_out);
+/* ndev, transport in use (FD_MGPU_NCCL / FD_MGPU_P2P), bytes that crossed NVLink in the last solve, and the device
+ * time (ms, max over devices) from the root's solve end to the last device's tables being ready */
+int fd_mgpu_info(const fd_mgpu* g, int32_t* ndev, int32_t* transport, int64_t* bcast_bytes, float* bcast_ms);
+/* vertex range [begin, end) of device slot `i` for n_vtx vertices (the partition fd_mgpu_eval uses) */
+int fd_mgpu_range(const fd_mgpu* g, int32_t i, int64_t n_vtx, int64_t* begin, int64_t* end);
+fd_ctx* fd_mgpu_ctx(fd_mgpu* g, int32_t i);
+const char* fd_mgpu_last_error(const fd_mgpu* g);
 
 /* ---- capture ------------------------------------------------------------------------------------------------
  * mesh P + polygons (CSR) and rig points + primitives (CSR; 2 vertices = segment, >= 3 = fan-triangulated
@@ -217,6 +272,8 @@ int fd_sop_cook(fd_sop* s, const float* mesh_P, int64_t n_vtx, const int32_t* po
                 float* falloff_out);
 const char* fd_sop_messages(fd_sop* s, int kind); /* 0 errors, 1 warnings, 2 messages */
 int fd_sop_fit_count(const fd_sop* s);
+/* 1 when the last cook bumped P's data ID: `!myGroup || !myGroup->isEmpty()` (SOP_FaceDeform.cpp:485-486) */
+int fd_sop_positions_bumped(const fd_sop* s);
 /* inputs >= 3 of the SOP (blendshapes of the morph-space pass, `morphspace` parm): n_shapes x n_pts x 3 floats, copied */
 int fd_sop_set_blendshapes(fd_sop* s, const float* shapes, int32_t n_shapes, int64_t n_pts, int64_t data_id);
 /* the "weights" detail attribute of the last cook (SOP_FaceDeform.cpp:474-480); returns their count */

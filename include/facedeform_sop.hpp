@@ -82,6 +82,9 @@ private:
     int m_shapes = 0;
 };
 
+// the `group` parm's pattern -> per-point membership (cookInputPointGroups, SOP_FaceDeform.cpp:155-173); false = syntax error
+bool resolvePointGroup(const char* pattern, int64_t npoints, std::vector<uint8_t>& mask);
+
 // status of a cook, the analogue of OP_ERROR + the node's message lists
 enum CookStatus { COOK_OK = 0, COOK_WARNING = 1, COOK_ERROR = 2 };
 
@@ -124,6 +127,8 @@ public:
     const ProximityCapture& capture() const { return m_mesh_capture; }
     fd_ctx* ctx() const { return m_ctx; }
     int fits() const { return m_fit_counter; } // how many times the system was factored (once per rest pose)
+    // whether the last cook bumped P's data ID: `!myGroup || !myGroup->isEmpty()` (SOP_FaceDeform.cpp:485-486)
+    bool positionsBumped() const { return m_p_bumped; }
 
 private:
     void addError(const std::string& s) { m_errors.push_back(s); }
@@ -145,6 +150,8 @@ private:
     int m_cap_maxedges = -1, m_cap_dofalloff = -1; // the parameters of the last capture (FIXME of SOP_FaceDeform.cpp:310)
     float m_cap_radius = -1.f;
     int m_fit_counter = 0;
+    bool m_p_bumped = true;
+    std::vector<float> m_group_dist; // capture distances with the points outside `group` pushed beyond every radius
     std::vector<std::string> m_errors, m_warnings, m_messages;
 };
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in facedeform_gpu.h but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert L.fd_abi_version() == 2
+    assert L.fd_abi_version() == 3
 
 
 def test_params_defaults_and_clamps_match_the_sop():
@@ -100,3 +100,25 @@ def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_mirror(tmp_path):
         kind, name, off = line.split()
         struct = FdParams if kind == "p" else FdReport
         assert getattr(struct, name).offset == int(off), (kind, name)
+
+
+def test_fit_equal_separates_fit_from_epilogue_parameters():
+    """fd_params_fit_equal: what FaceDeformOp's refit decision compares (the reference refits every cook, :331-363)."""
+    import ctypes as C
+    from facedeform_b200 import _lib, make_params
+    L = _lib.load()
+    eq = lambda a, b: L.fd_params_fit_equal(C.byref(a), C.byref(b))
+    base = make_params(model=1, radius=0.3)
+    for kw in (dict(tangent=1), dict(dofalloff=1), dict(falloffrate=3.0), dict(falloffradius=0.5), dict(maxedges=9),
+               dict(morphspace=1), dict(doclampweight=1), dict(group="0-10"), dict(strict_reference=1), dict(layers=7),
+               dict(qcoef=2.0)):
+        assert eq(base, make_params(model=1, radius=0.3, **kw)) == 1, kw
+    for kw in (dict(radius=0.31), dict(term=1), dict(kernel=1), dict(model=0), dict(eval_precision=2), dict(eval_path=1),
+               dict(factor_precision=1), dict(fidelity=1), dict(eval_tolerance=1e-6), {"lambda": 0.5}):
+        q = make_params(**{**dict(model=1, radius=0.3), **kw})
+        assert eq(base, q) == 0, kw
+    qnn = make_params(model=0)
+    assert eq(qnn, make_params(model=0, radius=7.0)) == 1      # QNN: `radius` is only the capture / falloff radius
+    assert eq(qnn, make_params(model=0, zcoef=4.0)) == 0
+    v1 = make_params(model=1, fidelity=1, layers=3)
+    assert eq(v1, make_params(model=1, fidelity=1, layers=4)) == 0

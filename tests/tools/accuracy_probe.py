@@ -1,4 +1,6 @@
-"""max |P_gpu - P_oracle| / bbox diagonal of the FP32 evaluation paths (tensor-core and FMA/SFU) by control-point count.
+"""max |P_gpu - P_oracle| / bbox diagonal of the evaluation paths (FP32 tensor-core and FMA/SFU forced, FD_EVAL_AUTO, FP64) by
+control-point count, next to the cancellation estimate S (fd_report.cancellation) and the error model 2^-24 S that
+FD_EVAL_AUTO decides with -- the calibration of ERR_COEF_* in csrc/fd_eval64.cu.
 Usage: python tests/tools/accuracy_probe.py [N ...]   (the oracle fit at N = 4096 takes ~15 s of CPU)"""
 import os
 import sys
@@ -25,13 +27,20 @@ def main():
         st, rad, W = o.fit(op, rig.rest, deform[frames])
         ref, _ = o.evaluate(op, rig.rest, rad, W, mesh.P[idx], nthreads=o.num_threads())
         row = {}
-        for name, path in (("tensor", 2), ("simt", 1)):
-            p = make_params(model=1, term=0, kernel=0, radius=R, eval_path=path, **{"lambda": 0.0})
+        S = 0.0
+        for name, path, prec in (("tensor", 2, 1), ("simt", 1, 1), ("auto", 0, 0), ("fp64", 0, 2)):
+            p = make_params(model=1, term=0, kernel=0, radius=R, eval_path=path, eval_precision=prec, **{"lambda": 0.0})
             m = ctx.fit(p, rig.rest).solve(deform)
             out, _ = m.eval(mesh.P)
+            rep = m.report()
+            S = max(S, rep.cancellation)
             row[name] = float(np.abs(out[frames][:, idx].astype(np.float64) - ref).max() / mesh.bbox_diag)
+            row[name + "_kernel"] = rep.eval_kernel
             m.close()
-        print(f"N={N:5d} F={F} max err / bbox diag: tensor {row['tensor']:.3e}  simt {row['simt']:.3e}", flush=True)
+        unit = 2.0 ** -24 * S / mesh.bbox_diag
+        print(f"N={N:5d} F={F} max err / bbox diag: tensor {row['tensor']:.3e} ({row['tensor'] / unit:.2f} x 2^-24 S)  "
+              f"simt {row['simt']:.3e} ({row['simt'] / unit:.2f} x)  auto {row['auto']:.3e} [kernel {row['auto_kernel']}]  "
+              f"fp64 {row['fp64']:.3e}   S = {S:.3e}, 2^-24 S / diag = {unit:.3e}", flush=True)
     ctx.close()
 
 
