@@ -510,7 +510,7 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
     if (e == cudaSuccess && m->ns) {
         // the definite (N - 4) x (N - 4) block of Q^T K Q, in place
         e = fd_launch_lu_nopivot_fused(ctx, m->d_A + (size_t)4 * m->lda + 4, m->lda, m->N - 4, m->d_ipiv, m->d_perm, m->d_flags,
-                                       m->d_pivstat, m->d_Tinv);
+                                       m->d_pivstat, m->d_Tinv, 1);
     } else if (e == cudaSuccess && m->f32ir) {
         // FP32 factorisation of fl32(A); d_A keeps the FP64 system for the residuals of the refinement (fd_refine.cu)
         e = fd_launch_to_f32(ctx, m->d_A, m->d_A32, (size_t)m->lda * m->n);
@@ -519,7 +519,7 @@ int fd_rbf_fit_dev(fd_ctx* ctx, const fd_params* params, const float* rest_ctrl_
                     : fd_launch_lu_f32(ctx, m->d_A32, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_win);
     } else if (e == cudaSuccess) {
         if (spd && !unfused) {
-            e = fd_launch_lu_nopivot_fused(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_Tinv);
+            e = fd_launch_lu_nopivot_fused(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_Tinv, 1);
         } else {
             e = spd ? fd_launch_lu_nopivot(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat)
                     : fd_launch_lu(ctx, m->d_A, m->lda, m->n, m->d_ipiv, m->d_perm, m->d_flags, m->d_pivstat, m->d_win);

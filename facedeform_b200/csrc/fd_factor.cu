@@ -35,7 +35,9 @@ __device__ __forceinline__ float2 fd_make2(float a, float b) { return make_float
 #define REAL double
 #define REAL2 double2
 #define FD_LU_NS lu_f64
+#define FD_LU_DMMA 1 // the tile product of the fused LU on the FP64 tensor pipe (mma.sync.m8n8k4.f64)
 #include "fd_factor_impl.inl"
+#undef FD_LU_DMMA
 #undef REAL
 #undef REAL2
 #undef FD_LU_NS
@@ -66,10 +68,11 @@ cudaError_t fd_launch_lu_nopivot(fd_ctx* ctx, double* d_A, int lda, int n, int* 
 {
     return lu_f64::launch_lu_nopivot(ctx, d_A, lda, n, d_ipiv, d_perm, d_flags, d_pivstat);
 }
+// sym != 0: the matrix is symmetric (K + lambda I with its polynomial border, or the reduced null-space block)
 cudaError_t fd_launch_lu_nopivot_fused(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
-                                       double* d_pivstat, double* d_Tinv)
+                                       double* d_pivstat, double* d_Tinv, int sym)
 {
-    return lu_f64::launch_lu_nopivot_fused(ctx, d_A, lda, n, d_ipiv, d_perm, d_flags, d_pivstat, d_Tinv);
+    return lu_f64::launch_lu_nopivot_fused(ctx, d_A, lda, n, d_ipiv, d_perm, d_flags, d_pivstat, d_Tinv, sym);
 }
 cudaError_t fd_launch_lu_f32(fd_ctx* ctx, float* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                              double* d_pivstat, int* d_win)

@@ -797,9 +797,17 @@ cudaError_t launch_lu(fd_ctx* ctx, REAL* d_A, int lda, int n, int* d_ipiv, int* 
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int FZ_THREADS = 256;
 constexpr int FZ_KC = 16;          // K chunk of the tile product
-constexpr int FZ_LDB = FZ_KC + 2;  // row stride of the U12 stage ([col][k], k contiguous)
 constexpr int FZ_TMAX = 128;       // largest CTA tile edge
-constexpr int FZ_SMEM_REALS = 2 * FZ_KC * FZ_TMAX + 2 * FZ_TMAX * FZ_LDB + 2 * NB * NB + NB;
+#ifdef FD_LU_DMMA
+// FP64: the tile product runs on the FP64 tensor pipe (mma.sync.m8n8k4.f64).  Both stage strides are = 4 mod 16 doubles,
+// which makes the fragment loads of a half warp (4 rows x 4 k) hit 16 different 8-byte banks.
+constexpr int FZ_LDA = FZ_TMAX + 4; // row stride of the L21 stage ([k][row], rows contiguous)
+constexpr int FZ_LDB = FZ_KC + 4;   // row stride of the U12 stage ([col][k], k contiguous)
+#else
+constexpr int FZ_LDA = FZ_TMAX;
+constexpr int FZ_LDB = FZ_KC + 2;
+#endif
+constexpr int FZ_SMEM_REALS = 2 * FZ_KC * FZ_LDA + 2 * FZ_TMAX * FZ_LDB + 2 * NB * NB + NB;
 
 __device__ __forceinline__ void fz_cp_async(REAL* smem_dst, const REAL* gsrc)
 {
@@ -833,6 +841,91 @@ __device__ __forceinline__ void fz_barrier(unsigned* counter, unsigned& target, 
     }
 }
 
+#ifdef FD_LU_DMMA
+// C[r0:r0+TM, c0:c0+TN] -= A[r0:, ka:kb] * A[ka:kb, c0:] on the FP64 tensor pipe; stores clipped to rows < r1, columns < c1.
+// kb - ka is a multiple of 16, r0 / ka of 32.  Loads beyond the matrix are clamped to valid addresses (results dropped).
+// 8 warps as 4 (rows) x 2 (columns); a warp owns (TM / 4) x (TN / 2) outputs = MT x NT accumulator tiles of 8 x 8 and
+// loads MT + NT fragments per MT * NT DMMAs (TM = TN = 128: 12 loads per 32 DMMAs = 8192 FMAs -- the DFMA version read
+// 16 bytes of shared memory per 16 FMAs and was bound by that).  The stage holds -L21 is not needed: the A fragment is
+// negated in registers (4 DADD per 32 DMMAs).
+template <int TM, int TN>
+__device__ __forceinline__ void fz_gemm_tile(REAL* A, int lda, int n, int r0, int r1, int c0, int c1, int ka, int kb,
+                                             REAL* s_a, REAL* s_b)
+{
+    constexpr int WR = TM / 4, WC = TN / 2, MT = WR / 8, NT = WC / 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2, fr = lane >> 2, fk = lane & 3;
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) {
+        const int c = c0 + wn * WC + ni * 8 + 2 * fk;
+        const double* col0 = A + (size_t)min(c, n - 1) * lda;
+        const double* col1 = A + (size_t)min(c + 1, n - 1) * lda;
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+            const int r = min(r0 + wm * WR + mi * 8 + fr, lda - 1);
+            acc[mi][ni][0] = __ldcg(col0 + r);
+            acc[mi][ni][1] = __ldcg(col1 + r);
+        }
+    }
+    auto issue = [&](int kc, int st) {
+        REAL* sa = s_a + st * FZ_KC * FZ_LDA;
+        for (int t = tid; t < FZ_KC * (TM / 2); t += FZ_THREADS) {
+            const int kk = t / (TM / 2), q = t % (TM / 2);
+            const int r = min(r0 + 2 * q, lda - 2);
+            fz_cp_async(sa + kk * FZ_LDA + 2 * q, A + (size_t)(ka + kc + kk) * lda + r);
+        }
+        REAL* sb = s_b + st * FZ_TMAX * FZ_LDB;
+        for (int t = tid; t < TN * (FZ_KC / 2); t += FZ_THREADS) {
+            const int cc = t / (FZ_KC / 2), q = t % (FZ_KC / 2);
+            const int c = min(c0 + cc, n - 1);
+            fz_cp_async(sb + cc * FZ_LDB + 2 * q, A + (size_t)c * lda + ka + kc + 2 * q);
+        }
+        fz_cp_commit();
+    };
+    const int nch = (kb - ka) / FZ_KC;
+    issue(0, 0);
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) {
+            issue((ch + 1) * FZ_KC, (ch + 1) & 1);
+            fz_cp_wait<1>();
+        } else {
+            fz_cp_wait<0>();
+        }
+        __syncthreads();
+        const double* sa = s_a + (ch & 1) * FZ_KC * FZ_LDA + fk * FZ_LDA + wm * WR + fr;
+        const double* sb = s_b + (ch & 1) * FZ_TMAX * FZ_LDB + (wn * WC + fr) * FZ_LDB + fk;
+#pragma unroll
+        for (int k4 = 0; k4 < FZ_KC / 4; ++k4) {
+            double af[MT], bf[NT];
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi) af[mi] = -sa[k4 * 4 * FZ_LDA + mi * 8];
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) bf[ni] = sb[ni * 8 * FZ_LDB + k4 * 4];
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < NT; ++ni)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
+                                 : "d"(af[mi]), "d"(bf[ni]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) {
+        const int c = c0 + wn * WC + ni * 8 + 2 * fk;
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+            const int r = r0 + wm * WR + mi * 8 + fr;
+            if (r < r1) {
+                if (c < c1) __stcg(A + (size_t)c * lda + r, acc[mi][ni][0]);
+                if (c + 1 < c1) __stcg(A + (size_t)(c + 1) * lda + r, acc[mi][ni][1]);
+            }
+        }
+    }
+}
+#else
 // C[r0:r0+TM, c0:c0+TN] -= A[r0:, ka:kb] * A[ka:kb, c0:]; stores clipped to rows < r1, columns < c1.  kb - ka is a
 // multiple of 16, r0 / ka of 32.  Loads beyond the matrix are clamped to valid addresses (their results are dropped).
 template <int TM, int TN>
@@ -854,11 +947,11 @@ __device__ __forceinline__ void fz_gemm_tile(REAL* A, int lda, int n, int r0, in
         }
     }
     auto issue = [&](int kc, int st) {
-        REAL* sa = s_a + st * FZ_KC * FZ_TMAX;
+        REAL* sa = s_a + st * FZ_KC * FZ_LDA;
         for (int t = tid; t < FZ_KC * (TM / 2); t += FZ_THREADS) {
             const int kk = t / (TM / 2), q = t % (TM / 2);
             const int r = min(r0 + 2 * q, lda - 2);
-            fz_cp_async(sa + kk * FZ_TMAX + 2 * q, A + (size_t)(ka + kc + kk) * lda + r);
+            fz_cp_async(sa + kk * FZ_LDA + 2 * q, A + (size_t)(ka + kc + kk) * lda + r);
         }
         REAL* sb = s_b + st * FZ_TMAX * FZ_LDB;
         for (int t = tid; t < TN * (FZ_KC / 2); t += FZ_THREADS) {
@@ -878,15 +971,15 @@ __device__ __forceinline__ void fz_gemm_tile(REAL* A, int lda, int n, int r0, in
             fz_cp_wait<0>();
         }
         __syncthreads();
-        const REAL* sa = s_a + (ch & 1) * FZ_KC * FZ_TMAX + 2 * tr;
+        const REAL* sa = s_a + (ch & 1) * FZ_KC * FZ_LDA + 2 * tr;
         const REAL* sb = s_b + (ch & 1) * FZ_TMAX * FZ_LDB + tcg * FZ_LDB;
 #pragma unroll 2
         for (int kk = 0; kk < FZ_KC; kk += 2) {
             REAL2 a0[MP], a1[MP], b[TNt];
 #pragma unroll
             for (int i = 0; i < MP; ++i) {
-                a0[i] = *reinterpret_cast<const REAL2*>(sa + kk * FZ_TMAX + 32 * i);
-                a1[i] = *reinterpret_cast<const REAL2*>(sa + (kk + 1) * FZ_TMAX + 32 * i);
+                a0[i] = *reinterpret_cast<const REAL2*>(sa + kk * FZ_LDA + 32 * i);
+                a1[i] = *reinterpret_cast<const REAL2*>(sa + (kk + 1) * FZ_LDA + 32 * i);
             }
 #pragma unroll
             for (int j = 0; j < TNt; ++j) b[j] = *reinterpret_cast<const REAL2*>(sb + 16 * j * FZ_LDB + kk);
@@ -923,6 +1016,8 @@ __device__ __forceinline__ void fz_gemm_tile(REAL* A, int lda, int n, int r0, in
     }
 }
 
+#endif
+
 // One K range applied to up to two rectangular regions (the L-shaped border: column panel + row panel; or the
 // interior alone), tiles dealt round-robin to the CTAs.  One call site per tile size keeps the kernel's code small:
 // every phase runs once per block step, so code that does not fit the instruction cache runs at fetch speed.
@@ -930,11 +1025,32 @@ struct FzRegions {
     int ra0, ra1, ca0, ca1; // region a: rows [ra0, ra1) x columns [ca0, ca1)
     int rb0, rb1, cb0, cb1; // region b
     int ka, kb;
+    int sym;                // symmetric matrix: region a starts on the diagonal (ra0 == ca0) and only its tiles that touch
+                            // the lower triangle (tile row >= tile column) are updated; region b is empty
 };
+
+// tiles of region a in the symmetric case: tile column j holds the tile rows j .. nrt - 1
+__device__ __forceinline__ int fz_sym_tiles(int nrt, int nct)
+{
+    const int full = min(nrt, nct);
+    return full * nrt - full * (full - 1) / 2;
+}
 
 template <int T>
 __device__ __noinline__ void fz_update(REAL* A, int lda, int n, const FzRegions R, REAL* s_a, REAL* s_b)
 {
+    if (R.sym) {
+        if (R.ra1 <= R.ra0 || R.ca1 <= R.ca0) return;
+        const int nrt = (R.ra1 - R.ra0 + T - 1) / T, nct = (R.ca1 - R.ca0 + T - 1) / T;
+        const int total = fz_sym_tiles(nrt, nct);
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            int j = 0, rem = t; // tile column j: nrt - j tiles
+            while (rem >= nrt - j) { rem -= nrt - j; ++j; }
+            const int i = j + rem;
+            fz_gemm_tile<T, T>(A, lda, n, R.ra0 + i * T, R.ra1, R.ca0 + j * T, R.ca1, R.ka, R.kb, s_a, s_b);
+        }
+        return;
+    }
     const int ta_r = R.ra1 > R.ra0 && R.ca1 > R.ca0 ? (R.ra1 - R.ra0 + T - 1) / T : 0;
     const int ta = ta_r * ((R.ca1 - R.ca0 + T - 1) / T);
     const int tb_r = R.rb1 > R.rb0 && R.cb1 > R.cb0 ? (R.rb1 - R.rb0 + T - 1) / T : 0;
@@ -952,6 +1068,10 @@ __device__ __noinline__ void fz_update(REAL* A, int lda, int n, const FzRegions 
 
 __device__ __forceinline__ int fz_tiles(const FzRegions& R, int T)
 {
+    if (R.sym) {
+        if (R.ra1 <= R.ra0 || R.ca1 <= R.ca0) return 0;
+        return fz_sym_tiles((R.ra1 - R.ra0 + T - 1) / T, (R.ca1 - R.ca0 + T - 1) / T);
+    }
     const int ta = R.ra1 > R.ra0 && R.ca1 > R.ca0 ? ((R.ra1 - R.ra0 + T - 1) / T) * ((R.ca1 - R.ca0 + T - 1) / T) : 0;
     const int tb = R.rb1 > R.rb0 && R.cb1 > R.cb0 ? ((R.rb1 - R.rb0 + T - 1) / T) * ((R.cb1 - R.cb0 + T - 1) / T) : 0;
     return ta + tb;
@@ -998,14 +1118,14 @@ __device__ __forceinline__ REAL fz_safe_rcp(REAL p) { return (p != (REAL)0 && is
 template <bool CLUSTER>
 __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int lda, int n, int nbo, int* ipiv, int* perm,
                                                                   int* flags, double* pivstat, double* Tinv,
-                                                                  unsigned* sync_counter, unsigned sync_base, int dbg)
+                                                                  unsigned* sync_counter, unsigned sync_base, int dbg, int sym)
 {
     extern __shared__ __align__(16) unsigned char fz_smem_raw[];
     long long tprobe[12];
     int tstep = 0;
 #define FZ_PROBE(i) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0 && tstep == dbg) tprobe[i] = clock64(); } while (0)
     REAL* s_a = reinterpret_cast<REAL*>(fz_smem_raw);
-    REAL* s_b = s_a + 2 * FZ_KC * FZ_TMAX;
+    REAL* s_b = s_a + 2 * FZ_KC * FZ_LDA;
     REAL* s_U = s_b + 2 * FZ_TMAX * FZ_LDB; // [NB][NB]: U11 (row j valid from column j & ~1 on)
     REAL* s_Lt = s_U + NB * NB;             // [NB][NB]: s_Lt[j][r] = L11[r][j]
     REAL* s_inv = s_Lt + NB * NB;           // 1 / u_jj
@@ -1094,15 +1214,21 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int l
                 // 32 dealt round-robin to the warps 1..7 of all CTAs; the first group's loads are in flight while
                 // warp 0 factors.  Two more "groups" apply the same two solves to the identity: the inverses of U11
                 // and L11 that the slab solve (fd_solve.cu) multiplies with.
+                // A symmetric matrix (the no-pivot LU is only taken for symmetric systems) has U = D L^T: U12 is the scaled
+                // transpose of L21, so the column groups disappear -- every row group writes its 32 rows of L21 and, scaled
+                // by the pivots, the matching 32 columns of U12.  Only the lower triangle of the trailing matrix is
+                // ever updated then (the tile sets below), half the flops of the factorisation.
                 REAL x[NB];
-                const int ngroups = 2 * ngr + (Tinv != nullptr ? 2 : 0);
+                const int ncg = sym ? 0 : ngr;          // column groups
+                const int g_inv = ngr + ncg;            // first of the two inverse "groups"
+                const int ngroups = g_inv + (Tinv != nullptr ? 2 : 0);
                 int g = (int)blockIdx.x + (int)G * (warp - 1);
                 auto load_group = [&](int gg) {
                     if (gg < ngr) {
                         const int r = min(ks + 32 * gg + lane, n - 1);
 #pragma unroll
                         for (int c = 0; c < NB; ++c) x[c] = __ldcg(A + (size_t)(k0 + c) * lda + r);
-                    } else if (gg < 2 * ngr) {
+                    } else if (gg < g_inv) {
                         const int c = min(ks + 32 * (gg - ngr) + lane, n - 1);
                         const REAL2* src = reinterpret_cast<const REAL2*>(A + (size_t)c * lda + k0);
 #pragma unroll
@@ -1126,7 +1252,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int l
 #pragma unroll 1
                 for (bool first = true; g < ngroups; g += (int)G * (FZ_THREADS / 32 - 1), first = false) {
                     if (!first) load_group(g);
-                    const bool row_kind = g < ngr || g == 2 * ngr;
+                    const bool row_kind = g < ngr || g == g_inv;
                     if (row_kind)
                         fz_row_solve(x, s_U, s_inv);
                     else
@@ -1136,15 +1262,21 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int l
                         if (r < n) {
 #pragma unroll
                             for (int c = 0; c < NB; ++c) __stcg(A + (size_t)(k0 + c) * lda + r, x[c]);
+                            if (sym) { // U12[c][r] = u_cc * L21[r][c]: column r of the row panel, 32 contiguous values
+                                REAL2* dst = reinterpret_cast<REAL2*>(A + (size_t)r * lda + k0);
+#pragma unroll
+                                for (int c = 0; c < NB; c += 2)
+                                    __stcg(dst + c / 2, fd_make2(x[c] * s_U[c * NB + c], x[c + 1] * s_U[(c + 1) * NB + c + 1]));
+                            }
                         }
-                    } else if (g < 2 * ngr) {
+                    } else if (g < g_inv) {
                         const int c = ks + 32 * (g - ngr) + lane;
                         if (c < n) {
                             REAL2* dst = reinterpret_cast<REAL2*>(A + (size_t)c * lda + k0);
 #pragma unroll
                             for (int r = 0; r < NB; r += 2) __stcg(dst + r / 2, fd_make2(x[r], x[r + 1]));
                         }
-                    } else if (g == 2 * ngr) { // x[c] = U11^-1[lane][c]; stored transposed: out[c * 32 + r] = inverse[r][c]
+                    } else if (g == g_inv) { // x[c] = U11^-1[lane][c]; stored transposed: out[c * 32 + r] = inverse[r][c]
                         double* out = Tinv + ((size_t)(k0 / NB) * 2 + 1) * NB * NB;
 #pragma unroll
                         for (int c = 0; c < NB; ++c) out[c * NB + lane] = (double)x[c];
@@ -1161,7 +1293,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int l
             FZ_PROBE(6);
             // ---- L-shaped border of the outer block, K = 32
             if (ks < Kend) {
-                const FzRegions R = {ks, n, ks, Kend, ks, Kend, Kend, n, k0, ks};
+                const FzRegions R = {ks, n, ks, Kend, ks, Kend, Kend, n, k0, ks, sym};
                 if (fz_tiles(R, 128) >= 2 * (int)G)
                     fz_update<128>(A, lda, n, R, s_a, s_b);
                 else
@@ -1171,7 +1303,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int l
         }
         if (Kend < n) {
             // ---- interior of the trailing matrix, K = nbo
-            const FzRegions R = {Kend, n, Kend, n, 0, 0, 0, 0, K0, Kend};
+            const FzRegions R = {Kend, n, Kend, n, 0, 0, 0, 0, K0, Kend, sym};
             if (fz_tiles(R, 128) >= (int)G)
                 fz_update<128>(A, lda, n, R, s_a, s_b);
             else
@@ -1212,8 +1344,9 @@ static unsigned fz_barrier_count(int n, int nbo)
 }
 
 cudaError_t launch_lu_nopivot_fused(fd_ctx* ctx, REAL* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
-                                    double* d_pivstat, double* d_Tinv)
+                                    double* d_pivstat, double* d_Tinv, int sym)
 {
+    if (ctx->dbg.lu_sym_off) sym = 0;
     const size_t smem = (size_t)FZ_SMEM_REALS * sizeof(REAL);
     const fd_debug_opts& o = ctx->dbg;
     int dbg = o.lu_debug;
@@ -1239,10 +1372,10 @@ cudaError_t launch_lu_nopivot_fused(fd_ctx* ctx, REAL* d_A, int lda, int n, int*
         cfg.numAttrs = 1;
         ctx->launches += 1;
         return cudaLaunchKernelEx(&cfg, k_lu_nopiv_fused<true>, d_A, lda, n, nbo, d_ipiv, d_perm, d_flags, d_pivstat, d_Tinv,
-                                  ctx->d_sync, base, dbg);
+                                  ctx->d_sync, base, dbg, sym);
     }
     const int G = ctx->sm_count;
-    void* args[] = {&d_A, &lda, &n, &nbo, &d_ipiv, &d_perm, &d_flags, &d_pivstat, &d_Tinv, &ctx->d_sync, &base, &dbg};
+    void* args[] = {&d_A, &lda, &n, &nbo, &d_ipiv, &d_perm, &d_flags, &d_pivstat, &d_Tinv, &ctx->d_sync, &base, &dbg, &sym};
     const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_lu_nopiv_fused<false>, dim3(G), dim3(FZ_THREADS), args, smem, s);
     if (e == cudaSuccess) { // the counter only moves when the kernel that advances it was really enqueued
         ctx->sync_base = base + (unsigned)G * fz_barrier_count(n, nbo);

@@ -196,7 +196,7 @@ cudaError_t fd_launch_lu_nopivot(fd_ctx* ctx, double* d_A, int lda, int n, int* 
                                  double* d_pivstat);
 // one persistent launch; also writes the inverted diagonal blocks (d_Tinv) the slab solve uses
 cudaError_t fd_launch_lu_nopivot_fused(fd_ctx* ctx, double* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
-                                       double* d_pivstat, double* d_Tinv);
+                                       double* d_pivstat, double* d_Tinv, int sym);
 // fd_solve.cu
 cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int F);
 cudaError_t fd_launch_solve_prebuilt(fd_ctx* ctx, fd_model* m, int nrhs);

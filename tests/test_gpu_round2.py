@@ -52,7 +52,7 @@ def _case(oracle, N, F, V, kernel=0):
 
 
 # ---- the sizes VERDICT r1 found untested: Gaussian at N = 1024 / 2048, one frame and wide batches -----------------------
-@pytest.mark.parametrize("N", [1024, 2048])
+@pytest.mark.parametrize("N", [256, 1024, 2048])
 @pytest.mark.parametrize("F", [1, 120, 240])
 def test_gaussian_auto_meets_the_tolerance_with_margin(ctx, oracle, N, F):
     """FD_EVAL_AUTO: max |P_gpu - P_oracle| <= 0.5 x 1e-5 x bbox diagonal (a 2x margin under the stated tolerance),
@@ -66,14 +66,17 @@ def test_gaussian_auto_meets_the_tolerance_with_margin(ctx, oracle, N, F):
     print(f"N={N} F={F}: AUTO kernel {rep.eval_kernel} cancellation {rep.cancellation:.3e} err/diag {err:.3e}")
     assert rep.eval_kernel in (1, 2, 3)
     assert err <= 0.5e-5, f"err/diag {err:.3e} with kernel {rep.eval_kernel}"
+    if N == 256 and F == 240:
+        assert rep.eval_kernel == 2  # BASELINE configs[1] stays on the tensor cores
     m.close()
 
 
 @pytest.mark.parametrize("N", [256, 1024, 2048])
 @pytest.mark.parametrize("path", [1, 2])
 def test_fp32_error_follows_the_cancellation_model(ctx, oracle, N, path):
-    """forced FP32 (FMA/SFU and tensor cores): the error stays below twice the model coef x 2^-24 x S that
-    FD_EVAL_AUTO decides with (S = fd_report.cancellation), and within the stated 1e-5 at the benchmark's N = 256."""
+    """forced FP32 (FMA/SFU and tensor cores): the error stays below the model coef x 2^-24 x S that FD_EVAL_AUTO
+    decides with (S = fd_report.cancellation; 25 % slack for samples the calibration did not see), and within the
+    stated 1e-5 at the benchmark's N = 256."""
     from facedeform_b200 import make_params
     F = 120
     rig, deform, P, R, ref, diag = _case(oracle, N, F, 4096)
@@ -83,10 +86,10 @@ def test_fp32_error_follows_the_cancellation_model(ctx, oracle, N, path):
     rep = m.report()
     assert rep.eval_kernel == path
     err = float(np.abs(out.astype(np.float64) - ref).max())
-    coef = 0.75 if path == 1 else 1.1
+    coef = 0.65 if path == 1 else 0.85
     model = coef * 2.0 ** -24 * rep.cancellation
     print(f"N={N} path={path}: err/diag {err / diag:.3e} model/diag {model / diag:.3e} ratio {err / model:.2f}")
-    assert err <= 2.0 * model
+    assert err <= 1.25 * model  # the coefficients are the largest ratios of the calibration run, rounded up
     if N == 256:
         assert err <= 1e-5 * diag
     m.close()

@@ -143,7 +143,8 @@ def test_cook_recaptures_when_the_capture_parameters_change():
     sop.parms.maxedges = 12                                  # wider rings: more vertices grouped, more of them fall off
     st, out_b, fall_b = sop.cook(mesh, rig, deform)
     assert st == 0 and not np.array_equal(fall_a, fall_b)
-    sop.parms.radius = 4 * rig.spacing                      # also the RBF radius: re-fit and re-capture
+    assert sop.L.fd_sop_fit_count(sop.h) == 1               # maxedges is a capture parameter: no re-fit
+    sop.parms.radius = 4 * rig.spacing                      # also the RBF radius (model = Multilayer): re-fit and re-capture
     st, out_c, fall_c = sop.cook(mesh, rig, deform)
-    assert st == 0 and not np.array_equal(fall_b, fall_c) and sop.L.fd_sop_fit_count(sop.h) == 3   # any parm change re-fits
+    assert st == 0 and not np.array_equal(fall_b, fall_c) and sop.L.fd_sop_fit_count(sop.h) == 2
     sop.close()
