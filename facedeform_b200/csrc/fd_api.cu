@@ -465,7 +465,7 @@ void fd_model_destroy(fd_model* m)
     void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
                       m->d_ctab32, m->d_W32, m->d_ctab64, m->d_tc_norm, m->d_tc_scale, m->d_tc_unscale,
                       m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win, m->d_ctab_pair, m->d_A32, m->d_B, m->d_R, m->d_D32,
-                      m->d_ir_norm, m->d_v1_R, m->d_v1_K, m->d_v1_V, m->d_v1_stack, m->d_ns, m->d_sel, m->d_est, m->d_wmax};
+                      m->d_ir_norm, m->d_v1_R, m->d_v1_K, m->d_v1_V, m->d_v1_stack, m->d_ns, m->d_sel, m->d_est, m->d_wmax, m->d_inv, m->d_inv_rhs};
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;
@@ -575,7 +575,11 @@ int fd_rbf_solve_dev(fd_model* m, const float* deform_ctrl_dev, int32_t n_ctrl, 
     if (m->ns) { // D' = Q^T D, z = S^-1 D'[4:], a = R^-1 (D'[:4] - K'[:4, 4:] z), w = Q [0; z]
         m->tc_packed_by_solve = false;
         e = fd_launch_ns_rhs(ctx, m, deform_ctrl_dev, frames);
-        if (e == cudaSuccess)
+        cudaError_t e_inv = cudaSuccess;
+        if (e == cudaSuccess && fd_try_inverse_solve(ctx, m, m->d_A + (size_t)4 * m->lda + 4, m->lda, m->N - 4, m->d_perm, m->d_Tinv,
+                                                     nullptr, frames, m->d_W + (size_t)4 * m->ldw, m->ldw, true, &e_inv))
+            e = e_inv; // per-cook fast path: one pass over the explicit inverse of the reduced block
+        else if (e == cudaSuccess)
             e = fd_launch_solve_sub(ctx, m->d_A + (size_t)4 * m->lda + 4, m->lda, m->N - 4, m->d_perm, m->d_Tinv,
                                     m->d_W + (size_t)4 * m->ldw, m->ldw, 3 * frames);
         if (e == cudaSuccess) e = fd_launch_ns_finish(ctx, m, frames);

@@ -120,6 +120,13 @@ struct fd_model {
                            // at the ROOT device's weight block, so the tables are built through peer loads over NVLink
     int* d_flags;    // FD_NUM_FLAGS
     double* d_pivstat; // [min |u_kk|, max |u_kk|]
+    // Per-cook solves (a handful of right-hand sides against a cached factorisation, the reference's one frame per cook,
+    // SOP_FaceDeform.cpp:215): from the second such solve on the explicit inverse of the factored block is kept and a
+    // solve is one pass over it (fd_solve.cu: k_inv_apply) instead of 2 n / 32 dependent block steps.
+    double* d_inv;      // n_f x ld_inv, row-major; n_f = the factored block (n, or N - 4 on the null-space path)
+    double* d_inv_rhs;  // n_f x 8 right-hand sides in original row order
+    int ld_inv;
+    int small_solves;   // solves with <= 8 right-hand sides seen so far
     // null-space path of multiquadric / thin plate (fd_nullspace.cu): d_A holds Q^T K Q, its [4:, 4:] block LU-factored;
     // d_ns = reflectors V (N x 4), tau (4), R (4 x 4), scratch (N)
     bool ns;
@@ -202,6 +209,11 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int
 cudaError_t fd_launch_solve_prebuilt(fd_ctx* ctx, fd_model* m, int nrhs);
 cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, const int* d_perm, const double* d_Tinv,
                                 double* d_W, int ldw, int nrhs);
+// per-cook fast path: true when the solve of `nrhs` right-hand sides was done through the explicit inverse (built on the
+// way when this is the second small solve).  rhs_in_W: the right-hand sides sit in W (original row order) instead of
+// being built from rest / deform.
+bool fd_try_inverse_solve(fd_ctx* ctx, fd_model* m, const double* d_A, int lda, int n_f, const int* d_perm, const double* d_Tinv,
+                          const float* d_deform, int F, double* d_W, int ldw, bool rhs_in_W, cudaError_t* err);
 // fd_nullspace.cu
 cudaError_t fd_launch_ns_transform(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_ns_rhs(fd_ctx* ctx, fd_model* m, const float* d_deform, int F);

@@ -23,13 +23,68 @@ __global__ void __launch_bounds__(256) k_build_rhs(const float* __restrict__ res
     const int i = blockIdx.y;
     if (c >= ldw) return;
     double v = 0.0;
-    const int src = perm[i];
+    const int src = perm ? perm[i] : i;
     if (c < 3 * F && src < N) {
         const int f = c / 3, k = c - 3 * f;
         const float d = deform[((size_t)f * N + src) * 3 + k] - rest[3 * src + k];
         v = (double)d;
     }
     B[(size_t)i * ldw + c] = v;
+}
+
+// ---- explicit inverse for per-cook solves -----------------------------------------------------------------------------
+// X[i][c] = (row i of the permuted identity): perm == NULL gives I, else W[i][c] = (perm[i] == c)
+__global__ void __launch_bounds__(256) k_identity_rhs(double* __restrict__ X, int n, int ld, const int* __restrict__ perm)
+{
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const int i = blockIdx.y;
+    if (c >= ld) return;
+    const int src = perm ? perm[i] : i;
+    X[(size_t)i * ld + c] = (c == src && c < n) ? 1.0 : 0.0;
+}
+
+// B8[c][q] = W[c][q] for q < nrhs (0 beyond): the right-hand sides out of the in-place weight block
+__global__ void __launch_bounds__(256) k_gather_rhs8(const double* __restrict__ W, int ldw, int n, int nrhs, double* __restrict__ B8)
+{
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= n * 8) return;
+    const int c = t >> 3, q = t & 7;
+    B8[t] = q < nrhs ? W[(size_t)c * ldw + q] : 0.0;
+}
+
+// out[i][q] = sum_c inv[i][c] * B8[c][q], q < nrhs <= 8.  One warp per row: the row of the inverse streams once,
+// coalesced (16 bytes per lane); B8 (n x 64 bytes) stays in L1 / L2.  Bound by the n^2 x 8 bytes of the inverse.
+__global__ void __launch_bounds__(256) k_inv_apply(const double* __restrict__ inv, int ld, int n, const double* __restrict__ B8,
+                                                   int nrhs, double* __restrict__ out, int ldo)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const double2* row = reinterpret_cast<const double2*>(inv + (size_t)i * ld);
+    double acc[8] = {};
+    for (int c2 = lane; 2 * c2 < n; c2 += 32) {
+        const double2 a = __ldcs(row + c2); // streamed: read once per solve
+        const int c = 2 * c2;
+        const double4* b0 = reinterpret_cast<const double4*>(B8 + (size_t)c * 8);
+        const double4 p0 = b0[0], p1 = b0[1];
+        acc[0] = fma(a.x, p0.x, acc[0]); acc[1] = fma(a.x, p0.y, acc[1]); acc[2] = fma(a.x, p0.z, acc[2]); acc[3] = fma(a.x, p0.w, acc[3]);
+        acc[4] = fma(a.x, p1.x, acc[4]); acc[5] = fma(a.x, p1.y, acc[5]); acc[6] = fma(a.x, p1.z, acc[6]); acc[7] = fma(a.x, p1.w, acc[7]);
+        if (c + 1 < n) {
+            const double4 q0 = b0[2], q1 = b0[3];
+            acc[0] = fma(a.y, q0.x, acc[0]); acc[1] = fma(a.y, q0.y, acc[1]); acc[2] = fma(a.y, q0.z, acc[2]); acc[3] = fma(a.y, q0.w, acc[3]);
+            acc[4] = fma(a.y, q1.x, acc[4]); acc[5] = fma(a.y, q1.y, acc[5]); acc[6] = fma(a.y, q1.z, acc[6]); acc[7] = fma(a.y, q1.w, acc[7]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    if (lane < ldo && lane < 8) { // padding columns of the weight block are zero, like after the sweeps
+        double v = acc[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) v = lane == q ? acc[q] : v;
+        out[(size_t)i * ldo + lane] = lane < nrhs ? v : 0.0;
+    }
 }
 
 // X_k = T_kk^-1 B_k for one diagonal block; one thread per right-hand-side column.
@@ -778,6 +833,11 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int
     cudaStream_t s = ctx->stream;
     const int n = m->n, nrhs = 3 * F, ldw = m->ldw;
     {
+        cudaError_t e_inv;
+        if (fd_try_inverse_solve(ctx, m, m->d_A, m->lda, n, m->d_perm, m->d_Tinv, d_deform, F, m->d_W, ldw, false, &e_inv))
+            return e_inv;
+    }
+    {
         // FP64 tensor-pipe slab solve: 8 right-hand sides per CTA
         const int n_pad = fd_round_up(n, SB);
         const size_t bytes8 = ((size_t)n_pad * S8_RC + 2 * S8_CHUNK_DOUBLES + 2 * S8_TINV_DOUBLES) * sizeof(double);
@@ -925,6 +985,49 @@ cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, 
         }
     }
     return cudaGetLastError();
+}
+
+// Per-cook fast path (see fd_model::d_inv).  The inverse is n_f solves against the identity through the ordinary sweeps,
+// so X = A^-1 includes the row interchanges and applies to right-hand sides in their original order.
+bool fd_try_inverse_solve(fd_ctx* ctx, fd_model* m, const double* d_A, int lda, int n_f, const int* d_perm, const double* d_Tinv,
+                          const float* d_deform, int F, double* d_W, int ldw, bool rhs_in_W, cudaError_t* err)
+{
+    *err = cudaSuccess;
+    const int nrhs = 3 * F;
+    if (nrhs > 8 || ctx->dbg.no_inverse || n_f < 256) return false; // small systems: the slab solve is already a few microseconds
+    cudaStream_t s = ctx->stream;
+    m->small_solves += 1;
+    if (!m->d_inv) {
+        if (m->small_solves < 2) return false; // a single solve per fit (fit + solve + eval per step) never pays for the inverse
+        const int ld = fd_round_up(n_f, 4);
+        cudaError_t e = cudaMallocAsync((void**)&m->d_inv, (size_t)n_f * ld * sizeof(double), s);
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&m->d_inv_rhs, (size_t)n_f * 8 * sizeof(double), s);
+        if (e != cudaSuccess) { // no memory for the inverse: keep solving through the sweeps
+            cudaGetLastError();
+            if (m->d_inv) { cudaFreeAsync(m->d_inv, s); m->d_inv = nullptr; }
+            m->small_solves = -1000000;
+            return false;
+        }
+        m->ld_inv = ld;
+        const int n_pad = fd_round_up(n_f, SB);
+        const bool slab = ((size_t)n_pad * S8_RC + 2 * S8_CHUNK_DOUBLES + 2 * S8_TINV_DOUBLES) * sizeof(double) <= 220 * 1024;
+        dim3 grid((ld + 255) / 256, n_f);
+        // the slab kernel gathers its rows through perm itself; the blocked sweeps expect the rows already interchanged
+        k_identity_rhs<<<grid, 256, 0, s>>>(m->d_inv, n_f, ld, slab ? nullptr : d_perm);
+        ctx->launches += 1;
+        e = fd_launch_solve_sub(ctx, d_A, lda, n_f, slab ? d_perm : nullptr, d_Tinv, m->d_inv, ld, n_f);
+        if (e != cudaSuccess) { *err = e; return true; }
+    }
+    if (rhs_in_W) {
+        k_gather_rhs8<<<(n_f * 8 + 255) / 256, 256, 0, s>>>(d_W, ldw, n_f, nrhs, m->d_inv_rhs);
+    } else {
+        dim3 grid(1, n_f);
+        k_build_rhs<<<grid, 8, 0, s>>>(m->d_rest, d_deform, nullptr, m->N, n_f, F, m->d_inv_rhs, 8);
+    }
+    k_inv_apply<<<(n_f + 7) / 8, 256, 0, s>>>(m->d_inv, m->ld_inv, n_f, m->d_inv_rhs, nrhs, d_W, ldw);
+    ctx->launches += 2;
+    *err = cudaGetLastError();
+    return true;
 }
 
 // the tables that depend on the centres and radii only (built once per fit; receivers build them when the radii

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU call B: tests, bench line (symmetric DMMA LU, recalibrated AUTO), accuracy calibration
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r2b_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/r2b_pytest.log
+timeout 1200 python -m pytest tests -m gpu -q -s > gpurun_out/r2b_pytest.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|FAILED|Error" gpurun_out/r2b_pytest.log | tail -15
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err; echo "bench rc=$?"; python - <<'PY'
 import json
 j = json.load(open("gpurun_out/r2b_bench.json"))
@@ -15,3 +15,4 @@ PY
 tail -3 gpurun_out/r2b_bench.err
 timeout 600 python tests/tools/accuracy_probe.py 256 1024 2048 4096 > gpurun_out/r2b_accuracy.log 2>&1; echo "accuracy rc=$?"; cat gpurun_out/r2b_accuracy.log
 grep -h "AUTO kernel\|path=" gpurun_out/r2b_pytest.log | head -30
+timeout 300 python profiles/tools/percook_probe.py > gpurun_out/r2b_percook.jsonl 2> gpurun_out/r2b_percook.err; echo "percook rc=$?"; cat gpurun_out/r2b_percook.jsonl; tail -3 gpurun_out/r2b_percook.err

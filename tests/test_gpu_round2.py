@@ -377,3 +377,30 @@ def test_sop_strict_reference_morph_space_quirk():
     assert st == 1 and "Can't compute weights for morphspace deformation" in sop.msgs(1)
     np.testing.assert_array_equal(d, plain)
     sop.close()
+
+
+@pytest.mark.parametrize("kernel,N", [(0, 600), (1, 600), (0, 2048)])
+def test_per_cook_solves_through_the_explicit_inverse(ctx, oracle, kernel, N):
+    """one frame per cook against a cached factorisation (the reference's usage, SOP_FaceDeform.cpp:215): from the second
+    small solve on the model applies its explicit inverse; the weights match the sweeps and the oracle."""
+    from facedeform_b200 import make_params
+    rig = synth.control_rig(N)
+    R = synth.default_radius(["gaussian", "multiquadric"][kernel], rig.spacing)
+    p = make_params(model=1, term=0, kernel=kernel, radius=R, **{"lambda": 0.0})
+    m = ctx.fit(p, rig.rest)
+    frames = [synth.deformed_rig(rig, 1, seed=40 + i) for i in range(3)]
+    m.solve(frames[0])
+    W_sweeps, _ = m.weights()                 # first small solve: block sweeps
+    m.solve(frames[1])                        # second: builds the inverse and applies it
+    m.solve(frames[0])                        # third: the inverse again, same input as the first
+    W_inv, _ = m.weights()
+    scale = np.abs(W_sweeps).max()
+    np.testing.assert_allclose(W_inv, W_sweeps, rtol=0, atol=1e-8 * scale)
+    st, rad, W = oracle.fit(_oparams(oracle, p), rig.rest, frames[0])
+    np.testing.assert_allclose(W_inv, W, rtol=0, atol=1e-7 * np.abs(W).max())
+    two = synth.deformed_rig(rig, 2, seed=50)   # 6 right-hand sides also take the inverse
+    m.solve(two)
+    W2, _ = m.weights()
+    st, rad, Wo = oracle.fit(_oparams(oracle, p), rig.rest, two)
+    np.testing.assert_allclose(W2, Wo, rtol=0, atol=1e-7 * np.abs(Wo).max())
+    m.close()
