@@ -242,30 +242,39 @@ __global__ void __launch_bounds__(256) k_few_step(const double* __restrict__ A, 
     if (2 * cg + 1 < nrhs) upd[(size_t)r * ldu + 2 * cg + 1] -= a1;
 }
 
-// Panel update of the blocked sweeps: B[r][c] -= sum_k T[r][kb + k] * B[kb + k][c] for r in [r_lo, r_hi), k < K.
-// T column-major (the LU factors), B row-major.  CTA tile 128 rows x 64 columns, 8 x 4 per thread, K in chunks of 16
-// through shared memory; FP64 FMA bound (64 flop per 6 shared-memory reads of 16 bytes).
+// Panel update of the blocked sweeps: C[r][c] -= sum_k T[r][kb + k] * X[kb + k][c] for r in [r_lo, r_hi), k < K.
+// T column-major (the LU factors, or any column-major operand), X and C row-major.  CTA tile 128 rows x 64 columns on the
+// FP64 tensor pipe (mma.sync.m8n8k4.f64): 8 warps as 4 x 2, a warp owns 32 x 32 outputs = 16 accumulator tiles and loads
+// 8 fragments per 16 DMMAs (4096 FMAs); K in chunks of 16 through shared memory, the next chunk's operands travel from
+// global memory into registers while the current chunk is multiplied.  Stage strides = 4 mod 16 doubles: the fragment
+// loads of a half warp (4 rows x 4 k) fall into 16 different 8-byte banks.  (The DFMA version it replaces read 96 bytes of
+// shared memory per 64 FMAs and reached ~8 TFLOP/s.)
 constexpr int PG_TM = 128, PG_TN = 64, PG_KC = 16;
-__global__ void __launch_bounds__(256, 2) k_panel_gemm(const double* __restrict__ A, int lda, int r_lo, int r_hi, int kb, int K,
-                                                    double* __restrict__ B, int ldw, int nrhs)
+constexpr int PG_LDA = PG_TM + 4, PG_LDX = PG_TN + 4;
+__device__ __forceinline__ void pg_tile_dmma(const double* __restrict__ T, int lda, int r_lo, int r_hi, int K,
+                                             const double* __restrict__ X, int ldx, double* __restrict__ C, int ldc, int nrhs)
 {
-    __shared__ __align__(16) double s_a[PG_KC][PG_TM + 2];
-    __shared__ __align__(16) double s_x[PG_KC][PG_TN + 2];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    __shared__ __align__(16) double s_a[PG_KC][PG_LDA]; // [k][row]
+    __shared__ __align__(16) double s_x[PG_KC][PG_LDX]; // [k][col]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2, fr = lane >> 2, fk = lane & 3;
     const int r0 = r_lo + blockIdx.y * PG_TM, c0 = blockIdx.x * PG_TN;
-    double acc[8][4] = {};
-    // the next chunk's operands travel from global memory into registers while the current chunk is multiplied
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     double pa[PG_KC * PG_TM / 256], px[PG_KC * PG_TN / 256];
     auto gload = [&](int k0) {
 #pragma unroll
         for (int u = 0; u < PG_KC * PG_TM / 256; ++u) {
             const int t = tid + 256 * u, k = t / PG_TM, i = t - k * PG_TM;
-            pa[u] = (k0 + k < K && r0 + i < r_hi) ? A[(size_t)(kb + k0 + k) * lda + r0 + i] : 0.0;
+            pa[u] = (k0 + k < K && r0 + i < r_hi) ? T[(size_t)(k0 + k) * lda + r0 + i] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < PG_KC * PG_TN / 256; ++u) {
             const int t = tid + 256 * u, k = t / PG_TN, j = t - k * PG_TN;
-            px[u] = (k0 + k < K && c0 + j < nrhs) ? B[(size_t)(kb + k0 + k) * ldw + c0 + j] : 0.0;
+            px[u] = (k0 + k < K && c0 + j < nrhs) ? X[(size_t)(k0 + k) * ldx + c0 + j] : 0.0;
         }
     };
     gload(0);
@@ -284,90 +293,53 @@ __global__ void __launch_bounds__(256, 2) k_panel_gemm(const double* __restrict_
         __syncthreads();
         if (k0 + PG_KC < K) gload(k0 + PG_KC);
 #pragma unroll
-        for (int k = 0; k < PG_KC; ++k) {
-            double a[8], x[4];
+        for (int k4 = 0; k4 < PG_KC / 4; ++k4) {
+            double af[4], bf[4];
 #pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(&s_a[k][ty * 8 + i]);
-                a[i] = v.x;
-                a[i + 1] = v.y;
-            }
+            for (int mi = 0; mi < 4; ++mi) af[mi] = s_a[k4 * 4 + fk][wm * 32 + mi * 8 + fr];
 #pragma unroll
-            for (int j = 0; j < 4; j += 2) { // columns {2 tx, 2 tx + 1} and {32 + 2 tx, 33 + 2 tx}: conflict-free 16-byte reads
-                const double2 v = *reinterpret_cast<const double2*>(&s_x[k][tx * 2 + 16 * j]);
-                x[j] = v.x;
-                x[j + 1] = v.y;
-            }
+            for (int ni = 0; ni < 4; ++ni) bf[ni] = s_x[k4 * 4 + fk][wn * 32 + ni * 8 + fr];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], x[j], acc[i][j]);
+                for (int ni = 0; ni < 4; ++ni)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
+                                 : "d"(af[mi]), "d"(bf[ni]));
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = r0 + ty * 8 + i;
+    for (int mi = 0; mi < 4; ++mi) {
+        const int r = r0 + wm * 32 + mi * 8 + fr;
         if (r >= r_hi) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = c0 + tx * 2 + (j & 1) + 32 * (j >> 1);
-            if (c < nrhs) B[(size_t)r * ldw + c] -= acc[i][j];
+        for (int ni = 0; ni < 4; ++ni) {
+            const int c = c0 + wn * 32 + ni * 8 + 2 * fk;
+            double* dst = C + (size_t)r * ldc + c;
+            if (c + 1 < nrhs) { // c is even and the row strides are multiples of 4 doubles: 16-byte aligned
+                double2 v = *reinterpret_cast<double2*>(dst);
+                v.x -= acc[mi][ni][0];
+                v.y -= acc[mi][ni][1];
+                *reinterpret_cast<double2*>(dst) = v;
+            } else if (c < nrhs) {
+                dst[0] -= acc[mi][ni][0];
+            }
         }
     }
 }
 
+__global__ void __launch_bounds__(256, 2) k_panel_gemm(const double* __restrict__ A, int lda, int r_lo, int r_hi, int kb, int K,
+                                                    double* __restrict__ B, int ldw, int nrhs)
+{
+    pg_tile_dmma(A + (size_t)kb * lda, lda, r_lo, r_hi, K, B + (size_t)kb * ldw, ldw, B, ldw, nrhs);
+}
+
 // C[r][c] -= sum_k A[r][k] X[k][c], r < rows, k < K: A column-major (lda), X and C row-major with the same row stride.
-// (the residual update of the layered fit, fd_api.cu; same tile as k_panel_gemm with separate operands)
+// (the residual update of the layered fit, fd_api.cu)
 __global__ void __launch_bounds__(256, 2) k_gemm_sub(const double* __restrict__ A, int lda, int rows, int K,
                                                      const double* __restrict__ X, double* __restrict__ C, int ldw, int nrhs)
 {
-    __shared__ __align__(16) double s_a[PG_KC][PG_TM + 2];
-    __shared__ __align__(16) double s_x[PG_KC][PG_TN + 2];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int r0 = blockIdx.y * PG_TM, c0 = blockIdx.x * PG_TN;
-    double acc[8][4] = {};
-    for (int k0 = 0; k0 < K; k0 += PG_KC) {
-        __syncthreads();
-        for (int t = tid; t < PG_KC * PG_TM; t += 256) {
-            const int k = t / PG_TM, i = t - k * PG_TM;
-            s_a[k][i] = (k0 + k < K && r0 + i < rows) ? A[(size_t)(k0 + k) * lda + r0 + i] : 0.0;
-        }
-        for (int t = tid; t < PG_KC * PG_TN; t += 256) {
-            const int k = t / PG_TN, j = t - k * PG_TN;
-            s_x[k][j] = (k0 + k < K && c0 + j < nrhs) ? X[(size_t)(k0 + k) * ldw + c0 + j] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < PG_KC; ++k) {
-            double a[8], x[4];
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(&s_a[k][ty * 8 + i]);
-                a[i] = v.x;
-                a[i + 1] = v.y;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(&s_x[k][tx * 2 + 16 * j]);
-                x[j] = v.x;
-                x[j + 1] = v.y;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], x[j], acc[i][j]);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = r0 + ty * 8 + i;
-        if (r >= rows) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = c0 + tx * 2 + (j & 1) + 32 * (j >> 1);
-            if (c < nrhs) C[(size_t)r * ldw + c] -= acc[i][j];
-        }
-    }
+    pg_tile_dmma(A, lda, 0, rows, K, X, ldw, C, ldw, nrhs);
 }
 
 // ---- slab solve: one CTA owns RC right-hand-side columns for the whole forward/backward substitution --------------
