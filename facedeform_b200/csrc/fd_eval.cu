@@ -146,7 +146,7 @@ __device__ __forceinline__ void finish_vertices(const EvalArgs& a, const T* __re
         float fo = fminf(d2 / a.radius2, 1.0f);                 // :423
         fo = powf(1.0f - fo, a.falloffrate);                    // :424
         if (skip) fo = 0.f;
-        if (a.falloff_out && blockIdx.y == 0) a.falloff_out[v] = fo;
+        if (a.falloff_out && f0 == 0) a.falloff_out[v] = fo;
         float tu[3], tv[3], tn[3];
         if (a.do_tangent) {
 #pragma unroll
@@ -259,8 +259,13 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32x2(const EvalArgs a)
     __shared__ __align__(16) float s_w[TJ * WPAD];
 
     if (a.sel && *a.sel != a.sel_id) return;
-    const int f0 = blockIdx.y * FC;
-    const int64_t vbase = (int64_t)blockIdx.x * (EVAL_THREADS * VPT) + threadIdx.x;
+    // persistent walk over (vertex tile, frame chunk) pairs, vertex tiles fastest: a grid of a few CTAs per SM costs
+    // nothing when FD_EVAL_AUTO settled on another kernel, and consecutive tiles reuse the chunk's weight rows in L2
+    const int64_t nbx = (a.V + EVAL_THREADS * VPT - 1) / (EVAL_THREADS * VPT);
+    const int64_t ntiles = nbx * ((a.F + FC - 1) / FC);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int f0 = (int)(tile / nbx) * FC;
+    const int64_t vbase = (tile % nbx) * (EVAL_THREADS * VPT) + threadIdx.x;
     float px[VPT], py[VPT], pz[VPT];
     float pos[VPT][3];
 #pragma unroll
@@ -342,13 +347,15 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32x2(const EvalArgs a)
 #pragma unroll
         for (int q = 0; q < 3 * FC; ++q) unpack2(acc2[g][q], acc[2 * g][q], acc[2 * g + 1][q]);
     finish_vertices<float, FC, VPT>(a, W, f0, ncol, vbase, px, py, pz, pos, acc);
+    } // tile
 }
 
 template <int KERNEL, int FC, int VP>
 cudaError_t launch_f32x2(fd_ctx* ctx, const EvalArgs& a)
 {
-    dim3 grid((unsigned)((a.V + EVAL_THREADS * 2 * VP - 1) / (EVAL_THREADS * 2 * VP)), (unsigned)((a.F + FC - 1) / FC));
-    k_eval_f32x2<KERNEL, FC, VP><<<grid, EVAL_THREADS, 0, ctx->stream>>>(a);
+    const int64_t ntiles = ((a.V + EVAL_THREADS * 2 * VP - 1) / (EVAL_THREADS * 2 * VP)) * ((a.F + FC - 1) / FC);
+    const int64_t cap = (int64_t)ctx->sm_count * 8; // up to 8 resident CTAs of 256 threads per SM
+    k_eval_f32x2<KERNEL, FC, VP><<<(unsigned)(ntiles < cap ? ntiles : cap), EVAL_THREADS, 0, ctx->stream>>>(a);
     ctx->launches += 1;
     return cudaGetLastError();
 }
@@ -357,6 +364,7 @@ template <int KERNEL>
 cudaError_t launch_f32x2_fc(fd_ctx* ctx, const EvalArgs& a)
 {
     const int vp_env = ctx->dbg.eval_vp;
+    if (a.F >= 8) return launch_f32x2<KERNEL, 8, 1>(ctx, a); // phi amortised over 8 frames: 15.5 packed instructions per pair
     if (a.F >= 4) return launch_f32x2<KERNEL, 4, 1>(ctx, a);
     if (a.F >= 2) return launch_f32x2<KERNEL, 2, 1>(ctx, a);
     // one frame: two packed pairs per thread when there are enough vertices to fill the GPU that way
@@ -514,7 +522,7 @@ cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64
     a.do_tangent = (m->prm.tangent && tu && tv && nrm) ? 1 : 0; // SOP_FaceDeform.cpp:293-294
     a.origin = m->d_rest;
     a.sel = sel;
-    if (!m->eval64 && !m->use_tc) { // FP32 FMA/SFU
+    if (!m->eval64 && (!m->use_tc || (sel && m->prm.eval_path != FD_PATH_TENSOR))) { // FP32 FMA/SFU
         a.sel_id = FD_SEL_SIMT;
         a.ctab = m->d_ctab32;
         a.W = m->d_W32;

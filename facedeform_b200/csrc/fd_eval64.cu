@@ -7,9 +7,9 @@
 // does.  After each solve k_wmax + k_cancel_select measure
 //        S = max_i sum_j max_c |w_jc| phi_j(c_i)            (the control points stand in for the vertices)
 // and choose, on the device (no host synchronisation between solve and evaluation), the FP32 kernel the caller's
-// eval_path asks for while  coef x 2^-24 x S  <=  0.6 x eval_tolerance x diag  (diag = the rig's bounding-box diagonal),
-// else the FP64 evaluation.  The evaluation launches both candidates; the one not chosen returns at its first
-// instruction.  The reference evaluates in FP64 (alglib::rbfcalc on double[3], SOP_FaceDeform.cpp:411-415).
+// eval_path allows with  coef x 2^-24 x S  <=  eval_tolerance x diag  (diag = the rig's bounding-box diagonal; tensor
+// cores before FMA/SFU), else the FP64 evaluation.  The evaluation launches every candidate; the ones not chosen return
+// at their first instruction.  The reference evaluates in FP64 (alglib::rbfcalc on double[3], SOP_FaceDeform.cpp:411-415).
 //
 // (2) k_eval64_mma: D[v][3f+k] = sum_j Phi[v][j] W[j][3f+k] with Phi generated on the fly in FP64 and contracted by
 // mma.sync.m8n8k4.f64 (DMMA).  A CTA owns 128 vertices x 96 columns (32 frames); per stage of 32 centres its 256
@@ -27,12 +27,13 @@ namespace {
 // (1) cancellation estimate + kernel choice
 // ---------------------------------------------------------------------------------------------------------------------
 
-// error of an FP32 evaluation <= coef x 2^-24 x S: coef = the largest ratio measured against the oracle over
-// N = 256 / 1024 / 2048 / 4096 control points (tests/tools/accuracy_probe.py: 0.82 tensor, 0.61 FMA/SFU), rounded up.
-// FP32 is kept while that prediction stays below AUTO_FRACTION of the tolerance.
-constexpr double ERR_COEF_SIMT = 0.65;
-constexpr double ERR_COEF_TENSOR = 0.85;
-constexpr double AUTO_FRACTION = 0.6;
+// max error of an FP32 evaluation <= coef x 2^-24 x S.  coef = the largest ratio measured against the oracle over
+// N = 256 / 1024 / 2048 control points x 120 frames x 4096 vertices (1.5 M values each; tests/test_gpu_round2.py,
+// tests/tools/accuracy_probe.py): 1.68 tensor cores (FP16 hi/lo splits, FP32 accumulation in the tensor core),
+// 0.93 FMA/SFU -- plus 20 %.  A kernel is eligible while its prediction stays within eval_tolerance x diag; the fastest
+// eligible one runs: tensor cores, then FMA/SFU, else FP64.
+constexpr double ERR_COEF_SIMT = 1.1;
+constexpr double ERR_COEF_TENSOR = 2.0;
 
 // wmax[j] = max_c |W[j][c]| over the nrhs solved columns (row j of the row-major weight block)
 __global__ void __launch_bounds__(128) k_wmax(const double* __restrict__ W, int ldw, int nrhs, int N, float* __restrict__ wmax)
@@ -59,8 +60,9 @@ struct SelectArgs {
     const float* wmax;
     const float* norm; // k_tc_norm: [4] = bounding-box diagonal of the control points
     int N, kernel;
-    int cand32;        // 1 FMA/SFU, 2 tensor cores
-    int want;          // 0 choose; 1 / 2 / 3 forced by eval_precision
+    int tensor_ok;     // the tensor-core tables exist for these weights (3F wide enough, eval_path allows it)
+    int simt_ok;       // eval_path allows the FMA/SFU kernel
+    int want;          // 0 choose; 1 / 2 / 3 forced by eval_precision / eval_path
     float tol;         // eval_tolerance
     unsigned long long* smax_bits; // max S as the bits of a non-negative double
     unsigned* done;
@@ -97,10 +99,10 @@ __global__ void __launch_bounds__(256) k_cancel_select(const SelectArgs a)
     const double diag = (double)a.norm[4];
     int sel = a.want;
     if (sel == 0) {
-        const double coef = a.cand32 == 2 ? ERR_COEF_TENSOR : ERR_COEF_SIMT;
         const double tol = a.tol > 0.f ? (double)a.tol : 1e-5;
-        const double err = coef * 5.9604644775390625e-08 * S;
-        sel = (err <= AUTO_FRACTION * tol * diag) ? a.cand32 : 3;
+        const double unit = 5.9604644775390625e-08 * S, lim = tol * diag;
+        sel = (a.tensor_ok && ERR_COEF_TENSOR * unit <= lim) ? FD_SEL_TENSOR
+            : (a.simt_ok && ERR_COEF_SIMT * unit <= lim) ? FD_SEL_SIMT : FD_SEL_FP64;
     }
     *a.sel = sel;
     a.est[0] = S;
@@ -353,7 +355,7 @@ cudaError_t fd_eval64_setup(fd_ctx* ctx)
 }
 
 // after a solve / commit: measure the cancellation and settle the evaluation kernel on the device
-cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int cand32, int want)
+cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int tensor_ok, int simt_ok, int want)
 {
     cudaStream_t s = ctx->stream;
     k_wmax<<<m->N, 128, 0, s>>>(fd_w_src(m), m->ldw, 3 * m->F, m->N, m->d_wmax);
@@ -364,7 +366,8 @@ cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int cand32, int wa
     a.norm = m->d_tc_norm;
     a.N = m->N;
     a.kernel = m->prm.kernel;
-    a.cand32 = cand32;
+    a.tensor_ok = tensor_ok;
+    a.simt_ok = simt_ok;
     a.want = want;
     a.tol = m->prm.eval_tolerance;
     a.smax_bits = reinterpret_cast<unsigned long long*>(m->d_est + 2);

@@ -43,7 +43,7 @@ struct fd_debug_opts {
     bool tc_nopair;         // FD_TC_NOPAIR: no CTA pairs in the tensor evaluation
     bool has_tc_debug;      // FD_TC_DEBUG set
     bool lu_sym_off;        // FD_LU_NOSYM: the fused LU ignores symmetry
-    bool lu_dfma;           // FD_LU_DFMA: DFMA tile product in the fused LU instead of DMMA
+    bool lu_no_lookahead;   // FD_LU_NOLA: the fused LU without the look-ahead warp (k_lu_nopiv_fused)
     int eval_vp;            // FD_EVAL_VP
     int tc_debug;           // FD_TC_DEBUG bits
     int lu_debug;           // FD_LU_DEBUG step
@@ -269,7 +269,7 @@ cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, in
 #define FD_SEL_TENSOR 2
 #define FD_SEL_FP64 3
 #define FD_MMA64_MIN_COLUMNS 48 // the FP64 evaluation takes the DMMA kernel from 3F >= 48 columns
-cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int cand32, int want);
+cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int tensor_ok, int simt_ok, int want);
 cudaError_t fd_launch_eval64_mma(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2, const float* tu,
                                  const float* tv, const float* nrm, float* P_out, float* falloff_out, const int* sel, int sel_id);
 // fd_capture.cu

@@ -52,38 +52,57 @@ __global__ void __launch_bounds__(256) k_gather_rhs8(const double* __restrict__ 
     B8[t] = q < nrhs ? W[(size_t)c * ldw + q] : 0.0;
 }
 
-// out[i][q] = sum_c inv[i][c] * B8[c][q], q < nrhs <= 8.  One warp per row: the row of the inverse streams once,
-// coalesced (16 bytes per lane); B8 (n x 64 bytes) stays in L1 / L2.  Bound by the n^2 x 8 bytes of the inverse.
+// out[i][q] = sum_c inv[i][c] * B8[c][q], q < NQ <= 8.  A CTA owns 16 rows (two per warp) and walks the columns in chunks
+// of 512: the chunk of right-hand sides is staged transposed in shared memory ([q][c]: conflict-free reads), the rows of
+// the inverse stream once, coalesced, straight from L2 / HBM -- the kernel is bound by those n^2 x 8 bytes.
+constexpr int IA_ROWS = 16, IA_CH = 512;
+template <int NQ>
 __global__ void __launch_bounds__(256) k_inv_apply(const double* __restrict__ inv, int ld, int n, const double* __restrict__ B8,
-                                                   int nrhs, double* __restrict__ out, int ldo)
+                                                   double* __restrict__ out, int ldo)
 {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= n) return;
-    const double2* row = reinterpret_cast<const double2*>(inv + (size_t)i * ld);
-    double acc[8] = {};
-    for (int c2 = lane; 2 * c2 < n; c2 += 32) {
-        const double2 a = __ldcs(row + c2); // streamed: read once per solve
-        const int c = 2 * c2;
-        const double4* b0 = reinterpret_cast<const double4*>(B8 + (size_t)c * 8);
-        const double4 p0 = b0[0], p1 = b0[1];
-        acc[0] = fma(a.x, p0.x, acc[0]); acc[1] = fma(a.x, p0.y, acc[1]); acc[2] = fma(a.x, p0.z, acc[2]); acc[3] = fma(a.x, p0.w, acc[3]);
-        acc[4] = fma(a.x, p1.x, acc[4]); acc[5] = fma(a.x, p1.y, acc[5]); acc[6] = fma(a.x, p1.z, acc[6]); acc[7] = fma(a.x, p1.w, acc[7]);
-        if (c + 1 < n) {
-            const double4 q0 = b0[2], q1 = b0[3];
-            acc[0] = fma(a.y, q0.x, acc[0]); acc[1] = fma(a.y, q0.y, acc[1]); acc[2] = fma(a.y, q0.z, acc[2]); acc[3] = fma(a.y, q0.w, acc[3]);
-            acc[4] = fma(a.y, q1.x, acc[4]); acc[5] = fma(a.y, q1.y, acc[5]); acc[6] = fma(a.y, q1.z, acc[6]); acc[7] = fma(a.y, q1.w, acc[7]);
+    __shared__ double s_b[NQ][IA_CH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * IA_ROWS + 2 * warp;
+    const double* row0 = inv + (size_t)min(r0, n - 1) * ld;
+    const double* row1 = inv + (size_t)min(r0 + 1, n - 1) * ld;
+    double acc0[NQ], acc1[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc0[q] = acc1[q] = 0.0;
+    for (int c0 = 0; c0 < n; c0 += IA_CH) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < IA_CH * NQ; t += 256) {
+            const int c = t / NQ, q = t - c * NQ;
+            s_b[q][c] = c0 + c < n ? B8[(size_t)(c0 + c) * 8 + q] : 0.0;
+        }
+        __syncthreads();
+        const int cend = min(IA_CH, n - c0);
+#pragma unroll 4
+        for (int c = lane; c < cend; c += 32) {
+            const double a0 = __ldcs(row0 + c0 + c), a1 = __ldcs(row1 + c0 + c); // streamed: read once per solve
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const double bq = s_b[q][c];
+                acc0[q] = fma(a0, bq, acc0[q]);
+                acc1[q] = fma(a1, bq, acc1[q]);
+            }
         }
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        for (int o = 16; o > 0; o >>= 1) {
+            acc0[q] += __shfl_xor_sync(0xffffffffu, acc0[q], o);
+            acc1[q] += __shfl_xor_sync(0xffffffffu, acc1[q], o);
+        }
     if (lane < ldo && lane < 8) { // padding columns of the weight block are zero, like after the sweeps
-        double v = acc[0];
+        double v0 = 0.0, v1 = 0.0;
 #pragma unroll
-        for (int q = 1; q < 8; ++q) v = lane == q ? acc[q] : v;
-        out[(size_t)i * ldo + lane] = lane < nrhs ? v : 0.0;
+        for (int q = 0; q < NQ; ++q) {
+            v0 = lane == q ? acc0[q] : v0;
+            v1 = lane == q ? acc1[q] : v1;
+        }
+        if (r0 < n) out[(size_t)r0 * ldo + lane] = v0;
+        if (r0 + 1 < n) out[(size_t)(r0 + 1) * ldo + lane] = v1;
     }
 }
 
@@ -996,7 +1015,10 @@ bool fd_try_inverse_solve(fd_ctx* ctx, fd_model* m, const double* d_A, int lda, 
         dim3 grid(1, n_f);
         k_build_rhs<<<grid, 8, 0, s>>>(m->d_rest, d_deform, nullptr, m->N, n_f, F, m->d_inv_rhs, 8);
     }
-    k_inv_apply<<<(n_f + 7) / 8, 256, 0, s>>>(m->d_inv, m->ld_inv, n_f, m->d_inv_rhs, nrhs, d_W, ldw);
+    const int ia_grid = (n_f + IA_ROWS - 1) / IA_ROWS;
+    if (nrhs <= 3) k_inv_apply<3><<<ia_grid, 256, 0, s>>>(m->d_inv, m->ld_inv, n_f, m->d_inv_rhs, d_W, ldw);
+    else if (nrhs <= 6) k_inv_apply<6><<<ia_grid, 256, 0, s>>>(m->d_inv, m->ld_inv, n_f, m->d_inv_rhs, d_W, ldw);
+    else k_inv_apply<8><<<ia_grid, 256, 0, s>>>(m->d_inv, m->ld_inv, n_f, m->d_inv_rhs, d_W, ldw);
     ctx->launches += 2;
     *err = cudaGetLastError();
     return true;
@@ -1025,9 +1047,10 @@ cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
     cudaError_t e = cudaSuccess;
     if (!m->tables_packed || m->receiver) e = fd_launch_pack_tables(ctx, m);
     if (e != cudaSuccess) return e;
-    if (m->use_tc) {
-        e = fd_launch_pack_tc(ctx, m);
-    } else {
+    // FD_EVAL_AUTO (Gaussian) keeps every FP32 candidate ready: the choice is made on the device after this pack
+    const bool want_simt = !m->use_tc || (m->auto_sel && m->prm.eval_path != FD_PATH_TENSOR);
+    if (m->use_tc) e = fd_launch_pack_tc(ctx, m);
+    if (e == cudaSuccess && want_simt) {
         dim3 grid((m->ldw32 + 255) / 256, m->n);
         k_pack_weights<<<grid, 256, 0, s>>>(fd_w_src(m), m->n, m->ldw, 3 * m->F, m->d_W32, m->ldw32, m->d_flags);
         ctx->launches += 1;
@@ -1035,7 +1058,7 @@ cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
     }
     // the cancellation of these weights, and with it the evaluation kernel of FD_EVAL_AUTO (Gaussian; fd_eval64.cu)
     if (e == cudaSuccess && !m->eval64 && m->prm.kernel == FD_KERNEL_GAUSSIAN)
-        e = fd_launch_cancel_select(ctx, m, m->use_tc ? FD_SEL_TENSOR : FD_SEL_SIMT,
+        e = fd_launch_cancel_select(ctx, m, m->use_tc ? 1 : 0, want_simt ? 1 : 0,
                                     m->auto_sel ? 0 : (m->use_tc ? FD_SEL_TENSOR : FD_SEL_SIMT));
     return e;
 }

@@ -112,9 +112,9 @@ typedef struct fd_params {
                                  :485-486) and the morph-space weights are computed only while !isComputed(), later cooks
                                  skip the pass with the reference's warning (:446-452).  0: the group restricts the
                                  deformation, the weights follow every cooked frame. */
-    float eval_tolerance;     /* default 1e-5: FD_EVAL_AUTO keeps the FP32 evaluation (FMA/SFU or tensor cores) only while
-                                 its predicted error stays below 0.6 x eval_tolerance x the control rig's bounding-box
-                                 diagonal, and switches to the FP64 evaluation otherwise */
+    float eval_tolerance;     /* default 1e-5: FD_EVAL_AUTO runs the fastest evaluation whose predicted maximum error stays
+                                 within eval_tolerance x the control rig's bounding-box diagonal: tensor cores (2.0 x 2^-24 S),
+                                 FMA/SFU FP32 (1.1 x 2^-24 S), else FP64; S = fd_report.cancellation */
     char group[64];           /* "group"  default ""  (all points)  :119-120  point-group pattern: "*", "7", "3-40",
                                  "0-100:2", "^5" (remove), space separated; resolved by the host mirror (facedeform_sop.hpp) */
 } fd_params;
