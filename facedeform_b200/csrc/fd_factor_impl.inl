@@ -1407,9 +1407,12 @@ __device__ __forceinline__ void fz_diag_factor(REAL (&a)[NB], REAL* s_U, REAL* s
 template <bool CLUSTER>
 __global__ void __launch_bounds__(LA_THREADS, 1) k_lu_fused_la(REAL* A, int lda, int n, int nbo, int* ipiv, int* perm, int* flags,
                                                                double* pivstat, double* Tinv, unsigned* sync_counter,
-                                                               unsigned sync_base)
+                                                               unsigned sync_base, int dbg)
 {
     extern __shared__ __align__(16) unsigned char la_smem_raw[];
+    __shared__ long long s_probe[12]; // FD_LU_DEBUG=<step>: cycle stamps of CTA 0 (development aid)
+    int tstep = 0;
+#define LA_PROBE(i) do { if (dbg && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8) && tstep == dbg) s_probe[i] = clock64(); } while (0)
     REAL* s_a = reinterpret_cast<REAL*>(la_smem_raw);
     REAL* s_b = s_a + 2 * FZ_KC * FZ_LDA;
     REAL* s_fac = s_b + 2 * FZ_TMAX * FZ_LDB;        // [2][U11 | L11^T | 1 / u]: the factors of the current and the next block
@@ -1465,6 +1468,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_lu_fused_la(REAL* A, int lda,
             REAL* sU = s_fac + buf * (2 * NB * NB + NB);
             REAL* sLt = sU + NB * NB;
             REAL* sInv = sLt + NB * NB;
+            ++tstep;
             if (diag_warp) {
                 // ================= diagonal warp: the factors of the NEXT block =================
                 if (!has_next) break;
@@ -1473,7 +1477,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_lu_fused_la(REAL* A, int lda,
                 REAL a[NB], mypiv;
                 int waited = 0;
                 if (la) {
+                    LA_PROBE(6);
                     la_bar_sync(4, LA_THREADS); // the workers have formed D' in shared memory
+                    LA_PROBE(7);
 #pragma unroll
                     for (int c = 0; c < NB; c += 2) {
                         const REAL2 v = *reinterpret_cast<const REAL2*>(s_D + lane * LA_LDL + c);
@@ -1494,6 +1500,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_lu_fused_la(REAL* A, int lda,
                         a[c] = (lane < nb2 && c < nb2) ? __ldcg(A + (size_t)(ks + c) * lda + ks + lane) : (lane == c ? (REAL)1 : (REAL)0);
                 }
                 fz_diag_factor(a, nU, nU + NB * NB, nU + 2 * NB * NB, lane, mypiv);
+                LA_PROBE(8);
                 if (blockIdx.x == 0) track(ks, nb2, mypiv);
                 la_bar_arrive(3, LA_THREADS);
                 if (CLUSTER && !waited) {
@@ -1537,7 +1544,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_lu_fused_la(REAL* A, int lda,
             // loads that do not depend on the factors start before the factors are awaited
             if (la && warp == 0) load_rows(0);
             else if (!(la && warp == 0) && g < ngroups) load_rows(g);
+            LA_PROBE(0);
             la_bar_sync(3, LA_THREADS); // the factors of this block are in sU / sLt / sInv
+            LA_PROBE(1);
             if (blockIdx.x == 0 && warp == 5 && lane < nb) { // the factored diagonal block goes back to the matrix
 #pragma unroll 1
                 for (int c = 0; c < nb; ++c)
@@ -1583,6 +1592,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_lu_fused_la(REAL* A, int lda,
                     }
                 }
                 la_bar_arrive(4, LA_THREADS); // the diagonal warp takes D' from here
+                LA_PROBE(2);
             }
 #pragma unroll 1
             for (; g < ngroups; g += (int)G * 8, have_first = false) {
@@ -1604,7 +1614,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_lu_fused_la(REAL* A, int lda,
                     for (int r = 0; r < NB; ++r) out[r] = (double)x[r];
                 }
             }
+            LA_PROBE(3);
             if (b1) fz_barrier<CLUSTER>(sync_counter, target, G);
+            LA_PROBE(4);
             if (b2) { // L-shaped border of the outer block, K = 32 (lower-triangle tiles only)
                 const FzRegions R = {ks, n, ks, Kend, 0, 0, 0, 0, k0, ks, 1};
                 fz_update<64>(A, lda, n, R, s_a, s_b);
@@ -1616,9 +1628,17 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_lu_fused_la(REAL* A, int lda,
                 fz_update<64>(A, lda, n, R, s_a, s_b);
                 fz_barrier<CLUSTER>(sync_counter, target, G);
             }
+            LA_PROBE(5);
             if (has_next && !la) la_bar_arrive(6, LA_THREADS); // the diagonal warp reads the next block from the matrix
         }
     }
+    if (dbg && blockIdx.x == 0 && tid == 0 && tstep >= dbg) {
+        printf("[fz-la] n=%d step %d cycles from the workers' step start: wait factors %lld | group 0 + D' %lld | other groups %lld | "
+               "barrier 1 %lld | update + barriers %lld || diagonal warp: waits for D' from %lld to %lld, factor done at %lld\n",
+               n, dbg, s_probe[1] - s_probe[0], s_probe[2] - s_probe[1], s_probe[3] - s_probe[2], s_probe[4] - s_probe[3],
+               s_probe[5] - s_probe[4], s_probe[6] - s_probe[0], s_probe[7] - s_probe[0], s_probe[8] - s_probe[0]);
+    }
+#undef LA_PROBE
     if (blockIdx.x == 0 && diag_warp && lane == 0) {
         flags[FD_FLAG_SINGULAR] = singular;
         flags[FD_FLAG_NONFINITE] = 0;
@@ -1681,10 +1701,10 @@ cudaError_t launch_lu_nopivot_fused(fd_ctx* ctx, REAL* d_A, int lda, int n, int*
             cfg.numAttrs = 1;
             ctx->launches += 1;
             return cudaLaunchKernelEx(&cfg, k_lu_fused_la<true>, d_A, lda, n, nbo, d_ipiv, d_perm, d_flags, d_pivstat, d_Tinv,
-                                      ctx->d_sync, base);
+                                      ctx->d_sync, base, dbg);
         }
         const int G = ctx->sm_count;
-        void* args[] = {&d_A, &lda, &n, &nbo, &d_ipiv, &d_perm, &d_flags, &d_pivstat, &d_Tinv, &ctx->d_sync, &base};
+        void* args[] = {&d_A, &lda, &n, &nbo, &d_ipiv, &d_perm, &d_flags, &d_pivstat, &d_Tinv, &ctx->d_sync, &base, &dbg};
         const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_lu_fused_la<false>, dim3(G), dim3(LA_THREADS), args, smem_la, s);
         if (e == cudaSuccess) {
             ctx->sync_base = base + (unsigned)G * fz_barrier_count(n, nbo);
