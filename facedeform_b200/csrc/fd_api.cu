@@ -72,7 +72,7 @@ void read_debug_opts(fd_debug_opts* o)
     o->tc_nopair = flag("FD_TC_NOPAIR");
     o->has_tc_debug = flag("FD_TC_DEBUG");
     o->lu_sym_off = flag("FD_LU_NOSYM");
-    o->lu_no_lookahead = flag("FD_LU_NOLA");
+    o->lu_lookahead = flag("FD_LU_LA");
     o->eval_vp = num("FD_EVAL_VP");
     o->tc_debug = num("FD_TC_DEBUG");
     o->lu_debug = num("FD_LU_DEBUG");

@@ -361,6 +361,132 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32x2(const EvalArgs a)
     } // tile
 }
 
+// FP32 FMA/SFU path for frame chunks of FC >= 4 (an even number of columns): the packed FMAs run along the COLUMNS.
+// A packed register holds the weights of two adjacent columns exactly as they lie in shared memory, so an LDS.128
+// delivers two ready operands; the other operand is (phi, phi), one MOV per basis value.  Per (vertex pair, centre):
+// 7 packed instructions for the two distances, 2 MUFU, 2 MOV, 3 FC FFMA2 and 2 + 3 FC / 4 shared-memory reads -- the
+// kernel sits on the FP32 pipe (an FFMA2 occupies it for two cycles), not on issue slots or shared-memory bandwidth.
+// (Packing along the vertices needs every weight duplicated: one MOV per FFMA2 when done in registers -- issue bound --
+// or twice the LDS.128 broadcasts when done in shared memory -- LSU bound: 0.98 ms and 1.40 ms at BASELINE configs[1].)
+// Lane-wise the same arithmetic per output as k_eval_simt<float> (same rounding per operation, same order over centres).
+template <int KERNEL, int FC, int VP>
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32c(const EvalArgs a)
+{
+    constexpr int VPT = 2 * VP;      // vertices per thread; the distances of a pair share packed instructions
+    constexpr int NC = 3 * FC;       // columns of the chunk (even)
+    static_assert(NC % 4 == 0, "column count must be a multiple of 4 (128-bit weight reads)");
+    __shared__ __align__(16) uint64_t s_c2[TJ * 4];  // (x, x), (y, y), (z, z), (parameter, parameter)
+    __shared__ __align__(16) float s_w[TJ * NC];
+
+    if (a.sel && *a.sel != a.sel_id) return;
+    const int64_t nbx = (a.V + EVAL_THREADS * VPT - 1) / (EVAL_THREADS * VPT);
+    const int64_t ntiles = nbx * ((a.F + FC - 1) / FC);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int f0 = (int)(tile / nbx) * FC;
+        const int64_t vbase = (tile % nbx) * (EVAL_THREADS * VPT) + threadIdx.x;
+        float px[VPT], py[VPT], pz[VPT];
+        float pos[VPT][3];
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            const int64_t v = vbase + (int64_t)u * EVAL_THREADS;
+            if (v < a.V) {
+                pos[u][0] = a.P[3 * v];
+                pos[u][1] = a.P[3 * v + 1];
+                pos[u][2] = a.P[3 * v + 2];
+            } else {
+                pos[u][0] = pos[u][1] = pos[u][2] = 0.f;
+            }
+            px[u] = pos[u][0];
+            py[u] = pos[u][1];
+            pz[u] = pos[u][2];
+        }
+        uint64_t px2[VP], py2[VP], pz2[VP];
+#pragma unroll
+        for (int g = 0; g < VP; ++g) {
+            px2[g] = pack2(px[2 * g], px[2 * g + 1]);
+            py2[g] = pack2(py[2 * g], py[2 * g + 1]);
+            pz2[g] = pack2(pz[2 * g], pz[2 * g + 1]);
+        }
+        uint64_t acc2[VPT][NC / 2]; // [vertex][column pair]
+#pragma unroll
+        for (int u = 0; u < VPT; ++u)
+#pragma unroll
+            for (int c = 0; c < NC / 2; ++c) acc2[u][c] = pack2(0.f, 0.f);
+
+        const float4* __restrict__ ctab = (const float4*)a.ctab;
+        const float* __restrict__ W = (const float*)a.W;
+        const int ncol = min(NC, 3 * (a.F - f0));
+
+        for (int j0 = 0; j0 < a.N; j0 += TJ) {
+            const int cnt = min(TJ, a.N - j0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < TJ; t += EVAL_THREADS) {
+                const float4 c = t < cnt ? ctab[j0 + t] : make_float4(0.f, 0.f, 0.f, KERNEL == FD_KERNEL_MULTIQUADRIC ? 1.f : 0.f);
+                s_c2[4 * t] = pack2(c.x, c.x);
+                s_c2[4 * t + 1] = pack2(c.y, c.y);
+                s_c2[4 * t + 2] = pack2(c.z, c.z);
+                s_c2[4 * t + 3] = pack2(c.w, c.w);
+            }
+            for (int t = threadIdx.x; t < TJ * NC; t += EVAL_THREADS) {
+                const int j = t / NC, c = t - j * NC;
+                s_w[t] = (j < cnt && c < ncol) ? W[(size_t)(j0 + j) * a.ldw + 3 * f0 + c] : 0.f;
+            }
+            __syncthreads();
+            const int jn = (cnt + 3) & ~3; // padded centres carry zero weights
+#pragma unroll 2
+            for (int j = 0; j < jn; ++j) {
+                const ulonglong2 cxy = *reinterpret_cast<const ulonglong2*>(&s_c2[4 * j]);
+                const ulonglong2 czw = *reinterpret_cast<const ulonglong2*>(&s_c2[4 * j + 2]);
+                uint64_t w2[NC / 2];
+#pragma unroll
+                for (int q = 0; q < NC / 2; q += 2) {
+                    const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(&s_w[j * NC + 2 * q]);
+                    w2[q] = t2.x;     // (w[2q], w[2q+1])
+                    w2[q + 1] = t2.y; // (w[2q+2], w[2q+3])
+                }
+#pragma unroll
+                for (int g = 0; g < VP; ++g) {
+                    const uint64_t dx = sub2(px2[g], cxy.x), dy = sub2(py2[g], cxy.y), dz = sub2(pz2[g], czw.x);
+                    const uint64_t r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                    float t0, t1, e0, e1;
+                    if (KERNEL == FD_KERNEL_GAUSSIAN) {
+                        unpack2(mul2(r2, czw.y), t0, t1);
+                        e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+                    } else if (KERNEL == FD_KERNEL_MULTIQUADRIC) {
+                        unpack2(add2(r2, czw.y), t0, t1);
+                        e0 = sqrt_approx(t0), e1 = sqrt_approx(t1);
+                    } else {
+                        unpack2(r2, t0, t1);
+                        e0 = phi<KERNEL>(t0, 0.f), e1 = phi<KERNEL>(t1, 0.f);
+                    }
+                    const uint64_t pa = pack2(e0, e0), pb = pack2(e1, e1);
+#pragma unroll
+                    for (int q = 0; q < NC / 2; ++q) {
+                        acc2[2 * g][q] = fma2(w2[q], pa, acc2[2 * g][q]);
+                        acc2[2 * g + 1][q] = fma2(w2[q], pb, acc2[2 * g + 1][q]);
+                    }
+                }
+            }
+        }
+        float acc[VPT][NC];
+#pragma unroll
+        for (int u = 0; u < VPT; ++u)
+#pragma unroll
+            for (int q = 0; q < NC / 2; ++q) unpack2(acc2[u][q], acc[u][2 * q], acc[u][2 * q + 1]);
+        finish_vertices<float, FC, VPT>(a, W, f0, ncol, vbase, px, py, pz, pos, acc);
+    } // tile
+}
+
+template <int KERNEL, int FC, int VP>
+cudaError_t launch_f32c(fd_ctx* ctx, const EvalArgs& a)
+{
+    const int64_t ntiles = ((a.V + EVAL_THREADS * 2 * VP - 1) / (EVAL_THREADS * 2 * VP)) * ((a.F + FC - 1) / FC);
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    k_eval_f32c<KERNEL, FC, VP><<<(unsigned)(ntiles < cap ? ntiles : cap), EVAL_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
 template <int KERNEL, int FC, int VP>
 cudaError_t launch_f32x2(fd_ctx* ctx, const EvalArgs& a)
 {
@@ -375,8 +501,10 @@ template <int KERNEL>
 cudaError_t launch_f32x2_fc(fd_ctx* ctx, const EvalArgs& a)
 {
     const int vp_env = ctx->dbg.eval_vp;
-    if (a.F >= 8) return launch_f32x2<KERNEL, 8, 1>(ctx, a); // phi amortised over 8 frames: 15.5 packed instructions per pair
-    if (a.F >= 4) return launch_f32x2<KERNEL, 4, 1>(ctx, a);
+    // frame chunks of 8 / 4: packed along the columns (k_eval_f32c); 4 vertices per thread when the mesh fills the GPU that way
+    const bool many = a.V >= (int64_t)ctx->sm_count * EVAL_THREADS * 4 * 2;
+    if (a.F >= 8) return many ? launch_f32c<KERNEL, 8, 2>(ctx, a) : launch_f32c<KERNEL, 8, 1>(ctx, a);
+    if (a.F >= 4) return many ? launch_f32c<KERNEL, 4, 2>(ctx, a) : launch_f32c<KERNEL, 4, 1>(ctx, a);
     if (a.F >= 2) return launch_f32x2<KERNEL, 2, 1>(ctx, a);
     // one frame: two packed pairs per thread when there are enough vertices to fill the GPU that way
     const bool wide = vp_env ? vp_env == 2 : a.V >= (int64_t)ctx->sm_count * EVAL_THREADS * 4 * 4;

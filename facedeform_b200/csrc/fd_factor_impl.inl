@@ -1680,10 +1680,12 @@ cudaError_t launch_lu_nopivot_fused(fd_ctx* ctx, REAL* d_A, int lda, int n, int*
     cudaStream_t s = ctx->stream;
     unsigned base = ctx->sync_base;
 #ifdef FD_LU_DMMA
-    // symmetric systems up to 2048 unknowns: the look-ahead kernel (a ninth warp factors the next diagonal block while the
-    // step's solves and trailing update run).  Beyond that the diagonal chain is < 20 % of a step and the 128 x 128 DMMA
-    // tiles of k_lu_nopiv_fused matter more.
-    if (sym && !o.lu_no_lookahead && n > NB && n <= 2048 + 8) {
+    // EXPERIMENTAL, off unless FD_LU_LA is set: the look-ahead kernel (a ninth warp factors the next diagonal block while
+    // the step's solves and trailing update run).  Measured on B200 it LOSES (n = 260: 0.205 ms against 0.152 ms): the
+    // diagonal warp's 32-pivot dependent chain shares its SM sub-partition's FP64 pipe with two worker warps, whose DMMAs
+    // hold the pipe 16 cycles each -- the chain stretches from ~300 to ~940 cycles per pivot (FD_LU_DEBUG probes,
+    // profiles/r2d_lu_probe.log) and becomes the critical path again.
+    if (sym && o.lu_lookahead && n > NB && n <= 2048 + 8) {
         const size_t smem_la = (size_t)LA_SMEM_REALS * sizeof(REAL);
         if (n <= cluster_max_n) {
             const int cs = o.lu_cluster ? o.lu_cluster : (n <= 64 ? 4 : (n <= 128 ? 8 : 16));

@@ -43,7 +43,7 @@ struct fd_debug_opts {
     bool tc_nopair;         // FD_TC_NOPAIR: no CTA pairs in the tensor evaluation
     bool has_tc_debug;      // FD_TC_DEBUG set
     bool lu_sym_off;        // FD_LU_NOSYM: the fused LU ignores symmetry
-    bool lu_no_lookahead;   // FD_LU_NOLA: the fused LU without the look-ahead warp (k_lu_nopiv_fused)
+    bool lu_lookahead;      // FD_LU_LA: the experimental look-ahead LU (k_lu_fused_la; slower on B200, see fd_factor_impl.inl)
     int eval_vp;            // FD_EVAL_VP
     int tc_debug;           // FD_TC_DEBUG bits
     int lu_debug;           // FD_LU_DEBUG step
