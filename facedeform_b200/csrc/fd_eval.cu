@@ -502,7 +502,8 @@ cudaError_t launch_f32x2_fc(fd_ctx* ctx, const EvalArgs& a)
 {
     const int vp_env = ctx->dbg.eval_vp;
     // frame chunks of 8 / 4: packed along the columns (k_eval_f32c); 4 vertices per thread when the mesh fills the GPU that way
-    const bool many = a.V >= (int64_t)ctx->sm_count * EVAL_THREADS * 4 * 2;
+    const int fc = a.F >= 8 ? 8 : 4;
+    const bool many = ((a.V + EVAL_THREADS * 4 - 1) / (EVAL_THREADS * 4)) * ((a.F + fc - 1) / fc) >= 2 * (int64_t)ctx->sm_count;
     if (a.F >= 8) return many ? launch_f32c<KERNEL, 8, 2>(ctx, a) : launch_f32c<KERNEL, 8, 1>(ctx, a);
     if (a.F >= 4) return many ? launch_f32c<KERNEL, 4, 2>(ctx, a) : launch_f32c<KERNEL, 4, 1>(ctx, a);
     if (a.F >= 2) return launch_f32x2<KERNEL, 2, 1>(ctx, a);
