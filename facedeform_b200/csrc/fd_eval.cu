@@ -254,13 +254,9 @@ template <int KERNEL, int FC, int VP>
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32x2(const EvalArgs a)
 {
     constexpr int VPT = 2 * VP; // VP packed pairs of vertices per thread
-    // Centres and weights sit in shared memory already DUPLICATED into FP32x2 registers' layout ((x, x), (w, w) ...): the
-    // inner loop feeds them to the packed instructions straight from LDS.128 broadcasts.  (Building the pairs in
-    // registers cost one MOV per weight and centre coordinate -- as many issue slots as the FFMA2s themselves.)
-    constexpr int TJC = 3 * FC > 12 ? 128 : 256;      // centres per stage (48 KB of static shared memory)
-    constexpr int WP2 = (3 * FC + 1) / 2 * 2;         // weight pairs per centre, even for 128-bit reads
-    __shared__ __align__(16) uint64_t s_c2[TJC * 4];  // (x, x), (y, y), (z, z), (parameter, parameter)
-    __shared__ __align__(16) uint64_t s_w2[TJC * WP2];
+    constexpr int WPAD = (3 * FC + 3) / 4 * 4;
+    __shared__ float4 s_c[TJ];
+    __shared__ __align__(16) float s_w[TJ * WPAD];
 
     if (a.sel && *a.sel != a.sel_id) return;
     // persistent walk over (vertex tile, frame chunk) pairs, vertex tiles fastest: a grid of a few CTAs per SM costs
@@ -303,52 +299,45 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32x2(const EvalArgs a)
     const float* __restrict__ W = (const float*)a.W;
     const int ncol = min(3 * FC, 3 * (a.F - f0));
 
-    for (int j0 = 0; j0 < a.N; j0 += TJC) {
-        const int cnt = min(TJC, a.N - j0);
+    for (int j0 = 0; j0 < a.N; j0 += TJ) {
+        const int cnt = min(TJ, a.N - j0);
         __syncthreads();
-        for (int t = threadIdx.x; t < TJC; t += EVAL_THREADS) {
-            const float4 c = t < cnt ? ctab[j0 + t] : make_float4(0.f, 0.f, 0.f, KERNEL == FD_KERNEL_MULTIQUADRIC ? 1.f : 0.f);
-            s_c2[4 * t] = pack2(c.x, c.x);
-            s_c2[4 * t + 1] = pack2(c.y, c.y);
-            s_c2[4 * t + 2] = pack2(c.z, c.z);
-            s_c2[4 * t + 3] = pack2(c.w, c.w);
-        }
-        for (int t = threadIdx.x; t < TJC * WP2; t += EVAL_THREADS) {
-            const int j = t / WP2, c = t - j * WP2;
-            const float w = (j < cnt && c < ncol) ? W[(size_t)(j0 + j) * a.ldw + 3 * f0 + c] : 0.f;
-            s_w2[t] = pack2(w, w);
+        for (int t = threadIdx.x; t < TJ; t += EVAL_THREADS)
+            s_c[t] = t < cnt ? ctab[j0 + t] : make_float4(0.f, 0.f, 0.f, KERNEL == FD_KERNEL_MULTIQUADRIC ? 1.f : 0.f);
+        for (int t = threadIdx.x; t < TJ * WPAD; t += EVAL_THREADS) {
+            const int j = t / WPAD, c = t - j * WPAD;
+            s_w[t] = (j < cnt && c < ncol) ? W[(size_t)(j0 + j) * a.ldw + 3 * f0 + c] : 0.f;
         }
         __syncthreads();
         const int jn = (cnt + 3) & ~3; // padded centres carry zero weights
 #pragma unroll 4
         for (int j = 0; j < jn; ++j) {
-            const ulonglong2 cxy = *reinterpret_cast<const ulonglong2*>(&s_c2[4 * j]);
-            const ulonglong2 czw = *reinterpret_cast<const ulonglong2*>(&s_c2[4 * j + 2]);
-            uint64_t w2[WP2];
+            const float4 c = s_c[j];
+            float w[WPAD];
 #pragma unroll
-            for (int q = 0; q < WP2; q += 2) {
-                const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(&s_w2[j * WP2 + q]);
-                w2[q] = t2.x;
-                w2[q + 1] = t2.y;
+            for (int q = 0; q < WPAD; q += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(&s_w[j * WPAD + q]);
+                w[q] = t4.x; w[q + 1] = t4.y; w[q + 2] = t4.z; w[q + 3] = t4.w;
             }
+            const uint64_t cx = pack2(c.x, c.x), cy = pack2(c.y, c.y), cz = pack2(c.z, c.z), cw = pack2(c.w, c.w);
 #pragma unroll
             for (int g = 0; g < VP; ++g) {
-                const uint64_t dx = sub2(px2[g], cxy.x), dy = sub2(py2[g], cxy.y), dz = sub2(pz2[g], czw.x);
+                const uint64_t dx = sub2(px2[g], cx), dy = sub2(py2[g], cy), dz = sub2(pz2[g], cz);
                 const uint64_t r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
                 float t0, t1;
                 uint64_t ph2;
                 if (KERNEL == FD_KERNEL_GAUSSIAN) {
-                    unpack2(mul2(r2, czw.y), t0, t1);
+                    unpack2(mul2(r2, cw), t0, t1);
                     ph2 = pack2(ex2_approx(t0), ex2_approx(t1));
                 } else if (KERNEL == FD_KERNEL_MULTIQUADRIC) {
-                    unpack2(add2(r2, czw.y), t0, t1);
+                    unpack2(add2(r2, cw), t0, t1);
                     ph2 = pack2(sqrt_approx(t0), sqrt_approx(t1));
                 } else {
                     unpack2(r2, t0, t1);
                     ph2 = pack2(phi<KERNEL>(t0, 0.f), phi<KERNEL>(t1, 0.f));
                 }
 #pragma unroll
-                for (int q = 0; q < 3 * FC; ++q) acc2[g][q] = fma2(w2[q], ph2, acc2[g][q]);
+                for (int q = 0; q < 3 * FC; ++q) acc2[g][q] = fma2(pack2(w[q], w[q]), ph2, acc2[g][q]);
             }
         }
     }
@@ -506,7 +495,7 @@ cudaError_t launch_f32x2_fc(fd_ctx* ctx, const EvalArgs& a)
     const bool many = ((a.V + EVAL_THREADS * 4 - 1) / (EVAL_THREADS * 4)) * ((a.F + fc - 1) / fc) >= 2 * (int64_t)ctx->sm_count;
     if (a.F >= 8) return many ? launch_f32c<KERNEL, 8, 2>(ctx, a) : launch_f32c<KERNEL, 8, 1>(ctx, a);
     if (a.F >= 4) return many ? launch_f32c<KERNEL, 4, 2>(ctx, a) : launch_f32c<KERNEL, 4, 1>(ctx, a);
-    if (a.F >= 2) return launch_f32x2<KERNEL, 2, 1>(ctx, a);
+    if (a.F >= 2) return launch_f32x2<KERNEL, 2, 1>(ctx, a); // one or two frames: packed along the vertices (k_eval_f32x2)
     // one frame: two packed pairs per thread when there are enough vertices to fill the GPU that way
     const bool wide = vp_env ? vp_env == 2 : a.V >= (int64_t)ctx->sm_count * EVAL_THREADS * 4 * 4;
     return wide ? launch_f32x2<KERNEL, 1, 2>(ctx, a) : launch_f32x2<KERNEL, 1, 1>(ctx, a);

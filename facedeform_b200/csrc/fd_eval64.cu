@@ -17,7 +17,10 @@
 // exp2 / sqrt / log from few DFMAs, fd_eval_common.cuh), the weight tile arrives with cp.async one stage ahead, and
 // every warp contracts its 32 x 48 sub-tile: 24 accumulator tiles, 10 fragment loads per 24 DMMAs.  Phi is computed
 // once per 96 columns instead of once per 1-2 frames (k_eval_f64), so the FP64 pipe spends ~85 % of its time in the
-// contraction.  Polynomial rows ride along as extra K rows [1, x, y, z].  Epilogue = the SOP's (gate, tangent
+// contraction.  (A warp-specialised variant -- 4 producer warps for Phi, 8 consumer warps for the DMMAs -- was measured
+// SLOWER, 2.98 ms against 2.41 ms at BASELINE configs[1]: DMMA and DFMA share the FP64 pipe, a DMMA holds it for 16
+// cycles, and a warp of dependent DFMA chains scheduled beside DMMA warps starves; the look-ahead LU failed the same way.)
+// Polynomial rows ride along as extra K rows [1, x, y, z].  Epilogue = the SOP's (gate, tangent
 // projection, falloff, P += disp: SOP_FaceDeform.cpp:405-438), in FP32 after the narrowing of :415.
 #include "fd_eval_common.cuh"
 
@@ -117,14 +120,13 @@ __global__ void __launch_bounds__(256) k_cancel_select(const SelectArgs a)
 constexpr int E_TM = 128;          // vertices per CTA tile
 constexpr int E_TN = 96;           // columns per CTA tile (32 frames)
 constexpr int E_KB = 32;           // centres per stage
-constexpr int E_CONSUMERS = 256;   // warps 0..7: DMMA + epilogue
-constexpr int E_PRODUCERS = 128;   // warps 8..11: Phi tiles + weight tiles
-constexpr int E_THREADS = E_CONSUMERS + E_PRODUCERS;
+constexpr int E_THREADS = 256;
 constexpr int E_LDA = E_KB + 4;    // = 4 mod 16: conflict-free A-fragment loads (see the lane map of fd_dmma884)
 constexpr int E_LDB = E_TN + 4;    // = 4 mod 16: conflict-free B-fragment loads
 constexpr int E_LDC = E_TN + 1;    // float staging of the accumulators for the epilogue
 constexpr int E_STAGE_DOUBLES = E_TM * E_LDA + E_KB * E_LDB;
-constexpr int E_SMEM_BYTES = 2 * E_STAGE_DOUBLES * 8 + 2 * E_KB * 5 * 8 + 128 * 16 + 64 * 8 + E_TM * E_LDC * 4;
+constexpr int E_SMEM_BYTES = 2 * E_STAGE_DOUBLES * 8 + E_KB * 5 * 8 + 128 * 16 + 64 * 8;
+static_assert(E_TM * E_LDC * 4 <= 2 * E_STAGE_DOUBLES * 8, "the epilogue staging reuses the pipeline buffers");
 
 struct Eval64Args {
     const double4* ctab; // Gaussian: (x, y, z, -1 / R^2); multiquadric / thin plate: (-2 (c - o), |c - o|^2 + prm)
@@ -152,124 +154,35 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
                  "r"(bytes)
                  : "memory");
 }
-// named barriers: one side arrives, the other waits (count = all 384 threads)
-__device__ __forceinline__ void e_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(E_THREADS) : "memory"); }
-__device__ __forceinline__ void e_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(E_THREADS) : "memory"); }
-constexpr int E_BAR_FULL = 2;   // + buffer: producers arrive, consumers wait
-constexpr int E_BAR_EMPTY = 4;  // + buffer: consumers arrive, producers wait
 
-// Warp-specialised: four producer warps generate the next Phi tile (FP64 pipe) and fetch the next weight tile
-// (cp.async) while the eight consumer warps contract the current one on the FP64 tensor pipe -- the two pipes are
-// separate (ncu: DMMA counts under the tensor pipe), so the basis functions cost the contraction nothing.  The
-// single-role version (every warp alternating between both phases) kept the tensor pipe 51 % busy: with two warps per
-// SM sub-partition the dependent DFMA chains of the basis functions left it idle half of the time.
 template <int KERNEL>
 __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
 {
     extern __shared__ __align__(16) unsigned char e64_smem[];
     if (a.sel && *a.sel != a.sel_id) return; // FD_EVAL_AUTO settled on an FP32 kernel
     double* s_stage = reinterpret_cast<double*>(e64_smem);                 // [2][A tile | B tile]
-    double* s_ctr = s_stage + 2 * E_STAGE_DOUBLES;                         // [2][32][5]: (a, b, c, d, s) of a stage's centres
-    double2* s_log = reinterpret_cast<double2*>(s_ctr + 2 * E_KB * 5);     // thin plate: fd_half_log64 table
+    double* s_ctr = s_stage + 2 * E_STAGE_DOUBLES;                         // [32][5]: (a, b, c, d, s) of the stage's centres
+    double2* s_log = reinterpret_cast<double2*>(s_ctr + E_KB * 5);         // thin plate: fd_half_log64 table
     double* s_exp = reinterpret_cast<double*>(s_log + 128);                // Gaussian: fd_exp2_64 table
-    float* s_C = reinterpret_cast<float*>(s_exp + 64);                     // epilogue staging of the accumulators
+    float* s_C = reinterpret_cast<float*>(e64_smem);                       // epilogue staging, reuses the stage buffers
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (KERNEL == FD_KERNEL_THINPLATE && tid < 128) fd_half_log64_table(s_log, tid);
     if (KERNEL == FD_KERNEL_GAUSSIAN && tid < 64) fd_exp2_64_table(s_exp, tid);
-    __syncthreads();
+    const int wm = warp & 3, wn = warp >> 2;       // warp tile: rows [32 wm, +32), columns [48 wn, +48)
+    const int fr = lane >> 2, fk = lane & 3;
+    const int row = tid & (E_TM - 1), khalf = tid >> 7; // Phi generation: this thread's vertex row and half of the stage's centres
     const double ox = (double)a.origin[0], oy = (double)a.origin[1], oz = (double)a.origin[2];
     const int Ktot = a.N + a.np;
     const int nstage = (Ktot + E_KB - 1) / E_KB;
     const int ncb = (3 * a.F + E_TN - 1) / E_TN;
     const int64_t n_vt = (a.V + E_TM - 1) / E_TM;
     const int64_t n_tiles = n_vt * ncb;
-    uint32_t it = 0; // stages issued / consumed so far (both roles count alike)
 
-    if (warp >= E_CONSUMERS / 32) {
-        // ================= producers =================
-        const int pt = tid - E_CONSUMERS; // 0..127 = the vertex row this thread generates
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t vt = tile / ncb;
-            const int c0 = (int)(tile - vt * ncb) * E_TN;
-            const int64_t v = vt * E_TM + pt;
-            double px = 0.0, py = 0.0, pz = 0.0;
-            if (v < a.V) {
-                px = (double)a.P[3 * v];
-                py = (double)a.P[3 * v + 1];
-                pz = (double)a.P[3 * v + 2];
-            }
-            const double qx = px - ox, qy = py - oy, qz = pz - oz;
-            const double pp = qx * qx + qy * qy + qz * qz;
-            for (int s = 0; s < nstage; ++s, ++it) {
-                const int b = it & 1;
-                if (it >= 2) e_bar_sync(E_BAR_EMPTY + b); // the consumers are done with this buffer
-                double* sA = s_stage + b * E_STAGE_DOUBLES;
-                double* sB = sA + E_TM * E_LDA;
-                double* sc = s_ctr + b * E_KB * 5;
-                // weight tile (rows beyond N + np and columns beyond ldw zero-filled)
-                for (int t = pt; t < E_KB * (E_TN / 2); t += E_PRODUCERS) {
-                    const int k = t / (E_TN / 2), q = t - k * (E_TN / 2);
-                    const int gk = s * E_KB + k, gc = c0 + 2 * q;
-                    const bool ok = gk < Ktot && gc < a.ldw;
-                    cp_async16_zfill(sB + k * E_LDB + 2 * q, a.W + (size_t)(ok ? gk : 0) * a.ldw + (ok ? gc : 0), ok);
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                // centre table of the stage in the form the distance wants: t = q . (a, b, c) + d + pp * s
-                if (pt < E_KB) {
-                    const int j = s * E_KB + pt;
-                    double ca = 0.0, cb_ = 0.0, cc = 0.0, cd = 0.0, cs = 0.0;
-                    if (j < a.N) {
-                        const double4 c = a.ctab[j];
-                        if (KERNEL == FD_KERNEL_GAUSSIAN) {
-                            const double scl = c.w * 1.4426950408889634074; // -log2(e) / R^2
-                            const double cx = c.x - ox, cy = c.y - oy, cz = c.z - oz;
-                            ca = -2.0 * scl * cx, cb_ = -2.0 * scl * cy, cc = -2.0 * scl * cz;
-                            cd = scl * (cx * cx + cy * cy + cz * cz);
-                            cs = scl;
-                        } else {
-                            ca = c.x, cb_ = c.y, cc = c.z, cd = c.w, cs = 1.0;
-                        }
-                    }
-                    double* d = sc + pt * 5;
-                    d[0] = ca, d[1] = cb_, d[2] = cc, d[3] = cd, d[4] = cs;
-                }
-                asm volatile("bar.sync 6, %0;" ::"n"(E_PRODUCERS) : "memory"); // the centre table is written
-                double* rowA = sA + pt * E_LDA;
-#pragma unroll 4
-                for (int kk = 0; kk < E_KB; kk += 2) {
-                    double ph[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int j = s * E_KB + kk + e;
-                        const double* c = sc + (kk + e) * 5; // warp-wide broadcast reads
-                        const double t = fma(qx, c[0], fma(qy, c[1], fma(qz, c[2], fma(pp, c[4], c[3]))));
-                        double val;
-                        if (KERNEL == FD_KERNEL_GAUSSIAN) val = fd_exp2_64(fmin(t, 0.0), s_exp);
-                        else if (KERNEL == FD_KERNEL_MULTIQUADRIC) val = fd_fast_sqrt64(t);
-                        else val = fmax(t, 0.0) * fd_half_log64(fmax(t, 0.0), s_log);
-                        if (j >= a.N) { // polynomial rows [1, x, y, z], then zero padding
-                            const int r = j - a.N;
-                            val = r >= a.np ? 0.0 : (r == 0 ? 1.0 : (r == 1 ? px : (r == 2 ? py : pz)));
-                        }
-                        ph[e] = val;
-                    }
-                    *reinterpret_cast<double2*>(rowA + kk) = make_double2(ph[0], ph[1]);
-                }
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __threadfence_block();
-                e_bar_arrive(E_BAR_FULL + b);
-            }
-        }
-        return;
-    }
-    // ================= consumers =================
-    const int wm = warp & 3, wn = warp >> 2;       // warp tile: rows [32 wm, +32), columns [48 wn, +48)
-    const int fr = lane >> 2, fk = lane & 3;
-    const int row = tid & (E_TM - 1), khalf = tid >> 7; // epilogue: this thread's vertex row and frame parity
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t vt = tile / ncb;
         const int cb = (int)(tile - vt * ncb);
+        const int c0 = cb * E_TN;
         const int64_t v = vt * E_TM + row;
         float pos[3] = {0.f, 0.f, 0.f};
         if (v < a.V) {
@@ -277,14 +190,87 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
             pos[1] = a.P[3 * v + 1];
             pos[2] = a.P[3 * v + 2];
         }
+        const double px = (double)pos[0], py = (double)pos[1], pz = (double)pos[2];
+        const double qx = px - ox, qy = py - oy, qz = pz - oz;
+        const double pp = qx * qx + qy * qy + qz * qz;
+
         double acc[4][6][2];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 6; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        for (int s = 0; s < nstage; ++s, ++it) {
-            const int b = it & 1;
-            e_bar_sync(E_BAR_FULL + b); // Phi tile + weight tile of this stage are in shared memory
+
+        // weight tile of stage s -> buffer b (cp.async, rows beyond N + np and columns beyond ldw zero-filled)
+        auto load_w = [&](int s, int b) {
+            double* sB = s_stage + b * E_STAGE_DOUBLES + E_TM * E_LDA;
+            for (int t = tid; t < E_KB * (E_TN / 2); t += E_THREADS) {
+                const int k = t / (E_TN / 2), q = t - k * (E_TN / 2);
+                const int gk = s * E_KB + k, gc = c0 + 2 * q;
+                const bool ok = gk < Ktot && gc < a.ldw;
+                cp_async16_zfill(sB + k * E_LDB + 2 * q, a.W + (size_t)(ok ? gk : 0) * a.ldw + (ok ? gc : 0), ok);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // centre table of stage s in the form the distance wants: t = q . (a, b, c) + d + pp * s
+        auto load_c = [&](int s) {
+            if (tid < E_KB) {
+                const int j = s * E_KB + tid;
+                double ca = 0.0, cb_ = 0.0, cc = 0.0, cd = 0.0, cs = 0.0;
+                if (j < a.N) {
+                    const double4 c = a.ctab[j];
+                    if (KERNEL == FD_KERNEL_GAUSSIAN) {
+                        const double sc = c.w * 1.4426950408889634074; // -log2(e) / R^2
+                        const double cx = c.x - ox, cy = c.y - oy, cz = c.z - oz;
+                        ca = -2.0 * sc * cx, cb_ = -2.0 * sc * cy, cc = -2.0 * sc * cz;
+                        cd = sc * (cx * cx + cy * cy + cz * cz);
+                        cs = sc;
+                    } else {
+                        ca = c.x, cb_ = c.y, cc = c.z, cd = c.w, cs = 1.0;
+                    }
+                }
+                double* d = s_ctr + tid * 5;
+                d[0] = ca, d[1] = cb_, d[2] = cc, d[3] = cd, d[4] = cs;
+            }
+        };
+        // this thread's 16 basis values of stage s -> A tile of buffer b
+        auto gen_phi = [&](int s, int b) {
+            double* sA = s_stage + b * E_STAGE_DOUBLES + row * E_LDA + khalf * 16;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 2) {
+                double ph[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int kk = khalf * 16 + jj + e;
+                    const int j = s * E_KB + kk;
+                    const double* c = s_ctr + kk * 5; // warp-wide broadcast reads
+                    const double t = fma(qx, c[0], fma(qy, c[1], fma(qz, c[2], fma(pp, c[4], c[3]))));
+                    double val;
+                    if (KERNEL == FD_KERNEL_GAUSSIAN) val = fd_exp2_64(fmin(t, 0.0), s_exp);
+                    else if (KERNEL == FD_KERNEL_MULTIQUADRIC) val = fd_fast_sqrt64(t);
+                    else val = fmax(t, 0.0) * fd_half_log64(fmax(t, 0.0), s_log);
+                    if (j >= a.N) { // polynomial rows [1, x, y, z], then zero padding
+                        const int r = j - a.N;
+                        val = r >= a.np ? 0.0 : (r == 0 ? 1.0 : (r == 1 ? px : (r == 2 ? py : pz)));
+                    }
+                    ph[e] = val;
+                }
+                *reinterpret_cast<double2*>(sA + jj) = make_double2(ph[0], ph[1]);
+            }
+        };
+
+        __syncthreads(); // the previous tile's epilogue has left the stage buffers
+        load_c(0);
+        load_w(0, 0);
+        __syncthreads();
+        gen_phi(0, 0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (int s = 0; s < nstage; ++s) {
+            const int b = s & 1;
+            __syncthreads(); // stage s complete (Phi + weights); every warp is done with buffer b ^ 1 and with s_ctr
+            if (s + 1 < nstage) {
+                load_w(s + 1, b ^ 1);
+                load_c(s + 1);
+            }
             const double* sA = s_stage + b * E_STAGE_DOUBLES + (wm * 32 + fr) * E_LDA + fk;
             const double* sB = s_stage + b * E_STAGE_DOUBLES + E_TM * E_LDA + fk * E_LDB + wn * 48 + fr;
 #pragma unroll
@@ -299,19 +285,22 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
 #pragma unroll
                     for (int ni = 0; ni < 6; ++ni) fd_dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
             }
-            e_bar_arrive(E_BAR_EMPTY + b); // the producers may refill this buffer
+            if (s + 1 < nstage) {
+                __syncthreads(); // s_ctr of stage s + 1 is written
+                gen_phi(s + 1, b ^ 1);
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
         }
-        // accumulators -> FP32 staging (the narrowing of SOP_FaceDeform.cpp:415); the previous tile's readers are done
-        asm volatile("bar.sync 1, %0;" ::"n"(E_CONSUMERS) : "memory");
+        __syncthreads(); // all warps are done with the stage buffers: they become the FP32 staging of the accumulators
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 6; ++ni) {
                 float* d = s_C + (wm * 32 + mi * 8 + fr) * E_LDC + wn * 48 + ni * 8 + 2 * fk;
-                d[0] = (float)acc[mi][ni][0];
+                d[0] = (float)acc[mi][ni][0]; // the narrowing of SOP_FaceDeform.cpp:415
                 d[1] = (float)acc[mi][ni][1];
             }
-        asm volatile("bar.sync 1, %0;" ::"n"(E_CONSUMERS) : "memory");
+        __syncthreads();
         // epilogue: thread = (vertex row, frames khalf, khalf + 2, ...)
         if (v < a.V) {
             const float d2 = a.dist2 ? a.dist2[v] : 0.f;
