@@ -245,25 +245,66 @@ def factor_table(ctx, sizes, cpu=True):
     return out
 
 
-def configs_table(ctx):
-    """phase times of BASELINE.json's other single-GPU configurations (C1, C3 multiquadric / thin plate, the C3 shape
-    with the Gaussian kernel, a slice of C5), device resident -- parity-test cases reported for context, not bench lines."""
+def _load_tool(name):
     import importlib.util
-    spec = importlib.util.spec_from_file_location("configs_probe", os.path.join(ROOT, "profiles", "tools", "configs_probe.py"))
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "profiles", "tools", name + ".py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    return mod
+
+
+def configs_table(ctx):
+    """phase times of BASELINE.json's other single-GPU configurations (C1, C3 multiquadric / thin plate, the C3 shape
+    with the Gaussian kernel, a slice of C5), C2 with FP32 forced (tensor cores), per-cook solves against a cached
+    factorisation and the DirectBSEdit passes -- device resident, reported for context, not bench lines."""
     import contextlib
     import io
+    mod = _load_tool("configs_probe")
     rows = {}
+    keys = ("N", "V", "F", "kernel", "assemble_ms", "factor_ms", "solve_ms", "eval_ms", "eval_vertex_frames_per_s", "eval_alg_tflops")
     with contextlib.redirect_stdout(io.StringIO()):
-        for name, N, V, F, kern in (("C1", 64, 10_000, 1, "gaussian"), ("C3", 2048, 1_000_000, 1, "multiquadric"),
-                                    ("C3_thin_plate", 2048, 1_000_000, 1, "thin_plate"),
-                                    ("C3_shape_gaussian", 2048, 1_000_000, 1, "gaussian"),
-                                    ("C5_slice", 4096, 65_536, 1000, "gaussian")):
-            r = mod.run(ctx, name, N, V, F, kern, 3)
-            rows[name] = {k: r[k] for k in ("N", "V", "F", "kernel", "assemble_ms", "factor_ms", "solve_ms", "eval_ms",
-                                            "eval_vertex_frames_per_s", "eval_alg_tflops")}
+        for name, N, V, F, kern, extra in (("C1", 64, 10_000, 1, "gaussian", {}), ("C3", 2048, 1_000_000, 1, "multiquadric", {}),
+                                           ("C3_thin_plate", 2048, 1_000_000, 1, "thin_plate", {}),
+                                           ("C3_shape_gaussian", 2048, 1_000_000, 1, "gaussian", {}),
+                                           ("C5_slice", 4096, 65_536, 1000, "gaussian", {}),
+                                           ("C5_slice_fp32_tensor", 4096, 65_536, 1000, "gaussian", {"eval_precision": 1}),
+                                           ("C2_fp32_tensor", 256, 100_000, 240, "gaussian", {"eval_precision": 1}),
+                                           ("C2_fp64", 256, 100_000, 240, "gaussian", {"eval_precision": 2})):
+            r = mod.run(ctx, name, N, V, F, kern, 3, **extra)
+            rows[name] = {k: r[k] for k in keys}
+            if extra:
+                rows[name]["eval_precision"] = ["AUTO", "FP32", "FP64"][extra["eval_precision"]]
+        try:
+            rows["dbse"] = _load_tool("dbse_dev_probe").run(ctx, 1_000_000, 32)
+        except Exception as ex:
+            rows["dbse"] = {"failed": str(ex)}
+        try:
+            rows["per_cook"] = per_cook_rows(ctx)
+        except Exception as ex:
+            rows["per_cook"] = {"failed": str(ex)}
     return rows
+
+
+def per_cook_rows(ctx):
+    """one frame per cook against a cached factorisation (the reference's usage): solve ms of cook 1 (sweeps), cook 2
+    (builds the explicit inverse) and the median of the following ones"""
+    import torch
+    from facedeform_b200 import make_params, synth
+    out = {}
+    for N, kern in ((2048, "gaussian"), (2048, "multiquadric"), (8192, "gaussian")):
+        rig = synth.control_rig(N)
+        d_rest = torch.from_numpy(rig.rest).cuda()
+        p = make_params(model=1, term=0, kernel=synth.KERNELS[kern], radius=synth.default_radius(kern, rig.spacing), **{"lambda": 0.0})
+        m = ctx.fit(p, d_rest)
+        ts = []
+        for i in range(6):
+            m.solve(torch.from_numpy(synth.deformed_rig(rig, 1, seed=10 + i)).cuda())
+            ctx.synchronize()
+            ts.append(ctx.phase_ms("solve"))
+        m.close()
+        out[f"{kern}_{N}"] = {"solve_ms_first": round(ts[0], 4), "solve_ms_builds_inverse": round(ts[1], 4),
+                              "solve_ms_steady": round(float(np.median(ts[2:])), 4)}
+    return out
 
 
 def describe(cfg):

@@ -311,6 +311,7 @@ int fd_dbse_init(fd_ctx* ctx, const float* rest_P, int64_t n_pts, const float* s
         k_dbse_build<<<grid, 256, 0, s>>>(h->d_b, d_shapes, h->m, h->lda, h->d_M32, h->d_QR);
         ctx->launches += 1;
         const int ncol = (int)(S < m ? S : m);
+        cudaEventRecord(ctx->ev_begin[FD_PH_FACTOR], s); // fd_ctx_phase_ms(ctx, 1): the QR alone, without the H2D copies
         for (int j = 0; j < ncol; ++j) {
             double* x = h->d_QR + (size_t)j * h->lda;
             k_qr_colnorm<<<h->nchunk, 256, 0, s>>>(x, h->m, j, h->d_part);
@@ -326,6 +327,8 @@ int fd_dbse_init(fd_ctx* ctx, const float* rest_P, int64_t n_pts, const float* s
                 ctx->launches += 3;
             }
         }
+        cudaEventRecord(ctx->ev_end[FD_PH_FACTOR], s);
+        ctx->phase_valid[FD_PH_FACTOR] = true;
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -345,8 +348,11 @@ int fd_dbse_compute_weights(fd_dbse* h, const float* pos, const float* rest, dou
     FD_CUDA_OK(ctx, cudaMemcpyAsync(h->d_a, pos, m * sizeof(float), cudaMemcpyHostToDevice, s));
     FD_CUDA_OK(ctx, cudaMemcpyAsync(h->d_b, rest, m * sizeof(float), cudaMemcpyHostToDevice, s));
     dim3 grid((unsigned)h->nchunk, (unsigned)h->S);
+    cudaEventRecord(ctx->ev_begin[FD_PH_SOLVE], s); // fd_ctx_phase_ms(ctx, 2): the two weight kernels
     k_dbse_wpart<<<grid, 256, 0, s>>>(h->d_QR, h->m, h->lda, h->d_a, h->d_b, h->d_part, h->nchunk);
     k_dbse_wsum<<<h->S, 256, 0, s>>>(h->d_part, h->nchunk, h->d_w, h->d_cw, 0, 0.f, 0.f);
+    cudaEventRecord(ctx->ev_end[FD_PH_SOLVE], s);
+    ctx->phase_valid[FD_PH_SOLVE] = true;
     ctx->launches += 2;
     FD_CUDA_OK(ctx, cudaGetLastError());
     if (weights_out) FD_CUDA_OK(ctx, cudaMemcpyAsync(weights_out, h->d_w, (size_t)h->S * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -366,10 +372,13 @@ int fd_dbse_displace(fd_dbse* h, const float* pos, const float* rest, int32_t do
     const size_t m = (size_t)h->m;
     FD_CUDA_OK(ctx, cudaMemcpyAsync(h->d_a, pos, m * sizeof(float), cudaMemcpyHostToDevice, s));
     FD_CUDA_OK(ctx, cudaMemcpyAsync(h->d_b, rest, m * sizeof(float), cudaMemcpyHostToDevice, s));
+    cudaEventRecord(ctx->ev_begin[FD_PH_EVAL], s); // fd_ctx_phase_ms(ctx, 3): the displacement kernels
     k_dbse_wsum<<<h->S, 256, 0, s>>>(nullptr, h->nchunk, h->d_w, h->d_cw, doclamp ? 1 : 0, doclamp ? weightrange[0] : 0.f,
                                      doclamp ? weightrange[1] : 0.f);
     k_dbse_displace<<<(unsigned)((m + 255) / 256), 256, (size_t)h->S * sizeof(float), s>>>(
         h->d_M32, h->m, h->S, h->d_cw, h->d_a, h->d_b, dofalloff, falloffradius, h->d_o);
+    cudaEventRecord(ctx->ev_end[FD_PH_EVAL], s);
+    ctx->phase_valid[FD_PH_EVAL] = true;
     ctx->launches += 2;
     FD_CUDA_OK(ctx, cudaGetLastError());
     FD_CUDA_OK(ctx, cudaMemcpyAsync(P_out, h->d_o, m * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -33,9 +33,10 @@ namespace {
 // max error of an FP32 evaluation <= coef x 2^-24 x S.  coef = the largest ratio measured against the oracle over
 // N = 256 / 1024 / 2048 control points x 120 frames x 4096 vertices (1.5 M values each; tests/test_gpu_round2.py,
 // tests/tools/accuracy_probe.py): 1.68 tensor cores (FP16 hi/lo splits, FP32 accumulation in the tensor core),
-// 0.93 FMA/SFU -- plus 20 %.  A kernel is eligible while its prediction stays within eval_tolerance x diag; the fastest
-// eligible one runs: tensor cores, then FMA/SFU, else FP64.
-constexpr double ERR_COEF_SIMT = 1.1;
+// 0.93 FMA/SFU -- plus 20 %; the FMA/SFU coefficient is raised further to 1.3 because the CPU emulation of the same
+// arithmetic (tests/tools/fp32_error_emulation.py) reaches 1.21 at N = 64.  A kernel is eligible while its prediction
+// stays within eval_tolerance x diag; the fastest eligible one runs: tensor cores, then FMA/SFU, else FP64.
+constexpr double ERR_COEF_SIMT = 1.3;
 constexpr double ERR_COEF_TENSOR = 2.0;
 
 // wmax[j] = max_c |W[j][c]| over the nrhs solved columns (row j of the row-major weight block)
