@@ -106,116 +106,6 @@ __global__ void __launch_bounds__(256) k_inv_apply(const double* __restrict__ in
     }
 }
 
-// X_k = T_kk^-1 B_k for one diagonal block; one thread per right-hand-side column.
-template <bool LOWER>
-__global__ void __launch_bounds__(128) k_trsm_diag(const double* __restrict__ A, int lda, int k0, int nb,
-                                                   double* __restrict__ B, int ldw, int nrhs)
-{
-    __shared__ double s_T[SB][SB + 1];
-    for (int t = threadIdx.x; t < SB * SB; t += blockDim.x) {
-        const int r = t % SB, c = t / SB;
-        s_T[r][c] = (r < nb && c < nb) ? A[(size_t)(k0 + c) * lda + k0 + r] : (r == c ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nrhs) return;
-    double x[SB];
-#pragma unroll
-    for (int j = 0; j < SB; ++j) x[j] = j < nb ? B[(size_t)(k0 + j) * ldw + c] : 0.0;
-    if (LOWER) {
-#pragma unroll
-        for (int j = 0; j < SB; ++j) {
-            const double xj = x[j];
-#pragma unroll
-            for (int r = j + 1; r < SB; ++r) x[r] -= s_T[r][j] * xj;
-        }
-    } else {
-#pragma unroll
-        for (int j = SB - 1; j >= 0; --j) {
-            const double xj = x[j] / s_T[j][j];
-            x[j] = xj;
-#pragma unroll
-            for (int r = 0; r < j; ++r) x[r] -= s_T[r][j] * xj;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < SB; ++j)
-        if (j < nb) B[(size_t)(k0 + j) * ldw + c] = x[j];
-}
-
-// B[rows][c] -= T[rows, k0:k0+nb] * X[k0:k0+nb][c]; rows below the block (LOWER) or above it (UPPER).
-// CTA tile: 64 rows x 32 columns, 256 threads, 8 rows per thread.
-// (`n` bounds the rows of the LOWER variant, `row_lo` those of the UPPER one: the blocked sweeps restrict both to a panel.)
-template <bool LOWER>
-__global__ void __launch_bounds__(256) k_trsm_update(const double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                     double* __restrict__ B, int ldw, int nrhs, int row_lo)
-{
-    __shared__ double s_t[SB][64 + 1]; // [k][row]
-    __shared__ double s_x[SB][32 + 1]; // [k][col]
-    const int row_begin = LOWER ? k0 + nb : row_lo;
-    const int row_end = LOWER ? n : k0;
-    const int r0 = row_begin + blockIdx.y * 64;
-    const int c0 = blockIdx.x * 32;
-    for (int t = threadIdx.x; t < SB * 64; t += 256) {
-        const int rr = t % 64, k = t / 64;
-        s_t[k][rr] = (k < nb && r0 + rr < row_end) ? A[(size_t)(k0 + k) * lda + r0 + rr] : 0.0;
-    }
-    for (int t = threadIdx.x; t < SB * 32; t += 256) {
-        const int cc = t % 32, k = t / 32;
-        s_x[k][cc] = (k < nb && c0 + cc < nrhs) ? B[(size_t)(k0 + k) * ldw + c0 + cc] : 0.0;
-    }
-    __syncthreads();
-    const int cc = threadIdx.x % 32, rg = threadIdx.x / 32;
-    double acc[8] = {};
-#pragma unroll 8
-    for (int k = 0; k < SB; ++k) {
-        const double xv = s_x[k][cc];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += s_t[k][rg * 8 + i] * xv;
-    }
-    if (c0 + cc < nrhs) { // loads first, stores after: `B[..] -= acc` would serialise on possible aliasing
-        double bv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = r0 + rg * 8 + i;
-            bv[i] = r < row_end ? B[(size_t)r * ldw + c0 + cc] : 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = r0 + rg * 8 + i;
-            if (r < row_end) B[(size_t)r * ldw + c0 + cc] = bv[i] - acc[i];
-        }
-    }
-}
-
-// X_k = T_kk^-1 B_k with the pre-inverted diagonal block (fd_model::d_Tinv, column-major 32 x 32): a small dense product
-// of independent FMAs instead of the 32-step dependent substitution of k_trsm_diag; one thread per right-hand side.
-__global__ void __launch_bounds__(128) k_trsm_diag_inv(const double* __restrict__ Tinv_blk, int k0, int nb,
-                                                       double* __restrict__ B, int ldw, int nrhs)
-{
-    __shared__ __align__(16) double s_I[SB * SB]; // s_I[k * 32 + r] = inverse[r][k]
-    for (int t = threadIdx.x; t < SB * SB; t += 128) s_I[t] = Tinv_blk[t];
-    __syncthreads();
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    if (c >= nrhs) return;
-    double x[SB];
-#pragma unroll
-    for (int r = 0; r < SB; ++r) x[r] = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < SB; ++k) {
-        const double b = k < nb ? B[(size_t)(k0 + k) * ldw + c] : 0.0;
-#pragma unroll
-        for (int r = 0; r < SB; r += 2) {
-            const double2 iv = *reinterpret_cast<const double2*>(&s_I[k * SB + r]);
-            x[r] = fma(iv.x, b, x[r]);
-            x[r + 1] = fma(iv.y, b, x[r + 1]);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < SB; ++r)
-        if (r < nb) B[(size_t)(k0 + r) * ldw + c] = x[r];
-}
-
 // ---- a handful of right-hand sides (one frame per cook, the reference's own usage): one launch per 32-row block step.
 // Every CTA recomputes x_k = T_kk^-1 b_k from the pre-inverted diagonal block (32 x 32 x nrhs FMAs, redundantly: cheaper
 // than a second launch), then updates its own 64 rows outside the block: upd[rows] -= T[rows, k-block] x_k.  Sources and
@@ -548,11 +438,12 @@ __device__ __forceinline__ void dmma8(double& c0, double& c1, double a, double b
 template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 // chunk of the panel of block column k0: rows [r0, r0 + 128) x columns [k0, k0 + 32) -> s_P[k][row]
-__device__ __forceinline__ void s8_prefetch_chunk(double* s_P, const double* __restrict__ A, int lda, int k0, int nb, int r0)
+__device__ __forceinline__ void s8_prefetch_chunk(double* s_P, const double* __restrict__ A, int lda, int k0, int nb, int r0,
+                                                  int n_pad)
 {
     for (int t = threadIdx.x; t < SB * (S8_CH / 2); t += S8_THREADS) {
         const int kk = t / (S8_CH / 2), q = t % (S8_CH / 2);
-        const int r = min(r0 + 2 * q, lda - 2); // rows past the matrix: any valid address, their results are masked
+        const int r = min(r0 + 2 * q, n_pad - 2); // rows past the (sub-)matrix: a valid address of the column, results masked
         cp_async16(s_P + kk * S8_LDP + 2 * q, A + (size_t)(k0 + min(kk, nb - 1)) * lda + r);
     }
 }
@@ -569,8 +460,10 @@ __global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __rest
                                                             const int* __restrict__ perm, const float* __restrict__ rest,
                                                             const float* __restrict__ deform, int F,
                                                             const double* __restrict__ Tinv, double* __restrict__ W, int ldw,
-                                                            const fd_tc_pack_args pk)
+                                                            const fd_tc_pack_args pk, int mode)
 {
+    // mode 0: L sweep then U sweep (a whole system); 1: L sweep only; 2: U sweep only -- the blocked solve of systems too
+    // large for one slab runs this kernel on 1024-row diagonal panels (A, Tinv, W offset to the panel; perm == NULL)
     extern __shared__ __align__(16) double s8_smem[];
     __shared__ double s_red[32][S8_RC + 1];
     __shared__ float s_scale[S8_RC];
@@ -597,14 +490,18 @@ __global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __rest
         }
         return;
     }
-    s8_prefetch_tinv(s_T, Tinv); // block 0 of L
+    const int s_begin = mode == 2 ? nblk : 0, s_end = mode == 1 ? nblk : 2 * nblk;
+    { // the inverse of the first step's diagonal block
+        const int blk0 = s_begin < nblk ? s_begin : 2 * nblk - 1 - s_begin;
+        s8_prefetch_tinv(s_T, Tinv + ((size_t)blk0 * 2 + (s_begin < nblk ? 0 : 1)) * SB * SB);
+    }
     cp_async_commit();
     // right-hand sides, permuted: delta subtracted in FP32 then widened (SOP_FaceDeform.cpp:276-284); pad rows are zero
     for (int t = tid; t < n_pad * S8_RC; t += S8_THREADS) {
         const int i = t / S8_RC, c = c0 + (t % S8_RC);
         double v = 0.0;
         if (i < n) {
-            const int src = perm[i];
+            const int src = perm ? perm[i] : i;
             if (!deform) { // right-hand sides prebuilt in W (the null-space path, fd_nullspace.cu)
                 if (c < ldw) v = W[(size_t)src * ldw + c];
             } else if (c < nrhs && src < N) {
@@ -615,16 +512,16 @@ __global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __rest
         s_B[t] = v;
     }
     int tbuf = 0, pbuf = 0;
-    // 2 * nblk block steps: L sweep down, then U sweep up
-    for (int step = 0; step < 2 * nblk; ++step) {
+    // 2 * nblk block steps: L sweep down, then U sweep up (or one of the two: mode)
+    for (int step = s_begin; step < s_end; ++step) {
         const bool lower = step < nblk;
         const int blk = lower ? step : 2 * nblk - 1 - step;
         const int k0 = blk * SB, nb = min(SB, n - k0);
         const int row_lo = lower ? k0 + SB : 0, row_hi = lower ? n : k0; // rows outside the block that depend on it
         const int nchunks = row_hi > row_lo ? (row_hi - row_lo + S8_CH - 1) / S8_CH : 0;
         // prefetch: first panel chunk of this step and the inverse of the next step's block (one cp.async group)
-        if (nchunks > 0) s8_prefetch_chunk(s_P + pbuf * S8_CHUNK_DOUBLES, A, lda, k0, nb, row_lo);
-        if (step + 1 < 2 * nblk) {
+        if (nchunks > 0) s8_prefetch_chunk(s_P + pbuf * S8_CHUNK_DOUBLES, A, lda, k0, nb, row_lo, n_pad);
+        if (step + 1 < s_end) {
             const int nblk_next = step + 1 < nblk ? step + 1 : 2 * nblk - 2 - step;
             s8_prefetch_tinv(s_T + (tbuf ^ 1) * S8_TINV_DOUBLES, Tinv + ((size_t)nblk_next * 2 + (step + 1 < nblk ? 0 : 1)) * SB * SB);
         }
@@ -653,7 +550,7 @@ __global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __rest
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int r0 = row_lo + ch * S8_CH;
                 if (ch + 1 < nchunks) {
-                    s8_prefetch_chunk(s_P + (pbuf ^ 1) * S8_CHUNK_DOUBLES, A, lda, k0, nb, r0 + S8_CH);
+                    s8_prefetch_chunk(s_P + (pbuf ^ 1) * S8_CHUNK_DOUBLES, A, lda, k0, nb, r0 + S8_CH, n_pad);
                     cp_async_commit();
                     cp_async_wait<1>();
                 } else {
@@ -838,7 +735,7 @@ cudaError_t fd_launch_solve(fd_ctx* ctx, fd_model* m, const float* d_deform, int
             if (m->use_tc && !ctx->dbg.no_fused_pack) fd_tc_pack_args_fill(m, &pk);
             const int cols = pk.enabled ? max(ldw, pk.ncol_pad) : ldw;
             k_solve_slab8<<<(cols + S8_RC - 1) / S8_RC, S8_THREADS, bytes8, s>>>(m->d_A, m->lda, n, m->N, m->d_perm, m->d_rest,
-                                                                                d_deform, F, m->d_Tinv, m->d_W, ldw, pk);
+                                                                                d_deform, F, m->d_Tinv, m->d_W, ldw, pk, 0);
             ctx->launches += 1;
             m->tc_packed_by_solve = pk.enabled != 0;
             return cudaGetLastError();
@@ -880,7 +777,7 @@ cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, 
             fd_tc_pack_args pk;
             pk.enabled = 0;
             k_solve_slab8<<<(ldw + S8_RC - 1) / S8_RC, S8_THREADS, bytes8, s>>>(d_A, lda, n, n, d_perm, nullptr, nullptr,
-                                                                              nrhs / 3, d_Tinv, d_W, ldw, pk);
+                                                                              nrhs / 3, d_Tinv, d_W, ldw, pk, 0);
             ctx->launches += 1;
             return cudaGetLastError();
         }
@@ -907,71 +804,36 @@ cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, 
         cudaFreeAsync(d_Y, s);
         return e;
     }
-    struct { const double* d_A; int lda; const double* d_Tinv; double* d_W; } mm = {d_A, lda, d_Tinv, d_W};
-    const auto* m = &mm;
-    // Blocked sweeps for systems whose slab does not fit in shared memory: panels of 256 rows.  Inside a panel the
-    // 32-row block steps touch only the panel's rows (rank-32 updates of <= 224 rows); the rows outside it take one
-    // rank-256 update (k_panel_gemm), so the right-hand sides are re-read n / 256 times instead of n / 32.
-    constexpr int PB = 256;
-    const int cblocks = (nrhs + 127) / 128;
-    if (nrhs < 64) { // a handful of right-hand sides: plain rank-32 sweeps (a GEMM tile would be mostly padding)
-        for (int k0 = 0; k0 < n; k0 += SB) { // L y = P b
-            const int nb = min(SB, n - k0);
-            k_trsm_diag<true><<<cblocks, 128, 0, s>>>(m->d_A, m->lda, k0, nb, m->d_W, ldw, nrhs);
-            ctx->launches += 1;
-            const int rows = n - k0 - nb;
-            if (rows > 0) {
-                dim3 grid((nrhs + 31) / 32, (rows + 63) / 64);
-                k_trsm_update<true><<<grid, 256, 0, s>>>(m->d_A, m->lda, n, k0, nb, m->d_W, ldw, nrhs, 0);
-                ctx->launches += 1;
-            }
-        }
-        for (int k0 = (n - 1) / SB * SB; k0 >= 0; k0 -= SB) { // U x = y
-            const int nb = min(SB, n - k0);
-            k_trsm_diag<false><<<cblocks, 128, 0, s>>>(m->d_A, m->lda, k0, nb, m->d_W, ldw, nrhs);
-            ctx->launches += 1;
-            if (k0 > 0) {
-                dim3 grid((nrhs + 31) / 32, (k0 + 63) / 64);
-                k_trsm_update<false><<<grid, 256, 0, s>>>(m->d_A, m->lda, n, k0, nb, m->d_W, ldw, nrhs, 0);
-                ctx->launches += 1;
-            }
-        }
-        return cudaGetLastError();
-    }
+    // Blocked sweeps for systems whose slab does not fit in shared memory: diagonal panels of 1024 rows.  Inside a panel
+    // the slab kernel runs its L (or U) sweep for every right-hand side (one launch, 8 columns per CTA, the panel's
+    // triangle streamed from L2, DMMA block products); the rows outside the panel take one rank-1024 update on the FP64
+    // tensor pipe (k_panel_gemm).  n = 4100: 5 + 5 slab launches and 4 + 4 GEMMs instead of ~540 block-step launches.
+    constexpr int PB = 1024;
+    const size_t slab_bytes = ((size_t)PB * S8_RC + 2 * S8_CHUNK_DOUBLES + 2 * S8_TINV_DOUBLES) * sizeof(double);
+    fd_tc_pack_args pk0;
+    pk0.enabled = 0;
+    const int slab_grid = (ldw + S8_RC - 1) / S8_RC;
     for (int p0 = 0; p0 < n; p0 += PB) { // L y = P b
         const int pe = min(p0 + PB, n);
-        for (int k0 = p0; k0 < pe; k0 += SB) {
-            const int nb = min(SB, pe - k0);
-            k_trsm_diag_inv<<<cblocks, 128, 0, s>>>(m->d_Tinv + (size_t)(k0 / SB) * 2 * SB * SB, k0, nb, m->d_W, ldw, nrhs);
-            ctx->launches += 1;
-            const int rows = pe - k0 - nb;
-            if (rows > 0) {
-                dim3 grid((nrhs + 31) / 32, (rows + 63) / 64);
-                k_trsm_update<true><<<grid, 256, 0, s>>>(m->d_A, m->lda, pe, k0, nb, m->d_W, ldw, nrhs, 0);
-                ctx->launches += 1;
-            }
-        }
+        k_solve_slab8<<<slab_grid, S8_THREADS, slab_bytes, s>>>(d_A + (size_t)p0 * lda + p0, lda, pe - p0, pe - p0, nullptr, nullptr,
+                                                              nullptr, nrhs / 3, d_Tinv + (size_t)(p0 / SB) * 2 * SB * SB,
+                                                              d_W + (size_t)p0 * ldw, ldw, pk0, 1);
+        ctx->launches += 1;
         if (pe < n) {
             dim3 grid((nrhs + PG_TN - 1) / PG_TN, (n - pe + PG_TM - 1) / PG_TM);
-            k_panel_gemm<<<grid, 256, 0, s>>>(m->d_A, m->lda, pe, n, p0, pe - p0, m->d_W, ldw, nrhs);
+            k_panel_gemm<<<grid, 256, 0, s>>>(d_A, lda, pe, n, p0, pe - p0, d_W, ldw, nrhs);
             ctx->launches += 1;
         }
     }
     for (int p0 = (n - 1) / PB * PB; p0 >= 0; p0 -= PB) { // U x = y
         const int pe = min(p0 + PB, n);
-        for (int k0 = p0 + (pe - p0 - 1) / SB * SB; k0 >= p0; k0 -= SB) {
-            const int nb = min(SB, pe - k0);
-            k_trsm_diag_inv<<<cblocks, 128, 0, s>>>(m->d_Tinv + ((size_t)(k0 / SB) * 2 + 1) * SB * SB, k0, nb, m->d_W, ldw, nrhs);
-            ctx->launches += 1;
-            if (k0 > p0) {
-                dim3 grid((nrhs + 31) / 32, (k0 - p0 + 63) / 64);
-                k_trsm_update<false><<<grid, 256, 0, s>>>(m->d_A, m->lda, n, k0, nb, m->d_W, ldw, nrhs, p0);
-                ctx->launches += 1;
-            }
-        }
+        k_solve_slab8<<<slab_grid, S8_THREADS, slab_bytes, s>>>(d_A + (size_t)p0 * lda + p0, lda, pe - p0, pe - p0, nullptr, nullptr,
+                                                              nullptr, nrhs / 3, d_Tinv + (size_t)(p0 / SB) * 2 * SB * SB,
+                                                              d_W + (size_t)p0 * ldw, ldw, pk0, 2);
+        ctx->launches += 1;
         if (p0 > 0) {
             dim3 grid((nrhs + PG_TN - 1) / PG_TN, (p0 + PG_TM - 1) / PG_TM);
-            k_panel_gemm<<<grid, 256, 0, s>>>(m->d_A, m->lda, 0, p0, p0, pe - p0, m->d_W, ldw, nrhs);
+            k_panel_gemm<<<grid, 256, 0, s>>>(d_A, lda, 0, p0, p0, pe - p0, d_W, ldw, nrhs);
             ctx->launches += 1;
         }
     }
