@@ -16,8 +16,8 @@
 // threads write the 128 x 32 Phi tile into shared memory (16 basis functions each: expanded distance, 4 DFMA;
 // exp2 / sqrt / log from few DFMAs, fd_eval_common.cuh), the weight tile arrives with cp.async one stage ahead, and
 // every warp contracts its 32 x 48 sub-tile: 24 accumulator tiles, 10 fragment loads per 24 DMMAs.  Phi is computed
-// once per 96 columns instead of once per 1-2 frames (k_eval_f64), so the FP64 pipe spends ~85 % of its time in the
-// contraction.  (A warp-specialised variant -- 4 producer warps for Phi, 8 consumer warps for the DMMAs -- was measured
+// once per 96 columns instead of once per 1-2 frames (k_eval_f64), and its generation for stage s + 1 is interleaved,
+// two values per K = 4 step, with the DMMAs of stage s in every warp's instruction stream.  (A warp-specialised variant -- 4 producer warps for Phi, 8 consumer warps for the DMMAs -- was measured
 // SLOWER, 2.98 ms against 2.41 ms at BASELINE configs[1]: DMMA and DFMA share the FP64 pipe, a DMMA holds it for 16
 // cycles, and a warp of dependent DFMA chains scheduled beside DMMA warps starves; the look-ahead LU failed the same way.)
 // Polynomial rows ride along as extra K rows [1, x, y, z].  Epilogue = the SOP's (gate, tangent
@@ -126,7 +126,7 @@ constexpr int E_LDA = E_KB + 4;    // = 4 mod 16: conflict-free A-fragment loads
 constexpr int E_LDB = E_TN + 4;    // = 4 mod 16: conflict-free B-fragment loads
 constexpr int E_LDC = E_TN + 1;    // float staging of the accumulators for the epilogue
 constexpr int E_STAGE_DOUBLES = E_TM * E_LDA + E_KB * E_LDB;
-constexpr int E_SMEM_BYTES = 2 * E_STAGE_DOUBLES * 8 + E_KB * 5 * 8 + 128 * 16 + 64 * 8;
+constexpr int E_SMEM_BYTES = 2 * E_STAGE_DOUBLES * 8 + 2 * E_KB * 5 * 8 + 128 * 16 + 64 * 8;
 static_assert(E_TM * E_LDC * 4 <= 2 * E_STAGE_DOUBLES * 8, "the epilogue staging reuses the pipeline buffers");
 
 struct Eval64Args {
@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
     extern __shared__ __align__(16) unsigned char e64_smem[];
     if (a.sel && *a.sel != a.sel_id) return; // FD_EVAL_AUTO settled on an FP32 kernel
     double* s_stage = reinterpret_cast<double*>(e64_smem);                 // [2][A tile | B tile]
-    double* s_ctr = s_stage + 2 * E_STAGE_DOUBLES;                         // [32][5]: (a, b, c, d, s) of the stage's centres
-    double2* s_log = reinterpret_cast<double2*>(s_ctr + E_KB * 5);         // thin plate: fd_half_log64 table
+    double* s_ctr = s_stage + 2 * E_STAGE_DOUBLES;                         // [2][32][5]: (a, b, c, d, s) of a stage's centres
+    double2* s_log = reinterpret_cast<double2*>(s_ctr + 2 * E_KB * 5);     // thin plate: fd_half_log64 table
     double* s_exp = reinterpret_cast<double*>(s_log + 128);                // Gaussian: fd_exp2_64 table
     float* s_C = reinterpret_cast<float*>(e64_smem);                       // epilogue staging, reuses the stage buffers
 
@@ -229,49 +229,51 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
                         ca = c.x, cb_ = c.y, cc = c.z, cd = c.w, cs = 1.0;
                     }
                 }
-                double* d = s_ctr + tid * 5;
+                double* d = s_ctr + (s & 1) * E_KB * 5 + tid * 5;
                 d[0] = ca, d[1] = cb_, d[2] = cc, d[3] = cd, d[4] = cs;
             }
         };
-        // this thread's 16 basis values of stage s -> A tile of buffer b
-        auto gen_phi = [&](int s, int b) {
-            double* sA = s_stage + b * E_STAGE_DOUBLES + row * E_LDA + khalf * 16;
+        // two of this thread's 16 basis values of stage s (pair jj / 2) -> A tile of buffer s & 1
+        auto gen_pair = [&](int s, int jj) {
+            double* sA = s_stage + (s & 1) * E_STAGE_DOUBLES + row * E_LDA + khalf * 16;
+            const double* sc = s_ctr + (s & 1) * E_KB * 5;
+            double ph[2];
 #pragma unroll
-            for (int jj = 0; jj < 16; jj += 2) {
-                double ph[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int kk = khalf * 16 + jj + e;
-                    const int j = s * E_KB + kk;
-                    const double* c = s_ctr + kk * 5; // warp-wide broadcast reads
-                    const double t = fma(qx, c[0], fma(qy, c[1], fma(qz, c[2], fma(pp, c[4], c[3]))));
-                    double val;
-                    if (KERNEL == FD_KERNEL_GAUSSIAN) val = fd_exp2_64(fmin(t, 0.0), s_exp);
-                    else if (KERNEL == FD_KERNEL_MULTIQUADRIC) val = fd_fast_sqrt64(t);
-                    else val = fmax(t, 0.0) * fd_half_log64(fmax(t, 0.0), s_log);
-                    if (j >= a.N) { // polynomial rows [1, x, y, z], then zero padding
-                        const int r = j - a.N;
-                        val = r >= a.np ? 0.0 : (r == 0 ? 1.0 : (r == 1 ? px : (r == 2 ? py : pz)));
-                    }
-                    ph[e] = val;
+            for (int e = 0; e < 2; ++e) {
+                const int kk = khalf * 16 + jj + e;
+                const int j = s * E_KB + kk;
+                const double* c = sc + kk * 5; // warp-wide broadcast reads
+                const double t = fma(qx, c[0], fma(qy, c[1], fma(qz, c[2], fma(pp, c[4], c[3]))));
+                double val;
+                if (KERNEL == FD_KERNEL_GAUSSIAN) val = fd_exp2_64(fmin(t, 0.0), s_exp);
+                else if (KERNEL == FD_KERNEL_MULTIQUADRIC) val = fd_fast_sqrt64(t);
+                else val = fmax(t, 0.0) * fd_half_log64(fmax(t, 0.0), s_log);
+                if (j >= a.N) { // polynomial rows [1, x, y, z], then zero padding
+                    const int r = j - a.N;
+                    val = r >= a.np ? 0.0 : (r == 0 ? 1.0 : (r == 1 ? px : (r == 2 ? py : pz)));
                 }
-                *reinterpret_cast<double2*>(sA + jj) = make_double2(ph[0], ph[1]);
+                ph[e] = val;
             }
+            *reinterpret_cast<double2*>(sA + jj) = make_double2(ph[0], ph[1]);
         };
 
+        // Software pipeline: while a warp contracts stage s it also produces its share of the Phi tile of stage s + 1, two
+        // basis values per K = 4 step, in the same instruction stream -- the dependent DFMA chains of the basis functions
+        // then hide behind the DMMAs instead of forming a phase of their own (that phase left the tensor pipe 51 % busy).
         __syncthreads(); // the previous tile's epilogue has left the stage buffers
         load_c(0);
         load_w(0, 0);
         __syncthreads();
-        gen_phi(0, 0);
+#pragma unroll
+        for (int jj = 0; jj < 16; jj += 2) gen_pair(0, jj);
+        if (nstage > 1) load_c(1);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         for (int s = 0; s < nstage; ++s) {
             const int b = s & 1;
-            __syncthreads(); // stage s complete (Phi + weights); every warp is done with buffer b ^ 1 and with s_ctr
-            if (s + 1 < nstage) {
-                load_w(s + 1, b ^ 1);
-                load_c(s + 1);
-            }
+            __syncthreads(); // stage s complete (Phi + weights), the centres of s + 1 are written; buffer b ^ 1 is free
+            const bool more = s + 1 < nstage;
+            if (more) load_w(s + 1, b ^ 1);
+            if (s + 2 < nstage) load_c(s + 2); // into the centre buffer of stage s, whose Phi tile is complete
             const double* sA = s_stage + b * E_STAGE_DOUBLES + (wm * 32 + fr) * E_LDA + fk;
             const double* sB = s_stage + b * E_STAGE_DOUBLES + E_TM * E_LDA + fk * E_LDB + wn * 48 + fr;
 #pragma unroll
@@ -285,12 +287,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < 6; ++ni) fd_dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                if (more) gen_pair(s + 1, 2 * k4);
             }
-            if (s + 1 < nstage) {
-                __syncthreads(); // s_ctr of stage s + 1 is written
-                gen_phi(s + 1, b ^ 1);
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads(); // all warps are done with the stage buffers: they become the FP32 staging of the accumulators
 #pragma unroll
