@@ -15,7 +15,7 @@
 // mma.sync.m8n8k4.f64 (DMMA).  A CTA owns 128 vertices x 96 columns (32 frames); per stage of 32 centres its 256
 // threads write the 128 x 32 Phi tile into shared memory (16 basis functions each: expanded distance, 4 DFMA;
 // exp2 / sqrt / log from few DFMAs, fd_eval_common.cuh), the weight tile arrives with cp.async one stage ahead, and
-// every warp contracts its 32 x 48 sub-tile: 24 accumulator tiles, 10 fragment loads per 24 DMMAs.  Phi is computed
+// each of the 16 warps contracts its 32 x 24 sub-tile: 12 accumulator tiles, 7 fragment loads per 12 DMMAs.  Phi is computed
 // once per 96 columns instead of once per 1-2 frames (k_eval_f64), and its generation for stage s + 1 is interleaved,
 // two values per K = 4 step, with the DMMAs of stage s in every warp's instruction stream.  (A warp-specialised variant -- 4 producer warps for Phi, 8 consumer warps for the DMMAs -- was measured
 // SLOWER, 2.98 ms against 2.41 ms at BASELINE configs[1]: DMMA and DFMA share the FP64 pipe, a DMMA holds it for 16
@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(256) k_cancel_select(const SelectArgs a)
 constexpr int E_TM = 128;          // vertices per CTA tile
 constexpr int E_TN = 96;           // columns per CTA tile (32 frames)
 constexpr int E_KB = 32;           // centres per stage
-constexpr int E_THREADS = 256;
+constexpr int E_THREADS = 512;     // 16 warps, 4 per SM sub-partition: the fixed issue delays of back-to-back DMMAs and the
+                                   // DFMA chains of the basis functions need that many to overlap (2 per sub-partition left the
+                                   // tensor pipe 51 % busy)
 constexpr int E_LDA = E_KB + 4;    // = 4 mod 16: conflict-free A-fragment loads (see the lane map of fd_dmma884)
 constexpr int E_LDB = E_TN + 4;    // = 4 mod 16: conflict-free B-fragment loads
 constexpr int E_LDC = E_TN + 1;    // float staging of the accumulators for the epilogue
@@ -170,9 +172,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (KERNEL == FD_KERNEL_THINPLATE && tid < 128) fd_half_log64_table(s_log, tid);
     if (KERNEL == FD_KERNEL_GAUSSIAN && tid < 64) fd_exp2_64_table(s_exp, tid);
-    const int wm = warp & 3, wn = warp >> 2;       // warp tile: rows [32 wm, +32), columns [48 wn, +48)
+    const int wm = warp & 3, wn = warp >> 2;       // warp tile: rows [32 wm, +32), columns [24 wn, +24)
     const int fr = lane >> 2, fk = lane & 3;
-    const int row = tid & (E_TM - 1), khalf = tid >> 7; // Phi generation: this thread's vertex row and half of the stage's centres
+    const int row = tid & (E_TM - 1), kq = tid >> 7; // Phi generation: this thread's vertex row and quarter of the stage's centres
     const double ox = (double)a.origin[0], oy = (double)a.origin[1], oz = (double)a.origin[2];
     const int Ktot = a.N + a.np;
     const int nstage = (Ktot + E_KB - 1) / E_KB;
@@ -195,11 +197,11 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
         const double qx = px - ox, qy = py - oy, qz = pz - oz;
         const double pp = qx * qx + qy * qy + qz * qz;
 
-        double acc[4][6][2];
+        double acc[4][3][2];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 6; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
         // weight tile of stage s -> buffer b (cp.async, rows beyond N + np and columns beyond ldw zero-filled)
         auto load_w = [&](int s, int b) {
@@ -233,14 +235,14 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
                 d[0] = ca, d[1] = cb_, d[2] = cc, d[3] = cd, d[4] = cs;
             }
         };
-        // two of this thread's 16 basis values of stage s (pair jj / 2) -> A tile of buffer s & 1
+        // two of this thread's 8 basis values of stage s (pair jj / 2) -> A tile of buffer s & 1
         auto gen_pair = [&](int s, int jj) {
-            double* sA = s_stage + (s & 1) * E_STAGE_DOUBLES + row * E_LDA + khalf * 16;
+            double* sA = s_stage + (s & 1) * E_STAGE_DOUBLES + row * E_LDA + kq * 8;
             const double* sc = s_ctr + (s & 1) * E_KB * 5;
             double ph[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int kk = khalf * 16 + jj + e;
+                const int kk = kq * 8 + jj + e;
                 const int j = s * E_KB + kk;
                 const double* c = sc + kk * 5; // warp-wide broadcast reads
                 const double t = fma(qx, c[0], fma(qy, c[1], fma(qz, c[2], fma(pp, c[4], c[3]))));
@@ -258,14 +260,14 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
         };
 
         // Software pipeline: while a warp contracts stage s it also produces its share of the Phi tile of stage s + 1, two
-        // basis values per K = 4 step, in the same instruction stream -- the dependent DFMA chains of the basis functions
+        // basis values per two K = 4 steps, in the same instruction stream -- the dependent DFMA chains of the basis functions
         // then hide behind the DMMAs instead of forming a phase of their own (that phase left the tensor pipe 51 % busy).
         __syncthreads(); // the previous tile's epilogue has left the stage buffers
         load_c(0);
         load_w(0, 0);
         __syncthreads();
 #pragma unroll
-        for (int jj = 0; jj < 16; jj += 2) gen_pair(0, jj);
+        for (int jj = 0; jj < 8; jj += 2) gen_pair(0, jj);
         if (nstage > 1) load_c(1);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         for (int s = 0; s < nstage; ++s) {
@@ -275,19 +277,19 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
             if (more) load_w(s + 1, b ^ 1);
             if (s + 2 < nstage) load_c(s + 2); // into the centre buffer of stage s, whose Phi tile is complete
             const double* sA = s_stage + b * E_STAGE_DOUBLES + (wm * 32 + fr) * E_LDA + fk;
-            const double* sB = s_stage + b * E_STAGE_DOUBLES + E_TM * E_LDA + fk * E_LDB + wn * 48 + fr;
+            const double* sB = s_stage + b * E_STAGE_DOUBLES + E_TM * E_LDA + fk * E_LDB + wn * 24 + fr;
 #pragma unroll
             for (int k4 = 0; k4 < E_KB / 4; ++k4) {
-                double af[4], bf[6];
+                double af[4], bf[3];
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi) af[mi] = sA[mi * 8 * E_LDA + k4 * 4];
 #pragma unroll
-                for (int ni = 0; ni < 6; ++ni) bf[ni] = sB[k4 * 4 * E_LDB + ni * 8];
+                for (int ni = 0; ni < 3; ++ni) bf[ni] = sB[k4 * 4 * E_LDB + ni * 8];
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 6; ++ni) fd_dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-                if (more) gen_pair(s + 1, 2 * k4);
+                    for (int ni = 0; ni < 3; ++ni) fd_dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                if (more && (k4 & 1)) gen_pair(s + 1, k4 - 1);
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
@@ -295,19 +297,19 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 6; ++ni) {
-                float* d = s_C + (wm * 32 + mi * 8 + fr) * E_LDC + wn * 48 + ni * 8 + 2 * fk;
+            for (int ni = 0; ni < 3; ++ni) {
+                float* d = s_C + (wm * 32 + mi * 8 + fr) * E_LDC + wn * 24 + ni * 8 + 2 * fk;
                 d[0] = (float)acc[mi][ni][0]; // the narrowing of SOP_FaceDeform.cpp:415
                 d[1] = (float)acc[mi][ni][1];
             }
         __syncthreads();
-        // epilogue: thread = (vertex row, frames khalf, khalf + 2, ...)
+        // epilogue: thread = (vertex row, frames kq, kq + 4, ...)
         if (v < a.V) {
             const float d2 = a.dist2 ? a.dist2[v] : 0.f;
             const bool skip = d2 > a.radius2;                                   // :408-410
             float fo = powf(1.0f - fminf(d2 / a.radius2, 1.0f), a.falloffrate); // :423-424
             if (skip) fo = 0.f;
-            if (a.falloff_out && cb == 0 && khalf == 0) a.falloff_out[v] = fo;
+            if (a.falloff_out && cb == 0 && kq == 0) a.falloff_out[v] = fo;
             float tu[3], tv[3], tn[3];
             if (a.do_tangent) {
 #pragma unroll
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
             }
             const int f0 = cb * (E_TN / 3);
             const int nf = min(E_TN / 3, a.F - f0);
-            for (int fi = khalf; fi < nf; fi += 2) {
+            for (int fi = kq; fi < nf; fi += 4) {
                 const float* src = s_C + row * E_LDC + 3 * fi;
                 float d[3] = {src[0], src[1], src[2]};
                 if (a.do_tangent) fd_project_to_tangents(tu, tv, tn, d);
