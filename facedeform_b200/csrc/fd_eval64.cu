@@ -12,11 +12,11 @@
 // at their first instruction.  The reference evaluates in FP64 (alglib::rbfcalc on double[3], SOP_FaceDeform.cpp:411-415).
 //
 // (2) k_eval64_mma: D[v][3f+k] = sum_j Phi[v][j] W[j][3f+k] with Phi generated on the fly in FP64 and contracted by
-// mma.sync.m8n8k4.f64 (DMMA).  A CTA owns 128 vertices x 96 columns (32 frames); per stage of 32 centres its 256
+// mma.sync.m8n8k4.f64 (DMMA).  A CTA owns 128 vertices x 192 columns (64 frames); per stage of 32 centres its 256
 // threads write the 128 x 32 Phi tile into shared memory (16 basis functions each: expanded distance, 4 DFMA;
 // exp2 / sqrt / log from few DFMAs, fd_eval_common.cuh), the weight tile arrives with cp.async one stage ahead, and
-// each of the 16 warps contracts its 32 x 24 sub-tile: 12 accumulator tiles, 7 fragment loads per 12 DMMAs.  Phi is computed
-// once per 96 columns instead of once per 1-2 frames (k_eval_f64), and its generation for stage s + 1 is interleaved,
+// each of the 16 warps contracts its 64 x 24 sub-tile: 24 accumulator tiles, 11 fragment loads per 24 DMMAs.  Phi is computed
+// once per 192 columns instead of once per 1-2 frames (k_eval_f64), and its generation for stage s + 1 is interleaved,
 // two values per K = 4 step, with the DMMAs of stage s in every warp's instruction stream.  (A warp-specialised variant -- 4 producer warps for Phi, 8 consumer warps for the DMMAs -- was measured
 // SLOWER, 2.98 ms against 2.41 ms at BASELINE configs[1]: DMMA and DFMA share the FP64 pipe, a DMMA holds it for 16
 // cycles, and a warp of dependent DFMA chains scheduled beside DMMA warps starves; the look-ahead LU failed the same way.)
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k_cancel_select(const SelectArgs a)
 // (2) FP64 evaluation on the FP64 tensor pipe
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int E_TM = 128;          // vertices per CTA tile
-constexpr int E_TN = 96;           // columns per CTA tile (32 frames)
+constexpr int E_TN = 192;          // columns per CTA tile (64 frames)
 constexpr int E_KB = 32;           // centres per stage
 constexpr int E_THREADS = 512;     // 16 warps, 4 per SM sub-partition: the fixed issue delays of back-to-back DMMAs and the
                                    // DFMA chains of the basis functions need that many to overlap (2 per sub-partition left the
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (KERNEL == FD_KERNEL_THINPLATE && tid < 128) fd_half_log64_table(s_log, tid);
     if (KERNEL == FD_KERNEL_GAUSSIAN && tid < 64) fd_exp2_64_table(s_exp, tid);
-    const int wm = warp & 3, wn = warp >> 2;       // warp tile: rows [32 wm, +32), columns [24 wn, +24)
+    const int wm = warp & 1, wn = warp >> 1;       // warp tile: rows [64 wm, +64), columns [24 wn, +24)
     const int fr = lane >> 2, fk = lane & 3;
     const int row = tid & (E_TM - 1), kq = tid >> 7; // Phi generation: this thread's vertex row and quarter of the stage's centres
     const double ox = (double)a.origin[0], oy = (double)a.origin[1], oz = (double)a.origin[2];
@@ -197,9 +197,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
         const double qx = px - ox, qy = py - oy, qz = pz - oz;
         const double pp = qx * qx + qy * qy + qz * qz;
 
-        double acc[4][3][2];
+        double acc[8][3][2];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
@@ -276,17 +276,17 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
             const bool more = s + 1 < nstage;
             if (more) load_w(s + 1, b ^ 1);
             if (s + 2 < nstage) load_c(s + 2); // into the centre buffer of stage s, whose Phi tile is complete
-            const double* sA = s_stage + b * E_STAGE_DOUBLES + (wm * 32 + fr) * E_LDA + fk;
+            const double* sA = s_stage + b * E_STAGE_DOUBLES + (wm * 64 + fr) * E_LDA + fk;
             const double* sB = s_stage + b * E_STAGE_DOUBLES + E_TM * E_LDA + fk * E_LDB + wn * 24 + fr;
 #pragma unroll
             for (int k4 = 0; k4 < E_KB / 4; ++k4) {
-                double af[4], bf[3];
+                double af[8], bf[3];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) af[mi] = sA[mi * 8 * E_LDA + k4 * 4];
+                for (int mi = 0; mi < 8; ++mi) af[mi] = sA[mi * 8 * E_LDA + k4 * 4];
 #pragma unroll
                 for (int ni = 0; ni < 3; ++ni) bf[ni] = sB[k4 * 4 * E_LDB + ni * 8];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < 3; ++ni) fd_dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
                 if (more && (k4 & 1)) gen_pair(s + 1, k4 - 1);
@@ -295,10 +295,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
         }
         __syncthreads(); // all warps are done with the stage buffers: they become the FP32 staging of the accumulators
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 3; ++ni) {
-                float* d = s_C + (wm * 32 + mi * 8 + fr) * E_LDC + wn * 24 + ni * 8 + 2 * fk;
+                float* d = s_C + (wm * 64 + mi * 8 + fr) * E_LDC + wn * 24 + ni * 8 + 2 * fk;
                 d[0] = (float)acc[mi][ni][0]; // the narrowing of SOP_FaceDeform.cpp:415
                 d[1] = (float)acc[mi][ni][1];
             }
