@@ -423,6 +423,12 @@ static void ctx_teardown(fd_ctx* ctx)
     for (int i = 0; i < FD_NUM_STAGE; ++i)
         if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
     if (ctx->d_sync) cudaFree(ctx->d_sync);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+        for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev_block[i]);
+        cudaEventDestroy(ctx->ev_copied);
+    }
     if (ctx->d_tc_dbg) cudaFree(ctx->d_tc_dbg);
     if (ctx->d_lu_dbg) cudaFree(ctx->d_lu_dbg);
     for (int i = 0; i < FD_PH_COUNT; ++i) {
@@ -868,13 +874,41 @@ int fd_eval_host_strided(fd_model* m, const float* P, int64_t n_vtx, const float
         FD_CUDA_OK(ctx, cudaMemcpyAsync(dV, tangentv, v3, cudaMemcpyHostToDevice, s));
         FD_CUDA_OK(ctx, cudaMemcpyAsync(dN, normal, v3, cudaMemcpyHostToDevice, s));
     }
-    st = fd_rbf_eval_dev(m, (const float*)dP, n_vtx, (const float*)dD, (const float*)dU, (const float*)dV,
-                         (const float*)dN, (float*)dO, (float*)dF);
-    if (st != FD_OK) return st;
-    if (out_pitch_bytes == v3)
-        FD_CUDA_OK(ctx, cudaMemcpyAsync(P_out, dO, v3 * (size_t)m->F, cudaMemcpyDeviceToHost, s));
-    else
-        FD_CUDA_OK(ctx, cudaMemcpy2DAsync(P_out, out_pitch_bytes, dO, v3, v3, (size_t)m->F, cudaMemcpyDeviceToHost, s));
+    // Wide batches: evaluate in blocks of 80 frames (one 240-column block of the tensor path) and read block i back on a
+    // second stream while block i + 1 is evaluated -- the D2H copy bounds this entry point (288 MB at C2), the kernels hide
+    // behind it.  Needs pinned host memory to overlap; pageable buffers still work, serialised by the driver.
+    constexpr int FB = 80;
+    const int F = m->F;
+    const int nblk = (F >= 2 * FB && v3 * (size_t)F >= ((size_t)32 << 20)) ? (F + FB - 1) / FB : 1;
+    if (nblk > 1 && !ctx->copy_stream) {
+        FD_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; ++i) FD_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_block[i], cudaEventDisableTiming));
+        FD_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+    }
+    if (nblk == 1) {
+        st = fd_rbf_eval_dev(m, (const float*)dP, n_vtx, (const float*)dD, (const float*)dU, (const float*)dV,
+                             (const float*)dN, (float*)dO, (float*)dF);
+        if (st != FD_OK) return st;
+        if (out_pitch_bytes == v3)
+            FD_CUDA_OK(ctx, cudaMemcpyAsync(P_out, dO, v3 * (size_t)F, cudaMemcpyDeviceToHost, s));
+        else
+            FD_CUDA_OK(ctx, cudaMemcpy2DAsync(P_out, out_pitch_bytes, dO, v3, v3, (size_t)F, cudaMemcpyDeviceToHost, s));
+    } else {
+        phase_begin(ctx, FD_PH_EVAL);
+        for (int b = 0; b < nblk; ++b) {
+            const int f0 = b * FB, fc = F - f0 < FB ? F - f0 : FB;
+            cudaError_t e = fd_launch_eval_frames(ctx, m, (const float*)dP, n_vtx, (const float*)dD, (const float*)dU, (const float*)dV,
+                                                  (const float*)dN, (float*)dO, (float*)dF, f0, fc);
+            if (e != cudaSuccess) { FD_SET_ERR(ctx, "eval: %s", cudaGetErrorString(e)); return FD_E_CUDA; }
+            FD_CUDA_OK(ctx, cudaEventRecord(ctx->ev_block[b & 7], s));
+            FD_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_block[b & 7], 0));
+            FD_CUDA_OK(ctx, cudaMemcpy2DAsync((char*)P_out + (size_t)f0 * out_pitch_bytes, out_pitch_bytes, (const char*)dO + (size_t)f0 * v3,
+                                              v3, v3, (size_t)fc, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        phase_end(ctx, FD_PH_EVAL);
+        FD_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+        FD_CUDA_OK(ctx, cudaStreamWaitEvent(s, ctx->ev_copied, 0)); // later work on the ctx stream may reuse the staging buffer
+    }
     if (dF) FD_CUDA_OK(ctx, cudaMemcpyAsync(falloff_out, dF, v1, cudaMemcpyDeviceToHost, s));
     FD_CUDA_OK(ctx, cudaStreamSynchronize(s));
     return FD_OK;

@@ -680,3 +680,19 @@ cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64
         return a.F >= 2 ? launch_f64<FD_KERNEL_THINPLATE, 2, 2>(ctx, a) : launch_f64<FD_KERNEL_THINPLATE, 1, 4>(ctx, a);
     return launch_kernel<double>(ctx, m->prm.kernel, a); // Gaussian in FP64
 }
+
+// the frames [f_begin, f_begin + f_count) only: a view of the model whose weight pointers start at the block's first
+// column (no kernel knows about it)
+cudaError_t fd_launch_eval_frames(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2, const float* tu,
+                                  const float* tv, const float* nrm, float* P_out, float* falloff_out, int f_begin, int f_count)
+{
+    if (f_begin == 0 && f_count == m->F) return fd_launch_eval(ctx, m, P, V, dist2, tu, tv, nrm, P_out, falloff_out);
+    fd_model view = *m;
+    view.F = f_count;
+    view.w_col0 = 3 * f_begin;
+    if (view.d_W32) view.d_W32 = m->d_W32 + 3 * f_begin;
+    view.d_W = m->d_W + 3 * f_begin; // f_begin is a multiple of 80: the 16-byte alignment of the FP64 rows is kept
+    if (m->use_tc && !fd_tc_view_frames(m, &view, f_begin)) return cudaErrorInvalidValue;
+    return fd_launch_eval(ctx, &view, P, V, dist2, tu, tv, nrm, P_out + (size_t)f_begin * (size_t)V * 3,
+                          f_begin == 0 ? falloff_out : nullptr);
+}

@@ -136,6 +136,7 @@ struct Eval64Args {
     const float* origin; // o = centre 0
     const double* W;     // (N + np) x ldw
     int ldw, N, np, F;
+    int ncol;            // readable columns from W on (ldw minus the offset of a frame-block view)
     const float* P;
     int64_t V;
     const float* dist2;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_eval64_mma(const Eval64Args a)
             for (int t = tid; t < E_KB * (E_TN / 2); t += E_THREADS) {
                 const int k = t / (E_TN / 2), q = t - k * (E_TN / 2);
                 const int gk = s * E_KB + k, gc = c0 + 2 * q;
-                const bool ok = gk < Ktot && gc < a.ldw;
+                const bool ok = gk < Ktot && gc < a.ncol;
                 cp_async16_zfill(sB + k * E_LDB + 2 * q, a.W + (size_t)(ok ? gk : 0) * a.ldw + (ok ? gc : 0), ok);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -393,6 +394,7 @@ cudaError_t fd_launch_eval64_mma(fd_ctx* ctx, const fd_model* m, const float* P,
     a.origin = m->d_rest;
     a.W = m->d_W;
     a.ldw = m->ldw;
+    a.ncol = m->ldw - m->w_col0;
     a.N = m->N;
     a.np = m->np;
     a.F = m->F;

@@ -1066,6 +1066,19 @@ cudaError_t fd_eval_tc_setup(fd_ctx* ctx)
     return e;
 }
 
+// A view of `m` that evaluates the frames [f_begin, f_begin + f_count) only: the weight tables' tensor maps re-encoded at
+// the block's first column (f_begin must be a multiple of 80 frames = one 240-column block) and the column scales offset.
+// Used by the host-pointer evaluation, which reads the result back block by block while the next block is evaluated.
+bool fd_tc_view_frames(const fd_model* m, fd_model* view, int f_begin)
+{
+    const int col0 = 3 * f_begin, ncol_pad = fd_tc_col_pad(m->F), Kpad = fd_tc_kpad(m->N);
+    if (col0 % tc::CB != 0 || col0 >= ncol_pad) return false;
+    view->d_tc_unscale = m->d_tc_unscale + col0;
+    view->d_tc_scale = m->d_tc_scale + col0;
+    return tc::make_map((CUtensorMap*)view->tc_map_hi, (unsigned short*)m->d_tc_wt_hi + (size_t)col0 * Kpad, Kpad, ncol_pad - col0) &&
+           tc::make_map((CUtensorMap*)view->tc_map_lo, (unsigned short*)m->d_tc_wt_lo + (size_t)col0 * Kpad, Kpad, ncol_pad - col0);
+}
+
 cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
                               const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out,
                               const int* sel, int sel_id)

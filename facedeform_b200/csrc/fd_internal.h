@@ -80,6 +80,11 @@ struct fd_ctx {
     const void* tc_out_ptr;
     int64_t tc_out_V;
     int tc_out_F;
+    // host-pointer evaluation of wide batches: the read-back of frame block i runs on copy_stream while block i + 1 is
+    // evaluated (created on first use)
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_block[8];
+    cudaEvent_t ev_copied;
 };
 // per-device kernel attributes (dynamic shared-memory limits, non-portable cluster sizes): function attributes are per
 // device, so every ctx sets them for its own device at creation (never behind a process-wide flag)
@@ -116,6 +121,7 @@ struct fd_model {
     int* d_win;      // 1 + 4*32 ints: the rows the current panel's interchanges touch and their composition
     double* d_Tinv;  // [ceil(n/32)][2][32x32]: inverses of the diagonal blocks of L and U
     double* d_W;     // n x ldw weights (solve in place over the right-hand sides)
+    int w_col0;            // frame-block views only (fd_launch_eval_frames): the first column the weight pointers were advanced to
     const double* d_W_src; // where the table builders read the weights from: NULL = d_W; fd_mgpu's p2p transport points it
                            // at the ROOT device's weight block, so the tables are built through peer loads over NVLink
     int* d_flags;    // FD_NUM_FLAGS
@@ -241,6 +247,10 @@ cudaError_t fd_launch_lu_f32(fd_ctx* ctx, float* d_A, int lda, int n, int* d_ipi
 cudaError_t fd_launch_lu_nopivot_f32(fd_ctx* ctx, float* d_A, int lda, int n, int* d_ipiv, int* d_perm, int* d_flags,
                                      double* d_pivstat);
 // fd_eval.cu
+// the frames [f_begin, f_begin + f_count) of the solved batch into P_out + f_begin * V * 3 (f_begin a multiple of 80)
+cudaError_t fd_launch_eval_frames(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2, const float* tu,
+                                  const float* tv, const float* nrm, float* P_out, float* falloff_out, int f_begin, int f_count);
+bool fd_tc_view_frames(const fd_model* m, fd_model* view, int f_begin); // fd_eval_tc.cu
 cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
                            const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out);
 // fd_eval_tc.cu

@@ -424,3 +424,23 @@ def test_per_cook_solves_through_the_explicit_inverse(ctx, oracle, kernel, N):
     st, rad, Wo = oracle.fit(_oparams(oracle, p), rig.rest, two)
     np.testing.assert_allclose(W2, Wo, rtol=0, atol=1e-7 * np.abs(Wo).max())
     m.close()
+
+
+@pytest.mark.parametrize("prec,F", [(0, 240), (1, 240), (2, 200), (1, 170)])
+def test_host_eval_in_frame_blocks_equals_one_launch(ctx, prec, F):
+    """the host-pointer evaluation of a wide batch runs in 80-frame blocks whose read-back overlaps the next block's
+    kernel; bit-identical to the single launch of the device-pointer entry (FMA/SFU under AUTO, tensor cores, FP64)."""
+    import torch
+    from facedeform_b200 import make_params
+    N, V = 256, 20_004
+    rig = synth.control_rig(N)
+    deform = synth.deformed_rig(rig, F)
+    mesh = synth.face_mesh(V, topology=False)
+    p = make_params(model=1, radius=2 * rig.spacing, eval_precision=prec, dofalloff=1, falloffrate=1.5, **{"lambda": 0.0})
+    d2 = np.random.default_rng(8).uniform(0, (2 * rig.spacing) ** 2, V).astype(np.float32)
+    m = ctx.fit(p, rig.rest).solve(deform)
+    host, hfall = m.eval(mesh.P, d2)                                   # host pointers: 3 blocks of 80 frames
+    dev, dfall = m.eval(torch.from_numpy(mesh.P).cuda(), torch.from_numpy(d2).cuda())   # device pointers: one launch
+    np.testing.assert_array_equal(host, dev.cpu().numpy())
+    np.testing.assert_array_equal(hfall, dfall.cpu().numpy())
+    m.close()
