@@ -441,6 +441,7 @@ def test_host_eval_in_frame_blocks_equals_one_launch(ctx, prec, F):
     m = ctx.fit(p, rig.rest).solve(deform)
     host, hfall = m.eval(mesh.P, d2)                                   # host pointers: 3 blocks of 80 frames
     dev, dfall = m.eval(torch.from_numpy(mesh.P).cuda(), torch.from_numpy(d2).cuda())   # device pointers: one launch
+    ctx.synchronize()                                                  # the *_dev entry points only enqueue on the ctx stream
     np.testing.assert_array_equal(host, dev.cpu().numpy())
     np.testing.assert_array_equal(hfall, dfall.cpu().numpy())
     m.close()
