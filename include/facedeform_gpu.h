@@ -114,7 +114,7 @@ typedef struct fd_params {
                                  deformation, the weights follow every cooked frame. */
     float eval_tolerance;     /* default 1e-5: FD_EVAL_AUTO runs the fastest evaluation whose predicted maximum error stays
                                  within eval_tolerance x the control rig's bounding-box diagonal: tensor cores (2.0 x 2^-24 S),
-                                 FMA/SFU FP32 (1.3 x 2^-24 S), else FP64; S = fd_report.cancellation */
+                                 FMA/SFU FP32 (1.3 ... 1.1 x 2^-24 S, falling with N), else FP64; S = fd_report.cancellation */
     char group[64];           /* "group"  default ""  (all points)  :119-120  point-group pattern: "*", "7", "3-40",
                                  "0-100:2", "^5" (remove), space separated; resolved by the host mirror (facedeform_sop.hpp) */
 } fd_params;

@@ -3,6 +3,7 @@
 # Outputs land in gpurun_out/r2_*; the summaries kept under profiles/ are made from them (profiles/README.md).
 mkdir -p gpurun_out
 nvidia-smi -L
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|FAILED|Error" gpurun_out/r2_pytest.log | tail -8
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err; echo "bench rc=$?"; tail -2 gpurun_out/r2_bench_1gpu.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2> gpurun_out/r2_bench_reference_arm.err; echo "reference rc=$?"
