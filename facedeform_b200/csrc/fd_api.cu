@@ -31,6 +31,7 @@ int stage(fd_ctx* ctx, int slot, size_t bytes, void** out)
             return e == cudaErrorMemoryAllocation ? FD_E_NOMEM : FD_E_CUDA;
         }
         ctx->stage_bytes[slot] = bytes;
+        if (ctx->dbg.poison) cudaMemsetAsync(ctx->stage_dev[slot], 0xFF, bytes, ctx->stream);
     }
     *out = ctx->stage_dev[slot];
     return FD_OK;
@@ -52,6 +53,7 @@ template <typename T> int dev_alloc(fd_ctx* ctx, T** p, size_t count)
         *p = nullptr;
         return e == cudaErrorMemoryAllocation ? FD_E_NOMEM : FD_E_CUDA;
     }
+    if (ctx->dbg.poison) cudaMemsetAsync(*p, 0xFF, (count ? count : 1) * sizeof(T), ctx->stream);
     return FD_OK;
 }
 
@@ -72,7 +74,7 @@ void read_debug_opts(fd_debug_opts* o)
     o->tc_nopair = flag("FD_TC_NOPAIR");
     o->has_tc_debug = flag("FD_TC_DEBUG");
     o->lu_sym_off = flag("FD_LU_NOSYM");
-    o->lu_lookahead = flag("FD_LU_LA");
+    o->poison = flag("FD_POISON");
     o->eval_vp = num("FD_EVAL_VP");
     o->tc_debug = num("FD_TC_DEBUG");
     o->lu_debug = num("FD_LU_DEBUG");

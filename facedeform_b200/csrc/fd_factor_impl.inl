@@ -820,8 +820,7 @@ __device__ __forceinline__ void fz_cp_async(REAL* smem_dst, const REAL* gsrc)
 __device__ __forceinline__ void fz_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_> __device__ __forceinline__ void fz_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-// barrier of the 256 worker threads (warps 0..7) of a fused-LU CTA.  The look-ahead kernel runs a ninth warp that factors the
-// next diagonal block on its own schedule, so the workers never use __syncthreads (barrier 0 would wait for it).
+// barrier of the 256 threads of a fused-LU CTA (named barrier 1: barrier 0 separates the diagonal block from its solves)
 __device__ __forceinline__ void fz_sync_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <bool CLUSTER>
@@ -1152,6 +1151,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int l
             const int ngr = (m2 + 31) >> 5; // groups of 32 rows of L21; as many groups of 32 columns of U12
             ++tstep;
             FZ_PROBE(0);
+            // The last block has no barrier behind it: CTA 0 alone factors it, inverts it and writes it back (a second CTA
+            // reading the raw block could find CTA 0's factors there).
+            if (m2 <= 0 && blockIdx.x != 0) break;
             // Warp 0 factors the diagonal block and takes no L21 / U12 group; the branches are exclusive so that the
             // preloaded x[] is not live (no registers reserved) inside the latency-critical pivot sequence.
             if (warp == 0) {
@@ -1226,7 +1228,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int l
                 const int ncg = sym ? 0 : ngr;          // column groups
                 const int g_inv = ngr + ncg;            // first of the two inverse "groups"
                 const int ngroups = g_inv + (Tinv != nullptr ? 2 : 0);
-                int g = (int)blockIdx.x + (int)G * (warp - 1);
+                int g = m2 <= 0 ? warp - 1 : (int)blockIdx.x + (int)G * (warp - 1);
                 auto load_group = [&](int gg) {
                     if (gg < ngr) {
                         const int r = min(ks + 32 * gg + lane, n - 1);
@@ -1248,11 +1250,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int l
                 };
                 if (g < ngroups) load_group(g);
                 asm volatile("bar.sync 0;" ::: "memory");
-                if (blockIdx.x == 0 && warp == 5 && lane < nb) { // the factored diagonal block goes back to the matrix
-#pragma unroll 1
-                    for (int c = 0; c < nb; ++c)
-                        __stcg(A + (size_t)(k0 + c) * lda + k0 + lane, c >= lane ? s_U[lane * NB + c] : s_Lt[c * NB + lane]);
-                }
 #pragma unroll 1
                 for (bool first = true; g < ngroups; g += (int)G * (FZ_THREADS / 32 - 1), first = false) {
                     if (!first) load_group(g);
@@ -1291,10 +1288,25 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int l
                     }
                 }
             }
-            if (m2 <= 0) break;
+            // The factored diagonal block goes back to the matrix only AFTER the step's grid barrier: every CTA reads the raw
+            // block from global memory at the top of the step (warp 0), and a CTA that leaves the previous barrier late must
+            // not find CTA 0's factors there (seen as run-to-run differences of L21 at n >= 4096).  Nothing inside the kernel
+            // reads the block again; s_U / s_Lt stay valid until warp 0 starts the next step, one barrier further on.
+            auto write_back_diag = [&]() {
+                if (blockIdx.x == 0 && warp == 5 && lane < nb) {
+#pragma unroll 1
+                    for (int c = 0; c < nb; ++c)
+                        __stcg(A + (size_t)(k0 + c) * lda + k0 + lane, c >= lane ? s_U[lane * NB + c] : s_Lt[c * NB + lane]);
+                }
+            };
+            if (m2 <= 0) {
+                write_back_diag(); // last block: CTA 0 is the only reader
+                break;
+            }
             FZ_PROBE(5);
             fz_barrier<CLUSTER>(sync_counter, target, G);
             FZ_PROBE(6);
+            write_back_diag();
             // ---- L-shaped border of the outer block, K = 32
             if (ks < Kend) {
                 const FzRegions R = {ks, n, ks, Kend, ks, Kend, Kend, n, k0, ks, sym};
@@ -1330,325 +1342,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_lu_nopiv_fused(REAL* A, int l
     }
 }
 
-#ifdef FD_LU_DMMA
-// ---------------------------------------------------------------------------------------------------------------
-// k_lu_fused_la: the fused no-pivot LU of a SYMMETRIC matrix with LOOK-AHEAD on the diagonal blocks.
-//
-// In k_lu_nopiv_fused a block step is a chain: diagonal block (one warp, 32 dependent pivots: ~13 k cycles at 329 per
-// pivot) -> L21 solves -> barrier -> trailing update -> barrier, and at n = 256 the diagonal chain alone is half of the
-// step.  Here a NINTH warp per CTA does nothing but diagonal blocks and runs one step ahead: as soon as the first 32
-// rows of L21 of step t exist (every CTA computes them redundantly: warp 0), the 8 worker warps form the next diagonal
-// block  D' = A[ks:ks+32, ks:ks+32] - L0 (D L0^T)  in shared memory (4 columns per warp) and hand it to the diagonal
-// warp, which factors it while the workers finish the L21 groups, cross the barrier and run the trailing update of
-// step t.  The factors of step t + 1 are then waiting in the other half of a double buffer when the workers arrive.
-// At the end of an outer block with nbo > 32 the pending update spans nbo columns; there the diagonal warp waits for
-// the interior update and reads the block from global memory (one exposed factorisation per outer block).
-// Synchronisation: named barriers 1 (workers only: everything fz_update / fz_barrier use), 3 (factors ready:
-// diagonal warp arrives, workers sync), 4 (D' ready: workers arrive, diagonal warp syncs), 6 (matrix complete: workers
-// arrive, diagonal warp syncs).  In cluster mode the hardware barrier counts every thread, so the diagonal warp takes
-// part with split arrive / wait: it arrives at once and waits only after its factorisation.
-// The pivot chain itself is shorter too: the next pivot's row element comes by shuffle from the lane that owns the
-// row, not through the shared-memory round trip of the row broadcast.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int LA_THREADS = 288;
-constexpr int LA_LDL = NB + 2;
-constexpr int LA_SMEM_REALS = 2 * FZ_KC * FZ_LDA + 2 * FZ_TMAX * FZ_LDB + 2 * (2 * NB * NB + NB) + 3 * NB * LA_LDL;
-
-__device__ __forceinline__ void la_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void la_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void la_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void la_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-
-// LU of a 32 x 32 block held one row per lane (a[c] = A[lane][c]); fully unrolled, static register indices.  Row j is
-// final at step j: its lane publishes it (s_U: U11 rows, from column j & ~1 on), the scaled column goes to s_Lt
-// (s_Lt[j][r] = L11[r][j]) and 1 / u_jj to s_inv.  Critical path per pivot: reciprocal -> l = a[j] / u_jj -> the element
-// a[j+1] -= l * u[j][j+1] with u[j][j+1] fetched by shuffle BEFORE the reciprocal is known -> shuffle of the new pivot.
-__device__ __forceinline__ void fz_diag_factor(REAL (&a)[NB], REAL* s_U, REAL* s_Lt, REAL* s_inv, int lane, REAL& mypiv)
-{
-    mypiv = 1;
-    REAL p = __shfl_sync(0xffffffffu, a[0], 0);
-    REAL inv = fz_safe_rcp(p);
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        REAL u1 = 0, a_next = 0, p_next = 1, inv_next = 1;
-        if (j + 1 < NB) u1 = __shfl_sync(0xffffffffu, a[j + 1], j); // U(j, j+1): row j is final
-        const REAL l = a[j] * inv; // meaningful for lanes > j; finished rows carry don't-care values
-        if (j + 1 < NB) {
-            a_next = fma(-l, u1, a[j + 1]);
-            p_next = __shfl_sync(0xffffffffu, a_next, j + 1);
-            inv_next = fz_safe_rcp(p_next);
-        }
-        if (lane == j) {
-            mypiv = p;
-            s_inv[j] = inv;
-#pragma unroll
-            for (int c = 0; c < NB; c += 2)
-                if (c + 1 >= j) *reinterpret_cast<REAL2*>(s_U + j * NB + c) = fd_make2(a[c], a[c + 1]);
-        }
-        s_Lt[j * NB + lane] = lane > j ? l : (lane == j ? (REAL)1 : (REAL)0);
-        __syncwarp();
-        if (j + 1 < NB) {
-            a[j + 1] = a_next;
-#pragma unroll
-            for (int c = 0; c < NB; c += 2) {
-                if (c + 1 > j + 1) {
-                    const REAL2 u = *reinterpret_cast<const REAL2*>(s_U + j * NB + c);
-                    if (c > j + 1) a[c] -= l * u.x;
-                    a[c + 1] -= l * u.y;
-                }
-            }
-        }
-        p = p_next;
-        inv = inv_next;
-    }
-    __syncwarp();
-}
-
-template <bool CLUSTER>
-__global__ void __launch_bounds__(LA_THREADS, 1) k_lu_fused_la(REAL* A, int lda, int n, int nbo, int* ipiv, int* perm, int* flags,
-                                                               double* pivstat, double* Tinv, unsigned* sync_counter,
-                                                               unsigned sync_base, int dbg)
-{
-    extern __shared__ __align__(16) unsigned char la_smem_raw[];
-    __shared__ long long s_probe[12]; // FD_LU_DEBUG=<step>: cycle stamps of CTA 0 (development aid)
-    int tstep = 0;
-#define LA_PROBE(i) do { if (dbg && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8) && tstep == dbg) s_probe[i] = clock64(); } while (0)
-    REAL* s_a = reinterpret_cast<REAL*>(la_smem_raw);
-    REAL* s_b = s_a + 2 * FZ_KC * FZ_LDA;
-    REAL* s_fac = s_b + 2 * FZ_TMAX * FZ_LDB;        // [2][U11 | L11^T | 1 / u]: the factors of the current and the next block
-    REAL* s_L0 = s_fac + 2 * (2 * NB * NB + NB);      // [NB][LA_LDL]: first 32 rows of L21
-    REAL* s_U0 = s_L0 + NB * LA_LDL;                  // the same rows scaled by the pivots: (U12 block)^T
-    REAL* s_D = s_U0 + NB * LA_LDL;                   // next diagonal block, row-major
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool diag_warp = warp == 8;
-    const unsigned G = gridDim.x;
-    unsigned target = sync_base;
-    double pmin = INFINITY, pmax = 0.0;
-    int singular = 0;
-    if (blockIdx.x == 0 && !diag_warp)
-        for (int i = tid; i < n; i += 256) {
-            ipiv[i] = i;
-            perm[i] = i;
-        }
-    // pivot statistics of a factored block (diagonal warp of CTA 0)
-    auto track = [&](int k0, int nb, REAL mypiv) {
-        const double v = lane < nb ? fabs((double)mypiv) : 1.0;
-        const bool bad = lane < nb && (!(v > 0.0) || !isfinite(v));
-        const unsigned badmask = __ballot_sync(0xffffffffu, bad);
-        if (badmask && !singular) singular = k0 + __ffs(badmask);
-        double lo = lane < nb ? v : INFINITY, hi = lane < nb ? v : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        }
-        pmin = fmin(pmin, lo);
-        pmax = fmax(pmax, hi);
-    };
-    if (diag_warp) { // block 0 straight from the matrix
-        REAL a[NB], mypiv;
-        const int nb = min(NB, n);
-#pragma unroll
-        for (int c = 0; c < NB; ++c) a[c] = (lane < nb && c < nb) ? __ldcg(A + (size_t)c * lda + lane) : (lane == c ? (REAL)1 : (REAL)0);
-        fz_diag_factor(a, s_fac, s_fac + NB * NB, s_fac + 2 * NB * NB, lane, mypiv);
-        if (blockIdx.x == 0) track(0, nb, mypiv);
-        la_bar_arrive(3, LA_THREADS);
-    }
-    int buf = 0;
-    for (int K0 = 0; K0 < n; K0 += nbo) {
-        const int Kend = min(K0 + nbo, n);
-#pragma unroll 1
-        for (int k0 = K0; k0 < Kend; k0 += NB, buf ^= 1) {
-            const int nb = min(NB, n - k0);
-            const int ks = k0 + nb, m2 = n - ks;
-            const int ngr = (m2 + 31) >> 5;
-            const bool has_next = m2 > 0;
-            const bool la = has_next && (nbo == NB || ks < Kend);   // the next block's pending update is this step's only
-            const bool b1 = m2 > 0, b2 = b1 && ks < Kend, b3 = (k0 + NB >= Kend) && Kend < n; // the barriers of this step
-            REAL* sU = s_fac + buf * (2 * NB * NB + NB);
-            REAL* sLt = sU + NB * NB;
-            REAL* sInv = sLt + NB * NB;
-            ++tstep;
-            if (diag_warp) {
-                // ================= diagonal warp: the factors of the NEXT block =================
-                if (!has_next) break;
-                REAL* nU = s_fac + (buf ^ 1) * (2 * NB * NB + NB);
-                const int nb2 = min(NB, n - ks);
-                REAL a[NB], mypiv;
-                int waited = 0;
-                if (la) {
-                    LA_PROBE(6);
-                    la_bar_sync(4, LA_THREADS); // the workers have formed D' in shared memory
-                    LA_PROBE(7);
-#pragma unroll
-                    for (int c = 0; c < NB; c += 2) {
-                        const REAL2 v = *reinterpret_cast<const REAL2*>(s_D + lane * LA_LDL + c);
-                        a[c] = v.x;
-                        a[c + 1] = v.y;
-                    }
-                    if (CLUSTER) la_cluster_arrive(); // barrier 1 of this step: arrive now, wait after the factorisation
-                } else {
-                    if (CLUSTER) {
-                        if (b1) { la_cluster_arrive(); la_cluster_wait(); }
-                        if (b2) { la_cluster_arrive(); la_cluster_wait(); }
-                        if (b3) { la_cluster_arrive(); la_cluster_wait(); }
-                        waited = 3;
-                    }
-                    la_bar_sync(6, LA_THREADS); // every update of the step is in the matrix
-#pragma unroll
-                    for (int c = 0; c < NB; ++c)
-                        a[c] = (lane < nb2 && c < nb2) ? __ldcg(A + (size_t)(ks + c) * lda + ks + lane) : (lane == c ? (REAL)1 : (REAL)0);
-                }
-                fz_diag_factor(a, nU, nU + NB * NB, nU + 2 * NB * NB, lane, mypiv);
-                LA_PROBE(8);
-                if (blockIdx.x == 0) track(ks, nb2, mypiv);
-                la_bar_arrive(3, LA_THREADS);
-                if (CLUSTER && !waited) {
-                    la_cluster_wait();
-                    if (b2) { la_cluster_arrive(); la_cluster_wait(); }
-                    if (b3) { la_cluster_arrive(); la_cluster_wait(); }
-                }
-                continue;
-            }
-            // ================= workers =================
-            // L21 = A21 U11^-1 in groups of 32 rows, one row per lane; a symmetric matrix has U12 = D L21^T, so every
-            // group also writes its 32 columns of U12.  Two more "groups" apply the solves to the identity: the inverses
-            // of U11 and L11 that the slab solve multiplies with.  Group 0 is done by warp 0 of EVERY CTA when the step
-            // looks ahead (each CTA forms D' itself); the others are dealt round-robin to the warps of all CTAs.
-            REAL x[NB];
-            const int first_g = la ? 1 : 0;
-            const int g_inv = ngr;
-            const int ngroups = ngr + (Tinv != nullptr ? 2 : 0);
-            int g = first_g + (int)blockIdx.x + (int)G * warp;
-            auto load_rows = [&](int gg) {
-                if (gg < ngr) {
-                    const int r = min(ks + 32 * gg + lane, n - 1);
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) x[c] = __ldcg(A + (size_t)(k0 + c) * lda + r);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) x[c] = c == lane ? (REAL)1 : (REAL)0;
-                }
-            };
-            auto store_rows = [&](int gg, bool to_global) {
-                const int r = ks + 32 * gg + lane;
-                if (r < n && to_global) {
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) __stcg(A + (size_t)(k0 + c) * lda + r, x[c]);
-                    REAL2* dst = reinterpret_cast<REAL2*>(A + (size_t)r * lda + k0); // U12[c][r] = u_cc L21[r][c]
-#pragma unroll
-                    for (int c = 0; c < NB; c += 2)
-                        __stcg(dst + c / 2, fd_make2(x[c] * sU[c * NB + c], x[c + 1] * sU[(c + 1) * NB + c + 1]));
-                }
-            };
-            // loads that do not depend on the factors start before the factors are awaited
-            if (la && warp == 0) load_rows(0);
-            else if (!(la && warp == 0) && g < ngroups) load_rows(g);
-            LA_PROBE(0);
-            la_bar_sync(3, LA_THREADS); // the factors of this block are in sU / sLt / sInv
-            LA_PROBE(1);
-            if (blockIdx.x == 0 && warp == 5 && lane < nb) { // the factored diagonal block goes back to the matrix
-#pragma unroll 1
-                for (int c = 0; c < nb; ++c)
-                    __stcg(A + (size_t)(k0 + c) * lda + k0 + lane, c >= lane ? sU[lane * NB + c] : sLt[c * NB + lane]);
-            }
-            bool have_first = !(la && warp == 0) && g < ngroups;
-            if (la) {
-                if (warp == 0) {
-                    fz_row_solve(x, sU, sInv);
-                    const bool valid = ks + lane < n;
-#pragma unroll
-                    for (int c = 0; c < NB; c += 2) {
-                        const REAL l0 = valid ? x[c] : (REAL)0, l1 = valid ? x[c + 1] : (REAL)0;
-                        *reinterpret_cast<REAL2*>(s_L0 + lane * LA_LDL + c) = fd_make2(l0, l1);
-                        *reinterpret_cast<REAL2*>(s_U0 + lane * LA_LDL + c) = fd_make2(l0 * sU[c * NB + c], l1 * sU[(c + 1) * NB + c + 1]);
-                    }
-                    store_rows(0, blockIdx.x == 0);
-                    if (g < ngroups) { load_rows(g); have_first = true; } // warp 0's share of the round-robin groups
-                }
-                fz_sync_workers();
-                // D'[lane][c] = A[ks + lane][ks + c] - sum_j L0[lane][j] U0[c][j], columns 4 warp .. 4 warp + 3
-                {
-                    REAL l0[NB];
-#pragma unroll
-                    for (int j = 0; j < NB; j += 2) {
-                        const REAL2 v = *reinterpret_cast<const REAL2*>(s_L0 + lane * LA_LDL + j);
-                        l0[j] = v.x;
-                        l0[j + 1] = v.y;
-                    }
-                    const int nb2 = min(NB, n - ks);
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const int c = 4 * warp + cc;
-                        REAL v = (lane < nb2 && c < nb2) ? __ldcg(A + (size_t)(ks + c) * lda + ks + lane) : (lane == c ? (REAL)1 : (REAL)0);
-                        REAL acc0 = 0, acc1 = 0;
-#pragma unroll
-                        for (int j = 0; j < NB; j += 2) {
-                            const REAL2 u = *reinterpret_cast<const REAL2*>(s_U0 + c * LA_LDL + j); // warp-wide broadcast
-                            acc0 = fma(l0[j], u.x, acc0);
-                            acc1 = fma(l0[j + 1], u.y, acc1);
-                        }
-                        s_D[lane * LA_LDL + c] = v - (acc0 + acc1); // padding rows / columns: L0 and U0 are zero there
-                    }
-                }
-                la_bar_arrive(4, LA_THREADS); // the diagonal warp takes D' from here
-                LA_PROBE(2);
-            }
-#pragma unroll 1
-            for (; g < ngroups; g += (int)G * 8, have_first = false) {
-                if (!have_first) load_rows(g);
-                if (g == g_inv + 1) {
-                    fz_col_solve(x, sLt);
-                } else {
-                    fz_row_solve(x, sU, sInv);
-                }
-                if (g < ngr) {
-                    store_rows(g, true);
-                } else if (g == g_inv) { // x[c] = U11^-1[lane][c]; stored transposed: out[c * 32 + r] = inverse[r][c]
-                    double* out = Tinv + ((size_t)(k0 / NB) * 2 + 1) * NB * NB;
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) out[c * NB + lane] = (double)x[c];
-                } else { // x[r] = L11^-1[r][lane]
-                    double* out = Tinv + ((size_t)(k0 / NB) * 2) * NB * NB + lane * NB;
-#pragma unroll
-                    for (int r = 0; r < NB; ++r) out[r] = (double)x[r];
-                }
-            }
-            LA_PROBE(3);
-            if (b1) fz_barrier<CLUSTER>(sync_counter, target, G);
-            LA_PROBE(4);
-            if (b2) { // L-shaped border of the outer block, K = 32 (lower-triangle tiles only)
-                const FzRegions R = {ks, n, ks, Kend, 0, 0, 0, 0, k0, ks, 1};
-                fz_update<64>(A, lda, n, R, s_a, s_b);
-                fz_barrier<CLUSTER>(sync_counter, target, G);
-            }
-            if (b3) { // interior of the trailing matrix, K = nbo (64 x 64 tiles only: nine warps leave 168 registers per
-                      // thread, too few for the 128 x 128 accumulator tile; systems that want it take k_lu_nopiv_fused)
-                const FzRegions R = {Kend, n, Kend, n, 0, 0, 0, 0, K0, Kend, 1};
-                fz_update<64>(A, lda, n, R, s_a, s_b);
-                fz_barrier<CLUSTER>(sync_counter, target, G);
-            }
-            LA_PROBE(5);
-            if (has_next && !la) la_bar_arrive(6, LA_THREADS); // the diagonal warp reads the next block from the matrix
-        }
-    }
-    if (dbg && blockIdx.x == 0 && tid == 0 && tstep >= dbg) {
-        printf("[fz-la] n=%d step %d cycles from the workers' step start: wait factors %lld | group 0 + D' %lld | other groups %lld | "
-               "barrier 1 %lld | update + barriers %lld || diagonal warp: waits for D' from %lld to %lld, factor done at %lld\n",
-               n, dbg, s_probe[1] - s_probe[0], s_probe[2] - s_probe[1], s_probe[3] - s_probe[2], s_probe[4] - s_probe[3],
-               s_probe[5] - s_probe[4], s_probe[6] - s_probe[0], s_probe[7] - s_probe[0], s_probe[8] - s_probe[0]);
-    }
-#undef LA_PROBE
-    if (blockIdx.x == 0 && diag_warp && lane == 0) {
-        flags[FD_FLAG_SINGULAR] = singular;
-        flags[FD_FLAG_NONFINITE] = 0;
-        pivstat[0] = pmin;
-        pivstat[1] = pmax;
-    }
-}
-
-// barriers per (n, nbo) of the look-ahead kernel: same count as k_lu_nopiv_fused
-#endif // FD_LU_DMMA
+// (A look-ahead variant -- a ninth warp per CTA factoring the next diagonal block while the workers run the trailing update --
+// was built and measured in round 2 and LOST on B200: n = 260 0.205 ms against 0.152 ms.  The diagonal warp's 32-pivot
+// dependent chain shares its SM sub-partition's FP64 pipe with the workers' DMMAs, which hold the pipe 16 cycles each; the
+// chain stretched from ~300 to ~940 cycles per pivot and stayed the critical path.  Probes: profiles/r2d_lu_probe.log;
+// the code is in the history at commit 648e060.)
 
 // number of barriers k_lu_nopiv_fused executes for (n, nbo): the host advances the counter base by G times this
 static unsigned fz_barrier_count(int n, int nbo)
@@ -1679,42 +1377,6 @@ cudaError_t launch_lu_nopivot_fused(fd_ctx* ctx, REAL* d_A, int lda, int n, int*
     nbo = max(NB, nbo / NB * NB);
     cudaStream_t s = ctx->stream;
     unsigned base = ctx->sync_base;
-#ifdef FD_LU_DMMA
-    // EXPERIMENTAL, off unless FD_LU_LA is set: the look-ahead kernel (a ninth warp factors the next diagonal block while
-    // the step's solves and trailing update run).  Measured on B200 it LOSES (n = 260: 0.205 ms against 0.152 ms): the
-    // diagonal warp's 32-pivot dependent chain shares its SM sub-partition's FP64 pipe with two worker warps, whose DMMAs
-    // hold the pipe 16 cycles each -- the chain stretches from ~300 to ~940 cycles per pivot (FD_LU_DEBUG probes,
-    // profiles/r2d_lu_probe.log) and becomes the critical path again.
-    if (sym && o.lu_lookahead && n > NB && n <= 2048 + 8) {
-        const size_t smem_la = (size_t)LA_SMEM_REALS * sizeof(REAL);
-        if (n <= cluster_max_n) {
-            const int cs = o.lu_cluster ? o.lu_cluster : (n <= 64 ? 4 : (n <= 128 ? 8 : 16));
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(cs);
-            cfg.blockDim = dim3(LA_THREADS);
-            cfg.dynamicSmemBytes = smem_la;
-            cfg.stream = s;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = cs;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            ctx->launches += 1;
-            return cudaLaunchKernelEx(&cfg, k_lu_fused_la<true>, d_A, lda, n, nbo, d_ipiv, d_perm, d_flags, d_pivstat, d_Tinv,
-                                      ctx->d_sync, base, dbg);
-        }
-        const int G = ctx->sm_count;
-        void* args[] = {&d_A, &lda, &n, &nbo, &d_ipiv, &d_perm, &d_flags, &d_pivstat, &d_Tinv, &ctx->d_sync, &base, &dbg};
-        const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_lu_fused_la<false>, dim3(G), dim3(LA_THREADS), args, smem_la, s);
-        if (e == cudaSuccess) {
-            ctx->sync_base = base + (unsigned)G * fz_barrier_count(n, nbo);
-            ctx->launches += 1;
-        }
-        return e;
-    }
-#endif
     if (n <= cluster_max_n) {
         // one cluster: 4 CTAs up to n = 64, 8 up to 128, else 16
         const int cs = o.lu_cluster ? o.lu_cluster : (n <= 64 ? 4 : (n <= 128 ? 8 : 16));
@@ -1756,12 +1418,6 @@ cudaError_t setup_attributes()
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_nopiv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_nopiv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_nopiv_fused<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-#ifdef FD_LU_DMMA
-    const int smem_la = (int)((size_t)LA_SMEM_REALS * sizeof(REAL));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_fused_la<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_la);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_fused_la<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_la);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lu_fused_la<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-#endif
     return e;
 }
 

@@ -43,13 +43,14 @@ struct fd_debug_opts {
     bool tc_nopair;         // FD_TC_NOPAIR: no CTA pairs in the tensor evaluation
     bool has_tc_debug;      // FD_TC_DEBUG set
     bool lu_sym_off;        // FD_LU_NOSYM: the fused LU ignores symmetry
-    bool lu_lookahead;      // FD_LU_LA: the experimental look-ahead LU (k_lu_fused_la; slower on B200, see fd_factor_impl.inl)
     int eval_vp;            // FD_EVAL_VP
     int tc_debug;           // FD_TC_DEBUG bits
     int lu_debug;           // FD_LU_DEBUG step
     int lu_nbo;             // FD_LU_NBO
     int lu_cluster_max_n;   // FD_LU_CLUSTER_MAX_N
     int lu_cluster;         // FD_LU_CLUSTER
+    bool poison;            // FD_POISON: every device allocation starts as 0xFF bytes (NaN / -1), so a read of memory the
+                            // library never wrote shows in the results instead of depending on what the pool held before
 };
 
 struct fd_ctx {

@@ -152,78 +152,84 @@ __global__ void __launch_bounds__(256) k_few_step(const double* __restrict__ A, 
 }
 
 // Panel update of the blocked sweeps: C[r][c] -= sum_k T[r][kb + k] * X[kb + k][c] for r in [r_lo, r_hi), k < K.
-// T column-major (the LU factors, or any column-major operand), X and C row-major.  CTA tile 128 rows x 64 columns on the
-// FP64 tensor pipe (mma.sync.m8n8k4.f64): 8 warps as 4 x 2, a warp owns 32 x 32 outputs = 16 accumulator tiles and loads
-// 8 fragments per 16 DMMAs (4096 FMAs); K in chunks of 16 through shared memory, the next chunk's operands travel from
-// global memory into registers while the current chunk is multiplied.  Stage strides = 4 mod 16 doubles: the fragment
-// loads of a half warp (4 rows x 4 k) fall into 16 different 8-byte banks.  (The DFMA version it replaces read 96 bytes of
-// shared memory per 64 FMAs and reached ~8 TFLOP/s.)
-constexpr int PG_TM = 128, PG_TN = 64, PG_KC = 16;
+// T column-major (the LU factors, or any column-major operand), X and C row-major.  CTA tile 128 x 128 on the FP64 tensor
+// pipe (mma.sync.m8n8k4.f64): 8 warps as 4 x 2, a warp owns 32 x 64 outputs = 32 accumulator tiles and loads 12 fragments
+// per 32 DMMAs (8192 FMAs); K in chunks of 16, double-buffered with cp.async (zero-filled beyond K, r_hi, nrhs).  Stage
+// strides = 4 mod 16 doubles: the fragment loads of a half warp (4 rows x 4 k) fall into 16 different 8-byte banks.
+constexpr int PG_TM = 128, PG_TN = 128, PG_KC = 16;
 constexpr int PG_LDA = PG_TM + 4, PG_LDX = PG_TN + 4;
+constexpr int PG_STAGE_DOUBLES = PG_KC * (PG_LDA + PG_LDX);
+constexpr int PG_SMEM_BYTES = 2 * PG_STAGE_DOUBLES * 8;
+__device__ __forceinline__ void pg_cp16(void* smem_dst, const void* gsrc, bool valid)
+{
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+                 "r"(bytes)
+                 : "memory");
+}
 __device__ __forceinline__ void pg_tile_dmma(const double* __restrict__ T, int lda, int r_lo, int r_hi, int K,
                                              const double* __restrict__ X, int ldx, double* __restrict__ C, int ldc, int nrhs)
 {
-    __shared__ __align__(16) double s_a[PG_KC][PG_LDA]; // [k][row]
-    __shared__ __align__(16) double s_x[PG_KC][PG_LDX]; // [k][col]
+    extern __shared__ __align__(16) double pg_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp & 3, wn = warp >> 2, fr = lane >> 2, fk = lane & 3;
     const int r0 = r_lo + blockIdx.y * PG_TM, c0 = blockIdx.x * PG_TN;
-    double acc[4][4][2];
+    double acc[4][8][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    double pa[PG_KC * PG_TM / 256], px[PG_KC * PG_TN / 256];
-    auto gload = [&](int k0) {
-#pragma unroll
-        for (int u = 0; u < PG_KC * PG_TM / 256; ++u) {
-            const int t = tid + 256 * u, k = t / PG_TM, i = t - k * PG_TM;
-            pa[u] = (k0 + k < K && r0 + i < r_hi) ? T[(size_t)(k0 + k) * lda + r0 + i] : 0.0;
+        for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    auto issue = [&](int k0, int st) {
+        double* sa = pg_smem + st * PG_STAGE_DOUBLES;
+        double* sx = sa + PG_KC * PG_LDA;
+        for (int t = tid; t < PG_KC * (PG_TM / 2); t += 256) {
+            const int k = t / (PG_TM / 2), q = t - k * (PG_TM / 2);
+            const bool ok = k0 + k < K && r0 + 2 * q < r_hi; // r_hi even or the pair's second row is a valid, masked address
+            pg_cp16(sa + k * PG_LDA + 2 * q, T + (size_t)(ok ? k0 + k : 0) * lda + (ok ? r0 + 2 * q : 0), ok);
         }
-#pragma unroll
-        for (int u = 0; u < PG_KC * PG_TN / 256; ++u) {
-            const int t = tid + 256 * u, k = t / PG_TN, j = t - k * PG_TN;
-            px[u] = (k0 + k < K && c0 + j < nrhs) ? X[(size_t)(k0 + k) * ldx + c0 + j] : 0.0;
+        for (int t = tid; t < PG_KC * (PG_TN / 2); t += 256) {
+            const int k = t / (PG_TN / 2), q = t - k * (PG_TN / 2);
+            const bool ok = k0 + k < K && c0 + 2 * q < nrhs;
+            pg_cp16(sx + k * PG_LDX + 2 * q, X + (size_t)(ok ? k0 + k : 0) * ldx + (ok ? c0 + 2 * q : 0), ok);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    gload(0);
-    for (int k0 = 0; k0 < K; k0 += PG_KC) {
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < PG_KC * PG_TM / 256; ++u) {
-            const int t = tid + 256 * u, k = t / PG_TM, i = t - k * PG_TM;
-            s_a[k][i] = pa[u];
-        }
-#pragma unroll
-        for (int u = 0; u < PG_KC * PG_TN / 256; ++u) {
-            const int t = tid + 256 * u, k = t / PG_TN, j = t - k * PG_TN;
-            s_x[k][j] = px[u];
+    const int nch = (K + PG_KC - 1) / PG_KC;
+    issue(0, 0);
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) {
+            issue((ch + 1) * PG_KC, (ch + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        if (k0 + PG_KC < K) gload(k0 + PG_KC);
+        const double* sa = pg_smem + (ch & 1) * PG_STAGE_DOUBLES + fk * PG_LDA + wm * 32 + fr;
+        const double* sx = pg_smem + (ch & 1) * PG_STAGE_DOUBLES + PG_KC * PG_LDA + fk * PG_LDX + wn * 64 + fr;
 #pragma unroll
         for (int k4 = 0; k4 < PG_KC / 4; ++k4) {
-            double af[4], bf[4];
+            double af[4], bf[8];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) af[mi] = s_a[k4 * 4 + fk][wm * 32 + mi * 8 + fr];
+            for (int mi = 0; mi < 4; ++mi) af[mi] = sa[k4 * 4 * PG_LDA + mi * 8];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) bf[ni] = s_x[k4 * 4 + fk][wn * 32 + ni * 8 + fr];
+            for (int ni = 0; ni < 8; ++ni) bf[ni] = sx[k4 * 4 * PG_LDX + ni * 8];
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
+                for (int ni = 0; ni < 8; ++ni)
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                                  : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1])
                                  : "d"(af[mi]), "d"(bf[ni]));
         }
+        __syncthreads();
     }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
         const int r = r0 + wm * 32 + mi * 8 + fr;
         if (r >= r_hi) continue;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int c = c0 + wn * 32 + ni * 8 + 2 * fk;
+        for (int ni = 0; ni < 8; ++ni) {
+            const int c = c0 + wn * 64 + ni * 8 + 2 * fk;
             double* dst = C + (size_t)r * ldc + c;
             if (c + 1 < nrhs) { // c is even and the row strides are multiples of 4 doubles: 16-byte aligned
                 double2 v = *reinterpret_cast<double2*>(dst);
@@ -237,7 +243,7 @@ __device__ __forceinline__ void pg_tile_dmma(const double* __restrict__ T, int l
     }
 }
 
-__global__ void __launch_bounds__(256, 2) k_panel_gemm(const double* __restrict__ A, int lda, int r_lo, int r_hi, int kb, int K,
+__global__ void __launch_bounds__(256, 1) k_panel_gemm(const double* __restrict__ A, int lda, int r_lo, int r_hi, int kb, int K,
                                                     double* __restrict__ B, int ldw, int nrhs)
 {
     pg_tile_dmma(A + (size_t)kb * lda, lda, r_lo, r_hi, K, B + (size_t)kb * ldw, ldw, B, ldw, nrhs);
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(256, 2) k_panel_gemm(const double* __restrict_
 
 // C[r][c] -= sum_k A[r][k] X[k][c], r < rows, k < K: A column-major (lda), X and C row-major with the same row stride.
 // (the residual update of the layered fit, fd_api.cu)
-__global__ void __launch_bounds__(256, 2) k_gemm_sub(const double* __restrict__ A, int lda, int rows, int K,
+__global__ void __launch_bounds__(256, 1) k_gemm_sub(const double* __restrict__ A, int lda, int rows, int K,
                                                      const double* __restrict__ X, double* __restrict__ C, int ldw, int nrhs)
 {
     pg_tile_dmma(A, lda, 0, rows, K, X, ldw, C, ldw, nrhs);
@@ -711,6 +717,8 @@ cudaError_t fd_solve_setup(fd_ctx* ctx)
     (void)ctx;
     cudaError_t e = cudaFuncSetAttribute(k_solve_slab8, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_solve_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_panel_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES);
     return e;
 }
 
@@ -788,6 +796,7 @@ cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, 
         double* d_Y = nullptr; // forward-substituted right-hand sides, n x 8
         cudaError_t e = cudaMallocAsync((void**)&d_Y, (size_t)n * FEW_MAX * sizeof(double), s);
         if (e != cudaSuccess) return e;
+        if (ctx->dbg.poison) cudaMemsetAsync(d_Y, 0xFF, (size_t)n * FEW_MAX * sizeof(double), s);
         for (int k0 = 0; k0 < n; k0 += SB) { // L y = b
             const int nb = min(SB, n - k0), rows = n - k0 - nb;
             k_few_step<true><<<max(1, (rows + 63) / 64), 256, 0, s>>>(d_A, lda, n, k0, nb, d_Tinv + (size_t)(k0 / SB) * 2 * SB * SB,
@@ -821,7 +830,7 @@ cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, 
         ctx->launches += 1;
         if (pe < n) {
             dim3 grid((nrhs + PG_TN - 1) / PG_TN, (n - pe + PG_TM - 1) / PG_TM);
-            k_panel_gemm<<<grid, 256, 0, s>>>(d_A, lda, pe, n, p0, pe - p0, d_W, ldw, nrhs);
+            k_panel_gemm<<<grid, 256, PG_SMEM_BYTES, s>>>(d_A, lda, pe, n, p0, pe - p0, d_W, ldw, nrhs);
             ctx->launches += 1;
         }
     }
@@ -833,7 +842,7 @@ cudaError_t fd_launch_solve_sub(fd_ctx* ctx, const double* d_A, int lda, int n, 
         ctx->launches += 1;
         if (p0 > 0) {
             dim3 grid((nrhs + PG_TN - 1) / PG_TN, (p0 + PG_TM - 1) / PG_TM);
-            k_panel_gemm<<<grid, 256, 0, s>>>(d_A, lda, 0, p0, p0, pe - p0, d_W, ldw, nrhs);
+            k_panel_gemm<<<grid, 256, PG_SMEM_BYTES, s>>>(d_A, lda, 0, p0, p0, pe - p0, d_W, ldw, nrhs);
             ctx->launches += 1;
         }
     }
@@ -862,6 +871,10 @@ bool fd_try_inverse_solve(fd_ctx* ctx, fd_model* m, const double* d_A, int lda, 
             return false;
         }
         m->ld_inv = ld;
+        if (ctx->dbg.poison) {
+            cudaMemsetAsync(m->d_inv, 0xFF, (size_t)n_f * ld * sizeof(double), s);
+            cudaMemsetAsync(m->d_inv_rhs, 0xFF, (size_t)n_f * 8 * sizeof(double), s);
+        }
         const int n_pad = fd_round_up(n_f, SB);
         const bool slab = ((size_t)n_pad * S8_RC + 2 * S8_CHUNK_DOUBLES + 2 * S8_TINV_DOUBLES) * sizeof(double) <= 220 * 1024;
         dim3 grid((ld + 255) / 256, n_f);
@@ -1036,7 +1049,7 @@ cudaError_t fd_launch_gemm_sub(fd_ctx* ctx, const double* d_A, int lda, int rows
                                int nrhs)
 {
     dim3 grid((nrhs + PG_TN - 1) / PG_TN, (rows + PG_TM - 1) / PG_TM);
-    k_gemm_sub<<<grid, 256, 0, ctx->stream>>>(d_A, lda, rows, K, d_X, d_C, ldw, nrhs);
+    k_gemm_sub<<<grid, 256, PG_SMEM_BYTES, ctx->stream>>>(d_A, lda, rows, K, d_X, d_C, ldw, nrhs);
     ctx->launches += 1;
     return cudaGetLastError();
 }

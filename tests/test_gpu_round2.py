@@ -445,3 +445,73 @@ def test_host_eval_in_frame_blocks_equals_one_launch(ctx, prec, F):
     np.testing.assert_array_equal(host, dev.cpu().numpy())
     np.testing.assert_array_equal(hfall, dfall.cpu().numpy())
     m.close()
+
+
+# ---- the persistent LU is a function of its input: repeated factorisations are bit-identical ----------------------------
+# (round 2 found CTA 0 writing the factored diagonal block back while a CTA that left the grid barrier late still read the
+#  raw block: ~30 % of the fits at N = 4096 came out different, a few of them wrong by 1e-1)
+@pytest.mark.parametrize("N,kernel,reps", [(4096, 0, 12), (1500, 0, 6), (2048, 1, 6), (300, 0, 6)])
+def test_repeated_fits_are_bit_identical(ctx, N, kernel, reps):
+    from facedeform_b200 import make_params
+    rig = synth.control_rig(N)
+    deform = synth.deformed_rig(rig, 2)
+    R = synth.default_radius(["gaussian", "multiquadric"][kernel], rig.spacing)
+    p = make_params(model=1, term=0, kernel=kernel, radius=R, eval_precision=2, **{"lambda": 0.0})
+    first = None
+    for _ in range(reps):
+        m = ctx.fit(p, rig.rest).solve(deform)
+        W = m.weights()[0]
+        m.close()
+        if first is None:
+            first = W
+        else:
+            np.testing.assert_array_equal(W, first)
+
+
+def test_fused_lu_agrees_with_the_per_step_launches():
+    """the one-launch LU against the per-block-column kernels (FD_LU_UNFUSED, read at context creation) at a size with
+    two-level blocking (outer blocks of 256)"""
+    from facedeform_b200 import Context, make_params
+    rig = synth.control_rig(4096)
+    deform = synth.deformed_rig(rig, 2)
+    R = synth.default_radius("gaussian", rig.spacing)
+    p = make_params(model=1, term=0, kernel=0, radius=R, eval_precision=2, **{"lambda": 0.0})
+    Ws = []
+    for unfused in (False, True):
+        if unfused:
+            os.environ["FD_LU_UNFUSED"] = "1"
+        try:
+            c = Context()
+        finally:
+            os.environ.pop("FD_LU_UNFUSED", None)
+        m = c.fit(p, rig.rest).solve(deform)
+        Ws.append(m.weights()[0])
+        m.close()
+        c.close()
+    assert np.abs(Ws[0] - Ws[1]).max() <= 1e-8 * np.abs(Ws[1]).max()
+
+
+def test_poisoned_allocations_change_nothing():
+    """FD_POISON fills every device allocation with 0xFF bytes: a kernel that reads memory the library never wrote would
+    turn the weights into NaN (or trip the non-finite flag) instead of depending on what the pool held before"""
+    from facedeform_b200 import Context, make_params
+    outs = []
+    for poison in (False, True):
+        if poison:
+            os.environ["FD_POISON"] = "1"
+        try:
+            c = Context()
+        finally:
+            os.environ.pop("FD_POISON", None)
+        for N, kernel, F in ((3500, 0, 40), (700, 2, 3)):
+            rig = synth.control_rig(N)
+            deform = synth.deformed_rig(rig, F)
+            mesh = synth.face_mesh(5_000, topology=False)
+            R = synth.default_radius(["gaussian", "multiquadric", "thin_plate"][kernel], rig.spacing)
+            m = c.fit(make_params(model=1, term=0, kernel=kernel, radius=R, **{"lambda": 0.0}), rig.rest).solve(deform)
+            outs.append(m.eval(mesh.P)[0])
+            assert m.report().terminationtype == 1
+            m.close()
+        c.close()
+    np.testing.assert_array_equal(outs[0], outs[2])
+    np.testing.assert_array_equal(outs[1], outs[3])
