@@ -558,14 +558,21 @@ def main():
         else:
             fp32_peak_tf = 148 * 128 * 2 * peaks["sm_max"] * 1e6 / 1e12
             roofline = {
-                "kernel": "k_eval_f32x2", "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s",
+                "kernel": "k_eval_f32c (FP32 FMA/SFU, packed FFMA2 along the columns)" if F_eval >= 4 else "k_eval_f32x2",
+                "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp32_peak_tf,
                 "peak_source": "derived: 148 SM x 128 FP32 lanes x 2 flop x clocks.max.sm (FP32 FMA issue is not in MEASURED_PEAKS.json)",
                 "traffic": None, "launch_ms": eval_ms_mean,
             }
         # DRAM traffic of one launch from the committed `ncu --set full` capture of this command (profiles/), C2 only
         try:
-            if args.config == "C2" and eval_kernel == 2:
+            if args.config == "C2" and eval_kernel == 1 and os.path.exists(os.path.join(ROOT, "profiles", "r2_eval_f32c_ncu_summary.json")):
+                src = "r2_eval_f32c_ncu_summary.json"
+                with open(os.path.join(ROOT, "profiles", src)) as f:
+                    nc = json.load(f)
+                roofline["traffic"] = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6
+                roofline["traffic_source"] = f"profiles/{src} (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+            elif args.config == "C2" and eval_kernel == 2:
                 src = "r2_eval_tc_ncu_summary.json"
                 if not os.path.exists(os.path.join(ROOT, "profiles", src)):
                     src = "r1e_eval_tc_ncu_summary.json"

@@ -113,7 +113,7 @@ struct EvalArgs {
 };
 
 // polynomial block + SOP epilogue (gate, tangent projection, falloff, position write), shared by the evaluation kernels
-template <typename T, int FC, int VPT>
+template <typename T, int FC, int VPT, int NT = EVAL_THREADS>
 __device__ __forceinline__ void finish_vertices(const EvalArgs& a, const T* __restrict__ W, int f0, int ncol, int64_t vbase,
                                                 const T (&px)[VPT], const T (&py)[VPT], const T (&pz)[VPT],
                                                 const float (&pos)[VPT][3], T (&acc)[VPT][3 * FC])
@@ -139,7 +139,7 @@ __device__ __forceinline__ void finish_vertices(const EvalArgs& a, const T* __re
     // epilogue: gate, tangent projection, falloff, position write
 #pragma unroll
     for (int u = 0; u < VPT; ++u) {
-        const int64_t v = vbase + (int64_t)u * EVAL_THREADS;
+        const int64_t v = vbase + (int64_t)u * NT;
         if (v >= a.V) continue;
         const float d2 = a.dist2 ? a.dist2[v] : 0.f;
         const bool skip = d2 > a.radius2;                       // SOP_FaceDeform.cpp:408-410
@@ -358,26 +358,27 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32x2(const EvalArgs a)
 // (Packing along the vertices needs every weight duplicated: one MOV per FFMA2 when done in registers -- issue bound --
 // or twice the LDS.128 broadcasts when done in shared memory -- LSU bound: 0.98 ms and 1.40 ms at BASELINE configs[1].)
 // Lane-wise the same arithmetic per output as k_eval_simt<float> (same rounding per operation, same order over centres).
-template <int KERNEL, int FC, int VP>
-__global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32c(const EvalArgs a)
+template <int KERNEL, int FC, int VP, int UNR = 2, int NT = EVAL_THREADS>
+__global__ void __launch_bounds__(NT) k_eval_f32c(const EvalArgs a)
 {
     constexpr int VPT = 2 * VP;      // vertices per thread; the distances of a pair share packed instructions
     constexpr int NC = 3 * FC;       // columns of the chunk (even)
+    constexpr int TJ = FC <= 8 ? 256 : 128; // centres per shared-memory stage (static shared memory: 48 KB)
     static_assert(NC % 4 == 0, "column count must be a multiple of 4 (128-bit weight reads)");
     __shared__ __align__(16) uint64_t s_c2[TJ * 4];  // (x, x), (y, y), (z, z), (parameter, parameter)
     __shared__ __align__(16) float s_w[TJ * NC];
 
     if (a.sel && *a.sel != a.sel_id) return;
-    const int64_t nbx = (a.V + EVAL_THREADS * VPT - 1) / (EVAL_THREADS * VPT);
+    const int64_t nbx = (a.V + NT * VPT - 1) / (NT * VPT);
     const int64_t ntiles = nbx * ((a.F + FC - 1) / FC);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int f0 = (int)(tile / nbx) * FC;
-        const int64_t vbase = (tile % nbx) * (EVAL_THREADS * VPT) + threadIdx.x;
+        const int64_t vbase = (tile % nbx) * (NT * VPT) + threadIdx.x;
         float px[VPT], py[VPT], pz[VPT];
         float pos[VPT][3];
 #pragma unroll
         for (int u = 0; u < VPT; ++u) {
-            const int64_t v = vbase + (int64_t)u * EVAL_THREADS;
+            const int64_t v = vbase + (int64_t)u * NT;
             if (v < a.V) {
                 pos[u][0] = a.P[3 * v];
                 pos[u][1] = a.P[3 * v + 1];
@@ -409,20 +410,20 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32c(const EvalArgs a)
         for (int j0 = 0; j0 < a.N; j0 += TJ) {
             const int cnt = min(TJ, a.N - j0);
             __syncthreads();
-            for (int t = threadIdx.x; t < TJ; t += EVAL_THREADS) {
+            for (int t = threadIdx.x; t < TJ; t += NT) {
                 const float4 c = t < cnt ? ctab[j0 + t] : make_float4(0.f, 0.f, 0.f, KERNEL == FD_KERNEL_MULTIQUADRIC ? 1.f : 0.f);
                 s_c2[4 * t] = pack2(c.x, c.x);
                 s_c2[4 * t + 1] = pack2(c.y, c.y);
                 s_c2[4 * t + 2] = pack2(c.z, c.z);
                 s_c2[4 * t + 3] = pack2(c.w, c.w);
             }
-            for (int t = threadIdx.x; t < TJ * NC; t += EVAL_THREADS) {
+            for (int t = threadIdx.x; t < TJ * NC; t += NT) {
                 const int j = t / NC, c = t - j * NC;
                 s_w[t] = (j < cnt && c < ncol) ? W[(size_t)(j0 + j) * a.ldw + 3 * f0 + c] : 0.f;
             }
             __syncthreads();
             const int jn = (cnt + 3) & ~3; // padded centres carry zero weights
-#pragma unroll 2
+#pragma unroll UNR
             for (int j = 0; j < jn; ++j) {
                 const ulonglong2 cxy = *reinterpret_cast<const ulonglong2*>(&s_c2[4 * j]);
                 const ulonglong2 czw = *reinterpret_cast<const ulonglong2*>(&s_c2[4 * j + 2]);
@@ -462,16 +463,16 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_f32c(const EvalArgs a)
         for (int u = 0; u < VPT; ++u)
 #pragma unroll
             for (int q = 0; q < NC / 2; ++q) unpack2(acc2[u][q], acc[u][2 * q], acc[u][2 * q + 1]);
-        finish_vertices<float, FC, VPT>(a, W, f0, ncol, vbase, px, py, pz, pos, acc);
+        finish_vertices<float, FC, VPT, NT>(a, W, f0, ncol, vbase, px, py, pz, pos, acc);
     } // tile
 }
 
-template <int KERNEL, int FC, int VP>
+template <int KERNEL, int FC, int VP, int UNR = 2, int NT = EVAL_THREADS>
 cudaError_t launch_f32c(fd_ctx* ctx, const EvalArgs& a)
 {
-    const int64_t ntiles = ((a.V + EVAL_THREADS * 2 * VP - 1) / (EVAL_THREADS * 2 * VP)) * ((a.F + FC - 1) / FC);
+    const int64_t ntiles = ((a.V + NT * 2 * VP - 1) / (NT * 2 * VP)) * ((a.F + FC - 1) / FC);
     const int64_t cap = (int64_t)ctx->sm_count * 8;
-    k_eval_f32c<KERNEL, FC, VP><<<(unsigned)(ntiles < cap ? ntiles : cap), EVAL_THREADS, 0, ctx->stream>>>(a);
+    k_eval_f32c<KERNEL, FC, VP, UNR, NT><<<(unsigned)(ntiles < cap ? ntiles : cap), NT, 0, ctx->stream>>>(a);
     ctx->launches += 1;
     return cudaGetLastError();
 }
@@ -492,6 +493,12 @@ cudaError_t launch_f32x2_fc(fd_ctx* ctx, const EvalArgs& a)
     const int vp_env = ctx->dbg.eval_vp;
     // frame chunks of 8 / 4: packed along the columns (k_eval_f32c); 4 vertices per thread when the mesh fills the GPU that way
     const int fc = a.F >= 8 ? 8 : 4;
+    // 12 frames per chunk when the mesh still fills the GPU: 36 accumulations per basis value instead of 24 (the distance and
+    // the kernel function are 7 of 31 FP32-pipe cycles per pair at 8 frames, 7 of 43 at 12; BASELINE configs[1]: 1.03 -> 0.93 ms;
+    // 212 registers, one CTA per SM like the 8-frame kernel's 172 -- 16 frames with two vertices per thread lost to the
+    // shared-memory reads, 384-thread CTAs and deeper unrolling moved nothing: profiles/r2_eval_f32c_variants.txt)
+    if (a.F >= 12 && ((a.V + EVAL_THREADS * 4 - 1) / (EVAL_THREADS * 4)) * ((a.F + 11) / 12) >= 2 * (int64_t)ctx->sm_count)
+        return launch_f32c<KERNEL, 12, 2>(ctx, a);
     const bool many = ((a.V + EVAL_THREADS * 4 - 1) / (EVAL_THREADS * 4)) * ((a.F + fc - 1) / fc) >= 2 * (int64_t)ctx->sm_count;
     if (a.F >= 8) return many ? launch_f32c<KERNEL, 8, 2>(ctx, a) : launch_f32c<KERNEL, 8, 1>(ctx, a);
     if (a.F >= 4) return many ? launch_f32c<KERNEL, 4, 2>(ctx, a) : launch_f32c<KERNEL, 4, 1>(ctx, a);

@@ -18,7 +18,8 @@ timeout 300 python profiles/tools/percook_probe.py > gpurun_out/r2_percook.jsonl
 timeout 300 python profiles/tools/eval64_probe.py > gpurun_out/r2_eval64.jsonl 2>/dev/null; echo "eval64 rc=$?"
 timeout 900 python tests/tools/accuracy_probe.py 256 1024 2048 4096 > gpurun_out/r2_accuracy.log 2>&1; cat gpurun_out/r2_accuracy.log
 FD_LU_DEBUG=3 timeout 120 python profiles/tools/lu_step_probe.py 256 1024 > gpurun_out/r2_lu_probe.log 2>&1
-FD_LU_DEBUG=3 timeout 120 python profiles/tools/lu_step_probe.py 256 1024 >> gpurun_out/r2_lu_probe.log 2>&1; cat gpurun_out/r2_lu_probe.log | tail -12
+tail -6 gpurun_out/r2_lu_probe.log
+for n in 300 1500 4096 8192; do timeout 300 python profiles/tools/lu_determinism_probe.py $n 16; done > gpurun_out/r2_lu_determinism.log 2>&1; grep -E "mode count|^it" gpurun_out/r2_lu_determinism.log | head -12
 (cd profiles/tools/ubench && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp64_tput fp64_tput.cu && ./fp64_tput) > gpurun_out/r2_fp64_tput.log 2>&1; tail -4 gpurun_out/r2_fp64_tput.log
 python - <<'PY'
 import json
