@@ -545,6 +545,16 @@ def main():
                 "note": "algorithmic flops; the split-precision scheme issues 3x that on the tensor pipe, so 1/3 is the ceiling of this fraction",
                 "traffic": None, "launch_ms": eval_ms_mean,
             }
+        elif eval_kernel == 4:
+            roofline = {
+                "kernel": "tcx::k_eval_tcx (tcgen05.mma kind::f16, exact integer leading digit + FP16 mid/lo: 8 MMAs per "
+                          "algorithmic MAC, Phi generated in FP64)",
+                "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                "frac": achieved_tf / peaks["bf16"], "peak_source": peaks["source"] + " bf16_tflops (burst; FP16 = BF16 rate)",
+                "note": "algorithmic flops; the scheme issues 8x that on the tensor pipe (N = 128 for 120 useful columns), so "
+                        "0.117 is the ceiling of this fraction",
+                "traffic": None, "launch_ms": eval_ms_mean,
+            }
         elif eval_kernel == 3:
             fp64_peak_tf = 148 * 64 * 2 * peaks["sm_max"] * 1e6 / 1e12
             roofline = {
@@ -572,6 +582,12 @@ def main():
                     nc = json.load(f)
                 roofline["traffic"] = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6
                 roofline["traffic_source"] = f"profiles/{src} (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
+            elif args.config == "C2" and eval_kernel == 4 and os.path.exists(os.path.join(ROOT, "profiles", "r2_eval_tcx_ncu_summary.json")):
+                src = "r2_eval_tcx_ncu_summary.json"
+                with open(os.path.join(ROOT, "profiles", src)) as f:
+                    nc = json.load(f)
+                roofline["traffic"] = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6
+                roofline["traffic_source"] = f"profiles/{src} (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
             elif args.config == "C2" and eval_kernel == 2:
                 src = "r2_eval_tc_ncu_summary.json"
                 if not os.path.exists(os.path.join(ROOT, "profiles", src)):
@@ -594,7 +610,8 @@ def main():
                        "l2": "per-pass output (%d frames x V x 12 B = %.0f MB) exceeds the 126 MB L2; no explicit flush" % (Fc, Fc * V * 12 / 1e6),
                        "precision": "FP64 assemble/factor/solve, %s evaluation (eval_precision %s)" % (
                            "FP64" if eval_kernel == 3 else "FP32", ["AUTO", "FP32", "FP64"][args.eval_precision]),
-                       "eval_kernel": {1: "FMA/SFU FP32", 2: "tensor cores (FP16 hi/lo)", 3: "FP64"}.get(eval_kernel),
+                       "eval_kernel": {1: "FMA/SFU FP32", 2: "tensor cores (FP16 hi/lo)", 3: "FP64",
+                                       4: "tensor cores (exact leading digit, FP64-class)"}.get(eval_kernel),
                        "cancellation": float(rep.cancellation),
                        "parallelism": f"vertex-range x{world}" + ("" if world == 1 else f", weights {wmode}")},
             "phase_ms_last_step": phases, "factor_ms": {"n_ctrl": N, "assemble": phases["assemble"], "factor": phases["factor"],

@@ -49,7 +49,7 @@ class FdReport(C.Structure):
     _fields_ = [
         ("terminationtype", C.c_int32), ("iterationscount", C.c_int32), ("n", C.c_int32), ("npoly", C.c_int32),
         ("frames", C.c_int32), ("reserved", C.c_int32), ("min_pivot", C.c_double), ("max_pivot", C.c_double),
-        ("residual", C.c_double), ("cancellation", C.c_double), ("eval_kernel", C.c_int32), ("reserved2", C.c_int32),
+        ("residual", C.c_double), ("cancellation", C.c_double), ("eval_kernel", C.c_int32), ("eval_inexact", C.c_int32),
     ]
 
 

@@ -121,7 +121,9 @@ int model_alloc(fd_ctx* ctx, const fd_params* params, int N, bool with_factor, f
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_pivstat, 2);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_ctab32, (size_t)fd_tc_kpad(N)); // padded: the tensor path bulk-copies 32-centre tiles
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_ctab_pair, (size_t)fd_tc_kpad(N));
-    if (st == FD_OK && (m->eval64 || m->auto_sel)) st = dev_alloc(ctx, &m->d_ctab64, (size_t)N);
+    if (st == FD_OK && (m->eval64 || m->auto_sel)) st = dev_alloc(ctx, &m->d_ctab64, (size_t)fd_tc_kpad(N)); // padded like d_ctab32
+    if (st == FD_OK && m->auto_sel) st = dev_alloc(ctx, &m->d_ctab_tcx, (size_t)fd_tc_kpad(N));
+    if (st == FD_OK && m->auto_sel) st = dev_alloc(ctx, &m->d_csc_tcx, (size_t)fd_tc_kpad(N));
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_tc_norm, 8);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_sel, 2);
     if (st == FD_OK) st = dev_alloc(ctx, &m->d_est, 4);
@@ -154,15 +156,25 @@ bool model_wants_tc(const fd_model* m, int F)
     return m->prm.eval_path == FD_PATH_TENSOR || 3 * F >= FD_TC_MIN_COLUMNS;
 }
 
+// Which evaluation kernel a batch of F frames takes.  Gaussian under FD_EVAL_AUTO with a wide batch: the exact-digit tensor-core
+// kernel (fd_eval_tcx.cu), whose error does not grow with the cancellation of the weights -- a static choice.  Otherwise the
+// FP32 tensor-core kernel when asked for / wide enough, and for FD_EVAL_AUTO the device-side choice among the FP32 kernels and
+// FP64 (fd_eval64.cu).
+void model_choose_eval(fd_model* m, int F)
+{
+    m->use_tcx = m->auto_sel && m->prm.eval_path != FD_PATH_SIMT && m->d_tcx_wt_mid && 3 * F >= FD_TC_MIN_COLUMNS;
+    m->use_tc = !m->use_tcx && model_wants_tc(m, F);
+}
+
 int model_reserve_frames(fd_model* m, int F)
 {
     fd_ctx* ctx = m->ctx;
     if (F <= m->capF) return FD_OK;
-    void* old[] = {m->d_W, m->d_W32, m->d_tc_scale, m->d_tc_unscale, m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_B, m->d_R, m->d_D32};
+    void* old[] = {m->d_W, m->d_W32, m->d_tc_scale, m->d_tc_unscale, m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_tcx_wt_mid, m->d_B, m->d_R, m->d_D32};
     for (void* b : old)
         if (b) cudaFreeAsync(b, ctx->stream);
     m->d_W = nullptr; m->d_W32 = nullptr; m->d_tc_scale = nullptr; m->d_tc_unscale = nullptr;
-    m->d_tc_wt_hi = nullptr; m->d_tc_wt_lo = nullptr; m->d_B = nullptr; m->d_R = nullptr; m->d_D32 = nullptr;
+    m->d_tc_wt_hi = nullptr; m->d_tc_wt_lo = nullptr; m->d_tcx_wt_mid = nullptr; m->d_B = nullptr; m->d_R = nullptr; m->d_D32 = nullptr;
     m->capF = 0;
     const int ld = fd_round_up(3 * F, 4);
     int st = dev_alloc(ctx, &m->d_W, (size_t)m->n * ld);
@@ -179,6 +191,17 @@ int model_reserve_frames(fd_model* m, int F)
         if (st == FD_OK) st = dev_alloc(ctx, &lo, cols * kpad);
         m->d_tc_wt_hi = hi;
         m->d_tc_wt_lo = lo;
+        if (st == FD_OK && m->auto_sel) { // the third table of the exact-digit kernel (its 120-column blocks fit the same padding)
+            unsigned short* mid = nullptr;
+            st = dev_alloc(ctx, &mid, cols * kpad);
+            m->d_tcx_wt_mid = mid;
+            if (st == FD_OK && !m->d_tcx_rowexp) st = dev_alloc(ctx, &m->d_tcx_rowexp, kpad + 4);
+            if (st == FD_OK && !m->d_tcx_rowmax) st = dev_alloc(ctx, &m->d_tcx_rowmax, kpad + 4);
+            if (st == FD_OK && !m->d_tcx_meta) {
+                st = dev_alloc(ctx, &m->d_tcx_meta, 2);
+                if (st == FD_OK) cudaMemsetAsync(m->d_tcx_meta, 0, 2 * sizeof(double), ctx->stream);
+            }
+        }
     }
     if (st != FD_OK) return st;
     m->capF = F;
@@ -387,7 +410,7 @@ int fd_ctx_create(fd_ctx** out, int device, void* stream)
     }
     // function attributes are per device: every ctx sets them for its own (one process may hold one ctx per GPU)
     if (fd_solve_setup(ctx) != cudaSuccess || fd_factor_setup(ctx) != cudaSuccess || fd_eval_tc_setup(ctx) != cudaSuccess ||
-        fd_eval64_setup(ctx) != cudaSuccess) {
+        fd_eval64_setup(ctx) != cudaSuccess || fd_eval_tcx_setup(ctx) != cudaSuccess) {
         fd_ctx_destroy(ctx);
         return FD_E_CUDA;
     }
@@ -473,7 +496,8 @@ void fd_model_destroy(fd_model* m)
     void* blocks[] = {m->d_rest, m->d_radii, m->d_A, m->d_ipiv, m->d_perm, m->d_W, m->d_flags, m->d_pivstat,
                       m->d_ctab32, m->d_W32, m->d_ctab64, m->d_tc_norm, m->d_tc_scale, m->d_tc_unscale,
                       m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win, m->d_ctab_pair, m->d_A32, m->d_B, m->d_R, m->d_D32,
-                      m->d_ir_norm, m->d_v1_R, m->d_v1_K, m->d_v1_V, m->d_v1_stack, m->d_ns, m->d_sel, m->d_est, m->d_wmax, m->d_inv, m->d_inv_rhs};
+                      m->d_ir_norm, m->d_v1_R, m->d_v1_K, m->d_v1_V, m->d_v1_stack, m->d_ns, m->d_sel, m->d_est, m->d_wmax, m->d_inv, m->d_inv_rhs,
+                      m->d_tcx_wt_mid, m->d_tcx_rowexp, m->d_tcx_rowmax, m->d_tcx_meta, m->d_ctab_tcx, m->d_csc_tcx};
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;
@@ -574,11 +598,11 @@ int fd_rbf_solve_dev(fd_model* m, const float* deform_ctrl_dev, int32_t n_ctrl, 
     m->F = frames;
     m->ldw = fd_round_up(3 * frames, 4);
     m->ldw32 = m->ldw;
-    m->use_tc = model_wants_tc(m, frames);
+    model_choose_eval(m, frames);
     phase_begin(ctx, FD_PH_SOLVE);
     // FD_FLAG_NONFINITE describes the weights of THIS solve (a NaN in one frame's rig must not poison later cooks of a
     // cached model); singular / zero-radius are properties of the fit and stay
-    cudaError_t e = cudaMemsetAsync(m->d_flags + FD_FLAG_NONFINITE, 0, sizeof(int), ctx->stream);
+    cudaError_t e = cudaMemsetAsync(m->d_flags + FD_FLAG_NONFINITE, 0, 2 * sizeof(int), ctx->stream);
     if (e != cudaSuccess) { FD_SET_ERR(ctx, "solve: %s", cudaGetErrorString(e)); return FD_E_CUDA; }
     if (m->ns) { // D' = Q^T D, z = S^-1 D'[4:], a = R^-1 (D'[:4] - K'[:4, 4:] z), w = Q [0; z]
         m->tc_packed_by_solve = false;
@@ -702,7 +726,7 @@ int fd_model_report(fd_model* m, fd_report* report)
         report->max_pivot = piv[1];
         report->cancellation = est[0];
         report->eval_kernel = m->solved ? (m->eval64 ? FD_SEL_FP64 : (sel ? sel : (m->use_tc ? FD_SEL_TENSOR : FD_SEL_SIMT))) : 0;
-        report->reserved2 = 0;
+        report->eval_inexact = flags[FD_FLAG_EVAL_INEXACT];
     }
     if (term != 1) { // SOP_FaceDeform.cpp:365-368
         FD_SET_ERR(ctx, "%s (terminationtype %d)", fd_status_string(FD_E_SINGULAR), term);
@@ -768,7 +792,7 @@ int fd_model_create_receiver(fd_ctx* ctx, const fd_params* params, const float* 
     m->F = frames;
     m->ldw = fd_round_up(3 * frames, 4);
     m->ldw32 = m->ldw;
-    m->use_tc = model_wants_tc(m, frames);
+    model_choose_eval(m, frames);
     // no host synchronisation: pageable sources are staged by the driver before the call returns, pinned or device
     // sources must stay valid until the ctx stream has consumed them (like every *_dev entry point)
     cudaError_t e = cudaMemcpyAsync(m->d_rest, rest_ctrl, (size_t)n_ctrl * 3 * sizeof(float), cudaMemcpyDefault, ctx->stream);
@@ -802,7 +826,7 @@ int fd_model_commit_weights(fd_model* m)
     fd_ctx* ctx = m->ctx;
     DeviceGuard g(ctx->device);
     if (!m->d_W || m->F < 1) { FD_SET_ERR(ctx, "commit: no weight block reserved"); return FD_E_STATE; }
-    cudaError_t e = cudaMemsetAsync(m->d_flags + FD_FLAG_NONFINITE, 0, sizeof(int), ctx->stream); // per commit, like a solve
+    cudaError_t e = cudaMemsetAsync(m->d_flags + FD_FLAG_NONFINITE, 0, 2 * sizeof(int), ctx->stream); // per commit, like a solve
     if (e == cudaSuccess) e = fd_launch_pack(ctx, m);
     if (e != cudaSuccess) { FD_SET_ERR(ctx, "commit: %s", cudaGetErrorString(e)); return FD_E_CUDA; }
     m->solved = true;
@@ -927,7 +951,7 @@ int fd_model_commit_from_peer(fd_model* m, const double* peer_W, const double* p
     DeviceGuard g(ctx->device);
     if (!m->d_W || m->F < 1) { FD_SET_ERR(ctx, "commit: no weight block reserved"); return FD_E_STATE; }
     cudaError_t e = cudaMemcpyPeerAsync(m->d_radii, ctx->device, peer_radii, peer_device, (size_t)m->N * sizeof(double), ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_flags + FD_FLAG_NONFINITE, 0, sizeof(int), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_flags + FD_FLAG_NONFINITE, 0, 2 * sizeof(int), ctx->stream);
     m->d_W_src = peer_W;
     if (e == cudaSuccess) e = fd_launch_pack(ctx, m);
     if (e == cudaSuccess) e = fd_launch_pull_weights(ctx, m);
@@ -1043,7 +1067,7 @@ extern "C" int fd_model_load(fd_ctx* ctx, const void* buf, size_t bytes, fd_mode
         if (st != FD_OK) { fd_model_destroy(m); return st; }
         m->F = h.F;
         m->ldw = m->ldw32 = h.ldw;
-        m->use_tc = model_wants_tc(m, h.F);
+        model_choose_eval(m, h.F);
     }
     Section sec[12];
     const int nsec = save_sections(m, h.has_factor != 0, sec);

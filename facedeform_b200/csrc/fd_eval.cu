@@ -637,6 +637,10 @@ cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64
     // (written after the solve, fd_eval64.cu) lets exactly one of them run -- no host synchronisation in between
     const int* sel = (!m->eval64 && m->auto_sel) ? m->d_sel : nullptr;
     cudaError_t e = cudaSuccess;
+    if (m->use_tcx) { // wide Gaussian batches under FD_EVAL_AUTO: the exact-digit tensor-core kernel, FP64 if its bound fails
+        e = fd_launch_eval_tcx(ctx, m, P, V, dist2, tu, tv, nrm, P_out, falloff_out, sel, FD_SEL_TCX);
+        if (!sel || e != cudaSuccess) return e;
+    }
     if (!m->eval64 && m->use_tc) {
         e = fd_launch_eval_tc(ctx, m, P, V, dist2, tu, tv, nrm, P_out, falloff_out, sel, FD_SEL_TENSOR);
         if (!sel || e != cudaSuccess) return e;
@@ -658,7 +662,7 @@ cudaError_t fd_launch_eval(fd_ctx* ctx, const fd_model* m, const float* P, int64
     a.do_tangent = (m->prm.tangent && tu && tv && nrm) ? 1 : 0; // SOP_FaceDeform.cpp:293-294
     a.origin = m->d_rest;
     a.sel = sel;
-    if (!m->eval64 && (!m->use_tc || (sel && m->prm.eval_path != FD_PATH_TENSOR))) { // FP32 FMA/SFU
+    if (!m->eval64 && !m->use_tcx && (!m->use_tc || (sel && m->prm.eval_path != FD_PATH_TENSOR))) { // FP32 FMA/SFU
         a.sel_id = FD_SEL_SIMT;
         a.ctab = m->d_ctab32;
         a.W = m->d_W32;
@@ -699,6 +703,7 @@ cudaError_t fd_launch_eval_frames(fd_ctx* ctx, const fd_model* m, const float* P
     view.w_col0 = 3 * f_begin;
     if (view.d_W32) view.d_W32 = m->d_W32 + 3 * f_begin;
     view.d_W = m->d_W + 3 * f_begin; // f_begin is a multiple of 80: the 16-byte alignment of the FP64 rows is kept
+    if (m->use_tcx && !fd_tcx_view_frames(m, &view, f_begin)) return cudaErrorInvalidValue;
     if (m->use_tc && !fd_tc_view_frames(m, &view, f_begin)) return cudaErrorInvalidValue;
     return fd_launch_eval(ctx, &view, P, V, dist2, tu, tv, nrm, P_out + (size_t)f_begin * (size_t)V * 3,
                           f_begin == 0 ? falloff_out : nullptr);

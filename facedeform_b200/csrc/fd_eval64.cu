@@ -39,6 +39,9 @@ namespace {
 // 1.3 at N <= 64 and decreases by 0.07 per doubling of N down to 1.1.  A kernel is eligible while its prediction stays
 // within eval_tolerance x diag; the fastest eligible one runs: tensor cores, then FMA/SFU, else FP64.
 constexpr double ERR_COEF_TENSOR = 2.0;
+// the exact-digit tensor-core kernel (fd_eval_tcx.cu): what is left is the truncation bias of its second accumulator, measured
+// 0.044 ... 0.06 x 2^-24 S at N = 256 ... 4096 (profiles/r2_accuracy.log) -- 2.5 x that
+constexpr double ERR_COEF_TCX = 0.15;
 __host__ __device__ inline double err_coef_simt(int N)
 {
     const double c = 1.3 - 0.07 * log2(fmax((double)N, 64.0) / 64.0);
@@ -72,6 +75,7 @@ struct SelectArgs {
     int N, kernel;
     int tensor_ok;     // the tensor-core tables exist for these weights (3F wide enough, eval_path allows it)
     int simt_ok;       // eval_path allows the FMA/SFU kernel
+    int tcx_ok;        // the exact-digit tensor-core tables exist for these weights
     int want;          // 0 choose; 1 / 2 / 3 forced by eval_precision / eval_path
     float tol;         // eval_tolerance
     unsigned long long* smax_bits; // max S as the bits of a non-negative double
@@ -112,6 +116,7 @@ __global__ void __launch_bounds__(256) k_cancel_select(const SelectArgs a)
         const double tol = a.tol > 0.f ? (double)a.tol : 1e-5;
         const double unit = 5.9604644775390625e-08 * S, lim = tol * diag;
         sel = (a.tensor_ok && ERR_COEF_TENSOR * unit <= lim) ? FD_SEL_TENSOR
+            : (a.tcx_ok && ERR_COEF_TCX * unit <= lim) ? FD_SEL_TCX
             : (a.simt_ok && err_coef_simt(a.N) * unit <= lim) ? FD_SEL_SIMT : FD_SEL_FP64;
     }
     *a.sel = sel;
@@ -367,7 +372,7 @@ cudaError_t fd_eval64_setup(fd_ctx* ctx)
 }
 
 // after a solve / commit: measure the cancellation and settle the evaluation kernel on the device
-cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int tensor_ok, int simt_ok, int want)
+cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int tensor_ok, int simt_ok, int tcx_ok, int want)
 {
     cudaStream_t s = ctx->stream;
     k_wmax<<<m->N, 128, 0, s>>>(fd_w_src(m), m->ldw, 3 * m->F, m->N, m->d_wmax);
@@ -381,6 +386,7 @@ cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int tensor_ok, int
     a.tensor_ok = tensor_ok;
     a.simt_ok = simt_ok;
     a.want = want;
+    a.tcx_ok = tcx_ok;
     a.tol = m->prm.eval_tolerance;
     a.smax_bits = reinterpret_cast<unsigned long long*>(m->d_est + 2);
     a.done = reinterpret_cast<unsigned*>(m->d_est + 3);

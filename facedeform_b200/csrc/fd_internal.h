@@ -18,6 +18,7 @@
 #define FD_FLAG_ZERO_RADIUS 0 // != 0: a QNN radius was zero (duplicate centres)      -> terminationtype -5
 #define FD_FLAG_SINGULAR 1    // k+1 of the first zero pivot                           -> terminationtype -3
 #define FD_FLAG_NONFINITE 2   // weights contain NaN/Inf                               -> terminationtype -3
+#define FD_FLAG_EVAL_INEXACT 3 // exact-digit tensor-core evaluation: a vertex left the exact range -> fd_report.eval_inexact
 
 // device staging slots owned by the ctx (host-pointer entry points copy through them)
 enum fd_stage_slot {
@@ -93,6 +94,7 @@ cudaError_t fd_solve_setup(fd_ctx* ctx);     // fd_solve.cu
 cudaError_t fd_factor_setup(fd_ctx* ctx);    // fd_factor.cu
 cudaError_t fd_eval_tc_setup(fd_ctx* ctx);   // fd_eval_tc.cu
 cudaError_t fd_eval64_setup(fd_ctx* ctx);    // fd_eval64.cu
+cudaError_t fd_eval_tcx_setup(fd_ctx* ctx);   // fd_eval_tcx.cu
 void fd_ctx_retain(fd_ctx* ctx);
 void fd_ctx_release(fd_ctx* ctx); // fd_api.cu
 
@@ -174,6 +176,16 @@ struct fd_model {
     void* d_tc_wt_lo;
     alignas(64) unsigned char tc_map_hi[FD_TMAP_BYTES]; // CUtensorMap
     alignas(64) unsigned char tc_map_lo[FD_TMAP_BYTES];
+    // exact-digit tensor-core evaluation (fd_eval_tcx.cu; Gaussian under FD_EVAL_AUTO with 3F >= 48): digit / mid / lo tables in
+    // d_tc_wt_hi / d_tcx_wt_mid / d_tc_wt_lo, 120-column blocks
+    bool use_tcx;
+    void* d_tcx_wt_mid;
+    double4* d_ctab_tcx; // per centre (Kpad): (a, b, c, d) of t = q . (a, b, c) + d + |q|^2 sc, q = p - centre 0 (per fit)
+    double* d_csc_tcx;   // per centre (Kpad): sc = -log2(e) / R^2
+    int* d_tcx_rowexp;   // per row: s_k (Kpad entries), then the digit width h chosen at pack time
+    float* d_tcx_rowmax; // per row: max_c |w_kc| 2^e_c
+    double* d_tcx_meta;  // scratch of the pack: the bits of max_i sum_k phi_k(c_i) rowmax_k
+    alignas(64) unsigned char tcx_map_mid[FD_TMAP_BYTES];
 };
 
 #define FD_CUDA_OK(ctx, call)                                                                      \
@@ -275,12 +287,20 @@ cudaError_t fd_launch_tc_norm(fd_ctx* ctx, fd_model* m);
 cudaError_t fd_launch_eval_tc(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2,
                               const float* tu, const float* tv, const float* nrm, float* P_out, float* falloff_out,
                               const int* sel, int sel_id);
+// fd_eval_tcx.cu
+int fd_tcx_ncb(int F);
+int fd_tcx_col_pad(int F);
+cudaError_t fd_launch_pack_tcx(fd_ctx* ctx, fd_model* m);
+bool fd_tcx_view_frames(const fd_model* m, fd_model* view, int f_begin);
+cudaError_t fd_launch_eval_tcx(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2, const float* tu,
+                               const float* tv, const float* nrm, float* P_out, float* falloff_out, const int* sel, int sel_id);
 // fd_eval64.cu
 #define FD_SEL_SIMT 1
 #define FD_SEL_TENSOR 2
 #define FD_SEL_FP64 3
+#define FD_SEL_TCX 4 // tensor cores, exact leading digit (fd_eval_tcx.cu)
 #define FD_MMA64_MIN_COLUMNS 48 // the FP64 evaluation takes the DMMA kernel from 3F >= 48 columns
-cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int tensor_ok, int simt_ok, int want);
+cudaError_t fd_launch_cancel_select(fd_ctx* ctx, fd_model* m, int tensor_ok, int simt_ok, int tcx_ok, int want);
 cudaError_t fd_launch_eval64_mma(fd_ctx* ctx, const fd_model* m, const float* P, int64_t V, const float* dist2, const float* tu,
                                  const float* tv, const float* nrm, float* P_out, float* falloff_out, const int* sel, int sel_id);
 // fd_capture.cu

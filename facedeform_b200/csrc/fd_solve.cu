@@ -663,7 +663,8 @@ __global__ void __launch_bounds__(S8_THREADS) k_solve_slab8(const double* __rest
 // FP64 centre table when the evaluation runs in double.  Flags non-finite weights.
 __global__ void __launch_bounds__(256) k_pack_tables(const float* __restrict__ rest, const double* __restrict__ radii,
                                                      int N, int Npad, int kernel, float4* __restrict__ ctab32,
-                                                     float* __restrict__ ctab_pair, double4* __restrict__ ctab64)
+                                                     float* __restrict__ ctab_pair, double4* __restrict__ ctab64,
+                                                     double4* __restrict__ ctabx, double* __restrict__ cscx)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Npad) return;
@@ -673,6 +674,11 @@ __global__ void __launch_bounds__(256) k_pack_tables(const float* __restrict__ r
         const float pad = kernel == FD_KERNEL_MULTIQUADRIC ? 1.f : 0.f;
         ctab32[j] = make_float4(0.f, 0.f, 0.f, pad);
         pr[0] = 0.f, pr[2] = 0.f, pr[4] = 0.f, pr[6] = pad;
+        if (ctab64) ctab64[j] = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (ctabx) {
+            ctabx[j] = make_double4(0.0, 0.0, 0.0, 0.0);
+            cscx[j] = 0.0;
+        }
         return;
     }
     const double R = radii[j];
@@ -685,6 +691,12 @@ __global__ void __launch_bounds__(256) k_pack_tables(const float* __restrict__ r
     const double prm32 = kernel == FD_KERNEL_GAUSSIAN ? prm * 1.4426950408889634074 : prm;
     ctab32[j] = make_float4(x, y, z, (float)prm32);
     pr[0] = x, pr[2] = y, pr[4] = z, pr[6] = (float)prm32;
+    if (ctabx) { // the exact-digit tensor-core kernel (Gaussian): t = log2 phi = sc |p - c|^2 expanded around centre 0
+        const double sc = prm * 1.4426950408889634074;
+        const double cx = (double)x - (double)rest[0], cy = (double)y - (double)rest[1], cz = (double)z - (double)rest[2];
+        ctabx[j] = make_double4(-2.0 * sc * cx, -2.0 * sc * cy, -2.0 * sc * cz, sc * (cx * cx + cy * cy + cz * cz));
+        cscx[j] = sc;
+    }
     if (ctab64) {
         if (kernel == FD_KERNEL_GAUSSIAN) {
             ctab64[j] = make_double4((double)x, (double)y, (double)z, prm);
@@ -906,7 +918,7 @@ cudaError_t fd_launch_pack_tables(fd_ctx* ctx, fd_model* m)
     cudaStream_t s = ctx->stream;
     const int npad = fd_tc_kpad(m->N);
     k_pack_tables<<<(npad + 255) / 256, 256, 0, s>>>(m->d_rest, m->d_radii, m->N, npad, m->prm.kernel, m->d_ctab32,
-                                                    reinterpret_cast<float*>(m->d_ctab_pair), m->d_ctab64);
+                                                    reinterpret_cast<float*>(m->d_ctab_pair), m->d_ctab64, m->d_ctab_tcx, m->d_csc_tcx);
     ctx->launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = fd_launch_tc_norm(ctx, m);
@@ -922,6 +934,11 @@ cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
     cudaError_t e = cudaSuccess;
     if (!m->tables_packed || m->receiver) e = fd_launch_pack_tables(ctx, m);
     if (e != cudaSuccess) return e;
+    if (m->use_tcx) { // the exact-digit tensor-core kernel while its (small) error bound holds, else FP64: settled on the device
+        e = fd_launch_pack_tcx(ctx, m);
+        if (e == cudaSuccess) e = fd_launch_cancel_select(ctx, m, 0, 0, 1, 0);
+        return e;
+    }
     // FD_EVAL_AUTO (Gaussian) keeps every FP32 candidate ready: the choice is made on the device after this pack
     const bool want_simt = !m->use_tc || (m->auto_sel && m->prm.eval_path != FD_PATH_TENSOR);
     if (m->use_tc) e = fd_launch_pack_tc(ctx, m);
@@ -933,7 +950,7 @@ cudaError_t fd_launch_pack(fd_ctx* ctx, fd_model* m)
     }
     // the cancellation of these weights, and with it the evaluation kernel of FD_EVAL_AUTO (Gaussian; fd_eval64.cu)
     if (e == cudaSuccess && !m->eval64 && m->prm.kernel == FD_KERNEL_GAUSSIAN)
-        e = fd_launch_cancel_select(ctx, m, m->use_tc ? 1 : 0, want_simt ? 1 : 0,
+        e = fd_launch_cancel_select(ctx, m, m->use_tc ? 1 : 0, want_simt ? 1 : 0, 0,
                                     m->auto_sel ? 0 : (m->use_tc ? FD_SEL_TENSOR : FD_SEL_SIMT));
     return e;
 }

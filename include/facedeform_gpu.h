@@ -134,8 +134,12 @@ typedef struct fd_report {
     double cancellation;     /* after a solve: S = max_i sum_j max_c |w_jc| phi_j(c_i), the size of the terms that cancel in
                                 the evaluation sum; an FP32 evaluation errs by about 2^-24 S */
     int32_t eval_kernel;     /* after a solve: the evaluation FD_EVAL_AUTO / FD_PATH_AUTO settled on: 1 FMA/SFU FP32,
-                                2 tensor cores (FP16 hi/lo splits), 3 FP64 */
-    int32_t reserved2;
+                                2 tensor cores (FP16 hi/lo splits), 3 FP64, 4 tensor cores with an exact leading digit
+                                (FP64-class accuracy; Gaussian under FD_EVAL_AUTO from 16 frames on) */
+    int32_t eval_inexact;    /* != 0: an evaluation with kernel 4 met a vertex whose leading-digit sum may have left the exact
+                                range (a mesh far outside the rig, or weights unlike those at the control points): that result
+                                is FP32-accurate only; re-evaluate with eval_precision = FD_EVAL_FP64 */
+
 } fd_report;
 
 int fd_abi_version(void);

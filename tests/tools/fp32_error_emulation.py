@@ -72,3 +72,46 @@ for name, pa, pb, terms in (("tensor3 (hh hl lh)", 2, 2, [(0, 0), (0, 1), (1, 0)
                             ("tensor6 (3-way)", 3, 3, [(0, 0), (0, 1), (1, 0), (0, 2), (2, 0), (1, 1)])):
     for trunc in (False, True):
         print(f"       {name:22s} accumulate {'RZ' if trunc else 'RN'}: {err(tensor(pa, pb, terms, trunc)):.2f}")
+
+
+# ---- error-free slices (Ozaki scheme): what DESIGN.md section 9 item 1 proposes ---------------------------------------------
+# Phi (computed in FP64) and the column-scaled weights are cut into SL-bit integer slices held in FP16; a slice-pair product is
+# an exact integer, and K_BLK of them add exactly in an FP32 accumulator while SL_A + SL_B + log2(K_BLK) <= 24.  The pair sums
+# are combined in FP64 (the epilogue).  The emulation checks the exactness claim (the largest |partial sum| in bits) and reports
+# the end-to-end error, which is only the truncation of Phi and W to their slices.
+def sliced(nsl_a, nsl_b, sl=8, k_blk=256, max_order=None):
+    K = N + 4
+    A = A64.copy()
+    A[:, N + 1:] = A64[:, N + 1:]                     # affine columns: coordinates (|x| < 4 here); scaled like Phi below
+    amax = np.abs(A).max(0)                           # per-K-row scale of the A operand (Phi <= 1; coordinates by their range)
+    a_scale = 2.0 ** -np.ceil(np.log2(np.maximum(amax, 1e-300)))  # A * a_scale in (-1, 1]
+    An = A * a_scale[None]
+    Wn = (W / a_scale[:, None])                       # keep the product unchanged
+    cs = 2.0 ** -np.ceil(np.log2(np.abs(Wn).max(0) + 1e-300))      # per-column power of two: |W| * cs <= 1
+    Wn = Wn * cs[None]
+    def cut(x, n):                                    # signed digits: x ~ sum_i d_i 2^(-sl (i+1)), |d_i| <= 2^(sl-1)
+        out, rem = [], x.copy()
+        for i in range(n):
+            d = np.rint(rem * 2.0 ** (sl * (i + 1)))
+            out.append(d)
+            rem = rem - d * 2.0 ** (-sl * (i + 1))
+        return out
+    Ad, Wd = cut(An, nsl_a), cut(Wn, nsl_b)
+    order = max_order if max_order is not None else max(nsl_a, nsl_b) - 1
+    acc = np.zeros((V, 3 * F))
+    worst_bits = 0.0
+    for i in range(nsl_a):
+        for j in range(nsl_b):
+            if i + j > order:
+                continue
+            for k0 in range(0, K, k_blk):
+                part = Ad[i][:, k0:k0 + k_blk] @ Wd[j][k0:k0 + k_blk]            # integers: exact in float64
+                worst_bits = max(worst_bits, float(np.log2(np.abs(part).max() + 1)))
+                acc += part * 2.0 ** (-sl * (i + j + 2))
+    return acc / cs[None], worst_bits, sum(1 for i in range(nsl_a) for j in range(nsl_b) if i + j <= order)
+
+
+for na, nb, sl in ((3, 3, 8), (4, 4, 8), (4, 4, 7)):
+    out, bits, pairs = sliced(na, nb, sl=sl, k_blk=256)
+    print(f"       sliced {na}x{nb} x {sl}-bit, K blocks of 256 ({pairs} MMAs): {err(out):.4f} x 2^-24 S   "
+          f"(largest partial sum {bits:.1f} bits: {'exact' if bits <= 24 else 'NOT exact'} in an FP32 accumulator)")
