@@ -547,12 +547,13 @@ def main():
             }
         elif eval_kernel == 4:
             roofline = {
-                "kernel": "tcx::k_eval_tcx (tcgen05.mma kind::f16, exact integer leading digit + FP16 mid/lo: 8 MMAs per "
+                "kernel": "tcx::k_eval_tcx (tcgen05.mma kind::f16, exact integer leading digit + FP16 mid/lo: 6 or 8 MMAs per "
                           "algorithmic MAC, Phi generated in FP64)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["bf16"], "peak_source": peaks["source"] + " bf16_tflops (burst; FP16 = BF16 rate)",
-                "note": "algorithmic flops; the scheme issues 8x that on the tensor pipe (N = 128 for 120 useful columns), so "
-                        "0.117 is the ceiling of this fraction",
+                "note": "algorithmic flops; the scheme issues 6.4x (digit width >= 9) or 8.5x that on the tensor pipe (N = 128 for "
+                        "120 useful columns), so 0.16 / 0.12 is the ceiling of this fraction; the kernel is bound by shared-memory "
+                        "bandwidth (DESIGN.md section 4)",
                 "traffic": None, "launch_ms": eval_ms_mean,
             }
         elif eval_kernel == 3:

@@ -113,8 +113,10 @@ typedef struct fd_params {
                                  skip the pass with the reference's warning (:446-452).  0: the group restricts the
                                  deformation, the weights follow every cooked frame. */
     float eval_tolerance;     /* default 1e-5: FD_EVAL_AUTO runs the fastest evaluation whose predicted maximum error stays
-                                 within eval_tolerance x the control rig's bounding-box diagonal: tensor cores (2.0 x 2^-24 S),
-                                 FMA/SFU FP32 (1.3 ... 1.1 x 2^-24 S, falling with N), else FP64; S = fd_report.cancellation */
+                                 within eval_tolerance x the control rig's bounding-box diagonal.  Gaussian, >= 16 frames: the
+                                 tensor cores with an exact leading digit (0.15 x 2^-24 S), else FP64; fewer frames: FMA/SFU
+                                 FP32 (1.3 ... 1.1 x 2^-24 S, falling with N), else FP64.  S = fd_report.cancellation
+                                  */
     char group[64];           /* "group"  default ""  (all points)  :119-120  point-group pattern: "*", "7", "3-40",
                                  "0-100:2", "^5" (remove), space separated; resolved by the host mirror (facedeform_sop.hpp) */
 } fd_params;

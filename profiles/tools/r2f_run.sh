@@ -1,14 +1,21 @@
 #!/bin/bash
-# round 2, GPU call F: column-packed FMA/SFU kernel
+# round 2, multi-GPU call after the exact-digit tensor-core kernel became FD_EVAL_AUTO's wide-batch path: the lines that changed
+# (C2 and C5 under AUTO); the multi-device tests again when asked for (second argument "tests").  FP32-forced lines: r2e_run.sh.
+N=${1:-2}
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r2f_pytest.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|FAILED|Error" gpurun_out/r2f_pytest.log | tail -10
-timeout 600 python bench.py --steps 20 --warmup 3 --no-configs-table --factor-sizes=256 --no-cpu-baseline > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err; echo "bench rc=$?"; python - <<'PY'
+nvidia-smi -L | head -8
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+if [ "$2" = "tests" ]; then
+  timeout 900 python -m pytest tests/test_gpu_round2.py -m gpu -q -k "mgpu or two_contexts or torchrun" > gpurun_out/r2f_pytest_$N.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|FAILED|Error" gpurun_out/r2f_pytest_$N.log | tail -6
+fi
+timeout 600 $TR bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/r2f_scale_c2_$N.json 2> gpurun_out/r2f_scale_c2_$N.err; echo "C2 rc=$?"
+timeout 900 $TR bench.py --gpus $N --config C5 --steps 2 --warmup 2 --no-e2e > gpurun_out/r2f_c5_auto_$N.json 2> gpurun_out/r2f_c5_auto_$N.err; echo "C5 auto rc=$?"
+python - <<PY
 import json
-j = json.load(open("gpurun_out/r2f_bench.json"))
-print({k: j[k] for k in ("value", "ms_per_step", "phase_ms_last_step", "gpu_launches", "dtype")})
-print(j["roofline"]["kernel"][:40], j["roofline"]["frac"], j["roofline"]["launch_ms"], j["config"]["eval_kernel"])
-print("e2e", j.get("e2e"))
+for f in ("r2f_scale_c2_$N", "r2f_c5_auto_$N"):
+    try:
+        j = json.load(open(f"gpurun_out/{f}.json"))
+        print(f, {k: j.get(k) for k in ("value", "ms_per_step", "n_gpus", "scaling", "dtype")}, j["config"]["eval_kernel"], j.get("comm", {}).get("ms_per_pass"), j.get("e2e", {}).get("ms_per_step"), j.get("e2e", {}).get("copy_only_ms_per_step"))
+    except Exception as ex:
+        print(f, "failed", ex)
 PY
-tail -3 gpurun_out/r2f_bench.err
-timeout 300 python profiles/tools/configs_probe.py --only C3g,C1 > gpurun_out/r2f_configs.jsonl 2>&1; cat gpurun_out/r2f_configs.jsonl
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eval_f32c -s 4 -c 1 -o gpurun_out/r2f_eval_f32c -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs-table --no-e2e --factor-sizes= > gpurun_out/r2f_ncu_f32c.log 2>&1; echo "ncu f32c rc=$?"

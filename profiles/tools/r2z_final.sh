@@ -9,7 +9,7 @@ timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_1gpu.jso
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2> gpurun_out/r2_bench_reference_arm.err; echo "reference rc=$?"
 BENCH_FAST="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs-table --no-e2e --factor-sizes="
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv $BENCH_FAST > gpurun_out/r2_ncu_launches.log 2>&1; echo "launch list rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eval_f32c -s 4 -c 1 -o gpurun_out/r2_eval_f32c -f $BENCH_FAST > gpurun_out/r2_ncu_a.log 2>&1; echo "ncu f32c rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eval_tcx -s 4 -c 1 -o gpurun_out/r2_eval_tcx -f $BENCH_FAST > gpurun_out/r2_ncu_a.log 2>&1; echo "ncu tcx rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_lu_nopiv_fused -s 4 -c 1 -o gpurun_out/r2_lu_fused -f $BENCH_FAST > gpurun_out/r2_ncu_b.log 2>&1; echo "ncu lu rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eval_tc -s 4 -c 1 -o gpurun_out/r2_eval_tc -f $BENCH_FAST --eval-precision 1 > gpurun_out/r2_ncu_c.log 2>&1; echo "ncu tc rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eval64_mma -s 4 -c 1 -o gpurun_out/r2_eval64_mma -f $BENCH_FAST --eval-precision 2 > gpurun_out/r2_ncu_d.log 2>&1; echo "ncu eval64 rc=$?"
