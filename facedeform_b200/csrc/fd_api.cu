@@ -688,9 +688,9 @@ int fd_model_report(fd_model* m, fd_report* report)
         const int term = flags[FD_FLAG_SINGULAR] ? -3 : 1;
         if (report) {
             const double canc = report->cancellation; // of the stacked evaluation model
-            const int ek = report->eval_kernel;
+            const int ek = report->eval_kernel, inexact = report->eval_inexact;
             *report = last; // pivots of the last layer
-            if (m->v1_eval) { report->cancellation = canc; report->eval_kernel = ek; }
+            if (m->v1_eval) { report->cancellation = canc; report->eval_kernel = ek; report->eval_inexact = inexact; }
             report->terminationtype = term;
             report->n = m->N * m->v1_layers;
             report->npoly = m->np;

@@ -110,7 +110,7 @@ struct Args {
     const int* sel;         // FD_EVAL_AUTO: the chosen evaluation kernel (device word) or NULL; the launch returns at once
     int sel_id;             // when *sel != sel_id
     int dbg_mode;           // FD_TC_DEBUG bits (timing experiments, results are then garbage): 2 no epilogue stores, 4 no Phi
-                            // arithmetic, 8 one MMA of eight
+                            // arithmetic, 8 one MMA of eight; 32: the exact-range check fires at 2^10 instead of 2^22 (tests its plumbing)
 };
 
 // x (|x| <= 2^11, FP64) -> the integer digit as a float (by integer arithmetic: no conversion) and the remainder |r| <= 1/2 as
@@ -373,7 +373,7 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
                 }
             }
             // four threads share a row (two k halves x two groups): each share within a quarter of the range keeps the sum inside
-            if (bound > 4194304.0f && v < a.V) atomicExch(&a.flags[FD_FLAG_EVAL_INEXACT], 1);
+            if (bound > ((a.dbg_mode & 32) ? 1024.0f : 4194304.0f) && v < a.V) atomicExch(&a.flags[FD_FLAG_EVAL_INEXACT], 1);
         }
     } else {
         // ================= epilogue warps: TMEM -> registers -> (transpose in shared memory) -> global =================

@@ -574,3 +574,60 @@ def test_exact_digit_kernel_epilogue_and_ragged_shapes(ctx, oracle):
         skip = d2 > np.float32(R) * np.float32(R)
         np.testing.assert_array_equal(out[:, skip], np.broadcast_to(mesh.P[skip], out[:, skip].shape))  # gated vertices keep P
         assert np.abs(out - ref).max() <= 1e-6 * mesh.bbox_diag
+
+
+@pytest.mark.parametrize("kw", [dict(model=0), dict(term=1), dict(term=2), dict(lam=1e-3), dict(fidelity=1, layers=2)])
+def test_exact_digit_kernel_on_other_systems(ctx, kw):
+    """QNN radii (per-centre radii in the bound and in Phi), constant / no polynomial term (fewer affine rows), smoothing, the
+    layered fit (stacked centres): FD_EVAL_AUTO's kernel 4 against the FP64 evaluation of the same weights"""
+    from facedeform_b200 import make_params
+    kw = dict(kw)
+    lam = kw.pop("lam", 0.0)
+    N, F, V = 700, 24, 6000
+    rig = synth.control_rig(N)
+    deform = synth.deformed_rig(rig, F)
+    mesh = synth.face_mesh(V, topology=False)
+    R = synth.default_radius("gaussian", rig.spacing)
+    outs = []
+    for prec in (0, 2):
+        base = dict(model=1, term=0, kernel=0, radius=R, eval_precision=prec)
+        base.update(kw)
+        m = ctx.fit(make_params(**base, **{"lambda": lam}), rig.rest).solve(deform)
+        out, _ = m.eval(mesh.P)
+        rep = m.report()
+        assert rep.eval_kernel == (4 if prec == 0 else 3) and rep.eval_inexact == 0
+        outs.append(out)
+        m.close()
+    assert np.abs(outs[0].astype(np.float64) - outs[1]).max() <= 1e-6 * mesh.bbox_diag
+
+
+def test_exact_digit_kernel_far_mesh_and_range_check():
+    """a mesh blown up 40x around the rig: the basis sums vanish, the affine rows grow -- their weights are small, so the leading
+    digits still sum exactly: no flag, FP64-class result.  The plumbing of the runtime check (fd_report.eval_inexact) is
+    exercised with its threshold lowered by a development knob (FD_TC_DEBUG=32, read at context creation)."""
+    from facedeform_b200 import Context, make_params
+    N, F, V = 256, 40, 4096
+    rig = synth.control_rig(N)
+    deform = synth.deformed_rig(rig, F)
+    mesh = synth.face_mesh(V, topology=False)
+    centre = rig.rest.mean(0)
+    P_far = ((mesh.P - centre) * 40.0 + centre).astype(np.float32)
+    R = synth.default_radius("gaussian", rig.spacing)
+    for knob in (False, True):
+        if knob:
+            os.environ["FD_TC_DEBUG"] = "32"
+        try:
+            c = Context()
+        finally:
+            os.environ.pop("FD_TC_DEBUG", None)
+        outs = []
+        for prec in (0, 2):
+            m = c.fit(make_params(model=1, term=0, kernel=0, radius=R, eval_precision=prec, **{"lambda": 0.0}), rig.rest).solve(deform)
+            out, _ = m.eval(P_far)
+            rep = m.report()
+            if prec == 0:
+                assert rep.eval_kernel == 4 and (rep.eval_inexact != 0) == knob
+            outs.append(out)
+            m.close()
+        c.close()
+        assert np.abs(outs[0].astype(np.float64) - outs[1]).max() <= 1e-6 * np.abs(outs[1]).max()
