@@ -23,7 +23,7 @@
 //     (lo x lo: 2^-26 per product) and the FP16 rounding of the lo parts (2^-25 per value) are far below that.  (Without the
 //     two mid x lo products the error was 7e-5 x diagonal at N = 4096, h = 5: they are 2^-14-2h of the full size.)
 //   * Phi is produced in FP64 -- an FP32 Phi alone would put 2^-24 S back -- with the kernel function good to 2^-34: 15 FP64
-//     instructions per basis value (expanded distance 4, exp2 by table + cubic 8, digit split 3) and ONE conversion (F64 <-> F32
+//     instructions per basis value (expanded distance 4, exp2 by a 16-entry table + quartic 8, digit split 3) and ONE conversion (F64 <-> F32
 //     conversions run at a quarter of the FP64 rate; the leading digit becomes a float by integer arithmetic).  Four values are
 //     carried side by side so the dependent chains overlap.  Amortised over 120 columns.
 // Net error ~2^-29 ... 2^-31 x S: measured 1e-7 x the rig's diagonal where the FP32 kernels give 5e-6 ... 2.5e-5
@@ -79,7 +79,7 @@ constexpr int SMEM_CENTRES = SMEM_BARRIERS + 512;
 constexpr int SMEM_SC = SMEM_CENTRES + CDEPTH * C_TILE_BYTES;
 constexpr int SMEM_ROWEXP = SMEM_SC + CDEPTH * S_TILE_BYTES;
 constexpr int SMEM_EXPTAB = SMEM_ROWEXP + CDEPTH * R_TILE_BYTES;
-constexpr int SMEM_COLSCALE = SMEM_EXPTAB + 64 * 8;
+constexpr int SMEM_COLSCALE = SMEM_EXPTAB + 16 * 8;
 constexpr int COLSCALE_RESIDENT_BLOCKS = 6;   // column scales of up to 6 column blocks (F <= 240) stay resident
 constexpr int SMEM_TOTAL = SMEM_COLSCALE + COLSCALE_RESIDENT_BLOCKS * CB * 4;
 static_assert(SMEM_TOTAL + 1024 <= 227 * 1024, "shared-memory budget");
@@ -124,19 +124,22 @@ __device__ __forceinline__ void split_digit(double x, float& hi, float& rem)
     hi = __int_as_float(0x4B400000 + k) - 12582912.0f; // (1.5 * 2^23 + k) - 1.5 * 2^23, exact for |k| < 2^22
 }
 
-// 2^(t + eadd) for t <= 0 with 2^-34 relative error: 2^(k / 64) from a table, 2^r - 1 (|r| <= 1 / 128) as a cubic; all FP64
+// 2^(t + eadd) for t <= 0 with 2^-34 relative error: 2^(k / 16) from a table, 2^r - 1 (|r| <= 1 / 32) as a quartic; all FP64.
+// Sixteen entries = one row of shared-memory banks: whatever entries the lanes of a warp pick, the look-up is conflict free
+// (a 64-entry table cost ~4 wavefronts per look-up, as much as the centre record).
 __device__ __forceinline__ double exp2_digit(double t, const double* __restrict__ s_tab, int eadd)
 {
     t = fmax(t, -200.0);                          // below 2^-200: nothing (and the exponent arithmetic stays in range)
-    const double magic = 6755399441055744.0;
-    const double kf = fma(t, 64.0, magic);
+    const double magic = 6755399441055744.0;      // 1.5 * 2^52: the low word of (x + magic) is rint(x)
+    const double kf = fma(t, 16.0, magic);
     const int k = __double2loint(kf);
-    const double r = fma(kf - magic, -0.015625, t); // t - k / 64 in [-1/128, 1/128]
-    const double r2 = r * r;                      // (c1 r) + r^2 (c2 + c3 r): two levels instead of three
-    const double q = fma(r2, fma(r, 0.05550410866482158, 0.2402265069591007), r * 0.6931471805599453); // r^4 ln2^4 / 24 < 4e-11
-    const double T = s_tab[k & 63];
+    const double r = fma(kf - magic, -0.0625, t); // t - k / 16 in [-1/32, 1/32]
+    const double r2 = r * r;                      // c1 r + r^2 (c2 + c3 r + c4 r^2): r^5 ln2^5 / 120 < 4e-11
+    const double p = fma(r2, 0.009618129107628477, fma(r, 0.05550410866482158, 0.2402265069591007));
+    const double q = fma(r2, p, r * 0.6931471805599453);
+    const double T = s_tab[k & 15];
     const double s = fma(T, q, T);
-    return __hiloint2double(__double2hiint(s) + (((k >> 6) + eadd) << 20), __double2loint(s));
+    return __hiloint2double(__double2hiint(s) + (((k >> 4) + eadd) << 20), __double2loint(s));
 }
 
 template <bool TANGENT>
@@ -177,7 +180,7 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 128) fd_exp2_64_table(s_exp, threadIdx.x - 64);
+    if (threadIdx.x >= 64 && threadIdx.x < 80) s_exp[threadIdx.x - 64] = exp2((double)(threadIdx.x - 64) / 16.0);
     if (warp == WARP_TMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -315,7 +318,6 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         uint32_t whi[4], wmid[4], wlo[4];
-#pragma unroll
                         { // eight values side by side: their dependent chains overlap
                             double x[8];
                             float pw[8];
@@ -350,7 +352,12 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
                             }
 #pragma unroll
                             for (int e2 = 0; e2 < 4; ++e2) {
-                                const __half2 h2 = __floats2half2_rn(hf[2 * e2], hf[2 * e2 + 1]); // exact: integers <= 2048
+                                // exact for integers <= 2048, i.e. always for Phi; an affine row of a vertex far outside the rig
+                                // can exceed it: what the FP16 digit drops goes into the remainder (zero otherwise)
+                                const __half2 h2 = __floats2half2_rn(hf[2 * e2], hf[2 * e2 + 1]);
+                                const float2 hb = __half22float2(h2);
+                                rf[2 * e2] += hf[2 * e2] - hb.x;
+                                rf[2 * e2 + 1] += hf[2 * e2 + 1] - hb.y;
                                 const __half2 m2 = __floats2half2_rn(rf[2 * e2], rf[2 * e2 + 1]);
                                 const float2 mb = __half22float2(m2);
                                 const __half2 l2 = __floats2half2_rn(rf[2 * e2] - mb.x, rf[2 * e2 + 1] - mb.y);

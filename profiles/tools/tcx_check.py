@@ -1,3 +1,7 @@
+"""FD_EVAL_AUTO (the exact-digit tensor-core kernel for batches of >= 16 frames) against the FP64 evaluation of the same weights on
+the full mesh, over shapes that exercise the kernel's edges: one partly filled 120-column block, vertex counts that are not a
+multiple of 128 / 4, K = N + 4 with a short last stage, N up to 4096.  Prints max |difference| / bbox diagonal.
+Usage: python profiles/tools/tcx_check.py [number of cases]"""
 import sys, time, numpy as np
 sys.path.insert(0, ".")
 from facedeform_b200 import Context, make_params, synth
