@@ -197,6 +197,8 @@ int model_reserve_frames(fd_model* m, int F)
             m->d_tcx_wt_mid = mid;
             if (st == FD_OK && !m->d_tcx_rowexp) st = dev_alloc(ctx, &m->d_tcx_rowexp, kpad + 4);
             if (st == FD_OK && !m->d_tcx_rowmax) st = dev_alloc(ctx, &m->d_tcx_rowmax, kpad + 4);
+            if (st == FD_OK && !m->d_tcx_ctab_eff) st = dev_alloc(ctx, &m->d_tcx_ctab_eff, kpad);
+            if (st == FD_OK && !m->d_tcx_pw) st = dev_alloc(ctx, &m->d_tcx_pw, kpad);
             if (st == FD_OK && !m->d_tcx_meta) {
                 st = dev_alloc(ctx, &m->d_tcx_meta, 2);
                 if (st == FD_OK) cudaMemsetAsync(m->d_tcx_meta, 0, 2 * sizeof(double), ctx->stream);
@@ -497,7 +499,8 @@ void fd_model_destroy(fd_model* m)
                       m->d_ctab32, m->d_W32, m->d_ctab64, m->d_tc_norm, m->d_tc_scale, m->d_tc_unscale,
                       m->d_tc_wt_hi, m->d_tc_wt_lo, m->d_Tinv, m->d_win, m->d_ctab_pair, m->d_A32, m->d_B, m->d_R, m->d_D32,
                       m->d_ir_norm, m->d_v1_R, m->d_v1_K, m->d_v1_V, m->d_v1_stack, m->d_ns, m->d_sel, m->d_est, m->d_wmax, m->d_inv, m->d_inv_rhs,
-                      m->d_tcx_wt_mid, m->d_tcx_rowexp, m->d_tcx_rowmax, m->d_tcx_meta, m->d_ctab_tcx, m->d_csc_tcx};
+                      m->d_tcx_wt_mid, m->d_tcx_rowexp, m->d_tcx_rowmax, m->d_tcx_meta, m->d_ctab_tcx, m->d_csc_tcx,
+                      m->d_tcx_ctab_eff, m->d_tcx_pw};
     for (void* b : blocks)
         if (b) cudaFreeAsync(b, s);
     delete m;

@@ -58,7 +58,7 @@ constexpr int A_SPLIT_BYTES = TM * BK * 2;    // 8192
 constexpr int B_SPLIT_BYTES = CB * BK * 2;    // 7680 = 15 swizzle atoms of 512 bytes
 constexpr int C_TILE_BYTES = BK * 32;         // a stage's 32 centres as double4: t = q . (a, b, c) + d + |q|^2 sc (q = p - centre 0)
 constexpr int S_TILE_BYTES = BK * 8;          // their sc = -log2(e) / R^2
-constexpr int R_TILE_BYTES = BK * 4;          // and their row exponents s_k (int32)
+constexpr int R_TILE_BYTES = BK * 4;          // and 2^(h - s_k) as floats (the scale of row k's digit)
 constexpr int CDEPTH = 8;                     // depth of the centre-tile ring
 constexpr int STAGE_BYTES = 3 * A_SPLIT_BYTES + 3 * B_SPLIT_BYTES; // 47616
 constexpr int PRODUCER_WARPS = 16;
@@ -78,21 +78,20 @@ constexpr int SMEM_BARRIERS = SMEM_EPI_STAGING + EPILOGUE_WARPS * EPI_WARP_FLOAT
 constexpr int SMEM_CENTRES = SMEM_BARRIERS + 512;
 constexpr int SMEM_SC = SMEM_CENTRES + CDEPTH * C_TILE_BYTES;
 constexpr int SMEM_ROWEXP = SMEM_SC + CDEPTH * S_TILE_BYTES;
-constexpr int SMEM_EXPTAB = SMEM_ROWEXP + CDEPTH * R_TILE_BYTES;
-constexpr int SMEM_COLSCALE = SMEM_EXPTAB + 16 * 8;
+constexpr int SMEM_COLSCALE = SMEM_ROWEXP + CDEPTH * R_TILE_BYTES;
 constexpr int COLSCALE_RESIDENT_BLOCKS = 6;   // column scales of up to 6 column blocks (F <= 240) stay resident
 constexpr int SMEM_TOTAL = SMEM_COLSCALE + COLSCALE_RESIDENT_BLOCKS * CB * 4;
-static_assert(SMEM_TOTAL + 1024 <= 227 * 1024, "shared-memory budget");
+static_assert(SMEM_TOTAL + 1024 + 1024 + 128 <= 227 * 1024, "shared-memory budget (dynamic + alignment slack + static)");
 static_assert(SMEM_CENTRES % 16 == 0 && STAGE_BYTES % 512 == 0 && B_SPLIT_BYTES % 512 == 0, "tile alignment");
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
 
 struct Args {
-    const double4* ctab;    // (a, b, c, d) per centre (see C_TILE_BYTES), padded with zeros to Kpad entries
+    const double4* ctab;    // (a, b, c, d + h - s_k) per centre (see C_TILE_BYTES; per solve: k_tcx_pack), Kpad entries
     const double* csc;      // sc per centre, padded
     const float* origin;    // centre 0
     const float* norm;      // (ox, oy, oz, s): affine-row coordinates x' = (x - o) * s
     const float* colscale;  // per column: 2^-e_c
-    const int* rowexp;      // per row k: s_k, padded to Kpad entries
+    const float* pw;        // per row k: 2^(h - s_k), Kpad entries
     const int* hbits;       // device word: h (chosen at pack time from the weights)
     int* flags;             // FD_FLAG_EVAL_INEXACT is raised when a vertex's leading-digit sum may leave the exact range
     int N, Kpad, Ktot, F, ncb;
@@ -109,8 +108,8 @@ struct Args {
     int vec_store_ok;       // V % 4 == 0 and P_out 16-byte aligned
     const int* sel;         // FD_EVAL_AUTO: the chosen evaluation kernel (device word) or NULL; the launch returns at once
     int sel_id;             // when *sel != sel_id
-    int dbg_mode;           // FD_TC_DEBUG bits (timing experiments, results are then garbage): 2 no epilogue stores, 4 no Phi
-                            // arithmetic, 8 one MMA of eight; 32: the exact-range check fires at 2^10 instead of 2^22 (tests its plumbing)
+    int dbg_mode;           // FD_TC_DEBUG bits (timing experiments, results are then garbage): 2 no epilogue stores, 8 one MMA
+                            // of eight; 32: the exact-range check fires at 2^10 instead of 2^22 (tests its plumbing)
 };
 
 // x (|x| <= 2^11, FP64) -> the integer digit as a float (by integer arithmetic: no conversion) and the remainder |r| <= 1/2 as
@@ -124,22 +123,94 @@ __device__ __forceinline__ void split_digit(double x, float& hi, float& rem)
     hi = __int_as_float(0x4B400000 + k) - 12582912.0f; // (1.5 * 2^23 + k) - 1.5 * 2^23, exact for |k| < 2^22
 }
 
-// 2^(t + eadd) for t <= 0 with 2^-34 relative error: 2^(k / 16) from a table, 2^r - 1 (|r| <= 1 / 32) as a quartic; all FP64.
-// Sixteen entries = one row of shared-memory banks: whatever entries the lanes of a warp pick, the look-up is conflict free
-// (a 64-entry table cost ~4 wavefronts per look-up, as much as the centre record).
-__device__ __forceinline__ double exp2_digit(double t, const double* __restrict__ s_tab, int eadd)
+// 2^t (t <= ~30; the caller has folded the row's digit exponent h - s_k into t) with 2^-34 relative error, all FP64:
+// t = k / 16 + r, 2^(k / 16) from a 16-entry table (one row of shared-memory banks: conflict free whatever entries the lanes of a
+// warp pick), 2^r - 1 = r (ln2 + r (c2 + r (c3 + r c4))) for |r| <= 1 / 32 (the r^5 term: ln2^5 / 120 / 32^5 < 4e-11).  Adding
+// 1.5 * 2^48 -- ulp 1 / 16 -- rounds t to a multiple of 1 / 16 and leaves k in the low word.  Below t = -200 (or for a negative
+// NaN) the result is 0; the test reads the high word only.  8 FP64 instructions (the version with fma(t, 16, magic), an Estrin
+// quartic, fmax(t, -200) and the exponent passed separately took 10 and twice the integer work).
+__device__ __forceinline__ double exp2_digit(double t, const double* __restrict__ s_tab)
 {
-    t = fmax(t, -200.0);                          // below 2^-200: nothing (and the exponent arithmetic stays in range)
-    const double magic = 6755399441055744.0;      // 1.5 * 2^52: the low word of (x + magic) is rint(x)
-    const double kf = fma(t, 16.0, magic);
-    const int k = __double2loint(kf);
-    const double r = fma(kf - magic, -0.0625, t); // t - k / 16 in [-1/32, 1/32]
-    const double r2 = r * r;                      // c1 r + r^2 (c2 + c3 r + c4 r^2): r^5 ln2^5 / 120 < 4e-11
-    const double p = fma(r2, 0.009618129107628477, fma(r, 0.05550410866482158, 0.2402265069591007));
-    const double q = fma(r2, p, r * 0.6931471805599453);
+    const double M = 422212465065984.0;           // 1.5 * 2^48
+    const double kf = t + M;
+    const int k = __double2loint(kf);             // rint(16 t)
+    const double r = t - (kf - M);                // in [-1/32, 1/32]
+    double p = fma(r, 0.009618129107628477, 0.05550410866482158);
+    p = fma(r, p, 0.2402265069591007);
+    p = fma(r, p, 0.6931471805599453);
     const double T = s_tab[k & 15];
-    const double s = fma(T, q, T);
-    return __hiloint2double(__double2hiint(s) + (((k >> 4) + eadd) << 20), __double2loint(s));
+    const double s = fma(T * r, p, T);            // in [0.97, 2.05): the exponent add below cannot carry wrongly
+    const int hi = __double2hiint(s) + ((k & ~15) << 16); // += floor(k / 16) << 20
+    return __hiloint2double((unsigned)__double2hiint(t) > 0xC0690000u ? 0 : hi, __double2loint(s));
+}
+
+struct ProducerRow {      // what a producer thread keeps per unit: its vertex relative to centre 0
+    double qx, qy, qz, pp;
+    float pxf, pyf, pzf;
+};
+
+// The thread's 16 values of a stage (row `row`, k = k0 + khalf * 16 ...): Phi_k 2^(h - s_k) -> digit / mid / lo FP16 -> the three
+// SWIZZLE_64B A tiles.  PLAIN: 32 centres, no affine rows, no padding.  Returns the thread's share of sum_k a_hi 2^(h - s_k).
+template <bool PLAIN>
+__device__ __forceinline__ float fill_stage_half(const Args& a, const ProducerRow& pr, const float4& nrm4, uint8_t* a_hi,
+                                                 const double4* __restrict__ s_ctr, const double* __restrict__ s_sc,
+                                                 const float* __restrict__ s_pw, const double* __restrict__ s_tab, int khalf,
+                                                 int swz, int k0, float bound)
+{
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t whi[4], wmid[4], wlo[4];
+        double x[8]; // eight values side by side: their dependent chains overlap
+        float pw[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int kk = khalf * 16 + h * 8 + e;
+            const double4 c = s_ctr[kk]; // warp-wide broadcasts
+            const double t = fma(pr.qx, c.x, fma(pr.qy, c.y, fma(pr.qz, c.z, fma(pr.pp, s_sc[kk], c.w))));
+            x[e] = exp2_digit(t, s_tab);
+            pw[e] = s_pw[kk];
+        }
+        if (!PLAIN) { // the last stage(s): affine rows [1, x', y', z'] after the centres, then zero padding
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = k0 + khalf * 16 + h * 8 + e;
+                if (k >= a.N) {
+                    const int r = k - a.N;
+                    const float cf = r >= a.Ktot - a.N ? 0.f
+                                   : r == 0 ? 1.f
+                                   : r == 1 ? (pr.pxf - nrm4.x) * nrm4.w
+                                   : r == 2 ? (pr.pyf - nrm4.y) * nrm4.w : (pr.pzf - nrm4.z) * nrm4.w;
+                    x[e] = (double)cf * (double)pw[e];
+                }
+            }
+        }
+        float hf[8], rf[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            split_digit(x[e], hf[e], rf[e]);
+            bound = fmaf(fabsf(hf[e]), pw[e], bound);
+        }
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+            const __half2 h2 = __floats2half2_rn(hf[2 * e2], hf[2 * e2 + 1]); // exact: integers <= 2048 -- always for Phi
+            if (!PLAIN) { // an affine row of a vertex far outside the rig can exceed that: what the FP16 digit drops goes into
+                const float2 hb = __half22float2(h2); // the remainder
+                rf[2 * e2] += hf[2 * e2] - hb.x;
+                rf[2 * e2 + 1] += hf[2 * e2 + 1] - hb.y;
+            }
+            const __half2 m2 = __floats2half2_rn(rf[2 * e2], rf[2 * e2 + 1]);
+            const float2 mb = __half22float2(m2);
+            const __half2 l2 = __floats2half2_rn(rf[2 * e2] - mb.x, rf[2 * e2 + 1] - mb.y);
+            whi[e2] = *reinterpret_cast<const uint32_t*>(&h2);
+            wmid[e2] = *reinterpret_cast<const uint32_t*>(&m2);
+            wlo[e2] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        const int off = ((khalf * 2 + h) ^ swz) * 16;
+        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+        *reinterpret_cast<uint4*>(a_hi + A_SPLIT_BYTES + off) = make_uint4(wmid[0], wmid[1], wmid[2], wmid[3]);
+        *reinterpret_cast<uint4*>(a_hi + 2 * A_SPLIT_BYTES + off) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+    }
+    return bound;
 }
 
 template <bool TANGENT>
@@ -160,7 +231,7 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
     const uint32_t bar_cfull = smem_u32(bars + 3 * STAGES + 4);            // [CDEPTH], count 1 + tx bytes
     const uint32_t bar_cempty = smem_u32(bars + 3 * STAGES + 4 + CDEPTH);  // [CDEPTH], count PRODUCER_WARPS / 2
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4 + 2 * CDEPTH);
-    double* s_exp = reinterpret_cast<double*>(smem + SMEM_EXPTAB);
+    __shared__ double s_exp[16]; // 2^(i / 16); static: the look-up address needs no base register
     float* s_colscale = reinterpret_cast<float*>(smem + SMEM_COLSCALE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -212,7 +283,7 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
                         mbar_expect_tx(bar_cfull + 8 * c, C_TILE_BYTES + S_TILE_BYTES + R_TILE_BYTES);
                         bulk_load_1d(smem_base + SMEM_CENTRES + c * C_TILE_BYTES, a.ctab + kc * BK, C_TILE_BYTES, bar_cfull + 8 * c);
                         bulk_load_1d(smem_base + SMEM_SC + c * S_TILE_BYTES, a.csc + kc * BK, S_TILE_BYTES, bar_cfull + 8 * c);
-                        bulk_load_1d(smem_base + SMEM_ROWEXP + c * R_TILE_BYTES, a.rowexp + kc * BK, R_TILE_BYTES, bar_cfull + 8 * c);
+                        bulk_load_1d(smem_base + SMEM_ROWEXP + c * R_TILE_BYTES, a.pw + kc * BK, R_TILE_BYTES, bar_cfull + 8 * c);
                     }
                     ++ic;
                     if (++kc == nk) kc = 0;
@@ -283,20 +354,21 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
         const int khalf = (pt >> 7) & 1;        // which half of the stage's 32 k this thread generates
         const int grp = pt >> 8;                // producer group: stages of its parity
         const float4 nrm4 = *reinterpret_cast<const float4*>(a.norm);
-        const int hbits = *a.hbits;
         const double ox = (double)a.origin[0], oy = (double)a.origin[1], oz = (double)a.origin[2];
+        const int swz = (row >> 1) & 3;
         uint32_t it = 0;
         for (int64_t u = unit0; u < n_units; u += ustride) {
             const int64_t vt = u / a.ncb;
             const int64_t v = vt * TM + row;
-            float pxf = 0.f, pyf = 0.f, pzf = 0.f;
+            ProducerRow pr;
+            pr.pxf = 0.f, pr.pyf = 0.f, pr.pzf = 0.f;
             if (v < a.V) {
-                pxf = a.P[3 * v];
-                pyf = a.P[3 * v + 1];
-                pzf = a.P[3 * v + 2];
+                pr.pxf = a.P[3 * v];
+                pr.pyf = a.P[3 * v + 1];
+                pr.pzf = a.P[3 * v + 2];
             }
-            const double qx = (double)pxf - ox, qy = (double)pyf - oy, qz = (double)pzf - oz;
-            const double pp = fma(qx, qx, fma(qy, qy, qz * qz));
+            pr.qx = (double)pr.pxf - ox, pr.qy = (double)pr.pyf - oy, pr.qz = (double)pr.pzf - oz;
+            pr.pp = fma(pr.qx, pr.qx, fma(pr.qy, pr.qy, pr.qz * pr.qz));
             float bound = 0.f; // this thread's share of sum_k a_hi 2^(h - s_k) >= sum_k |a_hi b_hi| for any column
             const uint32_t it0 = it;
             it += nk;
@@ -310,67 +382,11 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
                 uint8_t* a_hi = smem + s * STAGE_BYTES + row * (BK * 2);
                 const double4* s_ctr = reinterpret_cast<const double4*>(smem + SMEM_CENTRES + cs * C_TILE_BYTES);
                 const double* s_sc = reinterpret_cast<const double*>(smem + SMEM_SC + cs * S_TILE_BYTES);
-                const int* s_rexp = reinterpret_cast<const int*>(smem + SMEM_ROWEXP + cs * R_TILE_BYTES);
+                const float* s_pw = reinterpret_cast<const float*>(smem + SMEM_ROWEXP + cs * R_TILE_BYTES);
                 const int k0 = kb * BK;
-                const int swz = (row >> 1) & 3;
                 if (!(kb == nk - 1 && khalf >= tail_ksteps)) { // else: nothing but zero padding, the MMA issuer skips the step
-                    const bool plain = k0 + BK <= a.N;         // 32 centres, no affine rows, no padding
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t whi[4], wmid[4], wlo[4];
-                        { // eight values side by side: their dependent chains overlap
-                            double x[8];
-                            float pw[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const int kk = khalf * 16 + h * 8 + e;
-                                const double4 c = s_ctr[kk]; // warp-wide broadcasts
-                                const int eadd = hbits - s_rexp[kk];
-                                const double t = fma(qx, c.x, fma(qy, c.y, c.w)) + fma(qz, c.z, pp * s_sc[kk]);
-                                x[e] = (a.dbg_mode & 4) ? t : exp2_digit(t, s_exp, eadd);
-                                pw[e] = __int_as_float((127 + eadd) << 23);
-                            }
-                            if (!plain) { // the last stage(s): affine rows [1, x', y', z'] after the centres, then zero padding
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const int k = k0 + khalf * 16 + h * 8 + e;
-                                    if (k >= a.N) {
-                                        const int r = k - a.N;
-                                        const float cf = r >= a.Ktot - a.N ? 0.f
-                                                       : r == 0 ? 1.f
-                                                       : r == 1 ? (pxf - nrm4.x) * nrm4.w
-                                                       : r == 2 ? (pyf - nrm4.y) * nrm4.w : (pzf - nrm4.z) * nrm4.w;
-                                        x[e] = (double)cf * (double)pw[e];
-                                    }
-                                }
-                            }
-                            float hf[8], rf[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                split_digit(x[e], hf[e], rf[e]);
-                                bound = fmaf(fabsf(hf[e]), pw[e], bound);
-                            }
-#pragma unroll
-                            for (int e2 = 0; e2 < 4; ++e2) {
-                                // exact for integers <= 2048, i.e. always for Phi; an affine row of a vertex far outside the rig
-                                // can exceed it: what the FP16 digit drops goes into the remainder (zero otherwise)
-                                const __half2 h2 = __floats2half2_rn(hf[2 * e2], hf[2 * e2 + 1]);
-                                const float2 hb = __half22float2(h2);
-                                rf[2 * e2] += hf[2 * e2] - hb.x;
-                                rf[2 * e2 + 1] += hf[2 * e2 + 1] - hb.y;
-                                const __half2 m2 = __floats2half2_rn(rf[2 * e2], rf[2 * e2 + 1]);
-                                const float2 mb = __half22float2(m2);
-                                const __half2 l2 = __floats2half2_rn(rf[2 * e2] - mb.x, rf[2 * e2 + 1] - mb.y);
-                                whi[e2] = *reinterpret_cast<const uint32_t*>(&h2);
-                                wmid[e2] = *reinterpret_cast<const uint32_t*>(&m2);
-                                wlo[e2] = *reinterpret_cast<const uint32_t*>(&l2);
-                            }
-                        }
-                        const int off = ((khalf * 2 + h) ^ swz) * 16;
-                        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
-                        *reinterpret_cast<uint4*>(a_hi + A_SPLIT_BYTES + off) = make_uint4(wmid[0], wmid[1], wmid[2], wmid[3]);
-                        *reinterpret_cast<uint4*>(a_hi + 2 * A_SPLIT_BYTES + off) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
-                    }
+                    if (k0 + BK <= a.N) bound = fill_stage_half<true>(a, pr, nrm4, a_hi, s_ctr, s_sc, s_pw, s_exp, khalf, swz, k0, bound);
+                    else bound = fill_stage_half<false>(a, pr, nrm4, a_hi, s_ctr, s_sc, s_pw, s_exp, khalf, swz, k0, bound);
                 }
                 fence_proxy_async(); // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -568,12 +584,21 @@ __global__ void k_tcx_hbits(unsigned long long* __restrict__ bmax_bits, const fl
 __global__ void __launch_bounds__(256) k_tcx_pack(const double* __restrict__ W, int ldw, int N, int np, int ncol, int ncol_pad,
                                                   int Kpad, const float* __restrict__ norm, const float* __restrict__ scale,
                                                   const int* __restrict__ rowexp, const int* __restrict__ hbits,
-                                                  __half* __restrict__ Wt_hi, __half* __restrict__ Wt_mid, __half* __restrict__ Wt_lo)
+                                                  __half* __restrict__ Wt_hi, __half* __restrict__ Wt_mid, __half* __restrict__ Wt_lo,
+                                                  const double4* __restrict__ ctab, double4* __restrict__ ctab_eff,
+                                                  float* __restrict__ pw)
 {
     __shared__ double s_t[32][33];
     const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int h = *hbits;
+    if (blockIdx.x == 0 && ty == 0 && k0 + tx < Kpad) { // the evaluation's per-solve centre records: row k's digit exponent h - s_k
+        const int k = k0 + tx, e = h - rowexp[k];       // folded into the constant term of t, and 2^(h - s_k) as a float
+        double4 c = ctab[k];
+        c.w += (double)e;
+        ctab_eff[k] = c;
+        pw[k] = __int_as_float((127 + e) << 23);
+    }
     for (int r = ty; r < 32; r += 8) {
         const int k = k0 + r, c = c0 + tx;
         double v = 0.0;
@@ -617,7 +642,8 @@ cudaError_t fd_launch_pack_tcx(fd_ctx* ctx, fd_model* m)
     dim3 grid((ncol_pad + 31) / 32, (Kpad + 31) / 32);
     tcx::k_tcx_pack<<<grid, 256, 0, s>>>(fd_w_src(m), m->ldw, m->N, m->np, ncol, ncol_pad, Kpad, m->d_tc_norm, m->d_tc_scale,
                                          m->d_tcx_rowexp, m->d_tcx_rowexp + Kpad, (__half*)m->d_tc_wt_hi,
-                                         (__half*)m->d_tcx_wt_mid, (__half*)m->d_tc_wt_lo);
+                                         (__half*)m->d_tcx_wt_mid, (__half*)m->d_tc_wt_lo, m->d_ctab_tcx, m->d_tcx_ctab_eff,
+                                         m->d_tcx_pw);
     ctx->launches += 5;
     if (!tcx::make_map((CUtensorMap*)m->tc_map_hi, m->d_tc_wt_hi, Kpad, ncol_pad, tcx::BK, tcx::CB) ||
         !tcx::make_map((CUtensorMap*)m->tcx_map_mid, m->d_tcx_wt_mid, Kpad, ncol_pad, tcx::BK, tcx::CB) ||
@@ -655,7 +681,7 @@ cudaError_t fd_launch_eval_tcx(fd_ctx* ctx, const fd_model* m, const float* P, i
     a.sel = sel;
     a.sel_id = sel_id;
     a.dbg_mode = ctx->dbg.has_tc_debug ? ctx->dbg.tc_debug : 0;
-    a.ctab = m->d_ctab_tcx;
+    a.ctab = m->d_tcx_ctab_eff;
     a.csc = m->d_csc_tcx;
     a.origin = m->d_rest;
     a.norm = m->d_tc_norm;
@@ -665,7 +691,7 @@ cudaError_t fd_launch_eval_tcx(fd_ctx* ctx, const fd_model* m, const float* P, i
     a.Ktot = m->N + m->np;
     a.F = m->F;
     a.ncb = fd_tcx_ncb(m->F);
-    a.rowexp = m->d_tcx_rowexp;
+    a.pw = m->d_tcx_pw;
     a.hbits = m->d_tcx_rowexp + a.Kpad;
     a.flags = m->d_flags;
     a.P = P;

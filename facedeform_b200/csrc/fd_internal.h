@@ -185,6 +185,8 @@ struct fd_model {
     int* d_tcx_rowexp;   // per row: s_k (Kpad entries), then the digit width h chosen at pack time
     float* d_tcx_rowmax; // per row: max_c |w_kc| 2^e_c
     double* d_tcx_meta;  // scratch of the pack: the bits of max_i sum_k phi_k(c_i) rowmax_k
+    double4* d_tcx_ctab_eff; // per solve (Kpad): d_ctab_tcx with the row's digit exponent h - s_k added to d -- what the kernel reads
+    float* d_tcx_pw;     // per solve (Kpad): 2^(h - s_k)
     alignas(64) unsigned char tcx_map_mid[FD_TMAP_BYTES];
 };
 
