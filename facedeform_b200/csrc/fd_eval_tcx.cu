@@ -53,14 +53,15 @@ constexpr int TM = 128;                       // vertices per unit
 constexpr int CB = 120;                       // columns per unit (40 frames)
 constexpr int NMMA = 128;                     // N of the MMAs (multiple of 16)
 constexpr int BK = 32;                        // k per pipeline stage (64-byte rows -> SWIZZLE_64B)
-constexpr int STAGES = 4;
 constexpr int A_SPLIT_BYTES = TM * BK * 2;    // 8192
 constexpr int B_SPLIT_BYTES = CB * BK * 2;    // 7680 = 15 swizzle atoms of 512 bytes
+constexpr int A_STAGE_BYTES = 3 * A_SPLIT_BYTES; // 24576: the digit / mid / lo tiles of Phi for 32 centres
+constexpr int B_STAGE_BYTES = 3 * B_SPLIT_BYTES; // 23040: the digit / mid / lo weight tiles of one column block for 32 centres
 constexpr int C_TILE_BYTES = BK * 32;         // a stage's 32 centres as double4: t = q . (a, b, c) + d + |q|^2 sc (q = p - centre 0)
 constexpr int S_TILE_BYTES = BK * 8;          // their sc = -log2(e) / R^2
 constexpr int R_TILE_BYTES = BK * 4;          // and 2^(h - s_k) as floats (the scale of row k's digit)
 constexpr int CDEPTH = 8;                     // depth of the centre-tile ring
-constexpr int STAGE_BYTES = 3 * A_SPLIT_BYTES + 3 * B_SPLIT_BYTES; // 47616
+constexpr int MAX_SA = 4, MAX_SB = 5;         // barrier slots reserved for the two rings
 constexpr int PRODUCER_WARPS = 16;
 constexpr int EPILOGUE_WARPS = 4;             // one per TMEM lane quarter (leaves the producers 88 registers per thread)
 constexpr int THREADS = 32 * (2 + PRODUCER_WARPS + EPILOGUE_WARPS);
@@ -68,22 +69,38 @@ constexpr int WARP_EPI0 = PRODUCER_WARPS;
 constexpr int WARP_TMA = PRODUCER_WARPS + EPILOGUE_WARPS;
 constexpr int WARP_MMA = WARP_TMA + 1;
 constexpr int TMEM_COLS = 512;
-constexpr int UNIT_COLS = 256;                // TMEM columns of one unit: acc0 at +0, acc1 at +128
+constexpr int UNIT_COLS = 256;                // TMEM columns of one column block: acc0 at +0, acc1 at +128
 constexpr int ACC1_OFF = 128;
 constexpr int EPI_FRAMES = 8;
 constexpr int EPI_WARP_FLOATS = EPI_FRAMES * 96;
 constexpr int EPI_COLS = EPI_FRAMES * 3;
-constexpr int SMEM_EPI_STAGING = STAGES * STAGE_BYTES;
-constexpr int SMEM_BARRIERS = SMEM_EPI_STAGING + EPILOGUE_WARPS * EPI_WARP_FLOATS * 4;
-constexpr int SMEM_CENTRES = SMEM_BARRIERS + 512;
-constexpr int SMEM_SC = SMEM_CENTRES + CDEPTH * C_TILE_BYTES;
-constexpr int SMEM_ROWEXP = SMEM_SC + CDEPTH * S_TILE_BYTES;
-constexpr int SMEM_COLSCALE = SMEM_ROWEXP + CDEPTH * R_TILE_BYTES;
 constexpr int COLSCALE_RESIDENT_BLOCKS = 6;   // column scales of up to 6 column blocks (F <= 240) stay resident
-constexpr int SMEM_TOTAL = SMEM_COLSCALE + COLSCALE_RESIDENT_BLOCKS * CB * 4;
-static_assert(SMEM_TOTAL + 1024 + 1024 + 128 <= 227 * 1024, "shared-memory budget (dynamic + alignment slack + static)");
-static_assert(SMEM_CENTRES % 16 == 0 && STAGE_BYTES % 512 == 0 && B_SPLIT_BYTES % 512 == 0, "tile alignment");
-constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
+
+// Shared-memory layout.  A unit is 128 vertices x CBU column blocks: the Phi tiles of a stage (the expensive operand: FP64
+// arithmetic per value) are generated ONCE and multiplied with the weight tiles of CBU column blocks, so the two operands
+// live in rings of their own -- SA slots of Phi tiles, SB slots of weight tiles.
+//   CBU = 1: 4 + 4 slots, a weight slot is freed and filled together with the Phi slot of the same stage; two units in
+//            flight in tensor memory (ping-pong).
+//   CBU = 2: 3 + 5 slots; both column blocks' accumulators fill tensor memory (2 x 256 columns), the epilogue drains them
+//            while the producers fill the Phi ring for the next unit.
+template <int CBU>
+struct Lay {
+    static constexpr int SA = CBU == 1 ? 4 : 3;
+    static constexpr int SB = CBU == 1 ? 4 : 5;
+    static constexpr int B_RING = SA * A_STAGE_BYTES;
+    static constexpr int EPI_BUFS = CBU == 1 ? 1 : 2; // staging buffers per epilogue warp (two: a bulk store drains one while the next chunk fills the other)
+    static constexpr int EPI_STAGING = B_RING + SB * B_STAGE_BYTES;
+    static constexpr int BARRIERS = EPI_STAGING + EPILOGUE_WARPS * EPI_BUFS * EPI_WARP_FLOATS * 4;
+    static constexpr int CENTRES = BARRIERS + 512;
+    static constexpr int SC = CENTRES + CDEPTH * C_TILE_BYTES;
+    static constexpr int ROWEXP = SC + CDEPTH * S_TILE_BYTES;
+    static constexpr int COLSCALE = ROWEXP + CDEPTH * R_TILE_BYTES;
+    static constexpr int TOTAL = COLSCALE + COLSCALE_RESIDENT_BLOCKS * CB * 4;
+    static constexpr int ALLOC = TOTAL + 1024;
+    static_assert(SA <= MAX_SA && SB <= MAX_SB, "barrier slots");
+    static_assert(TOTAL + 1024 + 1024 + 128 <= 227 * 1024, "shared-memory budget (dynamic + alignment slack + static)");
+    static_assert(CENTRES % 16 == 0 && A_STAGE_BYTES % 1024 == 0 && B_STAGE_BYTES % 512 == 0 && B_RING % 1024 == 0, "tile alignment");
+};
 
 struct Args {
     const double4* ctab;    // (a, b, c, d + h - s_k) per centre (see C_TILE_BYTES; per solve: k_tcx_pack), Kpad entries
@@ -213,33 +230,42 @@ __device__ __forceinline__ float fill_stage_half(const Args& a, const ProducerRo
     return bound;
 }
 
-template <bool TANGENT>
+template <bool TANGENT, int CBU>
 __global__ void __launch_bounds__(THREADS, 1)
 k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_mid,
            const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_out)
 {
+    using L = Lay<CBU>;
+    constexpr int SA = L::SA, SB = L::SB;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     if (a.sel && *a.sel != a.sel_id) return; // uniform over the grid: nothing has been set up yet
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t smem_base = smem_u32(smem);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BARRIERS);
-    const uint32_t bar_full_a = smem_u32(bars + 0);          // [STAGES], count PRODUCER_WARPS / 2
-    const uint32_t bar_full_b = smem_u32(bars + STAGES);     // [STAGES], count 1 + tx bytes
-    const uint32_t bar_empty = smem_u32(bars + 2 * STAGES);  // [STAGES], count 1 (tcgen05.commit)
-    const uint32_t bar_tmem_full = smem_u32(bars + 3 * STAGES);        // [2], count 1: all MMAs of the unit retired
-    const uint32_t bar_tmem_empty = smem_u32(bars + 3 * STAGES + 2);   // [2], count EPILOGUE_WARPS: accumulators drained
-    const uint32_t bar_cfull = smem_u32(bars + 3 * STAGES + 4);            // [CDEPTH], count 1 + tx bytes
-    const uint32_t bar_cempty = smem_u32(bars + 3 * STAGES + 4 + CDEPTH);  // [CDEPTH], count PRODUCER_WARPS / 2
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4 + 2 * CDEPTH);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BARRIERS);
+    const uint32_t bar_full_a = smem_u32(bars + 0);                        // [SA], count PRODUCER_WARPS / 2
+    const uint32_t bar_full_b = smem_u32(bars + MAX_SA);                   // [SB], count 1 + tx bytes
+    const uint32_t bar_empty_a = smem_u32(bars + MAX_SA + MAX_SB);         // [SA], count 1 (tcgen05.commit)
+    const uint32_t bar_empty_b = smem_u32(bars + 2 * MAX_SA + MAX_SB);     // [SB], count 1 (tcgen05.commit; CBU = 1: unused,
+                                                                           //       the weight slot follows the Phi slot)
+    constexpr int NB = 2 * (MAX_SA + MAX_SB);
+    const uint32_t bar_tmem_full = smem_u32(bars + NB);                    // [2], count 1: all MMAs of the unit retired
+    const uint32_t bar_tmem_empty = smem_u32(bars + NB + 2);               // [2], count EPILOGUE_WARPS: accumulators drained
+    const uint32_t bar_cfull = smem_u32(bars + NB + 4);                    // [CDEPTH], count 1 + tx bytes
+    const uint32_t bar_cempty = smem_u32(bars + NB + 4 + CDEPTH);          // [CDEPTH], count PRODUCER_WARPS / 2
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + NB + 4 + 2 * CDEPTH);
+    static_assert((NB + 4 + 2 * CDEPTH + 1) * 8 <= 512, "barrier block");
     __shared__ double s_exp[16]; // 2^(i / 16); static: the look-up address needs no base register
-    float* s_colscale = reinterpret_cast<float*>(smem + SMEM_COLSCALE);
+    float* s_colscale = reinterpret_cast<float*>(smem + L::COLSCALE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < SA; ++s) {
             mbar_init(bar_full_a + 8 * s, PRODUCER_WARPS / 2);
+            mbar_init(bar_empty_a + 8 * s, 1);
+        }
+        for (int s = 0; s < SB; ++s) {
             mbar_init(bar_full_b + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty_b + 8 * s, 1);
         }
         mbar_init(bar_tmem_full, 1);
         mbar_init(bar_tmem_full + 8, 1);
@@ -261,90 +287,104 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    // unit = (vertex tile, group of CBU column blocks); ncbu groups per vertex tile, the last one may hold fewer blocks
     const int64_t unit0 = blockIdx.x, ustride = gridDim.x;
     const int nk = a.Kpad / BK;
     const int tail_ksteps = (a.Ktot - (nk - 1) * BK + 15) >> 4; // K=16 steps of the last stage that hold real rows (1 or 2)
     const int64_t n_vt = (a.V + TM - 1) / TM;
-    const int64_t n_units = n_vt * a.ncb;
+    const int ncbu = (a.ncb + CBU - 1) / CBU;
+    const int64_t n_units = n_vt * ncbu;
 
     if (warp == WARP_TMA) {
         // ================= TMA producer: weight tiles + centre tiles =================
-        uint32_t it = 0, ic = 0;
+        uint32_t it = 0, ic = 0, ib = 0; // stages, centre tiles, weight slots issued so far
         int kc = 0;
         const uint32_t my_units = (uint32_t)((n_units - unit0 + ustride - 1) / ustride);
         const uint32_t total = my_units * (uint32_t)nk;
         for (int64_t u = unit0; u < n_units; u += ustride) {
-            const int cb = (int)(u % a.ncb);
+            const int cb0 = (int)(u % ncbu) * CBU;
+            const int nj = min(CBU, a.ncb - cb0);
             for (int kb = 0; kb < nk; ++kb, ++it) {
                 while (ic < total && ic < it + CDEPTH) { // centre tiles run ahead; a busy slot is retried at the next stage
                     const int c = ic % CDEPTH;
                     if (!mbar_try_wait(bar_cempty + 8 * c, ((ic / CDEPTH) & 1) ^ 1)) break;
                     if (elect_one()) {
                         mbar_expect_tx(bar_cfull + 8 * c, C_TILE_BYTES + S_TILE_BYTES + R_TILE_BYTES);
-                        bulk_load_1d(smem_base + SMEM_CENTRES + c * C_TILE_BYTES, a.ctab + kc * BK, C_TILE_BYTES, bar_cfull + 8 * c);
-                        bulk_load_1d(smem_base + SMEM_SC + c * S_TILE_BYTES, a.csc + kc * BK, S_TILE_BYTES, bar_cfull + 8 * c);
-                        bulk_load_1d(smem_base + SMEM_ROWEXP + c * R_TILE_BYTES, a.pw + kc * BK, R_TILE_BYTES, bar_cfull + 8 * c);
+                        bulk_load_1d(smem_base + L::CENTRES + c * C_TILE_BYTES, a.ctab + kc * BK, C_TILE_BYTES, bar_cfull + 8 * c);
+                        bulk_load_1d(smem_base + L::SC + c * S_TILE_BYTES, a.csc + kc * BK, S_TILE_BYTES, bar_cfull + 8 * c);
+                        bulk_load_1d(smem_base + L::ROWEXP + c * R_TILE_BYTES, a.pw + kc * BK, R_TILE_BYTES, bar_cfull + 8 * c);
                     }
                     ++ic;
                     if (++kc == nk) kc = 0;
                 }
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                if (elect_one()) {
-                    const uint32_t sb = smem_base + s * STAGE_BYTES + 3 * A_SPLIT_BYTES;
-                    mbar_expect_tx(bar_full_b + 8 * s, 3 * B_SPLIT_BYTES);
-                    tma_load_2d(sb, &map_hi, bar_full_b + 8 * s, kb * BK, cb * CB);
-                    tma_load_2d(sb + B_SPLIT_BYTES, &map_mid, bar_full_b + 8 * s, kb * BK, cb * CB);
-                    tma_load_2d(sb + 2 * B_SPLIT_BYTES, &map_lo, bar_full_b + 8 * s, kb * BK, cb * CB);
+                for (int j = 0; j < nj; ++j, ++ib) {
+                    const int s = ib % SB;
+                    const uint32_t ph = (ib / SB) & 1;
+                    // CBU = 1: ib == it and SB == SA -- the weight slot is free when the stage's Phi slot is
+                    mbar_wait((CBU == 1 ? bar_empty_a : bar_empty_b) + 8 * s, ph ^ 1);
+                    if (elect_one()) {
+                        const uint32_t sb = smem_base + L::B_RING + s * B_STAGE_BYTES;
+                        mbar_expect_tx(bar_full_b + 8 * s, 3 * B_SPLIT_BYTES);
+                        tma_load_2d(sb, &map_hi, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
+                        tma_load_2d(sb + B_SPLIT_BYTES, &map_mid, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
+                        tma_load_2d(sb + 2 * B_SPLIT_BYTES, &map_lo, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else if (warp == WARP_MMA) {
         // ================= MMA issuer =================
-        uint32_t it = 0, unit_iter = 0;
+        uint32_t it = 0, ib = 0, unit_iter = 0;
         const uint64_t desc0 = make_desc_sw64(smem_base);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const bool wide_digit = *a.hbits >= 9; // mid x lo is then below 2^-32 of the full size: two MMAs (and their operand reads) less
         for (int64_t u = unit0; u < n_units; u += ustride, ++unit_iter) {
-            const int cb = (int)(u % a.ncb);
-            const int ncols = min(NMMA, (3 * a.F - cb * CB + 15) & ~15);
-            const uint32_t idesc = make_idesc(ncols);
-            const int ab = unit_iter & 1;
-            const uint32_t d0 = tmem_u + ab * UNIT_COLS, d1 = d0 + ACC1_OFF;
-            mbar_wait(bar_tmem_empty + 8 * ab, ((unit_iter >> 1) & 1) ^ 1); // the epilogue drained this unit slot (two units ago)
+            const int cb0 = (int)(u % ncbu) * CBU;
+            const int nj = min(CBU, a.ncb - cb0);
+            // CBU = 1: two units in flight (ping-pong), the epilogue drained this one's slot two units ago;
+            // CBU = 2: the unit's column blocks fill tensor memory, the epilogue drained it one unit ago
+            const int ab = CBU == 1 ? (int)(unit_iter & 1) : 0;
+            mbar_wait(bar_tmem_empty + 8 * ab, ((CBU == 1 ? unit_iter >> 1 : unit_iter) & 1) ^ 1);
             tc_fence_after();
             for (int kb = 0; kb < nk; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(bar_full_a + 8 * s, ph);
-                mbar_wait(bar_full_b + 8 * s, ph);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t a_hi = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
-                    const uint64_t a_mid = a_hi + (A_SPLIT_BYTES >> 4), a_lo = a_mid + (A_SPLIT_BYTES >> 4);
-                    const uint64_t b_hi = a_hi + (3 * A_SPLIT_BYTES >> 4);
-                    const uint64_t b_mid = b_hi + (B_SPLIT_BYTES >> 4), b_lo = b_mid + (B_SPLIT_BYTES >> 4);
-                    const int nsteps = kb != nk - 1 ? 2 : tail_ksteps; // the last stage: steps of pure zero padding are skipped
-                    for (int ks = 0; ks < nsteps; ++ks) {
-                        const uint64_t o = 2 * ks;                     // 32 bytes = 16 FP16 along K
-                        const uint32_t acc = (kb != 0 || ks != 0) ? 1u : 0u;
-                        umma_f16(d0, a_hi + o, b_hi + o, idesc, acc);  // integers: exact
-                        if (a.dbg_mode & 8) continue;
-                        umma_f16(d1, a_hi + o, b_mid + o, idesc, acc);
-                        umma_f16(d1, a_mid + o, b_hi + o, idesc, 1);
-                        umma_f16(d1, a_hi + o, b_lo + o, idesc, 1);
-                        umma_f16(d1, a_lo + o, b_hi + o, idesc, 1);
-                        umma_f16(d1, a_mid + o, b_mid + o, idesc, 1);
-                        if (wide_digit) continue;
-                        umma_f16(d1, a_mid + o, b_lo + o, idesc, 1);   // 2^-14 per product: 2^-14-2h of the full size, not
-                        umma_f16(d1, a_lo + o, b_mid + o, idesc, 1);   // negligible once the digit is narrow (h = 5: 2^-24)
+                const int s = it % SA;
+                mbar_wait(bar_full_a + 8 * s, (it / SA) & 1);
+                const int nsteps = kb != nk - 1 ? 2 : tail_ksteps; // the last stage: steps of pure zero padding are skipped
+                for (int j = 0; j < nj; ++j, ++ib) {
+                    const int sbs = ib % SB;
+                    mbar_wait(bar_full_b + 8 * sbs, (ib / SB) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int ncols = min(NMMA, (3 * a.F - (cb0 + j) * CB + 15) & ~15);
+                        const uint32_t idesc = make_idesc(ncols);
+                        const uint32_t d0 = tmem_u + (CBU == 1 ? ab : j) * UNIT_COLS, d1 = d0 + ACC1_OFF;
+                        const uint64_t a_hi = desc0 + (uint64_t)(s * (A_STAGE_BYTES >> 4));
+                        const uint64_t a_mid = a_hi + (A_SPLIT_BYTES >> 4), a_lo = a_mid + (A_SPLIT_BYTES >> 4);
+                        const uint64_t b_hi = desc0 + (uint64_t)((L::B_RING + sbs * B_STAGE_BYTES) >> 4);
+                        const uint64_t b_mid = b_hi + (B_SPLIT_BYTES >> 4), b_lo = b_mid + (B_SPLIT_BYTES >> 4);
+                        for (int ks = 0; ks < nsteps; ++ks) {
+                            const uint64_t o = 2 * ks;                     // 32 bytes = 16 FP16 along K
+                            const uint32_t acc = (kb != 0 || ks != 0) ? 1u : 0u;
+                            umma_f16(d0, a_hi + o, b_hi + o, idesc, acc);  // integers: exact
+                            if (a.dbg_mode & 8) continue;
+                            umma_f16(d1, a_hi + o, b_mid + o, idesc, acc);
+                            umma_f16(d1, a_mid + o, b_hi + o, idesc, 1);
+                            umma_f16(d1, a_hi + o, b_lo + o, idesc, 1);
+                            umma_f16(d1, a_lo + o, b_hi + o, idesc, 1);
+                            umma_f16(d1, a_mid + o, b_mid + o, idesc, 1);
+                            if (wide_digit) continue;
+                            umma_f16(d1, a_mid + o, b_lo + o, idesc, 1);   // 2^-14 per product: 2^-14-2h of the full size, not
+                            umma_f16(d1, a_lo + o, b_mid + o, idesc, 1);   // negligible once the digit is narrow (h = 5: 2^-24)
+                        }
+                        if (CBU != 1) umma_commit(bar_empty_b + 8 * sbs);            // the weight slot is free once these MMAs have read it
+                        if (j == nj - 1) {
+                            umma_commit(bar_empty_a + 8 * s);                        // and the Phi slot after the last column block
+                            if (kb == nk - 1) umma_commit(bar_tmem_full + 8 * ab);   // all accumulators of the unit complete
+                        }
                     }
-                    umma_commit(bar_empty + 8 * s);                          // the stage is free once these MMAs have read it
-                    if (kb == nk - 1) umma_commit(bar_tmem_full + 8 * ab);   // both accumulators complete
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else if (warp < PRODUCER_WARPS) {
@@ -358,7 +398,7 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
         const int swz = (row >> 1) & 3;
         uint32_t it = 0;
         for (int64_t u = unit0; u < n_units; u += ustride) {
-            const int64_t vt = u / a.ncb;
+            const int64_t vt = u / ncbu;
             const int64_t v = vt * TM + row;
             ProducerRow pr;
             pr.pxf = 0.f, pr.pyf = 0.f, pr.pzf = 0.f;
@@ -374,15 +414,15 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
             it += nk;
             for (int kb = (int)((grp ^ it0) & 1); kb < nk; kb += 2) {
                 const uint32_t itk = it0 + kb;
-                const int s = itk % STAGES;
-                const uint32_t ph = (itk / STAGES) & 1;
+                const int s = itk % SA;
+                const uint32_t ph = (itk / SA) & 1;
                 const int cs = itk % CDEPTH;
                 mbar_wait(bar_cfull + 8 * cs, (itk / CDEPTH) & 1); // the stage's centre tile
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);              // the A slot: the MMAs of stage itk - STAGES retired
-                uint8_t* a_hi = smem + s * STAGE_BYTES + row * (BK * 2);
-                const double4* s_ctr = reinterpret_cast<const double4*>(smem + SMEM_CENTRES + cs * C_TILE_BYTES);
-                const double* s_sc = reinterpret_cast<const double*>(smem + SMEM_SC + cs * S_TILE_BYTES);
-                const float* s_pw = reinterpret_cast<const float*>(smem + SMEM_ROWEXP + cs * R_TILE_BYTES);
+                mbar_wait(bar_empty_a + 8 * s, ph ^ 1);            // the Phi slot: the MMAs of stage itk - SA retired
+                uint8_t* a_hi = smem + s * A_STAGE_BYTES + row * (BK * 2);
+                const double4* s_ctr = reinterpret_cast<const double4*>(smem + L::CENTRES + cs * C_TILE_BYTES);
+                const double* s_sc = reinterpret_cast<const double*>(smem + L::SC + cs * S_TILE_BYTES);
+                const float* s_pw = reinterpret_cast<const float*>(smem + L::ROWEXP + cs * R_TILE_BYTES);
                 const int k0 = kb * BK;
                 if (!(kb == nk - 1 && khalf >= tail_ksteps)) { // else: nothing but zero padding, the MMA issuer skips the step
                     if (k0 + BK <= a.N) bound = fill_stage_half<true>(a, pr, nrm4, a_hi, s_ctr, s_sc, s_pw, s_exp, khalf, swz, k0, bound);
@@ -402,9 +442,9 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
         // ================= epilogue warps: TMEM -> registers -> (transpose in shared memory) -> global =================
         const int ew = warp - WARP_EPI0;
         const int q = warp & 3;               // TMEM lane quarter this warp may access
-        float* stg = reinterpret_cast<float*>(smem + SMEM_EPI_STAGING) + ew * EPI_WARP_FLOATS;
+        float* stg0 = reinterpret_cast<float*>(smem + L::EPI_STAGING) + ew * (L::EPI_BUFS * EPI_WARP_FLOATS);
         const int et = threadIdx.x - 32 * WARP_EPI0;
-        uint32_t unit_iter = 0;
+        uint32_t unit_iter = 0, nstore = 0;
         const bool resident_cs = a.ncb <= COLSCALE_RESIDENT_BLOCKS;
         const float hs = exp2f(-2.0f * (float)*a.hbits); // both operands carry 2^h
         if (resident_cs) {
@@ -412,17 +452,15 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
             asm volatile("bar.sync 2, %0;" ::"n"(32 * EPILOGUE_WARPS) : "memory");
         }
         for (int64_t u = unit0; u < n_units; u += ustride, ++unit_iter) {
-            const int cb = (int)(u % a.ncb);
-            const int64_t vt = u / a.ncb;
-            const int f_base = cb * (CB / 3);
-            const int nframes = min(CB / 3, a.F - f_base);
-            const float* s_cs = s_colscale + (resident_cs ? cb * CB : 0);
-            if (!resident_cs) {
+            const int cb0 = (int)(u % ncbu) * CBU;
+            const int nj = min(CBU, a.ncb - cb0);
+            const int64_t vt = u / ncbu;
+            if (!resident_cs) { // the column scales of the unit's blocks
                 asm volatile("bar.sync 2, %0;" ::"n"(32 * EPILOGUE_WARPS) : "memory");
-                for (int t = et; t < CB; t += 32 * EPILOGUE_WARPS) s_colscale[t] = a.colscale[cb * CB + t];
+                for (int t = et; t < nj * CB; t += 32 * EPILOGUE_WARPS) s_colscale[t] = a.colscale[cb0 * CB + t];
                 asm volatile("bar.sync 2, %0;" ::"n"(32 * EPILOGUE_WARPS) : "memory");
             }
-            const int ab = unit_iter & 1;
+            const int ab = CBU == 1 ? (int)(unit_iter & 1) : 0;
             const int chunk0 = ew >> 2; // with eight epilogue warps: the even (0) or the odd (1) column chunks
             const int64_t v_warp0 = vt * TM + q * 32;
             const int64_t v = v_warp0 + lane;
@@ -437,7 +475,7 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
                 skip = d2 > a.radius2;                                        // SOP_FaceDeform.cpp:408-410
                 fo = powf(1.0f - fminf(d2 / a.radius2, 1.0f), a.falloffrate); // :423-424
                 if (skip) fo = 0.f;
-                if (a.falloff_out && cb == 0 && chunk0 == 0) a.falloff_out[v] = fo;
+                if (a.falloff_out && cb0 == 0 && chunk0 == 0) a.falloff_out[v] = fo;
             }
             float tu[3] = {0, 0, 0}, tv[3] = {0, 0, 0}, tn[3] = {0, 0, 0};
             if (TANGENT && valid) {
@@ -452,64 +490,87 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
                 normalize3(tn);
             }
             const bool vec = a.vec_store_ok != 0;
-            mbar_wait(bar_tmem_full + 8 * ab, (unit_iter >> 1) & 1);
+            bool released = false;
+            mbar_wait(bar_tmem_full + 8 * ab, (CBU == 1 ? unit_iter >> 1 : unit_iter) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int ch = chunk0; ch * EPI_FRAMES < nframes; ch += EPILOGUE_WARPS / 4) {
-                if (a.dbg_mode & 2) continue;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * UNIT_COLS + ch * EPI_COLS;
-                float acc[EPI_COLS], acc1[EPI_COLS];
-                tmem_ld16(taddr, acc);
-                tmem_ld8(taddr + 16, acc + 16);
-                tmem_ld16(taddr + ACC1_OFF, acc1);
-                tmem_ld8(taddr + ACC1_OFF + 16, acc1 + 16);
-                if (vec && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the staging buffer is free
-                __syncwarp();
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < EPI_COLS; ++c) acc[c] = (acc[c] + acc1[c]) * (s_cs[ch * EPI_COLS + c] * hs); // powers of two: exact
-                if (vec) {
-                    // out = P + disp * falloff (a skipped vertex has falloff 0 and keeps P exactly), transposed through shared
-                    // memory into [frame][vertex][xyz] rows that one lane hands to the bulk-copy engine
-                    float* dst = stg + lane * 3;
-#pragma unroll
-                    for (int col = 0; col < EPI_COLS; ++col) {
-                        const int i = col / 3, k = col - 3 * i;
-                        const float p = k == 0 ? px : (k == 1 ? py : pz);
-                        dst[i * 96 + k] = fmaf(acc[col], fo, p);
+            for (int j = 0; j < nj; ++j) {
+                const int cb = cb0 + j;
+                const int f_base = cb * (CB / 3);
+                const int nframes = min(CB / 3, a.F - f_base);
+                const float* s_cs = s_colscale + (resident_cs ? cb : j) * CB;
+#pragma unroll 1
+                for (int ch = chunk0; ch * EPI_FRAMES < nframes; ch += EPILOGUE_WARPS / 4) {
+                    if (a.dbg_mode & 2) continue;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (CBU == 1 ? ab : j) * UNIT_COLS + ch * EPI_COLS;
+                    float acc[EPI_COLS], acc1[EPI_COLS];
+                    tmem_ld16(taddr, acc);
+                    tmem_ld8(taddr + 16, acc + 16);
+                    tmem_ld16(taddr + ACC1_OFF, acc1);
+                    tmem_ld8(taddr + ACC1_OFF + 16, acc1 + 16);
+                    float* stg = stg0 + (L::EPI_BUFS == 1 ? 0 : (nstore & 1) * EPI_WARP_FLOATS);
+                    if (vec && lane == 0) { // the staging buffer is free: the bulk store that read it last has done so
+                        if (L::EPI_BUFS == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     }
-                    fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     ::"l"(reinterpret_cast<uint64_t>(&map_out)), "r"(smem_u32(stg)),
-                                       "r"((int)(v_warp0 * 3)), "r"(f_base + ch * EPI_FRAMES)
-                                     : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    tmem_ld_wait();
+                    if (CBU != 1 && j == nj - 1 && (ch + EPILOGUE_WARPS / 4) * EPI_FRAMES >= nframes) {
+                        // single-buffered accumulators: the MMAs of the next unit may start as soon as this warp has read its last values
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tmem_empty + 8 * ab);
+                        released = true;
                     }
-                } else {
-                    // general path (V not a multiple of 4, unaligned output, tangent projection): per-lane stores
-                    const int fcnt = min(EPI_FRAMES, nframes - ch * EPI_FRAMES);
 #pragma unroll
-                    for (int i = 0; i < EPI_FRAMES; ++i) {
-                        if (i < fcnt) {
-                            float d[3] = {acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]};
-                            if (TANGENT) project_to_tangents(tu, tv, tn, d);
-                            if (valid) {
-                                float* dst = a.P_out + ((size_t)(f_base + ch * EPI_FRAMES + i) * (size_t)a.V + (size_t)v) * 3;
-                                dst[0] = skip ? px : px + d[0] * fo;
-                                dst[1] = skip ? py : py + d[1] * fo;
-                                dst[2] = skip ? pz : pz + d[2] * fo;
+                    for (int c = 0; c < EPI_COLS; ++c) acc[c] = (acc[c] + acc1[c]) * (s_cs[ch * EPI_COLS + c] * hs); // powers of two: exact
+                    if (vec) {
+                        // out = P + disp * falloff (a skipped vertex has falloff 0 and keeps P exactly), transposed through shared
+                        // memory into [frame][vertex][xyz] rows that one lane hands to the bulk-copy engine
+                        float* dst = stg + lane * 3;
+#pragma unroll
+                        for (int col = 0; col < EPI_COLS; ++col) {
+                            const int i = col / 3, k = col - 3 * i;
+                            const float p = k == 0 ? px : (k == 1 ? py : pz);
+                            dst[i * 96 + k] = fmaf(acc[col], fo, p);
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(reinterpret_cast<uint64_t>(&map_out)), "r"(smem_u32(stg)),
+                                           "r"((int)(v_warp0 * 3)), "r"(f_base + ch * EPI_FRAMES)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        ++nstore;
+                    } else {
+                        // general path (V not a multiple of 4, unaligned output, tangent projection): per-lane stores
+                        const int fcnt = min(EPI_FRAMES, nframes - ch * EPI_FRAMES);
+#pragma unroll
+                        for (int i = 0; i < EPI_FRAMES; ++i) {
+                            if (i < fcnt) {
+                                float d[3] = {acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]};
+                                if (TANGENT) project_to_tangents(tu, tv, tn, d);
+                                if (valid) {
+                                    float* dst = a.P_out + ((size_t)(f_base + ch * EPI_FRAMES + i) * (size_t)a.V + (size_t)v) * 3;
+                                    dst[0] = skip ? px : px + d[0] * fo;
+                                    dst[1] = skip ? py : py + d[1] * fo;
+                                    dst[2] = skip ? pz : pz + d[2] * fo;
+                                }
                             }
                         }
                     }
                 }
             }
-            if (vec && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tmem_empty + 8 * ab); // this warp's share of the unit is drained
+            if (L::EPI_BUFS == 1 && vec && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (!released) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tmem_empty + 8 * ab); // this warp's share of the unit is drained
+            }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory outlives the last bulk stores
     }
 
     tc_fence_before();
@@ -655,8 +716,10 @@ cudaError_t fd_launch_pack_tcx(fd_ctx* ctx, fd_model* m)
 cudaError_t fd_eval_tcx_setup(fd_ctx* ctx)
 {
     (void)ctx;
-    cudaError_t e = cudaFuncSetAttribute(tcx::k_eval_tcx<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::SMEM_ALLOC);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tcx::k_eval_tcx<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::SMEM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tcx::k_eval_tcx<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::Lay<1>::ALLOC);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tcx::k_eval_tcx<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::Lay<1>::ALLOC);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tcx::k_eval_tcx<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::Lay<2>::ALLOC);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tcx::k_eval_tcx<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::Lay<2>::ALLOC);
     return e;
 }
 
@@ -720,12 +783,21 @@ cudaError_t fd_launch_eval_tcx(fd_ctx* ctx, const fd_model* m, const float* P, i
     const CUtensorMap& mh = *(const CUtensorMap*)m->tc_map_hi;
     const CUtensorMap& mm = *(const CUtensorMap*)m->tcx_map_mid;
     const CUtensorMap& ml = *(const CUtensorMap*)m->tc_map_lo;
-    const int64_t n_units = ((V + tcx::TM - 1) / tcx::TM) * a.ncb;
+    // two column blocks per unit (the Phi tiles are generated once for both) whenever the batch has two
+    const int cbu = (a.ncb >= 2 && ctx->dbg.tcx_cbu != 1) ? 2 : 1;
+    const int64_t n_units = ((V + tcx::TM - 1) / tcx::TM) * ((a.ncb + cbu - 1) / cbu);
     const int grid = (int)(n_units < ctx->sm_count ? n_units : ctx->sm_count);
-    if (a.do_tangent)
-        tcx::k_eval_tcx<true><<<grid, tcx::THREADS, tcx::SMEM_ALLOC, ctx->stream>>>(a, mh, mm, ml, mo);
-    else
-        tcx::k_eval_tcx<false><<<grid, tcx::THREADS, tcx::SMEM_ALLOC, ctx->stream>>>(a, mh, mm, ml, mo);
+    if (cbu == 2) {
+        if (a.do_tangent)
+            tcx::k_eval_tcx<true, 2><<<grid, tcx::THREADS, tcx::Lay<2>::ALLOC, ctx->stream>>>(a, mh, mm, ml, mo);
+        else
+            tcx::k_eval_tcx<false, 2><<<grid, tcx::THREADS, tcx::Lay<2>::ALLOC, ctx->stream>>>(a, mh, mm, ml, mo);
+    } else {
+        if (a.do_tangent)
+            tcx::k_eval_tcx<true, 1><<<grid, tcx::THREADS, tcx::Lay<1>::ALLOC, ctx->stream>>>(a, mh, mm, ml, mo);
+        else
+            tcx::k_eval_tcx<false, 1><<<grid, tcx::THREADS, tcx::Lay<1>::ALLOC, ctx->stream>>>(a, mh, mm, ml, mo);
+    }
     ctx->launches += 1;
     return cudaGetLastError();
 }
