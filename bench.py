@@ -551,9 +551,9 @@ def main():
                           "algorithmic MAC, Phi generated in FP64)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["bf16"], "peak_source": peaks["source"] + " bf16_tflops (burst; FP16 = BF16 rate)",
-                "note": "algorithmic flops; the scheme issues 6.4x (digit width >= 9) or 8.5x that on the tensor pipe (N = 128 for "
-                        "120 useful columns), so 0.16 / 0.12 is the ceiling of this fraction; the kernel is bound by shared-memory "
-                        "bandwidth (DESIGN.md section 4)",
+                "note": "algorithmic flops; the scheme issues 6x (digit width >= 9) or 8x that on the tensor pipe (one N = 240 MMA "
+                        "serves two 120-column blocks), so 1/6 or 1/8 is the ceiling of this fraction; the kernel is bound by the "
+                        "FP64 generation of Phi and the MMAs' shared-memory operand reads (DESIGN.md section 4)",
                 "traffic": None, "launch_ms": eval_ms_mean,
             }
         elif eval_kernel == 3:
@@ -583,8 +583,8 @@ def main():
                     nc = json.load(f)
                 roofline["traffic"] = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6
                 roofline["traffic_source"] = f"profiles/{src} (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)"
-            elif args.config == "C2" and eval_kernel == 4 and os.path.exists(os.path.join(ROOT, "profiles", "r2_eval_tcx_ncu_summary.json")):
-                src = "r2_eval_tcx_ncu_summary.json"
+            elif args.config == "C2" and eval_kernel == 4 and os.path.exists(os.path.join(ROOT, "profiles", "r2l_eval_tcx_ncu_summary.json")):
+                src = "r2l_eval_tcx_ncu_summary.json"
                 with open(os.path.join(ROOT, "profiles", src)) as f:
                     nc = json.load(f)
                 roofline["traffic"] = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6

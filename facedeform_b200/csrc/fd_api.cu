@@ -82,6 +82,7 @@ void read_debug_opts(fd_debug_opts* o)
     o->lu_cluster_max_n = num("FD_LU_CLUSTER_MAX_N");
     o->lu_cluster = num("FD_LU_CLUSTER");
     o->tcx_cbu = num("FD_TCX_CBU");
+    o->tcx_narrow = num("FD_TCX_NARROW");
 }
 
 int check_params(fd_ctx* ctx, const fd_params* p)

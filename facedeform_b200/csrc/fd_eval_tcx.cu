@@ -56,7 +56,6 @@ constexpr int BK = 32;                        // k per pipeline stage (64-byte r
 constexpr int A_SPLIT_BYTES = TM * BK * 2;    // 8192
 constexpr int B_SPLIT_BYTES = CB * BK * 2;    // 7680 = 15 swizzle atoms of 512 bytes
 constexpr int A_STAGE_BYTES = 3 * A_SPLIT_BYTES; // 24576: the digit / mid / lo tiles of Phi for 32 centres
-constexpr int B_STAGE_BYTES = 3 * B_SPLIT_BYTES; // 23040: the digit / mid / lo weight tiles of one column block for 32 centres
 constexpr int C_TILE_BYTES = BK * 32;         // a stage's 32 centres as double4: t = q . (a, b, c) + d + |q|^2 sc (q = p - centre 0)
 constexpr int S_TILE_BYTES = BK * 8;          // their sc = -log2(e) / R^2
 constexpr int R_TILE_BYTES = BK * 4;          // and 2^(h - s_k) as floats (the scale of row k's digit)
@@ -83,13 +82,20 @@ constexpr int COLSCALE_RESIDENT_BLOCKS = 6;   // column scales of up to 6 column
 //            flight in tensor memory (ping-pong).
 //   CBU = 2: 3 + 5 slots; both column blocks' accumulators fill tensor memory (2 x 256 columns), the epilogue drains them
 //            while the producers fill the Phi ring for the next unit.
-template <int CBU>
+//   CBU = 2, WIDE: the two blocks' weight tiles lie back to back (240 rows per split) and ONE MMA of N = 240 serves both:
+//            the Phi operand is read from shared memory once per instruction instead of once per block (11.5 KB per 120
+//            cycles instead of 8 KB per 64 -- the tensor core's operand reads are the largest user of the shared-memory
+//            pipe), and no instruction computes 8 unused columns.  3 Phi slots + 2 weight slots of 45 KB.
+template <int CBU, bool WIDE = false>
 struct Lay {
+    static_assert(!WIDE || CBU == 2, "the wide MMA spans two column blocks");
     static constexpr int SA = CBU == 1 ? 4 : 3;
-    static constexpr int SB = CBU == 1 ? 4 : 5;
+    static constexpr int SB = CBU == 1 ? 4 : (WIDE ? 2 : 5);
+    static constexpr int B_SPLIT = WIDE ? 2 * B_SPLIT_BYTES : B_SPLIT_BYTES; // one split (digit, mid or lo) of a weight slot
+    static constexpr int B_SLOT = 3 * B_SPLIT;
     static constexpr int B_RING = SA * A_STAGE_BYTES;
     static constexpr int EPI_BUFS = CBU == 1 ? 1 : 2; // staging buffers per epilogue warp (two: a bulk store drains one while the next chunk fills the other)
-    static constexpr int EPI_STAGING = B_RING + SB * B_STAGE_BYTES;
+    static constexpr int EPI_STAGING = B_RING + SB * B_SLOT;
     static constexpr int BARRIERS = EPI_STAGING + EPILOGUE_WARPS * EPI_BUFS * EPI_WARP_FLOATS * 4;
     static constexpr int CENTRES = BARRIERS + 512;
     static constexpr int SC = CENTRES + CDEPTH * C_TILE_BYTES;
@@ -97,9 +103,11 @@ struct Lay {
     static constexpr int COLSCALE = ROWEXP + CDEPTH * R_TILE_BYTES;
     static constexpr int TOTAL = COLSCALE + COLSCALE_RESIDENT_BLOCKS * CB * 4;
     static constexpr int ALLOC = TOTAL + 1024;
+    static constexpr int ACC1 = WIDE ? 256 : ACC1_OFF;          // TMEM column of the second accumulator
+    static constexpr int BLOCK_COLS = WIDE ? CB : UNIT_COLS;    // TMEM column stride between the unit's column blocks
     static_assert(SA <= MAX_SA && SB <= MAX_SB, "barrier slots");
     static_assert(TOTAL + 1024 + 1024 + 128 <= 227 * 1024, "shared-memory budget (dynamic + alignment slack + static)");
-    static_assert(CENTRES % 16 == 0 && A_STAGE_BYTES % 1024 == 0 && B_STAGE_BYTES % 512 == 0 && B_RING % 1024 == 0, "tile alignment");
+    static_assert(CENTRES % 16 == 0 && A_STAGE_BYTES % 1024 == 0 && B_SLOT % 512 == 0 && B_RING % 1024 == 0, "tile alignment");
 };
 
 struct Args {
@@ -230,12 +238,12 @@ __device__ __forceinline__ float fill_stage_half(const Args& a, const ProducerRo
     return bound;
 }
 
-template <bool TANGENT, int CBU>
+template <bool TANGENT, int CBU, bool WIDE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_mid,
            const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_out)
 {
-    using L = Lay<CBU>;
+    using L = Lay<CBU, WIDE>;
     constexpr int SA = L::SA, SB = L::SB;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     if (a.sel && *a.sel != a.sel_id) return; // uniform over the grid: nothing has been set up yet
@@ -317,19 +325,36 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
                     ++ic;
                     if (++kc == nk) kc = 0;
                 }
-                for (int j = 0; j < nj; ++j, ++ib) {
+                if constexpr (WIDE) { // one slot holds the stage's weight tiles of both column blocks, block j at row 120 j of each split
                     const int s = ib % SB;
                     const uint32_t ph = (ib / SB) & 1;
-                    // CBU = 1: ib == it and SB == SA -- the weight slot is free when the stage's Phi slot is
-                    mbar_wait((CBU == 1 ? bar_empty_a : bar_empty_b) + 8 * s, ph ^ 1);
+                    mbar_wait(bar_empty_b + 8 * s, ph ^ 1);
                     if (elect_one()) {
-                        const uint32_t sb = smem_base + L::B_RING + s * B_STAGE_BYTES;
-                        mbar_expect_tx(bar_full_b + 8 * s, 3 * B_SPLIT_BYTES);
-                        tma_load_2d(sb, &map_hi, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
-                        tma_load_2d(sb + B_SPLIT_BYTES, &map_mid, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
-                        tma_load_2d(sb + 2 * B_SPLIT_BYTES, &map_lo, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
+                        const uint32_t sb = smem_base + L::B_RING + s * L::B_SLOT;
+                        mbar_expect_tx(bar_full_b + 8 * s, nj * 3 * B_SPLIT_BYTES);
+                        for (int j = 0; j < nj; ++j) {
+                            tma_load_2d(sb + j * B_SPLIT_BYTES, &map_hi, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
+                            tma_load_2d(sb + L::B_SPLIT + j * B_SPLIT_BYTES, &map_mid, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
+                            tma_load_2d(sb + 2 * L::B_SPLIT + j * B_SPLIT_BYTES, &map_lo, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
+                        }
                     }
                     __syncwarp();
+                    ++ib;
+                } else {
+                    for (int j = 0; j < nj; ++j, ++ib) {
+                        const int s = ib % SB;
+                        const uint32_t ph = (ib / SB) & 1;
+                        // CBU = 1: ib == it and SB == SA -- the weight slot is free when the stage's Phi slot is
+                        mbar_wait((CBU == 1 ? bar_empty_a : bar_empty_b) + 8 * s, ph ^ 1);
+                        if (elect_one()) {
+                            const uint32_t sb = smem_base + L::B_RING + s * L::B_SLOT;
+                            mbar_expect_tx(bar_full_b + 8 * s, 3 * B_SPLIT_BYTES);
+                            tma_load_2d(sb, &map_hi, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
+                            tma_load_2d(sb + B_SPLIT_BYTES, &map_mid, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
+                            tma_load_2d(sb + 2 * B_SPLIT_BYTES, &map_lo, bar_full_b + 8 * s, kb * BK, (cb0 + j) * CB);
+                        }
+                        __syncwarp();
+                    }
                 }
             }
         }
@@ -351,18 +376,22 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
                 const int s = it % SA;
                 mbar_wait(bar_full_a + 8 * s, (it / SA) & 1);
                 const int nsteps = kb != nk - 1 ? 2 : tail_ksteps; // the last stage: steps of pure zero padding are skipped
-                for (int j = 0; j < nj; ++j, ++ib) {
+                // WIDE: one instruction of N = 120 nj' columns serves all the unit's blocks (block j at TMEM column 120 j)
+                const int ngrp = WIDE ? 1 : nj;
+                for (int j = 0; j < ngrp; ++j, ++ib) {
                     const int sbs = ib % SB;
                     mbar_wait(bar_full_b + 8 * sbs, (ib / SB) & 1);
                     tc_fence_after();
                     if (elect_one()) {
-                        const int ncols = min(NMMA, (3 * a.F - (cb0 + j) * CB + 15) & ~15);
+                        const int cb_last = WIDE ? cb0 + nj - 1 : cb0 + j;
+                        const int real = min(CB, 3 * a.F - cb_last * CB); // columns of the (last) block that exist
+                        const int ncols = min(WIDE ? 2 * CB : NMMA, ((WIDE ? (nj - 1) * CB : 0) + real + 15) & ~15);
                         const uint32_t idesc = make_idesc(ncols);
-                        const uint32_t d0 = tmem_u + (CBU == 1 ? ab : j) * UNIT_COLS, d1 = d0 + ACC1_OFF;
+                        const uint32_t d0 = tmem_u + (CBU == 1 ? ab : j) * UNIT_COLS, d1 = d0 + L::ACC1;
                         const uint64_t a_hi = desc0 + (uint64_t)(s * (A_STAGE_BYTES >> 4));
                         const uint64_t a_mid = a_hi + (A_SPLIT_BYTES >> 4), a_lo = a_mid + (A_SPLIT_BYTES >> 4);
-                        const uint64_t b_hi = desc0 + (uint64_t)((L::B_RING + sbs * B_STAGE_BYTES) >> 4);
-                        const uint64_t b_mid = b_hi + (B_SPLIT_BYTES >> 4), b_lo = b_mid + (B_SPLIT_BYTES >> 4);
+                        const uint64_t b_hi = desc0 + (uint64_t)((L::B_RING + sbs * L::B_SLOT) >> 4);
+                        const uint64_t b_mid = b_hi + (L::B_SPLIT >> 4), b_lo = b_mid + (L::B_SPLIT >> 4);
                         for (int ks = 0; ks < nsteps; ++ks) {
                             const uint64_t o = 2 * ks;                     // 32 bytes = 16 FP16 along K
                             const uint32_t acc = (kb != 0 || ks != 0) ? 1u : 0u;
@@ -378,7 +407,7 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
                             umma_f16(d1, a_lo + o, b_mid + o, idesc, 1);   // negligible once the digit is narrow (h = 5: 2^-24)
                         }
                         if (CBU != 1) umma_commit(bar_empty_b + 8 * sbs);            // the weight slot is free once these MMAs have read it
-                        if (j == nj - 1) {
+                        if (j == ngrp - 1) {
                             umma_commit(bar_empty_a + 8 * s);                        // and the Phi slot after the last column block
                             if (kb == nk - 1) umma_commit(bar_tmem_full + 8 * ab);   // all accumulators of the unit complete
                         }
@@ -502,12 +531,12 @@ k_eval_tcx(const Args a, const __grid_constant__ CUtensorMap map_hi, const __gri
 #pragma unroll 1
                 for (int ch = chunk0; ch * EPI_FRAMES < nframes; ch += EPILOGUE_WARPS / 4) {
                     if (a.dbg_mode & 2) continue;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (CBU == 1 ? ab : j) * UNIT_COLS + ch * EPI_COLS;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (CBU == 1 ? ab * UNIT_COLS : j * L::BLOCK_COLS) + ch * EPI_COLS;
                     float acc[EPI_COLS], acc1[EPI_COLS];
                     tmem_ld16(taddr, acc);
                     tmem_ld8(taddr + 16, acc + 16);
-                    tmem_ld16(taddr + ACC1_OFF, acc1);
-                    tmem_ld8(taddr + ACC1_OFF + 16, acc1 + 16);
+                    tmem_ld16(taddr + L::ACC1, acc1);
+                    tmem_ld8(taddr + L::ACC1 + 16, acc1 + 16);
                     float* stg = stg0 + (L::EPI_BUFS == 1 ? 0 : (nstore & 1) * EPI_WARP_FLOATS);
                     if (vec && lane == 0) { // the staging buffer is free: the bulk store that read it last has done so
                         if (L::EPI_BUFS == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -713,13 +742,41 @@ cudaError_t fd_launch_pack_tcx(fd_ctx* ctx, fd_model* m)
     return cudaGetLastError();
 }
 
+namespace tcx {
+template <bool TANGENT, int CBU, bool WIDE>
+static cudaError_t set_smem_attr()
+{
+    return cudaFuncSetAttribute(k_eval_tcx<TANGENT, CBU, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<CBU, WIDE>::ALLOC);
+}
+template <bool TANGENT, int CBU, bool WIDE>
+static void launch(int grid, cudaStream_t st, const Args& a, const CUtensorMap& mh, const CUtensorMap& mm, const CUtensorMap& ml,
+                   const CUtensorMap& mo)
+{
+    k_eval_tcx<TANGENT, CBU, WIDE><<<grid, THREADS, Lay<CBU, WIDE>::ALLOC, st>>>(a, mh, mm, ml, mo);
+}
+template <bool TANGENT>
+static cudaError_t set_smem_attr_all()
+{
+    cudaError_t e = set_smem_attr<TANGENT, 1, false>();
+    if (e == cudaSuccess) e = set_smem_attr<TANGENT, 2, false>();
+    if (e == cudaSuccess) e = set_smem_attr<TANGENT, 2, true>();
+    return e;
+}
+template <bool TANGENT>
+static void launch_variant(int cbu, bool wide, int grid, cudaStream_t st, const Args& a, const CUtensorMap& mh,
+                           const CUtensorMap& mm, const CUtensorMap& ml, const CUtensorMap& mo)
+{
+    if (cbu == 1) launch<TANGENT, 1, false>(grid, st, a, mh, mm, ml, mo);
+    else if (wide) launch<TANGENT, 2, true>(grid, st, a, mh, mm, ml, mo);
+    else launch<TANGENT, 2, false>(grid, st, a, mh, mm, ml, mo);
+}
+} // namespace tcx
+
 cudaError_t fd_eval_tcx_setup(fd_ctx* ctx)
 {
     (void)ctx;
-    cudaError_t e = cudaFuncSetAttribute(tcx::k_eval_tcx<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::Lay<1>::ALLOC);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tcx::k_eval_tcx<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::Lay<1>::ALLOC);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tcx::k_eval_tcx<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::Lay<2>::ALLOC);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tcx::k_eval_tcx<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::Lay<2>::ALLOC);
+    cudaError_t e = tcx::set_smem_attr_all<false>();
+    if (e == cudaSuccess) e = tcx::set_smem_attr_all<true>();
     return e;
 }
 
@@ -787,17 +844,10 @@ cudaError_t fd_launch_eval_tcx(fd_ctx* ctx, const fd_model* m, const float* P, i
     const int cbu = (a.ncb >= 2 && ctx->dbg.tcx_cbu != 1) ? 2 : 1;
     const int64_t n_units = ((V + tcx::TM - 1) / tcx::TM) * ((a.ncb + cbu - 1) / cbu);
     const int grid = (int)(n_units < ctx->sm_count ? n_units : ctx->sm_count);
-    if (cbu == 2) {
-        if (a.do_tangent)
-            tcx::k_eval_tcx<true, 2><<<grid, tcx::THREADS, tcx::Lay<2>::ALLOC, ctx->stream>>>(a, mh, mm, ml, mo);
-        else
-            tcx::k_eval_tcx<false, 2><<<grid, tcx::THREADS, tcx::Lay<2>::ALLOC, ctx->stream>>>(a, mh, mm, ml, mo);
-    } else {
-        if (a.do_tangent)
-            tcx::k_eval_tcx<true, 1><<<grid, tcx::THREADS, tcx::Lay<1>::ALLOC, ctx->stream>>>(a, mh, mm, ml, mo);
-        else
-            tcx::k_eval_tcx<false, 1><<<grid, tcx::THREADS, tcx::Lay<1>::ALLOC, ctx->stream>>>(a, mh, mm, ml, mo);
-    }
+    // FD_TCX_NARROW=1: one MMA of N = 128 per column block instead of one of N = 240 for the unit's two (for comparison)
+    const bool wide = cbu == 2 && ctx->dbg.tcx_narrow == 0;
+    if (a.do_tangent) tcx::launch_variant<true>(cbu, wide, grid, ctx->stream, a, mh, mm, ml, mo);
+    else tcx::launch_variant<false>(cbu, wide, grid, ctx->stream, a, mh, mm, ml, mo);
     ctx->launches += 1;
     return cudaGetLastError();
 }

@@ -51,6 +51,7 @@ struct fd_debug_opts {
     int lu_cluster_max_n;   // FD_LU_CLUSTER_MAX_N
     int lu_cluster;         // FD_LU_CLUSTER
     int tcx_cbu;            // FD_TCX_CBU: 1 = the exact-digit evaluation takes one column block per unit (default: two)
+    int tcx_narrow;         // FD_TCX_NARROW: one MMA of N = 128 per column block instead of one of N = 240 for the unit's two
     bool poison;            // FD_POISON: every device allocation starts as 0xFF bytes (NaN / -1), so a read of memory the
                             // library never wrote shows in the results instead of depending on what the pool held before
 };
