@@ -29,13 +29,20 @@
 // Net error ~2^-29 ... 2^-31 x S: measured 1e-7 x the rig's diagonal where the FP32 kernels give 5e-6 ... 2.5e-5
 // (tests/tools/accuracy_probe.py; the CPU emulation of the scheme is in tests/tools/fp32_error_emulation.py).
 //
-// Structure (one persistent CTA per SM, 22 warps, the roles of fd_eval_tc.cu): units of 128 vertices x 120 columns (40 frames);
-//   warps 0..15  Phi producers (two groups alternating stages), three SWIZZLE_64B A tiles per 32-centre stage
-//   warps 16..19 epilogue: acc0 + acc1 from TMEM, un-scale, falloff, P +=, transpose, TMA store
-//   warp 20      TMA: three weight tiles W^T[120 cols][32 k] per stage (4-stage ring) + the centre tiles (FP64, own ring)
-//   warp 21      MMA issuer: per K=16 step 1 MMA into acc0 and 7 (5 when h >= 9) into acc1 (M=128, N=128: the 8 rows past a 120-row weight
-//                tile are whatever follows it in shared memory -- their accumulator columns are never read)
-// TMEM: two units in flight (ping-pong), each 2 x 128 columns.
+// Structure (one persistent CTA per SM, 22 warps, the roles of fd_eval_tc.cu).  A unit is 128 vertices x TWO 120-column blocks
+// (80 frames): the Phi tiles -- the expensive operand, FP64 arithmetic per value -- are generated once and multiplied with the
+// weight tiles of both blocks (one block per unit when the batch has only one: F <= 40).
+//   warps 0..15  Phi producers (two groups alternating stages), three SWIZZLE_64B A tiles per 32-centre stage; ring of 3 slots
+//   warps 16..19 epilogue: acc0 + acc1 from TMEM, un-scale, falloff, P +=, transpose, TMA store (two staging buffers per warp)
+//   warp 20      TMA: per stage the three weight tiles W^T[120 cols][32 k] of both blocks, back to back (240 rows per split: one
+//                weight slot = 45 KB, ring of 2) + the centre tiles (FP64, own ring of 8)
+//   warp 21      MMA issuer: per K=16 step 1 MMA into acc0 and 7 (5 when h >= 9) into acc1, M = 128, N = 240 -- the Phi operand
+//                is read from shared memory once per instruction for both blocks (11.5 KB per 120 cycles instead of 8 KB per 64:
+//                the tensor core's operand reads are the largest user of the shared-memory pipe)
+// TMEM: acc0 in columns 0..239, acc1 in 256..495 (block j at +120 j); the epilogue releases it after its last tcgen05.ld, and the
+// producers fill the Phi ring for the next unit meanwhile.  FD_TCX_NARROW=1 keeps one N = 128 MMA per block (3 + 5 slots),
+// FD_TCX_CBU=1 the one-block units with two units in flight in TMEM (4 + 4 slots): 0.38 / 0.51 ms where the default takes 0.35
+// (C2: 100k vertices x 256 control points x 240 frames; profiles/r2k_bench_fast_*.json).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
