@@ -601,38 +601,6 @@ def test_exact_digit_kernel_on_other_systems(ctx, kw):
     assert np.abs(outs[0].astype(np.float64) - outs[1]).max() <= 1e-6 * mesh.bbox_diag
 
 
-def test_exact_digit_kernel_variants_agree():
-    """The shipped kernel takes two 120-column blocks per unit with one N = 240 MMA for both; the development knobs
-    FD_TCX_NARROW=1 (one N = 128 MMA per block) and FD_TCX_CBU=1 (one block per unit, two units in flight in tensor memory)
-    select the earlier forms (read at context creation).  All three see the same digits and sum them in the same order along
-    K: the results agree far inside the FP64-class bound -- on a batch with an odd number of blocks and a partly filled last
-    one (100 frames = 2.5 blocks), with and without the vectorised store path (V % 4)."""
-    from facedeform_b200 import Context, make_params
-    N, F = 300, 100
-    rig = synth.control_rig(N)
-    deform = synth.deformed_rig(rig, F)
-    R = synth.default_radius("gaussian", rig.spacing)
-    for V in (12800, 4097):
-        mesh = synth.face_mesh(V, topology=False)
-        outs = {}
-        for name, env in (("default", {}), ("narrow", {"FD_TCX_NARROW": "1"}), ("one_block", {"FD_TCX_CBU": "1"})):
-            os.environ.update(env)
-            try:
-                c = Context()
-            finally:
-                for k in env:
-                    os.environ.pop(k, None)
-            m = c.fit(make_params(model=1, term=0, kernel=0, radius=R, **{"lambda": 0.0}), rig.rest).solve(deform)
-            out, _ = m.eval(mesh.P)
-            rep = m.report()
-            assert rep.eval_kernel == 4 and rep.eval_inexact == 0
-            outs[name] = out.astype(np.float64)
-            m.close()
-            c.close()
-        for name in ("narrow", "one_block"):
-            assert np.abs(outs[name] - outs["default"]).max() <= 1e-6 * mesh.bbox_diag, (name, V)
-
-
 def test_exact_digit_kernel_far_mesh_and_range_check():
     """a mesh blown up 40x around the rig: the basis sums vanish, the affine rows grow -- their weights are small, so the leading
     digits still sum exactly: no flag, FP64-class result.  The plumbing of the runtime check (fd_report.eval_inexact) is
