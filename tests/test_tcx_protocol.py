@@ -48,3 +48,34 @@ def test_the_model_sees_a_protocol_error():
         except (AssertionError, RuntimeError):
             caught += 1
     assert caught == 8
+
+
+# ---- tc::k_eval_tc (FP16 hi/lo tensor-core evaluation): the CTA-pair protocol -----------------------------------------------
+import tc_pair_protocol_model as pair_model  # noqa: E402
+
+
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("n_units", [1, 2, 5])
+def test_pair_protocol_no_deadlock_and_the_right_halves(pair, n_units):
+    """each CTA loads half of every weight tile and multicasts it to both; a slot is free when the MMAs of both have read it"""
+    for seed, nk in enumerate((1, 2, 3, 9, 20)):
+        assert pair_model.check(n_units, nk, pair, seed) > 0
+
+
+def test_the_pair_model_sees_a_slot_freed_by_one_cta_alone():
+    """sensitivity: with the `empty` barriers counting ONE commit in pair mode (the single-CTA value) a CTA refills a slot its
+    peer's MMAs may still read, or runs a phase ahead -- caught as a wrong / overwritten tile or a deadlock"""
+
+    class OneCommitFrees(pair_model.PairModel):
+        def __init__(self, *a):
+            super().__init__(*a)
+            for c in self.ctas:
+                c.empty = [pair_model.MBar(1) for _ in range(pair_model.STAGES)]
+
+    caught = 0
+    for seed in range(8):
+        try:
+            OneCommitFrees(5, 9, True, random.Random(seed)).run()
+        except (AssertionError, RuntimeError):
+            caught += 1
+    assert caught == 8
